@@ -1,0 +1,159 @@
+"""Pipeline descriptions shared by the parity tests, the oracle and the
+golden-vector generator.
+
+A ``spec`` is a plain dict (format documented in ``oracle/pipeline.py``).
+``build_fruit(mod, spec)`` instantiates it against any module that exposes the
+reference API -- ``fruits_b200`` (the product) or the real reference package
+(only inside ``oracle/gen_golden.py``, in the build container).
+"""
+import numpy as np
+
+
+def _seven_sieves():
+    # experiments/fruit_reduced.py:33-39
+    return ([["NPI", {"q": [0.5, 1.0], "inc": i}] for i in range(3)]
+            + [["MPI", {"q": [0.5, 1.0], "inc": i}] for i in range(3)]
+            + [["END", {}]])
+
+
+def _alt(words):
+    return {"alternate_sign": words}
+
+
+SPECS = {
+    # README.md:67-99 of the reference
+    "C1_readme": {"slices": [
+        {"preps": [["INC", {}]],
+         "iss": [{"words": {"of_weight": [2, 3]}, "mode": "extended"}],
+         "sieves": [["NPI", {"q": [0.5, 1.0]}], ["END", {}]]},
+        {"preps": [],
+         "iss": [{"words": {"of_weight": [2, 3]}, "mode": "extended"}],
+         "sieves": [["NPI", {}], ["END", {}]]},
+    ]},
+    # experiments/fruit_reduced.py:27-49 (slices 0-1; CosWISS slices are "next")
+    "C2_reduced": {"slices": [
+        {"preps": [["NEW", ["INC", {}]], ["STD", {}]],
+         "iss": [{"words": {"of_weight": [4, 2]}, "mode": "extended",
+                  "semiring": "reals", "weighting": ["Indices", {}]}],
+         "sieves": _seven_sieves(), "fit_sample_size": 1.0},
+        {"preps": [["NEW", ["INC", {}]]],
+         "iss": [{"words": _alt([24 * "[1]", 24 * "[2]", 12 * "[1][2]",
+                                 12 * "[2][1]"]),
+                  "mode": "extended", "semiring": "arctic"}],
+         "sieves": _seven_sieves(), "fit_sample_size": 1.0},
+    ]},
+    # experiments/fruit_general.py:28-51 (slices 0-1)
+    "C3_general": {"slices": [
+        {"preps": [["NEW", ["INC", {}]], ["STD", {}]],
+         "iss": [{"words": {"of_weight": [6, 2]}, "mode": "extended",
+                  "semiring": "reals", "weighting": ["Indices", {}]}],
+         "sieves": _seven_sieves(), "fit_sample_size": 1.0},
+        {"preps": [["NEW", ["INC", {}]]],
+         "iss": [{"words": _alt([48 * "[1]", 48 * "[2]", 24 * "[1][2]",
+                                 24 * "[2][1]"]),
+                  "mode": "extended", "semiring": "arctic"}],
+         "sieves": _seven_sieves(), "fit_sample_size": 1.0},
+    ]},
+    # experiments/fruit_twi.py:3-31
+    "C4_twi": {"slices": [
+        {"preps": [["INC", {}]],
+         "iss": [{"words": {"of_weight": [9, 1]}, "mode": "extended",
+                  "semiring": "reals", "weighting": ["L1", {}]}],
+         "sieves": [["NPI", {}], ["MPI", {}], ["END", {}]],
+         "fit_sample_size": 1.0},
+        {"preps": [],
+         "iss": [{"words": _alt([48 * "[1]"]), "mode": "extended",
+                  "semiring": "arctic"}],
+         "sieves": [["NPI", {}], ["END", {}]], "fit_sample_size": 1.0},
+    ]},
+    # throughput sweep (BASELINE.json configs[4])
+    "C5_sweep": {"slices": [
+        {"preps": [],
+         "iss": [{"words": {"of_weight": [4, 3]}, "mode": "extended"}],
+         "sieves": [["NPI", {"q": [0.5, 1.0]}], ["PPV", {}], ["MAX", {}],
+                    ["MIN", {}], ["END", {}]]},
+    ]},
+}
+
+
+def make_input(name: str, n: int = None) -> np.ndarray:
+    """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
+    overrides the number of series (same generator, first ``n`` rows)."""
+    shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512),
+              "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
+              "C5_sweep": (4096, 3, 1024)}
+    N, D, T = shapes[name]
+    n = N if n is None else n
+    if name == "C1_readme":
+        return np.random.default_rng(0).random((N, D, T))[:n]
+    if name == "C5_sweep":
+        return np.random.default_rng(1234).standard_normal((n, D, T))
+    return np.random.default_rng(0).standard_normal((n, D, T)).cumsum(axis=2)
+
+
+# ---------------------------------------------------------------------------
+
+def _words(mod, desc):
+    if isinstance(desc, dict):
+        if "of_weight" in desc:
+            return list(mod.words.of_weight(*desc["of_weight"]))
+        if "alternate_sign" in desc:
+            return list(mod.words.alternate_sign(_words(mod, desc["alternate_sign"])))
+        if "concat" in desc:
+            return [w for d in desc["concat"] for w in _words(mod, d)]
+        raise ValueError(desc)
+    return [mod.words.SimpleWord(w) for w in desc]
+
+
+def _prep(mod, desc):
+    name, args = desc
+    if name == "NEW":
+        return mod.preparation.NEW(None if args is None else _prep(mod, args))
+    return getattr(mod.preparation, name)(**args)
+
+
+def _weighting(mod, desc):
+    if desc is None:
+        return None
+    name, args = desc
+    return getattr(mod.iss.weighting, name)(**args)
+
+
+def _semiring(mod, name):
+    return {"reals": mod.iss.semiring.Reals,
+            "arctic": mod.iss.semiring.Arctic}[name]()
+
+
+def _sieve(mod, desc):
+    name, args = desc
+    args = dict(args)
+    for key in ("q", "cut"):
+        if isinstance(args.get(key), list):
+            args[key] = tuple(args[key])
+    return getattr(mod.sieving, name)(**args)
+
+
+def build_iss(mod, desc):
+    words = _words(mod, desc["words"])
+    if desc.get("alphas") is not None:
+        for w, a in zip(words, desc["alphas"]):
+            w.alpha = a
+    mode = (mod.ISSMode.EXTENDED if desc.get("mode", "single") == "extended"
+            else mod.ISSMode.SINGLE)
+    return mod.ISS(words, mode=mode,
+                   semiring=_semiring(mod, desc.get("semiring", "reals")),
+                   weighting=_weighting(mod, desc.get("weighting")))
+
+
+def build_fruit(mod, spec, name="fruit"):
+    fruit = mod.Fruit(name)
+    for slc in spec["slices"]:
+        fruit.cut()
+        for p in slc.get("preps", []):
+            fruit.add(_prep(mod, p))
+        for i in slc["iss"]:
+            fruit.add(build_iss(mod, i))
+        for s in slc["sieves"]:
+            fruit.add(_sieve(mod, s))
+        fruit.get_slice().fit_sample_size = slc.get("fit_sample_size", 1)
+    return fruit
