@@ -1,0 +1,17 @@
+"""fruits_b200 -- B200-native implementation of the FRUITS hot path.
+
+Drop-in for the Python API of irkri/fruits 1.0.0 on the path
+preparateur -> iterated-sums signature -> sieves (``Fruit`` / ``FruitSlice``
+``fit`` / ``transform``, ``ISS`` with ``SimpleWord`` words, ``ISSMode``, the
+``Reals`` and ``Arctic`` semirings, exponential weightings, ``INC`` / ``STD``
+/ ``NEW`` preparateurs, ``NPI`` / ``MPI`` / ``PPV`` / ``MAX`` / ``MIN`` /
+``END`` sieves).  All arithmetic runs in hand-written sm_100a CUDA
+(``fruits_b200/csrc``) behind the C ABI of ``include/fruits_b200.h``.
+"""
+from . import cache, callback, iss, preparation, seed, sieving
+from .fruit import Fruit, FruitSlice
+from .iss import semiring, words
+from .iss.cos import CosWISS
+from .iss.iss import ISS, ISSMode
+
+__version__ = "0.1.0"

@@ -1,0 +1,239 @@
+// prep.cu -- preparateurs, weighting lookups and raw-input cache kernels.
+//
+// These are the small data-parallel helpers either side of the ISS kernel.
+// They are bandwidth-trivial next to it (the path is
+// fp64-pipe bound), so they favour exactness over cleverness: every kernel
+// reproduces the reference's order of floating point operations.
+#include "common.cuh"
+
+namespace fb {
+
+// ---------------------------------------------------------------------------
+// fruits/cache.py:8-13 _increments: out[r][i] = x[r][i] - x[r][i-k], 0 for i<k.
+// pad_src != null: out[r][i] = pad_src[r][i] for i < k (INC(zero_padding=False),
+// fruits/preparation/transform.py:72-75).
+__global__ void increments_kernel(const double *__restrict__ X, const double *__restrict__ pad_src,
+                                  double *__restrict__ out, long long rows, int t, int k)
+{
+    const long long total = rows * t;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % t);
+        double v;
+        if (i >= k) v = X[idx] - X[idx - k];
+        else v = pad_src ? pad_src[idx] : 0.0;
+        out[idx] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
+// @TYPE@_pairwise_sum) so that np.mean / np.std along the last axis are
+// reproduced bit for bit.  F maps the element before it is added.
+template <class F>
+__device__ double pairwise_sum(const double *a, int n, F f)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res = __dadd_rn(res, f(a[i]));
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] = f(a[k]);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[k] = __dadd_rn(r[k], f(a[i + k]));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __dadd_rn(res, f(a[i]));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const double lo = pairwise_sum(a, n2, f);
+    const double hi = pairwise_sum(a + n2, n - n2, f);
+    return __dadd_rn(lo, hi);
+}
+
+// fruits/preparation/transform.py:132-144 STD(separately=True):
+// stats[r] = (mean, std + eps); one thread per row.
+__global__ void row_stats_kernel(const double *__restrict__ X, double *__restrict__ stats,
+                                 long long rows, int t, int div_std, double eps)
+{
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double *x = X + r * t;
+    const double mean = pairwise_sum(x, t, [](double v) { return v; }) / (double)t;
+    double sd = 1.0;
+    if (div_std) {
+        const double var = pairwise_sum(x, t, [mean](double v) {
+                               const double c = __dadd_rn(v, -mean);
+                               return __dmul_rn(c, c);
+                           }) / (double)t;
+        sd = sqrt(var);
+    }
+    stats[2 * r] = mean;
+    stats[2 * r + 1] = sd + eps;
+}
+
+__global__ void standardize_kernel(const double *__restrict__ X, const double *__restrict__ stats,
+                                   double *__restrict__ out, long long rows, int t)
+{
+    const long long total = rows * t;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / t;
+        out[idx] = (X[idx] - stats[2 * r]) / stats[2 * r + 1];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fruits/cache.py:25-40 _L1_sum/_L2_sum: cumsum of |dx| (or dx^2) of dim 0,
+// summed sequentially in time; one thread per series.
+__global__ void lsum_kernel(const double *__restrict__ X, double *__restrict__ out, long long n,
+                            long long d, int t, int l2)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *x = X + i * d * t;
+    double *o = out + i * t;
+    double acc = 0.0, prev = 0.0;
+    for (int j = 0; j < t; j++) {
+        const double cur = x[j];
+        const double inc = j ? __dadd_rn(cur, -prev) : 0.0;
+        prev = cur;
+        acc = __dadd_rn(acc, l2 ? __dmul_rn(inc, inc) : fabs(inc));
+        o[j] = acc;
+    }
+}
+
+// fruits/iss/weighting.py:151-158: optional r / (r[-1] + 1e-5), then
+// NRM (fruits/preparation/transform.py:184-198) per row, then * scale.
+// One warp per row; in-place allowed.
+__global__ void nrm_scale_kernel(const double *__restrict__ in, double *__restrict__ out,
+                                 long long rows, int t, int relative, double scale)
+{
+    const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const double *x = in + r * t;
+    double *o = out + r * t;
+    const double den = relative ? x[t - 1] + 1e-5 : 1.0;
+    double mn = d_inf(), mx = d_ninf();
+    for (int j = lane; j < t; j += 32) {
+        const double v = relative ? x[j] / den : x[j];
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    }
+    const double range = mx - mn;
+    for (int j = lane; j < t; j += 32) {
+        const double v = relative ? x[j] / den : x[j];
+        o[j] = (mn != mx) ? __dmul_rn((v - mn) / range, scale) : __dmul_rn(0.0, scale);
+    }
+}
+
+// fruits/cache.py:16-22 _coquantile: count(S[i,:] <= q*S[i,-1]); warp per row.
+__global__ void coquantile_kernel(const double *__restrict__ S, long long *__restrict__ out,
+                                  long long n, int t, double q)
+{
+    const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double *x = S + r * t;
+    const double thr = __dmul_rn(q, x[t - 1]);
+    int c = 0;
+    for (int j = lane; j < t; j += 32) c += (x[j] <= thr);
+#pragma unroll
+    for (int s = 16; s; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0) out[r] = c;
+}
+
+static inline unsigned grid_for(long long total, int block)
+{
+    long long g = (total + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > 148LL * 64) g = 148LL * 64;
+    return (unsigned)g;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_increments(const double *X, const double *pad_src, double *out, int64_t rows, int64_t t,
+                  int64_t k, void *stream)
+{
+    FB_REQUIRE(X && out && rows >= 0 && t >= 1 && k >= 0, "bad arguments");
+    if (rows == 0) return 0;
+    const int kk = (int)(k > t ? t : k);
+    increments_kernel<<<grid_for(rows * t, 256), 256, 0, (cudaStream_t)stream>>>(X, pad_src, out,
+                                                                                 rows, (int)t, kk);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_row_stats(const double *X, double *stats, int64_t rows, int64_t t, int div_std, double eps,
+                 void *stream)
+{
+    FB_REQUIRE(X && stats && rows >= 0 && t >= 1, "bad arguments");
+    if (rows == 0) return 0;
+    row_stats_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+        X, stats, rows, (int)t, div_std, eps);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_standardize(const double *X, const double *stats, double *out, int64_t rows, int64_t t,
+                   void *stream)
+{
+    FB_REQUIRE(X && stats && out && rows >= 0 && t >= 1, "bad arguments");
+    if (rows == 0) return 0;
+    standardize_kernel<<<grid_for(rows * t, 256), 256, 0, (cudaStream_t)stream>>>(X, stats, out,
+                                                                                  rows, (int)t);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_lsum(const double *X, double *out, int64_t n, int64_t d, int64_t t, int l2, void *stream)
+{
+    FB_REQUIRE(X && out && n >= 0 && d >= 1 && t >= 1, "bad arguments");
+    if (n == 0) return 0;
+    lsum_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(X, out, n, d, (int)t,
+                                                                            l2);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_nrm_scale(const double *in, double *out, int64_t rows, int64_t t, int relative,
+                 double scale, void *stream)
+{
+    FB_REQUIRE(in && out && rows >= 0 && t >= 1, "bad arguments");
+    if (rows == 0) return 0;
+    nrm_scale_kernel<<<(unsigned)((rows * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        in, out, rows, (int)t, relative, scale);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_coquantile(const double *S, int64_t *out, int64_t n, int64_t t, double q, void *stream)
+{
+    FB_REQUIRE(S && out && n >= 0 && t >= 1, "bad arguments");
+    if (n == 0) return 0;
+    coquantile_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        S, (long long *)out, n, (int)t, q);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,708 @@
+"""``Fruit`` and ``FruitSlice``: the pipeline container and the dispatch of the
+hot path (reference: ``fruits/fruit.py``).
+
+The reference walks a slice with one numba launch per word and per sieve
+(fruit.py:538-550).  Here a slice is compiled into one device plan and --
+whenever its preparateurs and sieves fit the fused kernel -- evaluated by a
+single CUDA launch per slice that reads X once and writes only the features
+(``csrc/lns.cuh``).  Everything else (several ISS in one slice, sieves with
+several cuts or quantile intervals, callbacks, fit) runs on the composed
+route: materialise chunks of iterated sums on the GPU and sieve them with the
+array kernels of ``csrc/sieve.cu``.  There is no CPU route.
+"""
+import ctypes
+import inspect
+from typing import Callable, Generator, Literal, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _backend as be
+from .cache import SharedSeedCache
+from .callback import AbstractCallback
+from .iss.iss import ISS
+from .preparation.abstract import Preparateur
+from .preparation.wrapper import NEW
+from .seed import Seed
+from .sieving.abstract import FeatureSieve, quantile_rows
+from .sieving.implicit import PPV
+from .sieving.segment import SegmentSieve
+
+_FEAT_CODE = {"CNT": be.FEAT_CNT, "AVG": be.FEAT_AVG, "PPV": be.FEAT_PPV,
+              "MAX": be.FEAT_MAX, "MIN": be.FEAT_MIN, "END": be.FEAT_END}
+
+
+class Fruit:
+    """Feature extractor using iterated sums; a list of
+    :class:`FruitSlice` objects whose features are concatenated
+    (reference: fruit.py:14-277, same methods)."""
+
+    def __init__(self, name: str = "") -> None:
+        self.name: str = name
+        self._slices: list = []
+        self._slc_index: int = 0
+        self._fitted: bool = False
+        self._iterator_index: int = -1
+
+    def cut(self, slice: Optional["FruitSlice"] = None) -> None:
+        """Adds a new (or the given) slice and switches to it."""
+        if slice is None:
+            slice = FruitSlice()
+        self._slices.append(slice)
+        self._slc_index = len(self._slices) - 1
+        self._fitted = False
+
+    def copycut(self) -> None:
+        """Adds a deep copy of the current slice and switches to it."""
+        self.cut(self.get_slice().deepcopy())
+
+    def get_slice(self, index: Optional[int] = None) -> "FruitSlice":
+        if index is None:
+            return self._slices[self._slc_index]
+        return self._slices[index]
+
+    def switch_slice(self, index: int) -> None:
+        if not (0 <= index < len(self._slices)):
+            raise IndexError("Index has to be in [0, len(self)-1]")
+        self._slc_index = index
+
+    def add(self, *objects: Union[Seed, Callable[[], Seed]]) -> None:
+        """Adds preparateurs, ISS or sieves to the current slice."""
+        if len(self._slices) == 0:
+            self.cut()
+        self._slices[self._slc_index].add(*objects)
+        self._fitted = False
+
+    def nfeatures(self) -> int:
+        return sum(slc.nfeatures() for slc in self._slices)
+
+    def fit(self, X, cache: Optional[SharedSeedCache] = None) -> None:
+        """Fits all slices (reference: fruit.py:121-136)."""
+        Xd = be.to_device(X)
+        cache_ = SharedSeedCache(Xd) if cache is None else cache
+        for slc in self._slices:
+            slc._fit_device(Xd, cache_)
+        self._fitted = True
+
+    def transform(self, X, callbacks: Optional[list] = None,
+                  cache: Optional[SharedSeedCache] = None):
+        """Feature matrix ``[n_series, nfeatures]`` of all slices
+        (reference: fruit.py:138-173)."""
+        if callbacks is None:
+            callbacks = []
+        if not self._fitted:
+            raise RuntimeError("Missing call of self.fit")
+        Xd = be.to_device(X)
+        result = self.transform_device(Xd, callbacks, cache)
+        if isinstance(X, torch.Tensor):
+            return result
+        return result.cpu().numpy()
+
+    def transform_device(self, Xd: torch.Tensor, callbacks=None, cache=None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``transform`` on device tensors; ``out`` may be a preallocated
+        ``[n, >= nfeatures]`` row-major tensor (or a view of rows of one)."""
+        callbacks = callbacks or []
+        cache_ = SharedSeedCache(Xd) if cache is None else cache
+        n = Xd.shape[0]
+        result = be.zeros((n, self.nfeatures())) if out is None else out
+        index = 0
+        for slc in self._slices:
+            for callback in callbacks:
+                callback.on_next_slice()
+            k = slc.nfeatures()
+            slc._transform_device(Xd, callbacks, cache_, result, index, sanitize=True)
+            index += k
+        return result
+
+    def fit_transform(self, X, callbacks: Optional[list] = None):
+        self.fit(X)
+        return self.transform(X, callbacks=callbacks)
+
+    def summary(self) -> str:
+        """Reference: fruit.py:186-213."""
+        summary = 80*"=" + "\n"
+        ident_string = "Fruit"
+        if self.name != "":
+            ident_string += f" {self.name!r}"
+        ident_string += f" -> Features: {self.nfeatures()}"
+        summary += "<" + f"{ident_string: ^78}" + ">\n"
+        summary += 80*"=" + "\n"
+        n = len(self._slices)
+        if n % 2 != 0:
+            n -= 1
+        for islc in range(0, n, 2):
+            summary += "|" + 38*"-" + "||" + 38*"-" + "|\n"
+            left = self._slices[islc].summary().split("\n")
+            right = self._slices[islc+1].summary().split("\n")
+            left += [38*" " for _ in range(len(right)-len(left))]
+            right += [38*" " for _ in range(len(left)-len(right))]
+            summary += "\n".join(f"|{l}||{r}|" for l, r in zip(left, right))
+            summary += "\n|" + 38*"-" + "||" + 38*"-" + "|\n"
+        if len(self._slices) % 2 != 0:
+            summary += "|" + 38*"-" + "|\n|"
+            summary += self._slices[-1].summary().replace("\n", "|\n|")
+            summary += "|\n|" + 38*"-" + "|\n"
+        summary += f"{'':=^80}"
+        return summary
+
+    def copy(self) -> "Fruit":
+        copy_ = Fruit(self.name + " (Copy)")
+        for slc in self._slices:
+            copy_.cut(slc.copy())
+        return copy_
+
+    def deepcopy(self) -> "Fruit":
+        copy_ = Fruit(self.name + " (Deepcopy)")
+        for slc in self._slices:
+            copy_.cut(slc.deepcopy())
+        return copy_
+
+    def label(self, index: int,
+              level: Literal["prepared", "iterated sums", "features"] = "features",
+              verbose: Literal[1, 2] = 1) -> str:
+        """Label of one feature / iterated sum / preparateur chain
+        (reference: fruit.py:229-261)."""
+        i = 0
+        while index >= 0:
+            if level == "prepared":
+                total = len(self.get_slice(i).get_preparateurs())
+            elif level == "iterated sums":
+                total = self.get_slice(i).niteratedsums()
+            elif level == "features":
+                total = self.get_slice(i).nfeatures()
+            if index < total:
+                return self.get_slice(i).label(index, level, verbose)
+            index -= total
+            i += 1
+        raise RuntimeError("Label index out of range")
+
+    def __len__(self) -> int:
+        return len(self._slices)
+
+    def __iter__(self) -> "Fruit":
+        self._iterator_index = -1
+        return self
+
+    def __next__(self) -> "FruitSlice":
+        if self._iterator_index < len(self._slices)-1:
+            self._iterator_index += 1
+            return self._slices[self._iterator_index]
+        raise StopIteration()
+
+    def __getitem__(self, index: int) -> "FruitSlice":
+        return self.get_slice(index)
+
+
+class FruitSlice:
+    """One slice of a Fruit: preparateurs -> ISS -> sieves
+    (reference: fruit.py:280-686, same methods)."""
+
+    def __init__(self) -> None:
+        self._preparateurs: list = []
+        self._iss: list = []
+        self._sieves: list = []
+        # one list of fitted sieve copies per iterated sum
+        self._sieves_extended: list = []
+        self._fitted: bool = False
+        self.fit_sample_size: Union[float, int] = 1
+        self._thr_memo = None
+
+    # -- configuration -----------------------------------------------------------
+    def add_preparateur(self, preparateur: Preparateur) -> None:
+        if not isinstance(preparateur, Preparateur):
+            raise TypeError
+        self._preparateurs.append(preparateur)
+        self._fitted = False
+
+    def get_preparateurs(self) -> list:
+        return self._preparateurs
+
+    def clear_preparateurs(self) -> None:
+        self._preparateurs = []
+        self._fitted = False
+
+    def add_iss(self, iss: ISS) -> None:
+        if not isinstance(iss, ISS):
+            raise TypeError
+        self._iss.append(iss)
+        self._fitted = False
+
+    def get_iss(self) -> list:
+        return self._iss
+
+    def clear_iss(self) -> None:
+        self._iss = []
+        self._sieves_extended = []
+        self._fitted = False
+
+    def add_sieve(self, sieve: FeatureSieve) -> None:
+        if not isinstance(sieve, FeatureSieve):
+            raise TypeError
+        self._sieves.append(sieve)
+        self._fitted = False
+
+    def get_sieves(self) -> list:
+        return self._sieves
+
+    def clear_sieves(self) -> None:
+        self._sieves = []
+        self._sieves_extended = []
+        self._fitted = False
+
+    def add(self, *objects: Union[Seed, Callable[[], Seed]]) -> None:
+        """Adds preparateurs, ISS or sieves (classes are instantiated)."""
+        for obj in objects:
+            if inspect.isclass(obj):
+                obj = obj()
+            if isinstance(obj, Preparateur):
+                self.add_preparateur(obj)
+            elif isinstance(obj, ISS):
+                self.add_iss(obj)
+            elif isinstance(obj, FeatureSieve):
+                self.add_sieve(obj)
+            else:
+                raise TypeError(f"Cannot add variable of type {type(obj)}")
+
+    def clear(self) -> None:
+        self.clear_preparateurs()
+        self.clear_iss()
+        self.clear_sieves()
+        self.fit_sample_size = 1
+
+    def nfeatures(self) -> int:
+        return sum(s.nfeatures() for s in self._sieves) * self.niteratedsums()
+
+    def niteratedsums(self) -> int:
+        return int(np.prod([iss.n_iterated_sums() for iss in self._iss]))
+
+    def _compile(self) -> None:
+        if not self._iss:
+            raise RuntimeError("No ISS given")
+        if not self._sieves:
+            raise RuntimeError("No feature sieves given")
+
+    def _select_fit_sample(self, X: torch.Tensor) -> torch.Tensor:
+        # same draws from the global numpy RNG as the reference (fruit.py:430-438)
+        if isinstance(self.fit_sample_size, int) and self.fit_sample_size == 1:
+            ind = np.random.randint(0, X.shape[0])
+            return X[ind:ind+1, :, :]
+        s = max(int(self.fit_sample_size * X.shape[0]), 1)
+        indices = np.random.choice(X.shape[0], size=s, replace=False)
+        idx = torch.as_tensor(indices, device=X.device, dtype=torch.long)
+        return X.index_select(0, idx)
+
+    # -- which route ---------------------------------------------------------------
+    def _fused_dims(self, n_dims: int):
+        """Per prepared dimension ``(raw_dim, inc, std)`` if the preparateurs
+        can be applied while the kernel loads X, else None."""
+        dims = [(d, 0, 0) for d in range(n_dims)]
+        for prep in self._preparateurs:
+            if isinstance(prep, NEW):
+                inner = prep._preparateur
+                if any(std for _, _, std in dims):
+                    return None
+                if inner is None:
+                    dims = dims + dims
+                elif inner._fusable() == "inc" and all(i == 0 for _, i, _ in dims):
+                    dims = dims + [(d, 1, 0) for d, _, _ in dims]
+                else:
+                    return None
+            else:
+                kind = prep._fusable()
+                if kind == "inc" and all(i == 0 and s == 0 for _, i, s in dims):
+                    dims = [(d, 1, 0) for d, _, _ in dims]
+                elif kind == "std" and all(s == 0 for _, _, s in dims):
+                    dims = [(d, i, 1) for d, i, _ in dims]
+                else:
+                    return None
+        return dims
+
+    def _fused_sieves(self):
+        """``(features, bounded_hi, bounded_mm)`` if all sieves fit the fused
+        kernel, else None.  ``features`` holds one ``(kind, arg)`` per sieve."""
+        feats, unit_q = [], {}
+        bounded_hi = bounded_mm = False
+        for sv in self._sieves:
+            f = sv._fused()
+            if f is None:
+                return None
+            kind, arg = f
+            if kind in ("CNT", "AVG"):
+                key = ("U", arg)
+                bounded_hi |= (sv._q[1] != 1.0) or (sv._q[0] > sv._q[1])
+            elif kind in ("MAX", "MIN"):
+                key = (kind, 0)
+                bounded_mm |= tuple(sv._q) != (-1.0, 1.0)
+            else:
+                key = None
+            if key is not None:
+                if unit_q.setdefault(key, tuple(sv._q)) != tuple(sv._q):
+                    return None
+            feats.append((_FEAT_CODE[kind], arg))
+        if len(feats) > be.FB_MAX_FEATS:
+            return None
+        if sum(1 for s in self._sieves if isinstance(s, PPV)) > 1:
+            return None
+        return feats, bounded_hi, bounded_mm
+
+    def _is_fusable(self, n_dims: int, callbacks) -> bool:
+        if callbacks or len(self._iss) != 1:
+            return False
+        w = self._iss[0].weighting
+        if w is not None and getattr(w, "_on_prepared", False):
+            return False
+        return self._fused_dims(n_dims) is not None and self._fused_sieves() is not None
+
+    # -- fit -------------------------------------------------------------------------
+    def fit(self, X, cache: Optional[SharedSeedCache] = None) -> None:
+        """Fits the slice (reference: fruit.py:456-496)."""
+        self._fit_device(be.to_device(X), cache)
+
+    def _prepare_device(self, X: torch.Tensor, cache, fit: bool, callbacks=()):
+        prepared = X
+        for prep in self._preparateurs:
+            prep._cache = cache
+            if fit:
+                prep._fit_device(prepared)
+            prepared = prep._transform_device(prepared)
+            for callback in callbacks:
+                callback.on_preparateur(prepared.cpu().numpy())
+        return prepared.contiguous()
+
+    def _iterate_iss_device(self, X: torch.Tensor, iss_index: int = 0,
+                            max_bytes: int = 1 << 30) -> Generator:
+        """Yield every iterated sum ``[n, t]`` in the reference's order
+        (fruit.py:440-454), materialised chunk by chunk on the GPU."""
+        if iss_index == len(self._iss):
+            yield X[:, 0, :]
+        else:
+            for _, chunk in self._iss[iss_index].iter_chunks(X, max_bytes):
+                for e in range(chunk.shape[0]):
+                    yield from self._iterate_iss_device(chunk[e][:, None, :], iss_index + 1,
+                                                        max_bytes)
+
+    def _fit_device(self, X: torch.Tensor, cache: Optional[SharedSeedCache] = None) -> None:
+        self._compile()
+        self._thr_memo = None
+        if X.dim() != 3:
+            raise ValueError("input must have shape (n_series, n_dimensions, length)")
+        if cache is None:
+            cache = SharedSeedCache(X)
+        sample = self._select_fit_sample(X)
+        prepared = self._prepare_device(sample, cache, fit=True)
+        for iss in self._iss:
+            iss._cache = cache
+            iss._check_input(prepared)
+        if not any(sieve.requires_fitting for sieve in self._sieves):
+            self._sieves_extended = []
+            self._fitted = True
+            return
+        self._sieves_extended = []
+        if len(self._iss) == 1:
+            self._fit_batched(prepared, cache)
+        else:
+            for itsum in self._iterate_iss_device(prepared):
+                sieves_copy = [sieve.copy() for sieve in self._sieves]
+                for sieve in sieves_copy:
+                    sieve._cache = cache
+                    sieve._fit_device(itsum.contiguous())
+                self._sieves_extended.append(sieves_copy)
+        self._fitted = True
+
+    def _fit_batched(self, prepared: torch.Tensor, cache) -> None:
+        """Fit all sieve copies of one chunk of iterated sums with batched
+        order statistics: one radix select per (increment depth, probability)
+        over ``[chunk, n_fit * t]`` instead of one np.quantile per sieve."""
+        iss = self._iss[0]
+        n, _, t = prepared.shape
+        for _, chunk in iss.iter_chunks(prepared, max_bytes=1 << 29):
+            G = chunk.shape[0]
+            copies = [[sieve.copy() for sieve in self._sieves] for _ in range(G)]
+            # replay the reference's RNG consumption: node-major, sieve order
+            draws = [[sv._draw(n) if isinstance(sv, PPV) else None for sv in row]
+                     for row in copies]
+            pre_cache, q_cache = {}, {}
+
+            def pretransformed(sv):
+                key = sv._inc if isinstance(sv, SegmentSieve) else 0
+                if key not in pre_cache:
+                    flat = chunk.reshape(G * n, t)
+                    pre_cache[key] = (flat if key == 0 else
+                                      sv._pre_transform_device(flat)).reshape(G, n * t)
+                return key, pre_cache[key]
+
+            def quant(sv, q):
+                key, V = pretransformed(sv)
+                if (key, q) not in q_cache:
+                    q_cache[(key, q)] = quantile_rows(V, q)
+                return q_cache[(key, q)]
+
+            for si, sieve in enumerate(self._sieves):
+                if isinstance(sieve, PPV):
+                    for e in range(G):
+                        sv = copies[e][si]
+                        sv._q = [x[0] for x in sv._q_c_input]
+                        for qi, (q, const) in enumerate(sv._q_c_input):
+                            if const:
+                                continue
+                            sel = draws[e][si][qi]
+                            if len(sel) == n:
+                                sv._q[qi] = quant(sv, q)[e]
+                            else:
+                                idx = torch.as_tensor(sel, device=chunk.device, dtype=torch.long)
+                                rows = chunk[e].index_select(0, idx).reshape(1, -1)
+                                sv._q[qi] = quantile_rows(rows, q)[0]
+                elif isinstance(sieve, SegmentSieve):
+                    need = [q for q in sieve._q if q not in (1.0, -1.0, 0)]
+                    vals = {q: quant(sieve, q) for q in need}
+                    for e in range(G):
+                        copies[e][si]._set_quantiles({q: vals[q][e] for q in need})
+                else:
+                    for e in range(G):
+                        copies[e][si]._fit_device(chunk[e])
+            for row in copies:
+                for sv in row:
+                    sv._cache = cache
+            self._sieves_extended.extend(copies)
+
+    # -- transform -------------------------------------------------------------------
+    def transform(self, X, callbacks: Optional[list] = None,
+                  cache: Optional[SharedSeedCache] = None):
+        """Features of this slice (reference: fruit.py:498-553)."""
+        if callbacks is None:
+            callbacks = []
+        if not self._fitted:
+            raise RuntimeError("Missing call of self.fit")
+        Xd = be.to_device(X)
+        out = be.zeros((Xd.shape[0], self.nfeatures()))
+        self._transform_device(Xd, callbacks, cache, out, 0, sanitize=False)
+        if isinstance(X, torch.Tensor):
+            return out
+        return out.cpu().numpy()
+
+    def _sieves_for(self, i: int) -> list:
+        return self._sieves_extended[i] if self._sieves_extended else self._sieves
+
+    def _threshold_table(self, n_emit: int) -> torch.Tensor:
+        """``[n_emit, FB_NTHR]`` table of the fused kernel (layout in
+        include/fruits_b200.h)."""
+        if self._thr_memo is not None and self._thr_memo[0] == n_emit:
+            return self._thr_memo[1]
+        tab = np.zeros((n_emit, be.FB_NTHR))
+        tab[:, 1::2] = np.inf
+        tab[:, 8] = -np.inf
+        tab[:, 10] = -np.inf
+        for e in range(n_emit):
+            for sv in self._sieves_for(e):
+                kind, arg = sv._fused()
+                if kind == "PPV":
+                    if not hasattr(sv, "_q"):
+                        raise RuntimeError("Missing call of PPV.fit()")
+                    tab[e, 6] = sv._q[0]
+                    continue
+                if kind == "END":
+                    continue
+                if not sv.requires_fitting:
+                    sv._get_unfitted_quantiles()
+                q = sv._quantiles
+                col = {"CNT": 2 * arg, "AVG": 2 * arg, "MAX": 8, "MIN": 10}[kind]
+                tab[e, col], tab[e, col + 1] = q[0], q[1]
+        dev = be.to_device(np.ascontiguousarray(tab))
+        self._thr_memo = (n_emit, dev)
+        return dev
+
+    def _transform_device(self, X: torch.Tensor, callbacks, cache, out: torch.Tensor,
+                          col0: int, sanitize: bool) -> None:
+        """Write the features of this slice into ``out[:, col0:col0+nfeatures]``."""
+        if not self._fitted:
+            raise RuntimeError("Missing call of self.fit")
+        if X.dim() != 3:
+            raise ValueError("input must have shape (n_series, n_dimensions, length)")
+        if cache is None:
+            cache = SharedSeedCache(X)
+        for iss in self._iss:
+            iss._cache = cache
+        if self._is_fusable(X.shape[1], callbacks):
+            self._transform_fused(X.contiguous(), cache, out, col0, sanitize)
+        else:
+            self._transform_composed(X, callbacks or [], cache, out, col0, sanitize)
+
+    def _transform_fused(self, X, cache, out, col0, sanitize) -> None:
+        iss = self._iss[0]
+        L = be.lib()
+        n, d, t = X.shape
+        dims = self._fused_dims(d)
+        if iss.max_dim() > len(dims):
+            raise IndexError(
+                f"words use dimension {iss.max_dim()} but the prepared input has {len(dims)}")
+        feats, bounded_hi, bounded_mm = self._fused_sieves()
+        sp = be.FbSievePlan()
+        sp.n_feats = len(feats)
+        for f, (kind, arg) in enumerate(feats):
+            sp.kind[f], sp.arg[f] = kind, arg
+        policy = L.fb_slice_policy(ctypes.byref(sp), int(bounded_hi), int(bounded_mm))
+        if policy < 0:
+            raise NotImplementedError("sieve combination not supported by the fused kernel")
+        plan = iss.device_plan(L.fb_slice_rows(policy), None, dims)
+        thr = self._threshold_table(plan.n_emit)
+        sp.thresholds = thr.data_ptr()
+        # statistics of the standardised dimensions the words actually use
+        stats = None
+        if any(dims[u][2] for u in plan.used_dims):
+            stats = be.zeros((n, len(plan.used_dims), 2))
+            for ui, u in enumerate(plan.used_dims):
+                raw, inc, std = dims[u]
+                if not std:
+                    continue
+                row = X[:, raw, :].contiguous()
+                if inc:
+                    from .preparation.transform import increments_device
+                    row = increments_device(row, 1)
+                std_prep = next(p for p in self._preparateurs if p._fusable() == "std")
+                st = std_prep._row_stats(row, std_prep._div_std, std_prep._eps)
+                stats[:, ui, :] = st
+        g, g_ld = iss._lookup(X)
+        batch = iss.batch(X, g, g_ld, stats)
+        if out.stride(1) != 1:
+            raise ValueError("feature matrix must be row-major")
+        be.check(L.fb_slice_features_ex(plan.byref(), ctypes.byref(batch), ctypes.byref(sp),
+                                        out.data_ptr(), out.stride(0), col0, policy,
+                                        int(sanitize), be.stream_ptr()))
+
+    def _transform_composed(self, X, callbacks, cache, out, col0, sanitize) -> None:
+        prepared = self._prepare_device(X, cache, fit=False, callbacks=callbacks)
+        for callback in callbacks:
+            callback.on_preparation_end(prepared.cpu().numpy())
+        n = prepared.shape[0]
+        nf_total = self.nfeatures()
+        buf = be.zeros((n, nf_total))
+        k = 0
+        for i, itsum in enumerate(self._iterate_iss_device(prepared)):
+            itsum = itsum.contiguous()
+            for callback in callbacks:
+                callback.on_iterated_sum(itsum.cpu().numpy())
+            pre_cache = {}
+            for sieve in self._sieves_for(i):
+                sieve._cache = cache
+                nf = sieve.nfeatures()
+                if isinstance(sieve, SegmentSieve):
+                    if not sieve.requires_fitting:
+                        sieve._get_unfitted_quantiles()
+                    if sieve._inc not in pre_cache:
+                        pre_cache[sieve._inc] = sieve._pre_transform_device(itsum)
+                    sieve._apply(pre_cache[sieve._inc], buf, k)
+                elif isinstance(sieve, PPV):
+                    if not hasattr(sieve, "_q"):
+                        raise RuntimeError("Missing call of PPV.fit()")
+                    sieve._apply(itsum, buf, k)
+                else:
+                    buf[:, k:k+nf] = sieve._transform_device(itsum)
+                for callback in callbacks:
+                    callback.on_sieve(buf[k:k+nf].cpu().numpy())
+                k += nf
+        for callback in callbacks:
+            callback.on_sieving_end(buf.cpu().numpy())
+        if sanitize:
+            be.check(be.lib().fb_nan_to_num(buf.data_ptr(), buf.numel(), be.stream_ptr()))
+        out[:, col0:col0 + nf_total] = buf
+
+    def fit_transform(self, X):
+        self.fit(X)
+        return self.transform(X)
+
+    # -- text ------------------------------------------------------------------------
+    def summary(self) -> str:
+        """Reference: fruit.py:561-597."""
+        summary = f"{f'FruitSlice -> {self.nfeatures()}': ^38}"
+        summary += "\n" + 38*"-" + "\n"
+        summary += f"{f'Preparateurs ({len(self._preparateurs)}):': <38}"
+        summary += "\n"
+        summary += "\n".join(f"{f'    + {x}': <38}" for x in self._preparateurs)
+        if len(self._preparateurs) == 0:
+            summary += 38*" "
+        summary += "\n"
+        summary += f"{f'ISS Calculators ({len(self._iss)}):': <38}"
+        if len(self._iss) == 0:
+            summary += 38*" "
+        for iss in self._iss:
+            summary += f"\n{f'    + {iss} -> {iss.n_iterated_sums()}': <38}"
+            summary += f"\n{f'       | words: {len(iss.words)}': <38}"
+            semiring = iss.semiring.__class__.__name__
+            summary += f"\n{f'       | semiring: {semiring}': <38}"
+            weighting = "None" if iss.weighting is None else iss.weighting.__class__.__name__
+            summary += f"\n{f'       | weighting: {weighting}': <38}"
+        if len(self._iss) == 0:
+            summary += "\n"
+        summary += f"\n{f'Sieves ({len(self._sieves)}):': <38}"
+        if len(self._sieves) == 0:
+            summary += "\n" + 38*" "
+        for sv in self._sieves:
+            name = sv.__class__.__name__
+            summary += f"\n{f'    + {name} -> {sv.nfeatures()}': <38}"
+        return summary
+
+    def copy(self) -> "FruitSlice":
+        """Shallow copy: same seed objects, no fitted state."""
+        copy_ = FruitSlice()
+        for preparateur in self._preparateurs:
+            copy_.add(preparateur)
+        for iss in self._iss:
+            copy_.add(iss)
+        for sieve in self._sieves:
+            copy_.add(sieve)
+        return copy_
+
+    def deepcopy(self) -> "FruitSlice":
+        """Deep copy: copied seeds, no fitted state."""
+        copy_ = FruitSlice()
+        for preparateur in self._preparateurs:
+            copy_.add(preparateur.copy())
+        for iss in self._iss:
+            copy_.add(iss.copy())
+        for sieve in self._sieves:
+            copy_.add(sieve.copy())
+        copy_.fit_sample_size = self.fit_sample_size
+        return copy_
+
+    def label(self, index: int,
+              level: Literal["prepared", "iterated sums", "features"] = "features",
+              verbose: Literal[1, 2] = 1) -> str:
+        """Reference: fruit.py:625-686."""
+        string = ""
+        if level == "prepared":
+            for i in range(index+1):
+                label = self._preparateurs[i].label()
+                if verbose == 1:
+                    label = label.split("(")[0]
+                string += f"{label} -> "
+            return "input" if string == "" else string[:-4]
+        for prep in self._preparateurs:
+            label = prep.label()
+            if verbose == 1:
+                label = label.split("(")[0]
+            string += f"{label} -> "
+        if string != "":
+            string = string[:-4] + " | "
+        findex = 0
+        if level == "features":
+            index, findex = map(int, divmod(
+                index, int(np.sum([s.nfeatures() for s in self._sieves]))))
+        n_i = self.niteratedsums()
+        for i in range(len(self.get_iss())):
+            word_index = int((index % n_i) // (n_i / self.get_iss()[i].n_iterated_sums()))
+            label = self.get_iss()[i].label(word_index)
+            if verbose == 1:
+                label = label.split(" : ")[0]
+            string += label + " -> "
+            n_i /= self.get_iss()[i].n_iterated_sums()
+        if level == "iterated sums":
+            return "input" if string == "" else string[:-4]
+        if string != "":
+            string = string[:-4] + " | "
+        for i in range(len(self._sieves)):
+            if findex < self._sieves[i].nfeatures():
+                string += self._sieves[i].label(findex)
+                return string
+            findex -= self._sieves[i].nfeatures()
+        raise RuntimeError("Feature index out of range")

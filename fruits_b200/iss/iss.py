@@ -1,0 +1,208 @@
+"""The ISS seed (reference: ``fruits/iss/iss.py:14-204``).
+
+``ISS.transform`` materialises the iterated sums ``[n_itsums, n_series,
+length]`` with the CUDA kernel of ``csrc/lns.cuh``.  Inside a
+:class:`~fruits_b200.fruit.FruitSlice` the same plan drives the fused kernel
+that applies the sieves in registers and never writes this tensor.
+"""
+from enum import Enum, auto
+from typing import Generator, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _backend as be
+from .._plan import DevicePlan, Trie
+from ..cache import SharedSeedCache
+from ..seed import Seed
+from .cache import CachePlan
+from .semiring import Arctic, Reals, Semiring
+from .weighting import Weighting
+from .words.word import SimpleWord, Word
+
+
+class ISSMode(Enum):
+    """Reference: iss.py:14-18."""
+    SINGLE = auto()
+    EXTENDED = auto()
+
+
+class ISS(Seed):
+    """Iterated sums signature of a list of words.
+
+    Args:
+        words: ``SimpleWord`` objects.
+        mode: ``ISSMode.SINGLE`` (one iterated sum per word) or
+            ``ISSMode.EXTENDED`` (additionally every prefix of every word
+            that was not already emitted by an earlier word).
+        semiring: ``Reals()`` (default) or ``Arctic()``.
+        weighting: optional exponential weighting.
+    """
+
+    def __init__(self, words: Sequence[Word], /, *, mode: ISSMode = ISSMode.SINGLE,
+                 semiring: Optional[Semiring] = None,
+                 weighting: Optional[Weighting] = None) -> None:
+        for w in words:
+            if not isinstance(w, SimpleWord):
+                raise NotImplementedError(
+                    "only SimpleWord objects can be evaluated on the GPU")
+        self.words = words
+        self.mode = mode
+        self.semiring = semiring if semiring is not None else Reals()
+        if not isinstance(self.semiring, (Reals, Arctic)):
+            raise NotImplementedError(
+                f"semiring {type(self.semiring).__name__} is not supported")
+        self._cache_plan = CachePlan(self.words if mode == ISSMode.EXTENDED else [])
+        self.weighting = weighting
+        self._trie_memo = None
+        self._plan_memo: dict = {}
+
+    @property
+    def requires_fitting(self) -> bool:
+        return False
+
+    # -- plan ------------------------------------------------------------------
+    def _weight_mode(self) -> int:
+        if self.weighting is None:
+            return be.WEIGHT_NONE
+        return be.WEIGHT_TOTAL if self.weighting.total else be.WEIGHT_NONTOTAL
+
+    def _signature(self):
+        return (tuple(str(w) for w in self.words),
+                tuple(tuple(float(a) for a in w.alpha) for w in self.words)
+                if self.weighting is not None else None,
+                self.mode, self.semiring._code, self._weight_mode())
+
+    def trie(self) -> Trie:
+        sig = self._signature()
+        if self._trie_memo is None or self._trie_memo[0] != sig:
+            plan = self._cache_plan._plan if self.mode == ISSMode.EXTENDED else None
+            self._trie_memo = (sig, Trie(self.words, plan, self.weighting is not None))
+            self._plan_memo = {}
+        return self._trie_memo[1]
+
+    def device_plan(self, rows_max: int, emit_range=None, dim_desc=None) -> DevicePlan:
+        trie = self.trie()
+        key = (rows_max, emit_range, None if dim_desc is None else tuple(dim_desc))
+        plan = self._plan_memo.get(key)
+        if plan is None:
+            sub = trie if emit_range is None else trie.subset(*emit_range)
+            plan = DevicePlan(sub, self.semiring._code, self._weight_mode(), rows_max, dim_desc)
+            self._plan_memo[key] = plan
+        return plan
+
+    def max_dim(self) -> int:
+        return max(len(el) for w in self.words for el in w)
+
+    def n_iterated_sums(self) -> int:
+        """Number of iterated sums ``transform`` returns (reference :135-150)."""
+        if self.mode == ISSMode.EXTENDED:
+            return self._cache_plan.n_iterated_sums()
+        return len(self.words)
+
+    # -- execution ---------------------------------------------------------------
+    def _lookup(self, X: torch.Tensor):
+        """-> (g tensor or None, row stride)"""
+        if self.weighting is None:
+            return None, 0
+        if hasattr(self, "_cache"):
+            self.weighting._cache = self._cache
+        else:
+            self.weighting._cache = SharedSeedCache(X)
+        g, shared = self.weighting.get_lookup_device(X)
+        g = g.contiguous()
+        if g.shape[-1] != X.shape[2]:
+            raise ValueError("weighting lookup has the wrong length")
+        if not shared and g.shape[0] < X.shape[0]:
+            raise ValueError("weighting lookup has fewer rows than the input")
+        return g, (0 if shared else g.shape[-1])
+
+    def _check_input(self, X: torch.Tensor) -> None:
+        if X.dim() != 3:
+            raise ValueError("input must have shape (n_series, n_dimensions, length)")
+        if self.max_dim() > X.shape[1]:
+            raise IndexError(
+                f"words use dimension {self.max_dim()} but the input has {X.shape[1]}")
+
+    def batch(self, X: torch.Tensor, g, g_ld, stats=None) -> be.FbBatch:
+        b = be.FbBatch()
+        b.X = X.data_ptr()
+        b.n, b.d, b.t = X.shape
+        b.g = be.ptr(g)
+        b.g_ld = g_ld
+        b.stats = be.ptr(stats)
+        return b
+
+    def materialize(self, X: torch.Tensor, emit_range=None, lookup=None) -> torch.Tensor:
+        """Iterated sums ``[emit_hi-emit_lo, n, t]`` of the emissions in
+        ``emit_range`` (all if None) on the device."""
+        self._check_input(X)
+        X = X.contiguous()
+        rows = be.lib().fb_slice_rows(be.POLICY_MAT)
+        plan = self.device_plan(rows, emit_range)
+        g, g_ld = self._lookup(X) if lookup is None else lookup
+        out = be.empty((plan.n_emit, X.shape[0], X.shape[2]))
+        import ctypes
+        batch = self.batch(X, g, g_ld)
+        be.check(be.lib().fb_iss_materialize(plan.byref(), ctypes.byref(batch), out.data_ptr(),
+                                             be.stream_ptr()))
+        return out
+
+    def iter_chunks(self, X: torch.Tensor, max_bytes: int = 1 << 30):
+        """Yield ``(emit_lo, tensor[g, n, t])`` over all emissions, at most
+        ``max_bytes`` per chunk."""
+        n_emit = self.n_iterated_sums()
+        per = X.shape[0] * X.shape[2] * 8
+        step = max(1, min(n_emit, max_bytes // max(per, 1)))
+        lookup = self._lookup(X.contiguous())
+        for lo in range(0, n_emit, step):
+            hi = min(n_emit, lo + step)
+            rng = None if (lo == 0 and hi == n_emit) else (lo, hi)
+            yield lo, self.materialize(X, rng, lookup)
+
+    def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
+        return self.materialize(X)
+
+    def batch_transform(self, X, batch_size: int = 1) -> Generator:
+        """Yields the iterated sums of ``batch_size`` words at a time
+        (reference :152-185)."""
+        if batch_size > len(self.words):
+            raise ValueError("batch_size too large, has to be < len(words)")
+        Xd = be.to_device(X)
+        had_cache = hasattr(self, "_cache")
+        if not had_cache:
+            self._cache = SharedSeedCache(Xd)
+        try:
+            lookup = self._lookup(Xd.contiguous())
+            i, e = 0, 0
+            while i < len(self.words):
+                nb = min(batch_size, len(self.words) - i)
+                if self.mode == ISSMode.EXTENDED:
+                    ne = self._cache_plan.n_iterated_sums(range(i, i + nb))
+                else:
+                    ne = nb
+                if ne > 0:
+                    res = self.materialize(Xd, (e, e + ne), lookup)
+                else:
+                    res = be.empty((0, Xd.shape[0], Xd.shape[2]))
+                yield res if isinstance(X, torch.Tensor) else res.cpu().numpy()
+                i += nb
+                e += ne
+        finally:
+            if not had_cache:
+                del self._cache
+
+    def _copy(self) -> "ISS":
+        return ISS(self.words, mode=self.mode, semiring=self.semiring,
+                   weighting=self.weighting)
+
+    def _label(self, index: int) -> str:
+        if self.mode == ISSMode.EXTENDED:
+            string = self._cache_plan.get_word_string(index)
+        else:
+            string = str(self.words[index])
+        if not isinstance(self.semiring, Reals):
+            string += " : " + self.semiring.__class__.__name__
+        if self.weighting is not None:
+            string += " : " + self.weighting.__class__.__name__
+        return string

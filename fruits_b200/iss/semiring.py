@@ -1,0 +1,44 @@
+"""Semirings of the iterated sums (reference: ``fruits/iss/semiring.py``).
+
+On the GPU a semiring is only a tag that selects the instantiation of the ISS
+kernel (``csrc/lns.cuh``): ``Reals`` (:161-231, sum / product, the standard
+iterated sums) and ``Arctic`` (:341-457, max / plus).  ``Bayesian``
+(:461-601) and ``Arctic(argmax=True)`` are not part of the accelerated path.
+"""
+from abc import ABC
+
+from .. import _backend as be
+
+
+class Semiring(ABC):
+    _code: int = -1
+
+    def __str__(self) -> str:
+        return self.__class__.__name__
+
+
+class Reals(Semiring):
+    """Field of real numbers with the usual sum and product (default)."""
+    _code = be.SEMIRING_REALS
+
+
+class Arctic(Semiring):
+    """Max-plus semiring: "sum" is the maximum, "product" the addition.
+
+    ``argmax=True`` (positions of the maxima, reference :234-279) is not
+    supported by the GPU path."""
+    _code = be.SEMIRING_ARCTIC
+
+    def __init__(self, argmax: bool = False) -> None:
+        if argmax:
+            raise NotImplementedError(
+                "Arctic(argmax=True) is outside the accelerated hot path")
+        self._argmax = False
+
+
+class Bayesian(Semiring):
+    """Max-times semiring on [0, 1] (reference :461-601): listed as "next" in
+    SURVEY.md section 8(f), not built yet."""
+
+    def __init__(self) -> None:
+        raise NotImplementedError("the Bayesian semiring is not built yet")

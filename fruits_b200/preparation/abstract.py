@@ -1,0 +1,20 @@
+"""Reference: ``fruits/preparation/abstract.py:9-20``."""
+from abc import ABC
+from typing import Any
+
+from ..seed import Seed
+
+
+class Preparateur(Seed, ABC):
+    """A preparateur maps ``X[n_series, n_dims, length]`` to another array of
+    the same kind before the iterated sums are calculated."""
+
+    def __eq__(self, other: Any) -> bool:
+        return False
+
+    __hash__ = object.__hash__
+
+    def _fusable(self):
+        """Per-dimension description ``[(source_dim, inc, std), ...]`` if the
+        ISS kernel can apply this preparateur while loading X, else None."""
+        return None

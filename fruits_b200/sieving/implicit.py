@@ -1,0 +1,136 @@
+"""Implicit sieves (reference: ``fruits/sieving/implicit.py``): ``PPV``
+(:11-153).  ``CPV`` (:156-213) is listed as "next" in SURVEY.md 8(f)."""
+__all__ = ["PPV", "CPV"]
+
+from typing import Union
+
+import numpy as np
+import torch
+
+from .. import _backend as be
+from .abstract import FeatureSieve, quantile_rows
+
+
+class PPV(FeatureSieve):
+    """Proportion of values ``>=`` a fitted quantile (deprecated in the
+    reference in favour of NPI, kept for drop-in compatibility).
+
+    Args as in the reference (implicit.py:25-53): ``quantile`` (value or
+    probability, or a list), ``constant`` (interpret as value), ``sample_size``
+    (fraction of series used for the quantile), ``segments``."""
+
+    def __init__(self, quantile: Union[list, float] = 0.5,
+                 constant: Union[list, bool] = False, sample_size: float = 1.0,
+                 segments: bool = False) -> None:
+        if isinstance(quantile, list):
+            if not isinstance(constant, list):
+                constant = [constant for _ in range(len(quantile))]
+            elif len(quantile) != len(constant):
+                raise ValueError("If 'quantile' is a list, then 'constant' "
+                                 "also has to be a list of same length or "
+                                 "a single boolean.")
+            for q, c in zip(quantile, constant):
+                if not c and not 0 <= q <= 1:
+                    raise ValueError("If 'constant' is set to False, "
+                                     "'quantile' has to be a value in [0,1]")
+        else:
+            quantile = [quantile]
+            if isinstance(constant, list):
+                if len(constant) > 1:
+                    raise ValueError("'constant' has to be a single boolean"
+                                     "if 'quantile' is a single float")
+            else:
+                constant = [constant]
+        if segments:
+            self._q_c_input = sorted(zip(list(set(quantile)), constant),
+                                     key=lambda x: x[0])
+        else:
+            self._q_c_input = list(zip(quantile, constant))
+        if not 0 < sample_size <= 1:
+            raise ValueError("'sample_size' has to be a float in (0, 1]")
+        self._sample_size = sample_size
+        if segments and len(quantile) == 1:
+            raise ValueError("If 'segments' is set to `True` then 'quantile'"
+                             "has to be a list of length >= 2.")
+        self._segments = segments
+
+    def _nfeatures(self) -> int:
+        if self._segments:
+            return len(self._q_c_input) - 1
+        return len(self._q_c_input)
+
+    def _draw(self, n_rows: int):
+        """Consume the global numpy RNG exactly like the reference does
+        (implicit.py:103-108): one ``choice`` per non-constant quantile."""
+        draws = []
+        for q, const in self._q_c_input:
+            if const:
+                draws.append(None)
+            else:
+                size = max(int(self._sample_size * n_rows), 1)
+                draws.append(np.random.choice(np.arange(n_rows), size=size, replace=False))
+        return draws
+
+    def _fit_device(self, X: torch.Tensor) -> None:
+        X = X.contiguous()
+        draws = self._draw(X.shape[0])
+        self._q = [x[0] for x in self._q_c_input]
+        for i, (q, const) in enumerate(self._q_c_input):
+            if const:
+                continue
+            sel = draws[i]
+            if len(sel) == X.shape[0]:
+                rows = X   # a permutation of all rows: same multiset of values
+            else:
+                idx = torch.as_tensor(sel, device=X.device, dtype=torch.long)
+                rows = X.index_select(0, idx)
+            self._q[i] = quantile_rows(rows.reshape(1, -1), q)[0]
+
+    def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
+        if not hasattr(self, "_q"):
+            raise RuntimeError("Missing call of PPV.fit()")
+        arr = X.contiguous()
+        out = be.empty((arr.shape[0], self.nfeatures()))
+        self._apply(arr, out, 0)
+        return out
+
+    def _apply(self, arr: torch.Tensor, out: torch.Tensor, col0: int) -> None:
+        n, t = arr.shape
+        q = be.to_device(np.array(self._q, dtype=np.float64))
+        be.check(be.lib().fb_ppv(arr.data_ptr(), arr.stride(0), q.data_ptr(), len(self._q),
+                                 int(self._segments), out.data_ptr(), out.stride(0), col0,
+                                 n, t, be.stream_ptr()))
+
+    def _fused(self):
+        if not self._segments and len(self._q_c_input) == 1:
+            return ("PPV", 0)
+        return None
+
+    def _copy(self) -> "PPV":
+        return PPV(quantile=[x[0] for x in self._q_c_input],
+                   constant=[x[1] for x in self._q_c_input],
+                   sample_size=self._sample_size, segments=self._segments)
+
+    def _summary(self) -> str:
+        string = f"PPV [sampling={self._sample_size}"
+        if self._segments:
+            string += ", segments"
+        string += f"] -> {self.nfeatures()}:"
+        for x in self._q_c_input:
+            string += f"\n   > {x[0]} | {x[1]}"
+        return string
+
+    def __str__(self) -> str:
+        return ("PPV("
+                f"quantile={[x[0] for x in self._q_c_input]}, "
+                f"constant={[x[1] for x in self._q_c_input]}, "
+                f"sample_size={self._sample_size}, "
+                f"segments={self._segments})")
+
+
+class CPV(PPV):
+    """Connected components of values above a quantile (reference :156-213):
+    not built yet."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        raise NotImplementedError("sieve CPV is not built yet")

@@ -1,0 +1,209 @@
+"""Segment sieves (reference: ``fruits/sieving/segment.py``): the common
+base with cuts and quantile thresholds (:14-104) and ``MAX`` (:107-152),
+``MIN`` (:155-200), ``END`` (:203-225).  ``CUR``/``AVG``/``STD`` are listed as
+"next" in SURVEY.md section 8(f)."""
+__all__ = ["MAX", "MIN", "END", "CUR", "AVG", "STD"]
+
+from abc import ABC
+from collections.abc import Sequence
+from typing import Literal, Optional, Union
+
+import numpy as np
+import torch
+
+from .. import _backend as be
+from ..cache import CacheType
+from .abstract import FeatureSieve, quantile_rows
+
+
+class SegmentSieve(FeatureSieve, ABC):
+    """Args:
+        cut: index (``X[:cut]``), float in [0, 1] (coquantile of the raw
+            input) or a sequence of those; default ``-1`` = whole series.
+        q: thresholds as probabilities; ``1.0`` means +inf, ``-1.0`` -inf and
+            ``0.0`` the value 0, anything else is a quantile fitted on the
+            data.  Features count / select values in ``(q_k, q_{k+1}]``.
+    """
+
+    _kind = -1
+    _inc = 0
+
+    def __init__(self, cut: Union[Sequence[float], float] = -1,
+                 q: Optional[Sequence[float]] = None,
+                 coquantile_norm: Literal["L1", "L2"] = "L2") -> None:
+        self._cut = cut if isinstance(cut, Sequence) else (cut,)
+        self._q = q if isinstance(q, Sequence) else (-1.0, 1.0)
+        self._coquantile_norm = coquantile_norm
+
+    @property
+    def requires_fitting(self) -> bool:
+        return any(q not in [-1, 0, 1] for q in self._q)
+
+    # -- thresholds ---------------------------------------------------------
+    def _pre_transform_device(self, X: torch.Tensor) -> torch.Tensor:
+        return X
+
+    def _set_quantiles(self, fitted: dict) -> None:
+        """``fitted`` maps a probability to its fitted value."""
+        qs = np.zeros(len(self._q))
+        for i, q in enumerate(self._q):
+            if q == 1.0:
+                qs[i] = np.inf
+            elif q == -1.0:
+                qs[i] = -np.inf
+            elif q != 0:
+                qs[i] = fitted[q]
+        self._quantiles = np.sort(qs)
+
+    def _fit_device(self, X: torch.Tensor) -> None:
+        # reference :66-75: np.quantile over the whole (pre-transformed) array
+        fitted = {}
+        need = [q for q in self._q if q not in (1.0, -1.0, 0)]
+        if need:
+            arr = self._pre_transform_device(X.contiguous()).reshape(1, -1)
+            for q in need:
+                fitted[q] = quantile_rows(arr, q)[0]
+        self._set_quantiles(fitted)
+
+    def _get_unfitted_quantiles(self) -> None:
+        # reference :77-85 (not sorted there either)
+        qs = np.zeros(len(self._q))
+        for i, q in enumerate(self._q):
+            if q == 1.0:
+                qs[i] = np.inf
+            elif q == -1.0:
+                qs[i] = -np.inf
+            elif q != 0:
+                raise RuntimeError("Sieve has not been fitted properly")
+        self._quantiles = qs
+
+    # -- cuts ------------------------------------------------------------------
+    def _default_cut(self) -> bool:
+        return len(self._cut) == 1 and not isinstance(self._cut[0], float) \
+            and self._cut[0] == -1
+
+    def _cuts_device(self, n: int, t: int):
+        """int64 ``[n, len(cut)+1]`` sorted cut indices (reference :51-64) or
+        None for the default (whole series)."""
+        if self._default_cut():
+            return None
+        cols = [torch.zeros(n, dtype=torch.float64, device=be.require_cuda())]
+        for cut in self._cut:
+            if isinstance(cut, float):
+                c = self._cache.get_device(CacheType.COQUANTILE,
+                                           str(cut) + ":" + self._coquantile_norm)
+                if c.shape[0] < n:
+                    raise ValueError("coquantile cache has fewer rows than the input")
+                cols.append(c[:n].to(torch.float64))
+            else:
+                v = cut if cut >= 0 else t + cut + 1
+                cols.append(torch.full((n,), float(v), dtype=torch.float64,
+                                       device=be.require_cuda()))
+        cuts = torch.sort(torch.stack(cols, dim=1), dim=1).values
+        return cuts.to(torch.int64).contiguous()
+
+    # -- transform ---------------------------------------------------------------
+    def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
+        if not self.requires_fitting:
+            self._get_unfitted_quantiles()
+        elif not hasattr(self, "_quantiles"):
+            raise RuntimeError("Sieve has not been fitted properly")
+        arr = self._pre_transform_device(X.contiguous())
+        n, t = arr.shape
+        out = be.empty((n, self.nfeatures()))
+        self._apply(arr, out, 0)
+        return out
+
+    def _apply(self, arr: torch.Tensor, out: torch.Tensor, col0: int) -> None:
+        """Sieve the pre-transformed ``arr[n, t]`` into ``out[:, col0:col0+nf]``."""
+        n, t = arr.shape
+        cuts = self._cuts_device(n, t)
+        q = be.to_device(np.ascontiguousarray(self._quantiles, dtype=np.float64))
+        be.check(be.lib().fb_segment_sieve(
+            arr.data_ptr(), arr.stride(0), be.ptr(cuts), len(self._cut) + 1, q.data_ptr(),
+            len(self._q), self._kind, out.data_ptr(), out.stride(0), col0, n, t,
+            be.stream_ptr()))
+
+    # -- bookkeeping -------------------------------------------------------------
+    def _nfeatures(self) -> int:
+        return len(self._cut) * (len(self._q) - 1)
+
+    def _copy(self):
+        return self.__class__(self._cut, self._q)
+
+    def __str__(self) -> str:
+        return f"{self.__class__.__name__}({self._cut}, {self._q})"
+
+    def _label(self, index: int) -> str:
+        r, m = divmod(index, len(self._q) - 1)
+        return (f"{self.__class__.__name__}"
+                f"!{self._cut[r]}![{self._q[m]}, {self._q[m+1]}]")
+
+    def _summary(self) -> str:
+        string = f"{self.__class__.__name__} -> {self.nfeatures()}:"
+        for x in self._cut:
+            string += f"\n   > {x}"
+        return string
+
+    def _fusable_shape(self) -> bool:
+        return self._default_cut() and len(self._q) == 2
+
+
+class MAX(SegmentSieve):
+    """Maximal value with ``q_k < x <= q_{k+1}`` per cut segment (0 if none)."""
+    _kind = be.SIEVE_MAX
+
+    def _fused(self):
+        return ("MAX", 0) if self._fusable_shape() else None
+
+
+class MIN(SegmentSieve):
+    """Minimal value with ``q_k < x <= q_{k+1}`` per cut segment (0 if none)."""
+    _kind = be.SIEVE_MIN
+
+    def _fused(self):
+        return ("MIN", 0) if self._fusable_shape() else None
+
+
+class END(SegmentSieve):
+    """Value at the end of every cut segment, ``X[:, cut-1]``."""
+    _kind = be.SIEVE_END
+
+    def _nfeatures(self) -> int:
+        # like the reference: len(cut) * (len(q) - 1) with the default q
+        return len(self._cut) * (len(self._q) - 1)
+
+    def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
+        # reference :210-219: no quantiles involved
+        arr = X.contiguous()
+        n, t = arr.shape
+        out = be.empty((n, len(self._cut)))
+        self._apply(arr, out, 0)
+        return out
+
+    def _apply(self, arr, out, col0) -> None:
+        n, t = arr.shape
+        cuts = self._cuts_device(n, t)
+        q = be.to_device(np.array([-np.inf, np.inf]))
+        be.check(be.lib().fb_segment_sieve(
+            arr.data_ptr(), arr.stride(0), be.ptr(cuts), len(self._cut) + 1, q.data_ptr(), 2,
+            self._kind, out.data_ptr(), out.stride(0), col0, n, t, be.stream_ptr()))
+
+    def _fused(self):
+        return ("END", 0) if self._default_cut() and len(self._q) == 2 else None
+
+
+def _next(name: str, ref: str):
+    class _Unsupported(SegmentSieve):
+        __doc__ = f"{name} (reference: {ref}) is not built yet (SURVEY.md section 8(f))."
+
+        def __init__(self, *args, **kwargs) -> None:
+            raise NotImplementedError(f"sieve {name} is not built yet")
+
+    _Unsupported.__name__ = _Unsupported.__qualname__ = name
+    return _Unsupported
+
+
+CUR = _next("CUR", "segment.py:228-274")
+AVG = _next("AVG", "segment.py:277-317")
+STD = _next("STD", "segment.py:320-358")

@@ -1,0 +1,241 @@
+/*
+ * fruits_b200.h -- C ABI of the B200-native FRUITS hot path.
+ *
+ * The reference (irkri/fruits 1.0.0) is pure Python + numba and has no FFI;
+ * its boundary is the Python class API.  This header is the boundary a
+ * maintainer of the reference would bind with ctypes:
+ * every entry point replaces one numba kernel / numpy call of the reference,
+ * cited as file:line relative to the reference checkout.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers (cudaMalloc'ed, 8-byte aligned)
+ *     unless the name ends in `_h` (host pointer);
+ *   - float64 arrays are C-ordered; `ld` arguments are row strides in elements;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous with
+ *     respect to the host unless stated otherwise;
+ *   - return value: 0 on success, a cudaError_t (> 0) for CUDA failures,
+ *     a negative FB_E* code for argument errors; fb_last_error() returns a
+ *     thread-local message.  There is no CPU fallback anywhere.
+ */
+#ifndef FRUITS_B200_H
+#define FRUITS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+#define FB_EINVAL  (-1)   /* bad argument */
+#define FB_ENOSUP  (-2)   /* configuration not supported by this build */
+
+/* ---- enums --------------------------------------------------------- */
+/* fruits/iss/semiring.py: Reals (:161), Arctic (:341) */
+#define FB_SEMIRING_REALS   0
+#define FB_SEMIRING_ARCTIC  1
+/* fruits/iss/semiring.py:27-35: no weighting, Weighting.total True/False */
+#define FB_WEIGHT_NONE      0
+#define FB_WEIGHT_TOTAL     1
+#define FB_WEIGHT_NONTOTAL  2
+
+/* Maximum number of rows (x32 lanes) one warp owns in the ISS kernel. */
+#define FB_MAX_ROWS 16
+/* Maximum number of distinct input dimensions one ISS plan may reference. */
+#define FB_MAX_USED_DIMS 7
+/* Time ring length of the ISS kernel; arctic word length must stay below
+ * FB_RING - 32. */
+#define FB_RING 256
+/* Maximum number of distinct alpha values in one weighted ISS plan. */
+#define FB_MAX_ALPHAS 4
+
+/* One trie node placed on one lane of one row of a warp ("slot").
+ * The host compiles ISS words into a prefix trie (fruits/iss/cache.py:17-37
+ * defines which prefixes are emitted) and lays the nodes out as
+ * blocks[n_blocks][FB rows][32 lanes]. */
+typedef struct fb_slot {
+    /* Reals: up to 16 letter occurrences, 4 bits each, applied in order:
+     *   bits[2:0] = used-dimension index (7 = constant one / padding),
+     *   bit 3     = 1: divide instead of multiply (negative exponent).
+     * Arctic: up to 8 (dimension, exponent) pairs, 8 bits each:
+     *   bits[2:0] = used-dimension index, bits[7:3] = signed exponent. */
+    uint32_t letter_lo;
+    uint32_t letter_hi;
+    int16_t parent;   /* slot index (row*32+lane) of the parent in this block, -1 = root */
+    int16_t emit;     /* index of the emitted iterated sum, -1 = not emitted */
+    uint8_t depth;    /* 1-based position of the letter in its word */
+    uint8_t aidx;     /* index into alphas[] of this level's alpha */
+    uint8_t weight;   /* number of occurrences / pairs used */
+    uint8_t flags;    /* bit0: slot valid, bit1: has children in this block */
+} fb_slot;
+
+/* How one used dimension is produced from the raw input on load
+ * (fruits/preparation/transform.py:15-89 INC, :92-158 STD,
+ *  fruits/preparation/wrapper.py:53-103 NEW). */
+typedef struct fb_dim {
+    int32_t raw_dim;   /* dimension of X to read */
+    int32_t inc;       /* 1: x[t]-x[t-1] with zero padding (INC(1,1,True)) */
+    int32_t std;       /* 1: (v - mean)/(denom) with stats[n][u][2] */
+    int32_t pad;
+} fb_dim;
+
+typedef struct fb_iss_plan {
+    int32_t semiring;      /* FB_SEMIRING_* */
+    int32_t weight_mode;   /* FB_WEIGHT_* */
+    int32_t n_blocks;      /* warp-blocks per series */
+    int32_t n_rows;        /* rows used per block (<= rows the kernel supports) */
+    int32_t n_emit;        /* number of emitted iterated sums */
+    int32_t n_used_dims;   /* <= FB_MAX_USED_DIMS */
+    int32_t n_alphas;      /* <= FB_MAX_ALPHAS */
+    int32_t max_depth;     /* longest word */
+    float   alphas[FB_MAX_ALPHAS];
+    fb_dim  dims[FB_MAX_USED_DIMS];
+    const fb_slot *slots;        /* device: [n_blocks][n_rows][32] */
+    const uint8_t *row_pub;      /* device: [n_blocks] number of leading rows that publish */
+    const uint8_t *row_weight;   /* device: [n_blocks][n_rows] max letter weight in the row */
+} fb_iss_plan;
+
+/* Input batch: X[n][d][t] float64 (fruits/fruit.py:138-173 transform input),
+ * optional lookup g (fruits/iss/weighting.py get_lookup): g_ld == 0 means one
+ * shared row g[t] (Indices / Plateaus), else g[n][t] with row stride g_ld.
+ * stats: [n][n_used_dims][2] = (mean, std + eps) for dims with std=1. */
+typedef struct fb_batch {
+    const double *X;
+    int64_t n, d, t;
+    const double *g;
+    int64_t g_ld;
+    const double *stats;
+} fb_batch;
+
+/* ---- sieve fusion --------------------------------------------------- */
+/* Feature kinds evaluated in the epilogue of the fused kernel; every kind
+ * follows one reference sieve (default cut = -1, i.e. the whole series):
+ *   CNT: NPI  fruits/sieving/increment.py:101-129
+ *   AVG: MPI  fruits/sieving/increment.py:132-163
+ *   PPV:      fruits/sieving/implicit.py:114-129
+ *   MAX/MIN:  fruits/sieving/segment.py:107-200
+ *   END:      fruits/sieving/segment.py:203-225 */
+#define FB_FEAT_CNT 0   /* arg = increment depth 0..2 */
+#define FB_FEAT_AVG 1   /* arg = increment depth 0..2 */
+#define FB_FEAT_PPV 2
+#define FB_FEAT_MAX 3
+#define FB_FEAT_MIN 4
+#define FB_FEAT_END 5
+#define FB_MAX_FEATS 16
+
+/* Threshold table layout per emitted iterated sum (row of FB_NTHR doubles):
+ *   [0..1] (lo, hi] of increment depth 0   [2..3] depth 1   [4..5] depth 2
+ *   [6]    PPV threshold                   [7] unused
+ *   [8..9] (lo, hi] of MAX                 [10..11] (lo, hi] of MIN */
+#define FB_NTHR 12
+
+typedef struct fb_sieve_plan {
+    int32_t n_feats;                 /* features per emitted iterated sum */
+    int32_t kind[FB_MAX_FEATS];      /* FB_FEAT_* */
+    int32_t arg[FB_MAX_FEATS];       /* increment depth for CNT/AVG */
+    const double *thresholds;        /* device: [n_emit][FB_NTHR] */
+} fb_sieve_plan;
+
+/* ---- entry points ---------------------------------------------------- */
+#if defined(__GNUC__)
+#define FB_API __attribute__((visibility("default")))
+#else
+#define FB_API
+#endif
+
+FB_API int fb_abi_version(void);
+FB_API const char *fb_last_error(void);
+/* sm count, compute capability and bytes of shared memory per block opt-in */
+FB_API int fb_device_info(int *sm_count, int *cc_major, int *cc_minor, int *smem_optin);
+
+/* -- ISS + sieves (the hot path) -- */
+
+/* Fused kernel variants ("policies"): the set of per-node accumulators that
+ * is compiled in.  fb_slice_policy() returns the smallest one covering a
+ * sieve plan (bounded_hi: some (lo, hi] interval has a finite hi;
+ * bounded_mm: MAX/MIN use an interval other than (-inf, +inf]).
+ * fb_slice_rows(policy) is the number of rows of 32 trie nodes one warp owns
+ * in that variant -- the block capacity the host must compile the plan for
+ * (policy 0 is the materialising kernel of fb_iss_materialize). */
+FB_API int fb_slice_policy(const fb_sieve_plan *sieves, int bounded_hi, int bounded_mm);
+FB_API int fb_slice_rows(int policy);
+
+/* Fused FruitSlice.transform (fruits/fruit.py:498-553): preparateur-on-load,
+ * ISS over the prefix trie, sieves in registers.  Writes
+ *   out[i*out_ld + col0 + emit*n_feats + f]   for i < n.
+ * sanitize != 0 applies np.nan_to_num(nan=0) (fruits/fruit.py:172) on store.
+ * The ISS tensor is never written to memory. */
+FB_API int fb_slice_features_ex(const fb_iss_plan *plan, const fb_batch *batch,
+                                const fb_sieve_plan *sieves, double *out, int64_t out_ld,
+                                int64_t col0, int policy, int sanitize, void *stream);
+/* Same with the most general policy (plan must be compiled for its rows). */
+FB_API int fb_slice_features(const fb_iss_plan *plan, const fb_batch *batch,
+                             const fb_sieve_plan *sieves, double *out, int64_t out_ld,
+                             int64_t col0, void *stream);
+
+/* ISS.transform / batch_transform (fruits/iss/iss.py:118-185,
+ * fruits/iss/semiring.py:93-201, :282-404): materialise every emitted
+ * iterated sum of the plan as out[e][n][t] (the host compiles one plan per
+ * chunk of words when the full tensor would not fit). */
+FB_API int fb_iss_materialize(const fb_iss_plan *plan, const fb_batch *batch, double *out,
+                              void *stream);
+
+/* -- preparateurs, lookups, raw-input cache -- */
+
+/* fruits/cache.py:8-13 _increments on rows x t; pad_src != NULL keeps the
+ * first k values of pad_src (INC(zero_padding=False), transform.py:72-75). */
+FB_API int fb_increments(const double *X, const double *pad_src, double *out, int64_t rows,
+                         int64_t t, int64_t k, void *stream);
+/* fruits/preparation/transform.py:132-144 STD(separately=True):
+ * stats[r] = (np.mean(row), np.std(row) + eps), numpy pairwise summation. */
+FB_API int fb_row_stats(const double *X, double *stats, int64_t rows, int64_t t, int div_std,
+                        double eps, void *stream);
+FB_API int fb_standardize(const double *X, const double *stats, double *out, int64_t rows,
+                          int64_t t, void *stream);
+/* fruits/cache.py:25-40 _L1_sum / _L2_sum of dimension 0: out[n][t]. */
+FB_API int fb_lsum(const double *X, double *out, int64_t n, int64_t d, int64_t t, int l2,
+                   void *stream);
+/* fruits/iss/weighting.py:151-158: optional r/(r[-1]+1e-5), NRM per row, * scale. */
+FB_API int fb_nrm_scale(const double *in, double *out, int64_t rows, int64_t t, int relative,
+                        double scale, void *stream);
+/* fruits/cache.py:16-22 _coquantile: out[i] = count(S[i,:] <= q*S[i,-1]). */
+FB_API int fb_coquantile(const double *S, int64_t *out, int64_t n, int64_t t, double q,
+                         void *stream);
+
+/* -- sieves on materialised arrays (stand-alone seeds, general cuts, fit) -- */
+
+/* fruits/sieving/increment.py:63-71 _pre_transform: inc > 0 increments,
+ * inc < 0 cumulative sums, inc == 0 copy. */
+FB_API int fb_pretransform(const double *Y, double *out, int64_t rows, int64_t t, int inc,
+                           void *stream);
+#define FB_SIEVE_NPI 0
+#define FB_SIEVE_MPI 1
+#define FB_SIEVE_MAX 2
+#define FB_SIEVE_MIN 3
+#define FB_SIEVE_XPI 4
+#define FB_SIEVE_LPI 5
+#define FB_SIEVE_END 6
+/* fruits/sieving/segment.py:107-225, increment.py:101-239 backends on
+ * V[rows][ld]; cuts[rows][nc] sorted with first column 0 (NULL: {0, t});
+ * q[nq] sorted thresholds; out[r*out_ld + col0 + seg*(nq-1) + k]. */
+FB_API int fb_segment_sieve(const double *V, int64_t ld, const int64_t *cuts, int nc,
+                            const double *q, int nq, int kind, double *out, int64_t out_ld,
+                            int64_t col0, int64_t rows, int64_t t, void *stream);
+/* fruits/sieving/implicit.py:114-129 PPV._transform. */
+FB_API int fb_ppv(const double *V, int64_t ld, const double *q, int nq, int segments, double *out,
+                  int64_t out_ld, int64_t col0, int64_t rows, int64_t t, void *stream);
+/* np.nan_to_num(a, nan=0.0) in place (fruits/fruit.py:172). */
+FB_API int fb_nan_to_num(double *a, int64_t total, void *stream);
+
+/* -- fit: exact order statistics for np.quantile (segment.py:66-75) -- */
+FB_API int64_t fb_order_stats_workspace(int64_t P);
+/* P problems of M doubles (problem p at V + p*ldp): lo[p] = x_(k),
+ * hi[p] = x_(min(k+1, M-1)) of the ascending order; NaN if any NaN. */
+FB_API int fb_order_stats(const double *V, int64_t ldp, int64_t P, int64_t M, int64_t k,
+                          double *lo, double *hi, void *work, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRUITS_B200_H */

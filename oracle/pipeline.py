@@ -241,7 +241,7 @@ def lookup(weighting, X, cache: RawCache):
         r = np.arange(1, l + 1)
         if args.get("relative", True):
             r = r / l
-        r = nrm(r[np.newaxis, np.newaxis, :].astype(np.float64))[0, 0, :] * scale
+        r = nrm(r[np.newaxis, np.newaxis, :])[0, 0, :] * scale
         return np.ones((n, l)) * r
     if name in ("L1", "L2"):
         # weighting.py:148-160 / 198-210: raw-input cache, dim 0

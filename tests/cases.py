@@ -1,0 +1,131 @@
+"""Seeded test cases shared by the golden-vector generator
+(``oracle/gen_golden.py``), the oracle tests and the GPU parity tests."""
+import numpy as np
+
+ISS_CASES = {
+    # name: (iss description, input shape, input kind)
+    "reals_w3d3_ext": ({"words": {"of_weight": [3, 3]}, "mode": "extended"},
+                       (5, 3, 96), "normal"),
+    "reals_w4d2_single": ({"words": {"of_weight": [4, 2]}, "mode": "single"},
+                          (3, 2, 64), "walk"),
+    "reals_neg": ({"words": ["[-1]", "[1][-1]", "[-11][2-2][1]", "[-1-1][22]"],
+                   "mode": "extended"}, (4, 2, 50), "uniform1"),
+    "reals_indices": ({"words": {"of_weight": [3, 2]}, "mode": "extended",
+                       "weighting": ["Indices", {}]}, (4, 2, 80), "std"),
+    "reals_indices_total": ({"words": {"of_weight": [3, 2]}, "mode": "extended",
+                             "weighting": ["Indices", {"total": True}]},
+                            (4, 2, 80), "std"),
+    "reals_L1": ({"words": {"of_weight": [4, 1]}, "mode": "extended",
+                  "weighting": ["L1", {}]}, (4, 1, 128), "walk"),
+    "reals_L2_total_alpha": ({"words": ["[1][1][1]", "[1][11]", "[11][1]"],
+                              "mode": "extended",
+                              "weighting": ["L2", {"total": True, "scale": 5}],
+                              "alphas": [[0.5, 1.0, 2.0], [0.5, 1.0],
+                                         [0.25, 1.0]]},
+                             (3, 1, 64), "walk"),
+    "reals_plateaus": ({"words": ["[1][2]", "[12][1]"], "mode": "single",
+                        "weighting": ["Plateaus", {"n": 4}]},
+                       (3, 2, 64), "normal"),
+    "arctic_alt24": ({"words": {"alternate_sign": [24 * "[1]", 12 * "[1][2]"]},
+                      "mode": "extended", "semiring": "arctic"},
+                     (4, 2, 100), "walk"),
+    "arctic_exp": ({"words": ["[111]", "[1][112]", "[12][111][2]", "[-1-1-1][2]"],
+                    "mode": "extended", "semiring": "arctic"},
+                   (4, 2, 70), "normal"),
+    "arctic_single": ({"words": ["[1][2][1]", "[2]", "[1][2]"],
+                       "mode": "single", "semiring": "arctic"},
+                      (4, 2, 70), "normal"),
+    "arctic_indices": ({"words": ["[1][1]", "[1][2][1]"], "mode": "extended",
+                        "semiring": "arctic", "weighting": ["Indices", {}]},
+                       (3, 2, 60), "normal"),
+    "arctic_L1_total": ({"words": ["[1][1]", "[1][2][1]"], "mode": "extended",
+                         "semiring": "arctic",
+                         "weighting": ["L1", {"total": True}]},
+                        (3, 2, 60), "walk"),
+}
+
+
+def make_iss_input(shape, kind, seed=7):
+    rng = np.random.default_rng(seed)
+    if kind == "normal":
+        return rng.standard_normal(shape)
+    if kind == "walk":
+        return rng.standard_normal(shape).cumsum(axis=2)
+    if kind == "uniform1":
+        return rng.random(shape) + 0.5
+    if kind == "std":
+        x = rng.standard_normal(shape).cumsum(axis=2)
+        return (x - x.mean(axis=2, keepdims=True)) / x.std(axis=2, keepdims=True)
+    raise ValueError(kind)
+
+
+SIEVE_CASES = {
+    "npi_default": ["NPI", {}],
+    "npi_q": ["NPI", {"q": [0.25, 0.5, 1.0], "inc": 1}],
+    "npi_inc0": ["NPI", {"q": [0.5, 1.0], "inc": 0}],
+    "npi_inc2": ["NPI", {"q": [-1.0, 0.3, 1.0], "inc": 2}],
+    "npi_incm1": ["NPI", {"q": [0.5, 1.0], "inc": -1}],
+    "npi_cuts": ["NPI", {"cut": [10, -1, 30], "q": [0.0, 0.6, 1.0]}],
+    "npi_cocuts": ["NPI", {"cut": [0.3, 0.7, -1]}],
+    "mpi_default": ["MPI", {}],
+    "mpi_q": ["MPI", {"q": [0.5, 1.0], "inc": 2}],
+    "mpi_cuts": ["MPI", {"cut": [0.5, -1], "q": [0.2, 0.8],
+                         "coquantile_norm": "L1"}],
+    "xpi": ["XPI", {"q": [0.5, 1.0]}],
+    "lpi": ["LPI", {"cut": [20, -1]}],
+    "max_default": ["MAX", {}],
+    "max_q": ["MAX", {"q": [-1.0, 0.5, 1.0]}],
+    "max_cuts": ["MAX", {"cut": [15, 0.5, -1]}],
+    "min_default": ["MIN", {}],
+    "min_q": ["MIN", {"q": [-1.0, 0.5, 1.0]}],
+    "min_cuts": ["MIN", {"cut": [15, -1], "coquantile_norm": "L1"}],
+    "end_default": ["END", {}],
+    "end_cuts": ["END", {"cut": [1, 17, 0.4, -1]}],
+    "ppv_default": ["PPV", {}],
+    "ppv_multi": ["PPV", {"quantile": [0.2, 0.0, 0.9],
+                          "constant": [False, True, False]}],
+    "ppv_segments": ["PPV", {"quantile": [0.2, 0.5, 0.9], "segments": True}],
+}
+
+
+
+def make_sieve_input():
+    """-> (raw [12,2,48] for the coquantile cache, Y [12,48] to sieve)"""
+    rng = np.random.default_rng(11)
+    raw = rng.standard_normal((12, 2, 48)).cumsum(axis=2)
+    Y = rng.standard_normal((12, 48)).cumsum(axis=1)
+    Y[3] = Y[3, 0] + 0.0 * Y[3]  # constant row
+    Y[5, 7:11] = Y[5, 6]         # ties
+    Y -= np.median(Y, axis=1, keepdims=True) - 0.25  # every row straddles 0.25
+    return raw, Y
+
+
+PREP_CASES = {
+    "inc": ["INC", {}],
+    "inc_shift3_depth2": ["INC", {"shift": 3, "depth": 2}],
+    "inc_nopad": ["INC", {"zero_padding": False}],
+    "std": ["STD", {}],
+    "std_novar": ["STD", {"var": False}],
+    "nrm": ["NRM", {}],
+    "new_inc": ["NEW", ["INC", {}]],
+    "new_none": ["NEW", None],
+}
+
+
+
+def make_prep_input():
+    X = np.random.default_rng(5).standard_normal((6, 3, 40)).cumsum(axis=2)
+    X[2, 1] = 4.0
+    return X
+
+
+PIPE_CASES = {
+    # name: (spec name, number of series)
+    "C1_readme": ("C1_readme", 200),
+    "C2_reduced": ("C2_reduced", 24),
+    "C3_general": ("C3_general", 4),
+    "C4_twi": ("C4_twi", 8),
+    "C5_sweep": ("C5_sweep", 32),
+}
+
+
