@@ -106,6 +106,7 @@ def lib() -> ctypes.CDLL:
         "fb_nan_to_num": ([vp, i64, vp], i32),
         "fb_order_stats_workspace": ([i64], i64),
         "fb_order_stats": ([vp, i64, i64, i64, i64, vp, vp, vp, vp], i32),
+        "fb_fp64_peak": ([vp, i32, i32, vp], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -123,7 +124,7 @@ EXPORTED = [
     "fb_iss_materialize", "fb_increments", "fb_row_stats", "fb_standardize",
     "fb_lsum", "fb_nrm_scale", "fb_coquantile", "fb_pretransform",
     "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_order_stats_workspace",
-    "fb_order_stats",
+    "fb_order_stats", "fb_fp64_peak",
 ]
 
 

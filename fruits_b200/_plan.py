@@ -129,7 +129,8 @@ def _encode_letter(expo, dim_index, arctic: bool):
         return val & 0xFFFFFFFF, (val >> 32) & 0xFFFFFFFF, len(pairs)
     occ = []
     for d, e in enumerate(expo):
-        occ += [(dim_index[d]) | (8 if e < 0 else 0)] * abs(e)
+        if e != 0:
+            occ += [(dim_index[d]) | (8 if e < 0 else 0)] * abs(e)
     if len(occ) > 15:
         raise NotImplementedError("letters with more than 15 occurrences")
     val = 0
@@ -199,7 +200,7 @@ class DevicePlan:
         slots["emit"] = -1
         slots["depth"] = 1
         slots["letter_lo"] = 0
-        row_pub = np.zeros(len(blocks), dtype=np.uint8)
+        row_pub = np.zeros(len(blocks), dtype=np.uint32)
         row_weight = np.zeros((len(blocks), n_rows), dtype=np.uint8)
         pad_lo = 0
         for i in range(8):
@@ -212,11 +213,13 @@ class DevicePlan:
                 lo, hi, w = _encode_letter(n.expo, dim_index, arctic)
                 has_child = any(c in members for c in n.children)
                 enc[v] = (lo, hi, w, has_child, own)
-            internal = sorted((v for v in enc if enc[v][3]), key=lambda v: (enc[v][2], v))
-            leaves = sorted((v for v in enc if not enc[v][3]), key=lambda v: (enc[v][2], v))
-            layout = internal + leaves
+            # heaviest letters first (rows become homogeneous in the number of
+            # multiplications), nodes with children first among equals
+            layout = sorted(enc, key=lambda v: (-enc[v][2], not enc[v][3], v))
             pos = {v: i for i, v in enumerate(layout)}
-            row_pub[bi] = -(-len(internal) // 32)
+            for i, v in enumerate(layout):
+                if enc[v][3]:
+                    row_pub[bi] |= np.uint32(1 << (i // 32))
             flat = slots[bi].reshape(-1)
             for i, v in enumerate(layout):
                 n = trie.nodes[v]

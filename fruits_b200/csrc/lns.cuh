@@ -20,10 +20,16 @@
 // contracts `tmp + el*Z`).  Time is walked sequentially, so unweighted Reals
 // and all Arctic results are bit-identical to the reference.
 //
+// A step is written phase by phase over all RMAX rows of the warp (publish,
+// gather parent + letter product, update, sieve), branch-free per row, so the
+// RMAX independent dependency chains interleave in the fp64 pipe.
+//
 // The sieves (POL) consume every value the moment it is produced; the
 // (series x node x time) tensor only exists in registers.
 #pragma once
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -36,11 +42,15 @@ constexpr int LNS_WARPS = 4;   // warps (independent tasks) per CTA
 constexpr int LNS_TILE = 32;   // time steps staged per tile (one per lane)
 constexpr int RING = FB_RING;
 constexpr int RING_MASK = FB_RING - 1;
+// row stride of the time rings in doubles: +2 keeps the rows of different
+// dimensions in different shared-memory banks (lanes of one row read up to
+// n_dims distinct x values at the same time position)
+constexpr int RS = FB_RING + 2;
 
 struct LnsParams {
     const fb_slot *slots;
-    const uint8_t *row_pub;
-    const uint8_t *row_weight;
+    const uint32_t *row_pub;     // [n_blocks] bit j: row j holds a node with children
+    const uint8_t *row_weight;   // [n_blocks][n_rows] max letter weight of the row
     const double *X;
     const double *g;
     const double *stats;
@@ -73,33 +83,37 @@ struct Policy {
 // doubles of shared memory one warp needs
 __host__ __device__ inline int lns_warp_doubles(int rmax, int du, int na, bool weighted)
 {
-    int n = (du + 1) * RING + rmax * 32 + 8;
-    if (weighted) n += (1 + 2 * na) * RING;
+    int n = (du + 1) * RS + rmax * 32 + 8;
+    if (weighted) n += (1 + 2 * na) * RS;
     return n;
 }
 
-// Product of the letter occurrences applied to v in the reference's order
-// (fruits/iss/semiring.py:143-149): one rounding per occurrence.
-__device__ __forceinline__ double letter_mul(double v, uint32_t l, const double *xp, int w)
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
 {
-#pragma unroll 1
-    for (int i = 0; i < w; i++) {
-        v = __dmul_rn(v, xp[(l & 7) * RING]);
-        l >>= 4;
-    }
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double lds(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
-
-// Same with divisions (negative exponents) and more than 8 occurrences: rare,
-// kept out of line so that the hot loop stays small.
-static __device__ __noinline__ double letter_muldiv(double v, uint32_t lo, uint32_t hi, const double *xp,
-                                             int w)
+__device__ __forceinline__ void sts(uint32_t addr, double v)
 {
-    uint32_t l = lo;
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// Letter occurrences beyond the second of a Reals letter (11% of the nodes of
+// the sweep configuration), divisions (negative exponents) and letters longer
+// than 8 occurrences: generic loop, kept out of the unrolled fast path.
+static __device__ __noinline__ double letter_tail(double v, uint32_t lo, uint32_t hi,
+                                                  uint32_t xs_pos, int from, int w)
+{
+    uint32_t l = (from < 8) ? (lo >> (4 * from)) : (hi >> (4 * (from - 8)));
 #pragma unroll 1
-    for (int i = 0; i < w; i++) {
+    for (int i = from; i < w; i++) {
         if (i == 8) l = hi;
-        const double xv = xp[(l & 7) * RING];
+        const double xv = lds(xs_pos + (l & 7) * (RS * 8));
         v = (l & 8) ? __ddiv_rn(v, xv) : __dmul_rn(v, xv);
         l >>= 4;
     }
@@ -118,6 +132,10 @@ lns_kernel(const LnsParams P)
     constexpr bool ACC2 = NONTOTAL;
     // previous output kept separately (weighted total modes: out != state)
     constexpr bool OUTP = TOTAL;
+    constexpr bool SKEW = !REALS;   // per-lane time (arctic)
+    // rows whose 3rd / 4th letter occurrence is applied inline (the host sorts
+    // the rows by letter weight, heaviest first)
+    constexpr int NHEAVY = RMAX < 2 ? RMAX : 2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * LNS_WARPS + warp;
@@ -130,16 +148,22 @@ lns_kernel(const LnsParams P)
 
     extern __shared__ double smem[];
     double *xs = smem + (size_t)warp * lns_warp_doubles(RMAX, du, na, WEIGHTED);
-    double *pub = xs + (du + 1) * RING;       // [RMAX*32] + identity at [RMAX*32]
+    double *pub = xs + (du + 1) * RS;       // [RMAX*32] + identity at [RMAX*32]
     double *gs = pub + RMAX * 32 + 8;         // [RING]           (weighted only)
-    double *ep = gs + RING;                   // [na][RING] exp(+alpha g)
-    double *em = ep + na * RING;              // [na][RING] exp(-alpha g)
-    (void)gs; (void)ep; (void)em;
+    double *ep = gs + RS;                   // [na][RING] exp(+alpha g)
+    double *em = ep + na * RS;              // [na][RING] exp(-alpha g)
+    const uint32_t xs_a = smem_addr(xs), pub_a = smem_addr(pub);
+    const uint32_t gs_a = smem_addr(gs), ep_a = smem_addr(ep);
+    const uint32_t em_off = (uint32_t)na * RS * 8;   // em = ep + em_off
+    (void)gs_a; (void)ep_a; (void)em_off; (void)em;
 
     // ---- per-slot registers ------------------------------------------------
     uint32_t let[RMAX];      // letter occurrences / pairs (low word)
-    int par[RMAX];           // index into pub[] of the parent value
-    int meta[RMAX];          // depth-1 (bits 0-7), aidx (8-9), parent aidx (10-11), emit>=0 (12)
+    uint32_t par[RMAX];      // shared address of the parent's published value
+    uint32_t xo0[RMAX];      // shared address of the ring row of occurrence / pair 0
+    uint32_t xo1[RMAX];      // ... of occurrence / pair 1 (constant-one row if none)
+    uint32_t eo[WEIGHTED ? RMAX : 1];   // shared address of this slot's exp(+alpha g) row
+    int meta[(SKEW || WEIGHTED) ? RMAX : 1];  // skew (bits 0-7), aidx (8-9), parent aidx (10-11)
     double S[RMAX];          // running iterated sum / running max
     double A2[ACC2 ? RMAX : 1];
     double OP[OUTP ? RMAX : 1];
@@ -158,12 +182,19 @@ lns_kernel(const LnsParams P)
     long long matoff[POL::MAT ? RMAX : 1];
 
     const fb_slot *slots = P.slots + (size_t)blk * nrows * 32;
-    const int rpub = P.row_pub[blk];
+    const uint32_t pubmask = P.row_pub[blk];
+    // The host sorts the rows of a block by letter weight, heaviest first, so
+    // "rows with at least k occurrences" is a prefix: n2, n3, n4 rows.  Rows
+    // with more than 4 occurrences or with divisions finish in letter_tail.
+    int n2 = 0, n3 = 0, n4 = 0;
+    uint32_t slowmask = 0, divmask = 0;
     unsigned long long wpack = 0;   // 4 bits of max letter weight per row
-    unsigned slowmask = 0;          // rows with divisions or more than 8 occurrences
+    const uint32_t one_row = xs_a + (uint32_t)du * RS * 8;
 #pragma unroll
     for (int j = 0; j < RMAX; j++) {
-        let[j] = 0; par[j] = RMAX * 32; meta[j] = 0;
+        let[j] = 0; par[j] = pub_a + RMAX * 32 * 8; xo0[j] = one_row; xo1[j] = one_row;
+        if (WEIGHTED) eo[j] = ep_a;
+        if (SKEW || WEIGHTED) meta[j] = 0;
         S[j] = REALS ? 0.0 : d_ninf();
         if (ACC2) A2[j] = REALS ? 0.0 : d_ninf();
         if (OUTP) OP[j] = 0.0;
@@ -180,15 +211,32 @@ lns_kernel(const LnsParams P)
         if (j < nrows) {
             const fb_slot sl = slots[j * 32 + lane];
             let[j] = sl.letter_lo;
-            par[j] = sl.parent >= 0 ? sl.parent : RMAX * 32;
-            const int paidx = (sl.flags >> 4) & 3;
-            meta[j] = ((sl.depth ? sl.depth - 1 : 0) & 255) | ((sl.aidx & 3) << 8) | (paidx << 10) |
-                      ((sl.emit >= 0) << 12);
+            if (sl.parent >= 0) par[j] = pub_a + (uint32_t)sl.parent * 8;
             const int w = P.row_weight[blk * nrows + j];
             wpack |= (unsigned long long)(w & 15) << (4 * j);
-            if (REALS && (w > 8 || __any_sync(0xffffffffu, (sl.letter_lo & 0x88888888u) ||
-                                                               (sl.letter_hi & 0x88888888u))))
-                slowmask |= 1u << j;
+            if (w > 1) n2 = j + 1;
+            if (w > 2) n3 = j + 1;
+            if (w > 3) n4 = j + 1;
+            if (w > 4 || (w > 2 && j >= NHEAVY)) slowmask |= 1u << j;
+            if (REALS) {
+                // occurrences beyond the letter are padded with the constant-one row
+                const bool div = (sl.letter_lo & 0x88888888u) || (sl.letter_hi & 0x88888888u);
+                if (__any_sync(0xffffffffu, div)) {
+                    // whole letter through the generic loop; the fast path sees ones
+                    divmask |= 1u << j;
+                    slowmask |= 1u << j;
+                    let[j] = (uint32_t)du * 0x11111111u;
+                }
+                xo0[j] = xs_a + (let[j] & 7) * (RS * 8);
+                xo1[j] = xs_a + ((let[j] >> 4) & 7) * (RS * 8);
+            } else {
+                xo0[j] = xs_a + (sl.letter_lo & 7) * (RS * 8);
+                xo1[j] = xs_a + ((sl.letter_lo >> 8) & 7) * (RS * 8);
+            }
+            const int paidx = (sl.flags >> 4) & 3;
+            if (SKEW || WEIGHTED)
+                meta[j] = ((sl.depth ? sl.depth - 1 : 0) & 255) | ((sl.aidx & 3) << 8) | (paidx << 10);
+            if (WEIGHTED) eo[j] = ep_a + (uint32_t)(sl.aidx & 3) * RS * 8;
             if (sl.emit >= 0) {
                 if (POL::MAT) matoff[j] = ((long long)sl.emit * P.n + n) * T;
                 if (!POL::MAT) {
@@ -206,8 +254,8 @@ lns_kernel(const LnsParams P)
 
     // identity of the semiring's product for root-level slots
     if (lane < 8) pub[RMAX * 32 + lane] = REALS ? 1.0 : 0.0;
-    // constant-one row used to pad letters (Reals) / harmless for Arctic
-    for (int i = lane; i < RING; i += 32) xs[du * RING + i] = 1.0;
+    // constant-one row used to pad letters (Reals); arctic pads with exponent 0
+    for (int i = lane; i < RING; i += 32) xs[du * RS + i] = 1.0;
 
     const double *Xn = P.X + (size_t)n * P.d * T;
     const double *gn = WEIGHTED ? (P.g + (size_t)(P.g_ld ? n * P.g_ld : 0)) : nullptr;
@@ -244,7 +292,7 @@ lns_kernel(const LnsParams P)
                         v = (v - st[0]) / st[1];
                     }
                 }
-                xs[u * RING + pos] = v;
+                xs[u * RS + pos] = v;
             }
         }
         if (WEIGHTED) {
@@ -253,10 +301,203 @@ lns_kernel(const LnsParams P)
 #pragma unroll
             for (int a = 0; a < FB_MAX_ALPHAS; a++)
                 if (a < na) {
-                    ep[a * RING + pos] = exp(ga * alpha[a]);
-                    em[a * RING + pos] = exp(-ga * alpha[a]);
+                    ep[a * RS + pos] = exp(ga * alpha[a]);
+                    em[a * RS + pos] = exp(-ga * alpha[a]);
                 }
         }
+    };
+
+    // ---- one time step over all rows -------------------------------------------
+    // FIRST: global step 0 of a Reals kernel (increments are zero-padded:
+    // the first increment is 0, not y[0] - 0).
+    auto step = [&](auto first_tag, const int s) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        const uint32_t pos8 = (uint32_t)(s & RING_MASK) * 8;
+        // -- publish (the value the children need this step) --
+        // (every phase is predicated, not branched: a branch per row costs more
+        // than the few instructions it would skip)
+#pragma unroll
+        for (int j = 0; j < RMAX; j++) {
+            double pv;
+            if (REALS) {
+                if (TOTAL) pv = __dmul_rn(S[j], lds(eo[j] + em_off + pos8));
+                else if (NONTOTAL) pv = __dmul_rn(A2[j], lds(eo[j] + em_off + pos8));
+                else pv = S[j];
+            } else {
+                pv = TOTAL ? OP[j] : (NONTOTAL ? A2[j] : S[j]);
+            }
+            if (pubmask & (1u << j)) sts(pub_a + (uint32_t)(j * 32 + lane) * 8, pv);
+        }
+        __syncwarp();
+        // -- gather the parent value and apply the letter --
+        double v[RMAX];
+        uint32_t lpos[SKEW ? RMAX : 1];   // per-lane ring offset (arctic skew)
+        bool act[SKEW ? RMAX : 1], fst[SKEW ? RMAX : 1];
+#pragma unroll
+        for (int j = 0; j < RMAX; j++) {
+            v[j] = lds(par[j]);
+            if (REALS) {
+                v[j] = __dmul_rn(v[j], lds(xo0[j] + pos8));
+            } else {
+                const int tl = s - (meta[j] & 255);
+                act[j] = (unsigned)tl < (unsigned)T;
+                fst[j] = (tl == 0);
+                lpos[j] = (uint32_t)(tl & RING_MASK) * 8;
+                const double e0 = (double)(((int)(let[j] << 24)) >> 27);
+                v[j] = fma(e0, lds(xo0[j] + lpos[j]), v[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RMAX; j++) {          // 2nd occurrence / pair
+            if (j < n2) {
+                if (REALS) {
+                    v[j] = __dmul_rn(v[j], lds(xo1[j] + pos8));
+                } else {
+                    const double e1 = (double)(((int)(let[j] << 16)) >> 27);
+                    v[j] = fma(e1, lds(xo1[j] + lpos[j]), v[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 2; k < 4; k++) {             // 3rd and 4th occurrence / pair:
+#pragma unroll
+            for (int j = 0; j < NHEAVY; j++) {    // only the heaviest rows, inline
+                if (j < (k == 2 ? n3 : n4)) {
+                    if (REALS) {
+                        const uint32_t a = xs_a + ((let[j] >> (4 * k)) & 7) * (RS * 8) + pos8;
+                        v[j] = __dmul_rn(v[j], lds(a));
+                    } else {
+                        const uint32_t a = xs_a + ((let[j] >> (8 * k)) & 7) * (RS * 8) + lpos[j];
+                        const double e = (double)(((int)(let[j] << (24 - 8 * k))) >> 27);
+                        v[j] = fma(e, lds(a), v[j]);
+                    }
+                }
+            }
+        }
+        if (slowmask) {                           // rare: generic remainder of long letters
+#pragma unroll
+            for (int j = 0; j < RMAX; j++) {
+                if (slowmask & (1u << j)) {
+                    const int w = (int)((wpack >> (4 * j)) & 15);
+                    const fb_slot *sl = slots + j * 32 + lane;
+                    const int from = (divmask & (1u << j)) ? 0 : (j < NHEAVY ? 4 : 2);
+                    if (REALS) {
+                        v[j] = letter_tail(v[j], sl->letter_lo, sl->letter_hi, xs_a + pos8, from, w);
+                    } else {
+                        uint32_t l = (from == 2) ? (sl->letter_lo >> 16) : sl->letter_hi;
+#pragma unroll 1
+                        for (int i = from; i < w; i++) {
+                            if (i == 4 && from == 2) l = sl->letter_hi;
+                            const double e = (double)(((int)(l << 24)) >> 27);
+                            v[j] = fma(e, lds(xs_a + (l & 7) * (RS * 8) + lpos[j]), v[j]);
+                            l >>= 8;
+                        }
+                    }
+                }
+            }
+        }
+        // -- update the running sums and feed the sieves --
+#pragma unroll
+        for (int j = 0; j < RMAX; j++) {
+            double out, outprev;
+            bool first = FIRST, active = true;
+            if (REALS) {
+                if (TOTAL) {
+                    const double vv = __dmul_rn(v[j], lds(eo[j] + pos8));
+                    const double c = __dadd_rn(S[j], vv);
+                    S[j] = c;
+                    out = __dmul_rn(c, lds(eo[j] + em_off + pos8));
+                    outprev = OP[j];
+                    OP[j] = out;
+                } else {
+                    outprev = S[j];
+                    out = __dadd_rn(outprev, v[j]);
+                    S[j] = out;
+                    if (NONTOTAL) {
+                        if (pubmask & (1u << j))
+                            A2[j] = __dadd_rn(A2[j], __dmul_rn(v[j], lds(eo[j] + pos8)));
+                    }
+                }
+            } else {
+                active = act[j];
+                first = fst[j];
+                const int a = (meta[j] >> 8) & 3;
+                if (TOTAL) {
+                    const double gv = lds(gs_a + lpos[j]);
+                    const double vv = fma(gv, alpha[a], v[j]);
+                    const double m = active ? fmax(S[j], vv) : S[j];
+                    S[j] = m;
+                    outprev = OP[j];
+                    out = fma(-gv, alpha[a], m);
+                    if (active) OP[j] = out;
+                } else if (NONTOTAL) {
+                    const double gv = lds(gs_a + lpos[j]);
+                    double vv = v[j];
+                    if ((meta[j] & 255) > 0) vv = fma(-gv, alpha[(meta[j] >> 10) & 3], vv);
+                    outprev = S[j];
+                    out = active ? fmax(outprev, vv) : outprev;
+                    S[j] = out;
+                    if (pubmask & (1u << j)) {
+                        const double v2 = fma(gv, alpha[a], vv);
+                        if (active) A2[j] = fmax(A2[j], v2);
+                    }
+                } else {
+                    outprev = S[j];
+                    out = active ? fmax(outprev, v[j]) : outprev;
+                    S[j] = out;
+                }
+            }
+            // -- consume the value --
+            if (POL::MAT) {
+                if (active && matoff[j] >= 0)
+                    P.out[matoff[j] + (REALS ? s : s - (meta[j] & 255))] = out;
+            } else {
+                if (POL::U0) {
+                    bool sel = out > thr0l[j];
+                    if (POL::HI) sel = sel && (out <= thr0h[j]);
+                    if (SKEW) sel = sel && active;
+                    if (sel) c01[j] += 1u;
+                    if (POL::SUM0) s0[j] = __dadd_rn(s0[j], sel ? out : 0.0);
+                }
+                if (POL::NEED_D1) {
+                    const double d1 = first ? 0.0 : __dadd_rn(out, -outprev);
+                    if (POL::U1) {
+                        bool sel = d1 > thr1l[j];
+                        if (POL::HI) sel = sel && (d1 <= thr1h[j]);
+                        if (SKEW) sel = sel && active;
+                        if (sel) c01[j] += 0x10000u;
+                        if (POL::SUM1) s1[j] = __dadd_rn(s1[j], sel ? d1 : 0.0);
+                    }
+                    if (POL::U2) {
+                        const double d2 = __dadd_rn(d1, -d1p[j]);
+                        d1p[j] = (SKEW && !active) ? d1p[j] : d1;
+                        bool sel = d2 > thr2l[j];
+                        if (POL::HI) sel = sel && (d2 <= thr2h[j]);
+                        if (SKEW) sel = sel && active;
+                        if (sel) c2p[j] += 1u;
+                        if (POL::SUM2) s2[j] = __dadd_rn(s2[j], sel ? d2 : 0.0);
+                    }
+                }
+                if (POL::PPV) {
+                    bool sel = out >= thrp[j];
+                    if (SKEW) sel = sel && active;
+                    if (sel) c2p[j] += 0x10000u;
+                }
+                if (POL::MAX) {
+                    bool sel = out > mx[j];
+                    if (POL::MMB) sel = sel && (out > mxl[j]) && (out <= mxh[j]);
+                    if (SKEW) sel = sel && active;
+                    mx[j] = sel ? out : mx[j];
+                }
+                if (POL::MIN) {
+                    bool sel = out < mn[j];
+                    if (POL::MMB) sel = sel && (out > mnl[j]) && (out <= mnh[j]);
+                    if (SKEW) sel = sel && active;
+                    mn[j] = sel ? out : mn[j];
+                }
+            }
+        }
+        __syncwarp();
     };
 
     const int skew_max = REALS ? 0 : (P.max_depth - 1);
@@ -266,145 +507,18 @@ lns_kernel(const LnsParams P)
     __syncwarp();
 
     for (int s0_ = 0; s0_ < nsteps; s0_ += LNS_TILE) {
-        // prefetch the next tile into registers while this one is computed
+        // prefetch the next tile into L1 while this one is computed
         const int tnext = s0_ + LNS_TILE;
         const bool have_next = tnext < T;
         if (have_next) prefetch_tile(tnext);
         const int send = min(LNS_TILE, nsteps - s0_);
-        for (int ss = 0; ss < send; ss++) {
-            const int s = s0_ + ss;
-            // -- publish (value the children need this step) --
-#pragma unroll
-            for (int j = 0; j < RMAX; j++) {
-                if (j < rpub) {
-                    double pv;
-                    if (REALS) {
-                        if (TOTAL) pv = S[j] * em[((meta[j] >> 8) & 3) * RING + (s & RING_MASK)];
-                        else if (NONTOTAL) pv = A2[j] * em[((meta[j] >> 8) & 3) * RING + (s & RING_MASK)];
-                        else pv = S[j];
-                    } else {
-                        if (TOTAL) pv = OP[j];
-                        else if (NONTOTAL) pv = A2[j];
-                        else pv = S[j];
-                    }
-                    pub[j * 32 + lane] = pv;
-                }
-            }
-            __syncwarp();
-            // -- update every slot --
-#pragma unroll
-            for (int j = 0; j < RMAX; j++) {
-                if (j < nrows) {
-                    const int w = (int)((wpack >> (4 * j)) & 15);
-                    double v = pub[par[j]];
-                    double out, outprev;
-                    bool first, active;
-                    if (REALS) {
-                        const int pos = s & RING_MASK;
-                        first = (s == 0);
-                        active = true;
-                        if (slowmask & (1u << j))
-                            v = letter_muldiv(v, let[j], slots[j * 32 + lane].letter_hi, xs + pos, w);
-                        else
-                            v = letter_mul(v, let[j], xs + pos, w);
-                        const int a = (meta[j] >> 8) & 3;
-                        if (TOTAL) {
-                            v = __dmul_rn(v, ep[a * RING + pos]);
-                            const double c = __dadd_rn(S[j], v);
-                            S[j] = c;
-                            out = __dmul_rn(c, em[a * RING + pos]);
-                            outprev = OP[j];
-                            OP[j] = out;
-                        } else {
-                            outprev = S[j];
-                            out = __dadd_rn(outprev, v);
-                            S[j] = out;
-                            if (NONTOTAL) {
-                                if (j < rpub)
-                                    A2[j] = __dadd_rn(A2[j], __dmul_rn(v, ep[a * RING + pos]));
-                            }
-                        }
-                    } else {
-                        const int tl = s - (meta[j] & 255);
-                        active = (unsigned)tl < (unsigned)T;
-                        first = (tl == 0);
-                        const int pos = tl & RING_MASK;
-                        uint32_t l = let[j];
-                        const double *xp = xs + pos;
-#pragma unroll 1
-                        for (int i = 0; i < w; i++) {
-                            if (i == 4) l = slots[j * 32 + lane].letter_hi;
-                            const double e = (double)(((int)(l << 24)) >> 27);
-                            v = fma(e, xp[(l & 7) * RING], v);
-                            l >>= 8;
-                        }
-                        const int a = (meta[j] >> 8) & 3;
-                        if (TOTAL) {
-                            const double gv = gs[pos];
-                            v = fma(gv, alpha[a], v);
-                            const double m = active ? fmax(S[j], v) : S[j];
-                            S[j] = m;
-                            outprev = OP[j];
-                            out = fma(-gv, alpha[a], m);
-                            if (active) OP[j] = out;
-                        } else if (NONTOTAL) {
-                            const double gv = gs[pos];
-                            if ((meta[j] & 255) > 0) v = fma(-gv, alpha[(meta[j] >> 10) & 3], v);
-                            outprev = S[j];
-                            out = active ? fmax(outprev, v) : outprev;
-                            S[j] = out;
-                            if (j < rpub) {
-                                const double v2 = fma(gv, alpha[a], v);
-                                if (active) A2[j] = fmax(A2[j], v2);
-                            }
-                        } else {
-                            outprev = S[j];
-                            out = active ? fmax(outprev, v) : outprev;
-                            S[j] = out;
-                        }
-                    }
-                    // -- consume the value --
-                    if (POL::MAT) {
-                        if (active && matoff[j] >= 0)
-                            P.out[matoff[j] + (REALS ? s : s - (meta[j] & 255))] = out;
-                    } else if (active) {
-                        if (POL::U0) {
-                            bool sel = out > thr0l[j];
-                            if (POL::HI) sel = sel && (out <= thr0h[j]);
-                            c01[j] += sel ? 1u : 0u;
-                            if (POL::SUM0) s0[j] = __dadd_rn(s0[j], sel ? out : 0.0);
-                        }
-                        if (POL::NEED_D1) {
-                            const double d1 = first ? 0.0 : __dadd_rn(out, -outprev);
-                            if (POL::U1) {
-                                bool sel = d1 > thr1l[j];
-                                if (POL::HI) sel = sel && (d1 <= thr1h[j]);
-                                c01[j] += sel ? 0x10000u : 0u;
-                                if (POL::SUM1) s1[j] = __dadd_rn(s1[j], sel ? d1 : 0.0);
-                            }
-                            if (POL::U2) {
-                                const double d2 = __dadd_rn(d1, -d1p[j]);
-                                d1p[j] = d1;
-                                bool sel = d2 > thr2l[j];
-                                if (POL::HI) sel = sel && (d2 <= thr2h[j]);
-                                c2p[j] += sel ? 1u : 0u;
-                                if (POL::SUM2) s2[j] = __dadd_rn(s2[j], sel ? d2 : 0.0);
-                            }
-                        }
-                        if (POL::PPV) c2p[j] += (out >= thrp[j]) ? 0x10000u : 0u;
-                        if (POL::MAX) {
-                            if (POL::MMB) { if (out > mxl[j] && out <= mxh[j]) mx[j] = fmax(mx[j], out); }
-                            else mx[j] = fmax(mx[j], out);
-                        }
-                        if (POL::MIN) {
-                            if (POL::MMB) { if (out > mnl[j] && out <= mnh[j]) mn[j] = fmin(mn[j], out); }
-                            else mn[j] = fmin(mn[j], out);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
+        int ss = 0;
+        if (REALS && s0_ == 0) {
+            step(std::true_type{}, 0);
+            ss = 1;
         }
+#pragma unroll 1
+        for (; ss < send; ss++) step(std::false_type{}, s0_ + ss);
         if (have_next) stage_tile(tnext);
         __syncwarp();
     }
@@ -462,7 +576,6 @@ int lns_launch(const LnsParams &p, cudaStream_t stream)
     auto kern = lns_kernel<RMAX, SEMI, WM, POL>;
     size_t smem = (size_t)LNS_WARPS *
                   lns_warp_doubles(RMAX, p.du, p.na, WM != FB_WEIGHT_NONE) * sizeof(double);
-    if (const char *dbg = getenv("FB_DEBUG_SMEM_EXTRA")) smem += (size_t)atoi(dbg);
     static size_t configured = 0;
     if (smem > configured) {
         FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -16,7 +16,7 @@ using PolG   = Policy<false, 1, 1, 1, 1,  1, 1,  1,  1,  1,  1,  1>;  // everyth
 
 enum PolicyId { POL_MAT = 0, POL_A, POL_D, POL_P, POL_M, POL_G, POL_COUNT };
 
-constexpr int RMAX_MAT = 16, RMAX_A = 16, RMAX_D = 12, RMAX_P = 8, RMAX_M = 8, RMAX_G = 4;
+constexpr int RMAX_MAT = 16, RMAX_A = 16, RMAX_D = 12, RMAX_P = 7, RMAX_M = 8, RMAX_G = 4;
 
 template <int RMAX, class POL>
 int lns_dispatch_mode(const LnsParams &p, int semiring, int wm, cudaStream_t st)

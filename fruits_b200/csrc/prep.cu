@@ -237,3 +237,35 @@ int fb_coquantile(const double *S, int64_t *out, int64_t n, int64_t t, double q,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// fp64 pipe microbenchmark: the denominator of the roofline fraction.
+// MEASURED_PEAKS.json holds HBM and bf16 peaks only, so bench.py measures the
+// DFMA peak live with this kernel (8 independent FMA chains per thread).
+namespace fb {
+__global__ void fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5,
+           r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+            r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+        }
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+}  // namespace fb
+
+extern "C" {
+/* Launches grid x 256 threads, each doing iters*64 DFMAs; out needs grid*256
+ * doubles.  FLOPs = grid*256*iters*64*2. */
+int fb_fp64_peak(double *out, int grid, int iters, void *stream)
+{
+    FB_REQUIRE(out && grid > 0 && iters > 0, "bad arguments");
+    fb::fp64_peak_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, iters, 0.9999999, 1e-9);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+}

@@ -85,18 +85,95 @@ class Fruit:
         self._fitted = True
 
     def transform(self, X, callbacks: Optional[list] = None,
-                  cache: Optional[SharedSeedCache] = None):
+                  cache: Optional[SharedSeedCache] = None, out=None):
         """Feature matrix ``[n_series, nfeatures]`` of all slices
-        (reference: fruit.py:138-173)."""
+        (reference: fruit.py:138-173).
+
+        ``out`` (not in the reference) is an optional preallocated float64
+        numpy array ``[n_series, nfeatures]`` that receives the features;
+        with page-locked ``X`` and ``out`` the copies run asynchronously."""
         if callbacks is None:
             callbacks = []
         if not self._fitted:
             raise RuntimeError("Missing call of self.fit")
-        Xd = be.to_device(X)
-        result = self.transform_device(Xd, callbacks, cache)
-        if isinstance(X, torch.Tensor):
-            return result
-        return result.cpu().numpy()
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            return self.transform_device(X, callbacks, cache)
+        return self._transform_host(X, callbacks, cache, out)
+
+    def _transform_host(self, X, callbacks, cache, out):
+        """Host input: stream row chunks through the GPU so that the upload of
+        chunk i+1 and the download of chunk i-1 overlap the kernels of chunk i
+        (three streams, two device buffers per direction)."""
+        Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(self._check_host(X)))
+        if Xh.dtype != torch.float64:
+            raise TypeError(f"input must be float64, got {Xh.dtype}")
+        if Xh.dim() != 3:
+            raise ValueError("input must have shape (n_series, n_dimensions, length)")
+        n, nf = Xh.shape[0], self.nfeatures()
+        if out is None:
+            out = np.empty((n, nf), dtype=np.float64)
+        elif out.shape != (n, nf) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array [n_series, nfeatures]")
+        oh = torch.from_numpy(out)
+        row_bytes = Xh[0].numel() * 8 + nf * 8 if n else 1
+        rows = max(1, min(n, (256 << 20) // max(row_bytes, 1)))
+        # every step of transform is independent per series, so row chunks can
+        # be processed on their own (a user-supplied cache refers to all rows)
+        single = bool(callbacks) or cache is not None or n <= rows
+        if single:
+            res = self.transform_device(be.to_device(Xh), callbacks, cache)
+            oh.copy_(res)
+            return out
+        dev = be.require_cuda()
+        main = torch.cuda.current_stream()
+        up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        up.wait_stream(main)
+        xb = [torch.empty((rows,) + tuple(Xh.shape[1:]), dtype=torch.float64, device=dev)
+              for _ in range(2)]
+        fb = [torch.empty((rows, nf), dtype=torch.float64, device=dev) for _ in range(2)]
+        x_ready, x_free, f_ready, f_free = [None] * 2, [None] * 2, [None] * 2, [None] * 2
+        starts = list(range(0, n, rows))
+
+        def upload(i):
+            b, lo = i % 2, starts[i]
+            hi = min(n, lo + rows)
+            with torch.cuda.stream(up):
+                if x_free[b] is not None:
+                    up.wait_event(x_free[b])
+                xb[b][:hi - lo].copy_(Xh[lo:hi], non_blocking=True)
+                x_ready[b] = torch.cuda.Event()
+                x_ready[b].record(up)
+
+        upload(0)
+        for i, lo in enumerate(starts):
+            b, hi = i % 2, min(n, lo + rows)
+            if i + 1 < len(starts):
+                upload(i + 1)
+            main.wait_event(x_ready[b])
+            if f_free[b] is not None:
+                main.wait_event(f_free[b])
+            self.transform_device(xb[b][:hi - lo], None, None, out=fb[b][:hi - lo])
+            x_free[b] = torch.cuda.Event()
+            x_free[b].record(main)
+            f_ready[b] = torch.cuda.Event()
+            f_ready[b].record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(f_ready[b])
+                oh[lo:hi].copy_(fb[b][:hi - lo], non_blocking=True)
+                f_free[b] = torch.cuda.Event()
+                f_free[b].record(down)
+        main.wait_stream(down)
+        main.synchronize()
+        return out
+
+    @staticmethod
+    def _check_host(X):
+        X = np.asarray(X)
+        if X.dtype != np.float64:
+            # the reference's numba signatures only accept float64
+            raise TypeError(f"input must be float64, got {X.dtype}")
+        return X
 
     def transform_device(self, Xd: torch.Tensor, callbacks=None, cache=None,
                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -523,6 +600,8 @@ class FruitSlice:
             cache = SharedSeedCache(X)
         for iss in self._iss:
             iss._cache = cache
+        if X.shape[0] == 0:
+            return
         if self._is_fusable(X.shape[1], callbacks):
             self._transform_fused(X.contiguous(), cache, out, col0, sanitize)
         else:

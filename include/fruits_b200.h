@@ -92,7 +92,7 @@ typedef struct fb_iss_plan {
     float   alphas[FB_MAX_ALPHAS];
     fb_dim  dims[FB_MAX_USED_DIMS];
     const fb_slot *slots;        /* device: [n_blocks][n_rows][32] */
-    const uint8_t *row_pub;      /* device: [n_blocks] number of leading rows that publish */
+    const uint32_t *row_pub;     /* device: [n_blocks] bit j set: row j holds a node with children */
     const uint8_t *row_weight;   /* device: [n_blocks][n_rows] max letter weight in the row */
 } fb_iss_plan;
 
@@ -234,6 +234,11 @@ FB_API int64_t fb_order_stats_workspace(int64_t P);
  * hi[p] = x_(min(k+1, M-1)) of the ascending order; NaN if any NaN. */
 FB_API int fb_order_stats(const double *V, int64_t ldp, int64_t P, int64_t M, int64_t k,
                           double *lo, double *hi, void *work, void *stream);
+
+/* -- measurement -- */
+/* fp64 FMA microbenchmark (grid x 256 threads x iters*64 DFMA each; out holds
+ * grid*256 doubles): the measured fp64 roof bench.py reports against. */
+FB_API int fb_fp64_peak(double *out, int grid, int iters, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,54 @@
+"""Comparison helpers shared by the oracle and GPU parity tests."""
+import numpy as np
+
+
+def assert_exact(got, ref, what=""):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+    assert same.all(), (f"{what}: {(~same).sum()} of {same.size} values differ, "
+                        f"first at {np.argwhere(~same)[:3].tolist()}")
+
+
+def rowmax_rel_err(got, ref):
+    """|got-ref| / max(|ref|, rowmax|ref|): the parity metric of SURVEY.md
+    section 8(d) for floating point iterated sums."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    if ref.size == 0:
+        return np.zeros(ref.shape)
+    same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+    fin = np.where(np.isfinite(ref), ref, 0.0)
+    scale = np.maximum(np.abs(fin), np.max(np.abs(fin), axis=-1, keepdims=True))
+    with np.errstate(invalid="ignore"):
+        err = np.where(same, 0.0, np.abs(got - ref))
+    return err / (scale + 1e-300)
+
+
+def assert_close(got, ref, rtol, what=""):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    rel = rowmax_rel_err(got, ref)
+    assert np.all(rel <= rtol), f"{what}: max rel err {rel.max():.3e} > {rtol}"
+
+
+def fitted_thresholds(fruit):
+    """All fitted thresholds of a product Fruit in slice/node/sieve order."""
+    rows = []
+    for slc in fruit:
+        for sieves in slc._sieves_extended:
+            for sv in sieves:
+                q = getattr(sv, "_quantiles", None)
+                if q is None:
+                    q = getattr(sv, "_q", [])
+                rows.append(np.asarray(q, dtype=np.float64).ravel())
+    return np.concatenate(rows) if rows else np.zeros(0)
+
+
+def oracle_thresholds(of):
+    rows = []
+    for slc in of.slices:
+        for sieves in slc.sieves_extended:
+            for sv in sieves:
+                q = sv.fitted_q if sv.name == "PPV" else sv.quantiles
+                rows.append(np.asarray(q, dtype=np.float64).ravel())
+    return np.concatenate(rows) if rows else np.zeros(0)

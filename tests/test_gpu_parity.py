@@ -1,0 +1,428 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the
+C ABI of libfruits_b200.so via the Python mirror of the reference API, against
+(a) the frozen outputs of the real reference (tests/golden), (b) the CPU
+oracle on other seeded inputs, (c) the reference's hand-computed vectors and
+(d) size-independent properties at larger sizes.
+
+Bars: bit-exact for the arctic semiring, the unweighted real semiring, word
+enumeration, thresholds and integer-valued sieves; |a-b| <= 1e-9 *
+max(|b|, rowmax|b|) for exponentially weighted real iterated sums (exp() on
+the device differs from the host libm in the last ulp); 1e-12 for MPI means
+(the reference's own summation order is unspecified under numba fastmath).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fruits_b200 as fruits
+import specs
+from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, make_iss_input,
+                   make_prep_input, make_sieve_input)
+from helpers import (assert_close, assert_exact, fitted_thresholds, oracle_thresholds,
+                     rowmax_rel_err)
+
+pytestmark = pytest.mark.gpu
+
+X_1 = np.array([
+    [[-4, 0.8, 0, 5, -3], [2.0, 1, 0, 0, -7]],
+    [[5.0, 8, 2, 6, 0], [-5, -1, -4, -0.5, -8]],
+])
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from fruits_b200 import _backend as be
+    be.lib()   # fails loudly if the CUDA library is missing
+
+
+def _exact_iss(desc):
+    return desc.get("weighting") is None or desc.get("semiring") == "arctic"
+
+
+# ---------------------------------------------------------------------------
+# (a) frozen reference outputs
+
+@pytest.mark.parametrize("name", sorted(ISS_CASES))
+def test_iss_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "iss.npz"))
+    desc, shape, kind = ISS_CASES[name]
+    X = make_iss_input(shape, kind)
+    res = specs.build_iss(fruits, desc).transform(X)
+    if _exact_iss(desc):
+        assert_exact(res, g[name], name)
+    else:
+        assert_close(res, g[name], 1e-9, name)
+
+
+@pytest.mark.parametrize("name", sorted(SIEVE_CASES))
+def test_sieve_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sieves.npz"))
+    raw, Y = make_sieve_input()
+    sv = specs._sieve(fruits, SIEVE_CASES[name])
+    sv._cache = fruits.cache.SharedSeedCache(raw)
+    np.random.seed(3)
+    sv.fit(Y)
+    res = sv.transform(Y)
+    thr = sv._q if SIEVE_CASES[name][0] == "PPV" else sv._quantiles
+    assert_exact(np.array(thr, dtype=np.float64), g[name + "_thr"], name + " thresholds")
+    if SIEVE_CASES[name][0] in ("MPI", "XPI"):
+        assert_close(res, g[name], 1e-12, name)
+    else:
+        assert_exact(res, g[name], name)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in PREP_CASES if n != "nrm"))
+def test_prep_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "preps.npz"))
+    X = make_prep_input()
+    p = specs._prep(fruits, PREP_CASES[name])
+    p.fit(X)
+    assert_exact(p.transform(X), g[name], name)
+
+
+def test_nrm_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "preps.npz"))
+    assert_exact(fruits.preparation.NRM().transform(make_prep_input()), g["nrm"], "nrm")
+
+
+@pytest.mark.parametrize("name", sorted(PIPE_CASES))
+def test_pipeline_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
+    spec_name, n = PIPE_CASES[name]
+    X = specs.make_input(spec_name, n)
+    fruit = specs.build_fruit(fruits, specs.SPECS[spec_name])
+    np.random.seed(0)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    assert res.shape == g["features"].shape and res.dtype == np.float64
+    if name in ("C1_readme", "C5_sweep"):
+        assert_exact(fitted_thresholds(fruit), g["thresholds"], name + " thresholds")
+        assert_exact(res, g["features"], name + " features")
+    else:
+        assert_close(fitted_thresholds(fruit), g["thresholds"], 1e-9, name + " thresholds")
+        _assert_features_close(res, g["features"], name)
+
+
+def _assert_features_close(res, ref, what):
+    """Weighted slices: values within 1e-9; an integer count may move by one
+    when an increment sits within rounding of its threshold."""
+    scale = np.maximum(np.abs(ref), 1.0)
+    bad = np.abs(res - ref) > 1e-9 * scale
+    assert bad.mean() <= 2e-4, f"{what}: {bad.sum()} of {bad.size} features beyond 1e-9"
+    assert np.all(np.abs(res - ref)[bad] <= 1.0 + 1e-9), what
+
+
+# ---------------------------------------------------------------------------
+# (c) the reference's hand-computed vectors
+
+def test_reference_kat_reals():
+    # reference: tests/signature/test_simple.py:11-41
+    words = [fruits.words.SimpleWord(s) for s in
+             ["[1]", "[2]", "[11]", "[12]", "[1][1]", "[1][2]"]]
+    correct = (
+        np.array([[-4, -3.2, -3.2, 1.8, -1.2], [5, 13, 15, 21, 21]]),
+        np.array([[2, 3, 3, 3, -4], [-5, -6, -10, -10.5, -18.5]]),
+        np.array([[16, 16.64, 16.64, 41.64, 50.64], [25, 89, 93, 129, 129]]),
+        np.array([[-8, -7.2, -7.2, -7.2, 13.8], [-25, -33, -41, -44, -44]]),
+        np.array([[0, -3.2, -3.2, -19.2, -24.6], [0, 40, 66, 156, 156]]),
+        np.array([[0., -4., -4., -4., -16.6], [0, -5, -57, -64.5, -232.5]]),
+    )
+    results = fruits.ISS(words).batch_transform(X_1, batch_size=1)
+    for i, result in enumerate(results):
+        np.testing.assert_allclose(correct[i], result[0, :, :])
+    np.testing.assert_allclose(correct[0],
+                               fruits.ISS([words[0].copy()]).fit_transform(X_1)[0])
+
+
+def test_reference_kat_arctic():
+    # reference: tests/signature/test_semiring.py:10-33
+    words = [fruits.words.SimpleWord(s) for s in
+             ["[1]", "[2]", "[11]", "[12]", "[1][1]", "[1][2]"]]
+    correct = (
+        np.array([[-4, 0.8, 0.8, 5, 5], [5, 8, 8, 8, 8]]),
+        np.array([[2, 2, 2, 2, 2], [-5, -1, -1, -0.5, -0.5]]),
+        np.array([[-8, 1.6, 1.6, 10, 10], [10, 16, 16, 16, 16]]),
+        np.array([[-2, 1.8, 1.8, 5, 5], [0, 7, 7, 7, 7]]),
+        np.array([[-8, 1.6, 1.6, 10, 10], [10, 16, 16, 16, 16]]),
+        np.array([[-2, 1.8, 1.8, 5., 5.], [0., 7., 7., 7.5, 7.5]]),
+    )
+    results = fruits.ISS(words, semiring=fruits.iss.semiring.Arctic()).batch_transform(
+        X_1, batch_size=1)
+    for i, result in enumerate(results):
+        np.testing.assert_allclose(correct[i], result[0])
+
+
+def test_reference_kat_two_slices():
+    # reference: tests/core/test_branches.py:61-86
+    fruit = fruits.Fruit()
+    w = [fruits.words.SimpleWord(s) for s in
+         ["[1]", "[2]", "[11]", "[12]", "[1][1]", "[1][2]"]]
+    fruit.add(fruits.ISS(w[:3]))
+    fruit.add(fruits.sieving.MAX)
+    fruit.cut()
+    fruit.add(fruits.ISS(w[3:]))
+    fruit.add(fruits.sieving.MIN)
+    assert fruit.nfeatures() == 6
+    features = fruit.fit_transform(X_1)
+    np.testing.assert_allclose(np.array([
+        [1.8, 3., 50.64, -8., -24.6, -16.6],
+        [21, -5, 129, -44, 0, -232.5]]), features)
+
+
+def test_reference_kat_sieves():
+    # reference: tests/sieving/test_explicit.py (MAX/MIN/END/NPI on X_1[:, 0, :])
+    Y = X_1[:, 0, :]
+    np.testing.assert_allclose(fruits.sieving.MAX().fit_transform(Y), [[5], [8]])
+    np.testing.assert_allclose(fruits.sieving.MIN().fit_transform(Y), [[-4], [0]])
+    np.testing.assert_allclose(fruits.sieving.END().fit_transform(Y), [[-3], [0]])
+    np.testing.assert_allclose(fruits.sieving.NPI().fit_transform(Y), [[2], [2]])
+    np.testing.assert_allclose(fruits.sieving.END(cut=[1, 3, -1]).fit_transform(Y),
+                               [[-4, 0, -3], [5, 2, 0]])
+
+
+def test_theoretical_identity():
+    # reference: tests/signature/test_simple.py:44-51: <[1][1], ISS>_T = -T/2
+    X = np.random.default_rng(3).random((25, 1, 100))
+    X = (X - X.mean(axis=-1, keepdims=True)) / X.std(axis=-1, keepdims=True)
+    res = fruits.ISS([fruits.words.SimpleWord("[1][1]")]).fit_transform(X)
+    np.testing.assert_allclose(np.ones((25,)) * -50, res[0, :, -1])
+
+
+# ---------------------------------------------------------------------------
+# (b) oracle on other seeded inputs, edge cases
+
+def _oracle_iss(X, desc):
+    from oracle import pipeline as orc
+    return np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1), (2, 3, 2), (3, 3, 31), (3, 3, 32), (2, 3, 33),
+                                   (5, 3, 257), (1, 3, 1000), (130, 3, 64), (2, 3, 5000)])
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
+def test_iss_shapes_vs_oracle(shape, semiring):
+    desc = {"words": {"of_weight": [3, 3]}, "mode": "extended", "semiring": semiring}
+    X = np.random.default_rng(shape[2]).standard_normal(shape)
+    assert_exact(specs.build_iss(fruits, desc).transform(X), _oracle_iss(X, desc), str(shape))
+
+
+def test_iss_many_blocks_vs_oracle():
+    # 1,351 nodes: several kernel blocks with duplicated ancestors
+    desc = {"words": {"of_weight": [6, 2]}, "mode": "extended"}
+    X = np.random.default_rng(1).standard_normal((3, 2, 96)) * 0.7
+    assert_exact(specs.build_iss(fruits, desc).transform(X), _oracle_iss(X, desc), "w6d2")
+
+
+def test_iss_long_letter_and_deep_word():
+    desc = {"words": ["[111111111]", "[11111111111][2]", 60 * "[1]"], "mode": "extended"}
+    X = 0.9 + 0.2 * np.random.default_rng(2).random((2, 2, 70))
+    assert_exact(specs.build_iss(fruits, desc).transform(X), _oracle_iss(X, desc), "long")
+    desc = {"words": {"alternate_sign": [100 * "[1]"]}, "mode": "extended",
+            "semiring": "arctic"}
+    assert_exact(specs.build_iss(fruits, desc).transform(X), _oracle_iss(X, desc), "deep")
+
+
+def test_iss_custom_alpha_vs_oracle():
+    desc = {"words": ["[1][2][1]", "[1][2][2]", "[2][11]"], "mode": "extended",
+            "weighting": ["Indices", {"scale": 3}],
+            "alphas": [[0.5, 1.0, 2.0], [0.5, 0.25, 1.0], [1.0, 1.0]]}
+    X = np.random.default_rng(4).standard_normal((4, 2, 90))
+    assert_close(specs.build_iss(fruits, desc).transform(X), _oracle_iss(X, desc), 1e-9, "alpha")
+    desc["semiring"] = "arctic"
+    assert_exact(specs.build_iss(fruits, desc).transform(X), _oracle_iss(X, desc), "alpha arctic")
+
+
+def test_extended_equals_stacked_single():
+    # reference: tests/signature/test_cache.py:29-80
+    X = np.random.default_rng(5).random((10, 3, 100))
+    ext = fruits.ISS([fruits.words.SimpleWord("[11][21][331][22]")],
+                     mode=fruits.ISSMode.EXTENDED).fit_transform(X)
+    single = fruits.ISS([fruits.words.SimpleWord(s) for s in
+                         ["[11]", "[11][12]", "[11][12][133]", "[11][12][133][22]"]]
+                        ).fit_transform(X)
+    assert_exact(ext, single, "extended vs single")
+
+
+def test_torch_input_stays_on_device():
+    X = torch.randn(4, 3, 50, dtype=torch.float64, device="cuda")
+    iss = fruits.ISS(fruits.words.of_weight(2, 3))
+    res = iss.transform(X)
+    assert isinstance(res, torch.Tensor) and res.is_cuda
+    assert_exact(res.cpu().numpy(), iss.transform(X.cpu().numpy()), "torch vs numpy")
+
+
+def test_input_validation():
+    iss = fruits.ISS(fruits.words.of_weight(2, 3))
+    with pytest.raises(TypeError):
+        iss.transform(np.zeros((2, 3, 10), dtype=np.float32))
+    with pytest.raises(IndexError):
+        iss.transform(np.zeros((2, 2, 10)))
+    fruit = specs.build_fruit(fruits, specs.SPECS["C1_readme"])
+    with pytest.raises(RuntimeError, match="Missing call of self.fit"):
+        fruit.transform(np.zeros((2, 3, 10)))
+
+
+def test_empty_batch():
+    fruit = specs.build_fruit(fruits, specs.SPECS["C5_sweep"])
+    np.random.seed(0)
+    fruit.fit(specs.make_input("C5_sweep", 4))
+    assert fruit.transform(np.zeros((0, 3, 1024))).shape == (0, 2225)
+
+
+@pytest.mark.parametrize("name,n,seed", [("C1_readme", 37, 1), ("C5_sweep", 70, 2),
+                                         ("C2_reduced", 16, 3), ("C4_twi", 5, 4)])
+def test_pipeline_vs_oracle_other_seeds(name, n, seed):
+    from oracle import pipeline as orc
+    spec = specs.SPECS[name]
+    shape = {"C1_readme": (n, 3, 77), "C5_sweep": (n, 3, 300), "C2_reduced": (n, 1, 200),
+             "C4_twi": (n, 3, 333)}[name]
+    X = np.random.default_rng(seed).standard_normal(shape).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(seed)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    of = orc.OracleFruit(spec)
+    np.random.seed(seed)
+    of.fit(X)
+    ref = of.transform(X)
+    if name in ("C1_readme", "C5_sweep"):
+        assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+        assert_exact(res, ref, name)
+    else:
+        assert_close(fitted_thresholds(fruit), oracle_thresholds(of), 1e-9, "thresholds")
+        _assert_features_close(res, ref, name)
+
+
+def test_transform_on_unseen_data_and_fit_sample_fraction():
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [3, 2]}, "mode": "extended"}],
+                        "sieves": [["NPI", {"q": [0.3, 1.0]}], ["PPV", {"sample_size": 0.5}],
+                                   ["MAX", {"q": [-1.0, 0.7]}], ["END", {}]],
+                        "fit_sample_size": 0.4}]}
+    rng = np.random.default_rng(9)
+    Xtr, Xte = rng.standard_normal((20, 2, 150)), rng.standard_normal((9, 2, 150))
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(11)
+    fruit.fit(Xtr)
+    after_gpu = np.random.random()
+    np.random.seed(11)
+    of.fit(Xtr)
+    after_cpu = np.random.random()
+    assert after_gpu == after_cpu, "global RNG consumed differently from the reference"
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    # MAX on an empty selection raises in the reference (np.max of an empty
+    # array); compare only where the oracle defines a value
+    assert_exact(fruit.transform(Xte), of.transform(Xte), "unseen data")
+
+
+def test_fused_equals_composed_route():
+    """The fused kernel and the materialise+sieve route give identical bits."""
+    X = specs.make_input("C5_sweep", 24)
+    fruit = specs.build_fruit(fruits, specs.SPECS["C5_sweep"])
+    np.random.seed(0)
+    fruit.fit(X)
+    fused = fruit.transform(X)
+    composed = fruit.transform(X, callbacks=[fruits.callback.AbstractCallback()])
+    assert_exact(fused, composed, "fused vs composed")
+
+
+def test_general_sieves_composed_route():
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {"depth": 2}]],
+                        "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended",
+                                 "semiring": "arctic"}],
+                        "sieves": [["NPI", {"cut": [10, 0.5, -1], "q": [0.2, 0.6, 1.0]}],
+                                   ["END", {"cut": [5, -1]}], ["LPI", {}], ["XPI", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(8).standard_normal((12, 2, 64)).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(2)
+    fruit.fit(X)
+    np.random.seed(2)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    assert_exact(fruit.transform(X), of.transform(X), "composed route")
+
+
+def test_chained_iss():
+    # reference: tests/signature/test_consecutive.py -- ISS of ISS in one slice
+    from oracle import pipeline as orc
+    spec = {"slices": [{"iss": [{"words": ["[1]", "[12]"]}, {"words": ["[1][1]", "[11]"]}],
+                        "sieves": [["END", {}], ["NPI", {}]]}]}
+    X = np.random.default_rng(6).standard_normal((5, 2, 40))
+    fruit = specs.build_fruit(fruits, spec)
+    assert fruit.nfeatures() == 8
+    assert_exact(fruit.fit_transform(X), orc.OracleFruit(spec).fit_transform(X), "chained")
+
+
+def test_callbacks_receive_host_arrays():
+    seen = {"itsum": 0, "prep": 0, "end": 0}
+
+    class CB(fruits.callback.AbstractCallback):
+        def on_iterated_sum(self, X):
+            assert isinstance(X, np.ndarray) and X.shape == (6, 100)
+            seen["itsum"] += 1
+
+        def on_preparateur(self, X):
+            seen["prep"] += 1
+
+        def on_sieving_end(self, X):
+            seen["end"] += 1
+
+    X = specs.make_input("C1_readme", 6)
+    fruit = specs.build_fruit(fruits, specs.SPECS["C1_readme"])
+    fruit.fit(X)
+    fruit.transform(X, callbacks=[CB()])
+    assert seen == {"itsum": 36, "prep": 1, "end": 2}
+
+
+# ---------------------------------------------------------------------------
+# (d) size-independent properties at larger sizes
+
+def test_sweep_large_batch_properties():
+    """C5 pipeline on 20,000 series: a subset equals the oracle bit for bit,
+    rows are independent (permutation equivariance) and runs are idempotent."""
+    from oracle import pipeline as orc
+    spec = specs.SPECS["C5_sweep"]
+    rng = np.random.default_rng(77)
+    X = rng.standard_normal((20000, 3, 1024))
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(5)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    assert res.shape == (20000, 2225) and np.isfinite(res).all()
+    assert_exact(fruit.transform(X), res, "idempotence")
+    perm = rng.permutation(20000)[:4000]
+    assert_exact(fruit.transform(X[perm]), res[perm], "row independence")
+    pick = np.sort(rng.choice(20000, 48, replace=False))
+    of = orc.OracleFruit(spec)
+    np.random.seed(5)
+    of.fit(X)          # same RNG draw -> same fit row
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    assert_exact(res[pick], of.transform(X[pick]), "subset vs oracle")
+    # NPI counts are integers in [0, T]; PPV in [0, 1]; MIN <= END <= MAX
+    f = res.reshape(20000, 445, 5)
+    assert np.all(f[..., 0] == np.round(f[..., 0])) and f[..., 0].min() >= 0
+    assert f[..., 0].max() <= 1024 and 0 <= f[..., 1].min() and f[..., 1].max() <= 1
+    assert np.all(f[..., 3] <= f[..., 4]) and np.all(f[..., 4] <= f[..., 2])
+
+
+def test_twi_full_length_subset():
+    from oracle import pipeline as orc
+    spec = specs.SPECS["C4_twi"]
+    X = specs.make_input("C4_twi", 600)
+    fruit = specs.build_fruit(fruits, spec)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    pick = np.arange(0, 600, 100)
+    of = orc.OracleFruit(spec)
+    of.fit(X[pick])
+    ref = of.transform(X[pick])
+    # slice 1 (arctic, columns 1533:) is bit-exact, slice 0 is L1-weighted
+    assert_exact(res[pick][:, 1533:], ref[:, 1533:], "arctic slice")
+    _assert_features_close(res[pick][:, :1533], ref[:, :1533], "weighted slice")

@@ -1,0 +1,212 @@
+"""CPU tests of the host-side mirror of the reference API: word algebra, cache
+plan, trie compilation, labels / summary, error behaviour, and that the C ABI
+library loads and exports every symbol declared in include/fruits_b200.h
+(no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fruits_b200 as fruits
+import specs
+from fruits_b200 import _backend as be
+from fruits_b200._plan import Trie
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_word_enumeration_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "words.npz"))
+    for key in g.files:
+        if key.startswith("of_weight_"):
+            _, _, w, d = key.split("_")
+            words = fruits.words.of_weight(int(w), int(d))
+            assert "|".join(str(x) for x in words) == str(g[key])
+            assert fruits.iss.CachePlan(words)._plan == list(g[f"plan_{w}_{d}"])
+    base = [24 * "[1]", 24 * "[2]", 12 * "[1][2]", 12 * "[2][1]", "[112][2][1]"]
+    alt = fruits.words.alternate_sign([fruits.words.SimpleWord(b) for b in base])
+    assert "|".join(str(x) for x in alt) == str(g["alternate_sign"])
+    assert fruits.iss.CachePlan(alt)._plan == list(g["alternate_sign_plan"])
+    for i in range(4):
+        s = str(g[f"parse_{i}_str"])
+        assert np.array_equal(fruits.words.SimpleWord(s).exponents(), g[f"parse_{i}"])
+
+
+def test_word_counts():
+    # reference: tests/signature/test_simple.py:54-57
+    for n in range(1, 7):
+        assert len(fruits.words.of_weight(n, dim=1)) == 2 ** (n - 1)
+    assert len(fruits.words.of_weight(4, dim=2)) == 82
+
+
+def test_cache_plan_reference_golden():
+    # reference: tests/signature/test_cache.py:11-26
+    words = [fruits.words.SimpleWord(s) for s in [
+        "[1][11][3][11]", "[11][13][11][1][3]", "[1][13][1]", "[11][13][111][13][11]",
+        "[3][11][111]", "[1][11][2]", "[11][2]", "[11][13][111][13][2]",
+        "[3][11][1112][21]"]]
+    plan = fruits.iss.CachePlan(words)
+    assert plan._plan == [4, 5, 2, 3, 3, 1, 1, 1, 2]
+    assert plan.n_iterated_sums() == 22
+    assert plan.get_word_string(0) == "[1]"
+    assert plan.get_word_string(4) == "[11]"
+    assert plan.get_word_index(4) == 1
+
+
+def test_simpleword_behaviour():
+    w = fruits.words.SimpleWord("[12][122]")
+    assert list(w) == [[1, 1], [1, 2]]
+    assert w == fruits.words.SimpleWord("[21][212]")
+    assert str(w) == "[12][122]" and len(w) == 2
+    assert np.array_equal(w.alpha, np.ones(2, dtype=np.float32))
+    w.alpha = [0.5, 2]
+    assert w.alpha.dtype == np.float32
+    with pytest.raises(ValueError):
+        w.alpha = [1.0]
+    with pytest.raises(ValueError):
+        fruits.words.SimpleWord("[1][a]")
+    w.multiply("[3]")
+    assert list(w) == [[1, 1, 0], [1, 2, 0], [0, 0, 1]]
+    c = w.copy()
+    assert c == w and c is not w
+    neg = fruits.words.SimpleWord("[-1-12][(-11)3]")
+    assert neg.exponents()[0, 0] == -2 and neg.exponents()[1, 10] == -1
+
+
+@pytest.mark.parametrize("name,slice_idx,n_nodes", [
+    ("C1_readme", 0, 18), ("C2_reduced", 0, 115), ("C2_reduced", 1, 188),
+    ("C3_general", 0, 1351), ("C3_general", 1, 380), ("C4_twi", 0, 511),
+    ("C4_twi", 1, 96), ("C5_sweep", 0, 445)])
+def test_trie_sizes(name, slice_idx, n_nodes):
+    # emitted iterated sums per config
+    fruit = specs.build_fruit(fruits, specs.SPECS[name])
+    iss = fruit.get_slice(slice_idx).get_iss()[0]
+    assert iss.n_iterated_sums() == n_nodes
+    trie = Trie(iss.words, iss._cache_plan._plan, iss.weighting is not None)
+    assert len(trie.emits) == n_nodes
+    # every prefix is computed once: no more nodes than emissions here
+    assert len(trie.nodes) == n_nodes
+    # emission order = words in order, each its new prefixes shortest first
+    seen, e = set(), 0
+    for w in iss.words:
+        letters = str(w).split("]")[:-1]
+        for k in range(len(letters)):
+            prefix = "]".join(letters[:k + 1]) + "]"
+            if prefix not in seen:
+                seen.add(prefix)
+                node = trie.nodes[trie.emits[e]]
+                assert node.depth == k + 1
+                e += 1
+    assert e == n_nodes
+
+
+def test_trie_duplicate_emission_and_single_mode():
+    words = [fruits.words.SimpleWord(s) for s in ["[12]", "[21]", "[1][2]", "[1]"]]
+    trie = Trie(words, None, False)           # SINGLE: one emission per word
+    assert len(trie.emits) == 4
+    assert len({id(trie.nodes[e]) for e in trie.emits}) == 4
+    sub = trie.subset(2, 4)
+    assert len(sub.emits) == 2 and all(e is not None for e in sub.emits)
+
+
+def test_feature_counts_and_labels(golden_dir):
+    for name in ("C1_readme", "C2_reduced", "C3_general", "C4_twi", "C5_sweep"):
+        g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
+        fruit = specs.build_fruit(fruits, specs.SPECS[name])
+        nf = int(g["nfeatures"])
+        assert fruit.nfeatures() == nf
+        idx = sorted(set(np.linspace(0, nf - 1, 23).astype(int)))
+        assert "|".join(fruit.label(i) for i in idx) == str(g["labels"])
+        assert fruit.summary() == str(g["summary"])
+    # SURVEY.md appendix B
+    fruit = specs.build_fruit(fruits, specs.SPECS["C1_readme"])
+    assert fruit.label(0) == "INC | [11] | NPI[inc=1]!-1![0.5, 1.0]"
+    assert fruit.label(36) == "[11] | NPI[inc=1]!-1![0.0, 1.0]"
+
+
+def test_reference_feature_counts():
+    # reference: tests/core/test_fruit.py:11-41 (738 features)
+    fruit = fruits.Fruit()
+    fruit.add(fruits.preparation.INC())
+    fruit.add(fruits.ISS(fruits.words.of_weight(4, dim=2), mode=fruits.ISSMode.EXTENDED))
+    fruit.add(fruits.sieving.NPI(q=(0.5, 1.0)), fruits.sieving.MPI(q=(0.5, 1.0)))
+    fruit.add(fruits.sieving.MAX, fruits.sieving.MIN, fruits.sieving.END,
+              fruits.sieving.PPV(quantile=[0.2, 0.5], constant=False))
+    assert fruit.nfeatures() == 115 * 7
+
+
+def test_error_behaviour():
+    fruit = fruits.Fruit()
+    with pytest.raises(RuntimeError, match="Missing call of self.fit"):
+        fruit.transform(np.zeros((2, 1, 8)))
+    fruit.cut()
+    with pytest.raises(TypeError):
+        fruit.add(3)
+    with pytest.raises(IndexError):
+        fruit.switch_slice(5)
+    slc = fruits.FruitSlice()
+    with pytest.raises(RuntimeError, match="No ISS given"):
+        slc._compile()
+    slc.add(fruits.ISS([fruits.words.SimpleWord("[1]")]))
+    with pytest.raises(RuntimeError, match="No feature sieves given"):
+        slc._compile()
+    iss = fruits.ISS(fruits.words.of_weight(2, 1))
+    with pytest.raises(ValueError):
+        next(iss.batch_transform(np.zeros((1, 1, 4)), batch_size=10))
+    with pytest.raises(NotImplementedError):
+        fruits.semiring.Arctic(argmax=True)
+    with pytest.raises(NotImplementedError):
+        fruits.ISS([fruits.words.Word()])
+    with pytest.raises(NotImplementedError):
+        fruits.preparation.MAV()
+    with pytest.raises(ValueError):
+        fruits.preparation.INC(depth=0)
+    with pytest.raises(ValueError):
+        fruits.iss.weighting.Plateaus(1)
+
+
+def test_fusability_rules():
+    for name in ("C1_readme", "C2_reduced", "C3_general", "C4_twi", "C5_sweep"):
+        fruit = specs.build_fruit(fruits, specs.SPECS[name])
+        for slc in fruit:
+            assert slc._is_fusable(6, None), name
+    slc = fruits.FruitSlice()
+    slc.add(fruits.ISS(fruits.words.of_weight(2, 1)), fruits.sieving.NPI(cut=(10, -1)))
+    assert not slc._is_fusable(1, None)      # several cuts -> composed route
+    slc = fruits.FruitSlice()
+    slc.add(fruits.preparation.INC(depth=2), fruits.ISS(fruits.words.of_weight(2, 1)),
+            fruits.sieving.END)
+    assert not slc._is_fusable(1, None)      # INC depth 2 is not fused on load
+    slc = fruits.FruitSlice()
+    slc.add(fruits.preparation.NEW(fruits.preparation.INC()), fruits.preparation.STD)
+    assert slc._fused_dims(2) == [(0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 1)]
+
+
+def test_drop_in_alias():
+    import fruits as alias
+    assert alias.Fruit is fruits.Fruit
+    assert alias.iss.weighting.Indices is fruits.iss.weighting.Indices
+    assert alias.semiring.Arctic is fruits.semiring.Arctic
+    assert alias.words.of_weight is fruits.words.of_weight
+    assert alias.sieving.NPI is fruits.sieving.NPI
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fruits_b200.h")).read()
+    declared = set(re.findall(r"FB_API\s+[\w\s\*]+?\b(fb_\w+)\s*\(", header))
+    assert declared == set(be.EXPORTED), declared ^ set(be.EXPORTED)
+    lib = ctypes.CDLL(be.LIB_PATH)       # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert be.lib().fb_abi_version() == 1
+    assert be.lib().fb_slice_rows(be.POLICY_MAT) >= 1
+
+
+def test_struct_layouts_match_header():
+    assert be.SLOT_DTYPE.itemsize == 16
+    assert ctypes.sizeof(be.FbDim) == 16
+    assert ctypes.sizeof(be.FbBatch) == 56
+    assert ctypes.sizeof(be.FbSievePlan) == 4 + 4 * 16 * 2 + 4 + 8
+    assert ctypes.sizeof(be.FbIssPlan) == 8 * 4 + 4 * 4 + 7 * 16 + 3 * 8

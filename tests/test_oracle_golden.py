@@ -1,0 +1,146 @@
+"""CPU tests: the oracle against the frozen outputs of the real reference
+(tests/golden/*.npz, written by oracle/gen_golden.py) and against the
+reference's own hand-computed known-answer vectors."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import specs
+from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, make_iss_input,
+                   make_prep_input, make_sieve_input)
+from helpers import assert_close, assert_exact, oracle_thresholds
+from oracle import pipeline as orc
+
+# fixed array of the reference's tests (tests/signature/test_simple.py:5-8)
+X_1 = np.array([
+    [[-4, 0.8, 0, 5, -3], [2.0, 1, 0, 0, -7]],
+    [[5.0, 8, 2, 6, 0], [-5, -1, -4, -0.5, -8]],
+])
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_words_and_plans(golden_dir):
+    g = np.load(os.path.join(golden_dir, "words.npz"))
+    for key in g.files:
+        if key.startswith("of_weight_"):
+            _, _, w, d = key.split("_")
+            words = orc.of_weight(int(w), int(d))
+            assert "|".join(words) == str(g[key])
+            assert orc.cache_plan(words) == list(g[f"plan_{w}_{d}"])
+    # reference golden: tests/signature/test_cache.py:11-26
+    words = ["[1][11][3][11]", "[11][13][11][1][3]", "[1][13][1]",
+             "[11][13][111][13][11]", "[3][11][111]", "[1][11][2]", "[11][2]",
+             "[11][13][111][13][2]", "[3][11][1112][21]"]
+    assert orc.cache_plan(words) == [4, 5, 2, 3, 3, 1, 1, 1, 2]
+
+
+def test_reference_kat_reals():
+    # tests/signature/test_simple.py:11-33
+    words = ["[1]", "[2]", "[11]", "[12]", "[1][1]", "[1][2]"]
+    correct = (
+        np.array([[-4, -3.2, -3.2, 1.8, -1.2], [5, 13, 15, 21, 21]]),
+        np.array([[2, 3, 3, 3, -4], [-5, -6, -10, -10.5, -18.5]]),
+        np.array([[16, 16.64, 16.64, 41.64, 50.64], [25, 89, 93, 129, 129]]),
+        np.array([[-8, -7.2, -7.2, -7.2, 13.8], [-25, -33, -41, -44, -44]]),
+        np.array([[0, -3.2, -3.2, -19.2, -24.6], [0, 40, 66, 156, 156]]),
+        np.array([[0., -4., -4., -4., -16.6], [0, -5, -57, -64.5, -232.5]]),
+    )
+    res = list(orc.iss_iter(X_1, {"words": words}, orc.RawCache(X_1)))
+    for r, c in zip(res, correct):
+        np.testing.assert_allclose(c, r)
+
+
+def test_reference_kat_arctic():
+    # tests/signature/test_semiring.py:10-33
+    words = ["[1]", "[2]", "[11]", "[12]", "[1][1]", "[1][2]"]
+    res = list(orc.iss_iter(X_1, {"words": words, "semiring": "arctic"}, orc.RawCache(X_1)))
+    correct = (
+        np.array([[-4, 0.8, 0.8, 5, 5], [5, 8, 8, 8, 8]]),
+        np.array([[2, 2, 2, 2, 2], [-5, -1, -1, -0.5, -0.5]]),
+        np.array([[-8, 1.6, 1.6, 10, 10], [10, 16, 16, 16, 16]]),
+        np.array([[-2, 1.8, 1.8, 5, 5], [0, 7, 7, 7, 7]]),
+        np.array([[-8, 1.6, 1.6, 10, 10], [10, 16, 16, 16, 16]]),
+        np.array([[-2, 1.8, 1.8, 5., 5.], [0., 7., 7., 7.5, 7.5]]),
+    )
+    for r, c in zip(res, correct):
+        np.testing.assert_allclose(c, r)
+
+
+def test_reference_kat_features():
+    # tests/core/test_branches.py:61-86
+    spec = {"slices": [
+        {"iss": [{"words": ["[1]", "[2]", "[11]"]}], "sieves": [["MAX", {}]]},
+        {"iss": [{"words": ["[12]", "[1][1]", "[1][2]"]}], "sieves": [["MIN", {}]]},
+    ]}
+    of = orc.OracleFruit(spec)
+    feats = of.fit_transform(X_1)
+    np.testing.assert_allclose(np.array([
+        [1.8, 3., 50.64, -8., -24.6, -16.6],
+        [21, -5, 129, -44, 0, -232.5]]), feats)
+
+
+@pytest.mark.parametrize("name", sorted(ISS_CASES))
+def test_iss_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "iss.npz"))
+    desc, shape, kind = ISS_CASES[name]
+    X = make_iss_input(shape, kind)
+    assert sha(X) == str(g[name + "_xsha"]), "seeded input changed"
+    res = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    if desc.get("weighting") is None:
+        assert_exact(res, g[name], name)
+    else:
+        # exp() comes from the host libm: identical in the image that froze
+        # the vectors, within an ulp elsewhere
+        assert_close(res, g[name], 1e-12, name)
+
+
+@pytest.mark.parametrize("name", sorted(SIEVE_CASES))
+def test_sieve_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sieves.npz"))
+    raw, Y = make_sieve_input()
+    assert sha(Y) == str(g["Y_xsha"])
+    sv = orc.OracleSieve(SIEVE_CASES[name])
+    np.random.seed(3)
+    sv.fit(Y)
+    res = sv.transform(Y, orc.RawCache(raw))
+    thr = sv.fitted_q if sv.name == "PPV" else sv.quantiles
+    assert_exact(np.array(thr, dtype=np.float64), g[name + "_thr"], name + " thresholds")
+    if sv.name in ("MPI", "XPI"):
+        assert_close(res, g[name], 1e-12, name)
+    else:
+        assert_exact(res, g[name], name)
+
+
+@pytest.mark.parametrize("name", sorted(PREP_CASES))
+def test_prep_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, "preps.npz"))
+    X = make_prep_input()
+    assert sha(X) == str(g["xsha"])
+    assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
+
+
+@pytest.mark.parametrize("name", sorted(PIPE_CASES))
+def test_pipeline_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
+    spec_name, n = PIPE_CASES[name]
+    spec = specs.SPECS[spec_name]
+    X = specs.make_input(spec_name, n)
+    assert sha(X) == str(g["xsha"])
+    of = orc.OracleFruit(spec)
+    np.random.seed(0)
+    of.fit(X)
+    res = of.transform(X)
+    assert of.nfeatures() == int(g["nfeatures"])
+    if name in ("C1_readme", "C5_sweep"):
+        assert_exact(oracle_thresholds(of), g["thresholds"], name + " thresholds")
+        assert_exact(res, g["features"], name + " features")
+    else:
+        assert_close(oracle_thresholds(of), g["thresholds"], 1e-11, name + " thresholds")
+        scale = np.maximum(np.abs(g["features"]), 1.0)
+        bad = np.abs(res - g["features"]) > 1e-9 * scale
+        assert bad.mean() < 1e-3, f"{bad.sum()} features beyond 1e-9"
