@@ -215,36 +215,19 @@ def run_ours(args):
     gather = world > 1 and not args.no_gather
     n_chunks = 8 if gather else 1
     rows = S // n_chunks
-    assert rows * n_chunks == S
-    if gather:
-        # assembled matrix, chunk-major: series (rank r, chunk c, row i) lives at
-        # full[c, r, i]; every rank ends up with all features
-        full = torch.empty((n_chunks, world, rows, N_FEATS), dtype=torch.float64, device=dev)
-        local_out = torch.empty((2, rows, N_FEATS), dtype=torch.float64, device=dev)
-        comm = torch.cuda.Stream(device=dev)
-    else:
-        out = torch.empty((S, N_FEATS), dtype=torch.float64, device=dev)
+    from fruits_b200.parallel import transform_sharded
+    # N > 1: every rank ends up with the assembled [N*S, F] feature matrix
+    # (rank-major rows); the all-gather of row chunk c overlaps the kernel of c+1
+    out = torch.empty(((world if gather else 1) * S, N_FEATS), dtype=torch.float64, device=dev)
+
+    def compute(x, o):
+        fruit.transform_device(x, out=o)
 
     def step():
-        if not gather:
-            fruit.transform_device(X, out=out)
-            return
-        cur = torch.cuda.current_stream()
-        for c in range(n_chunks):
-            buf = local_out[c % 2]
-            if c >= 2:
-                cur.wait_event(free_ev[c % 2])
-            fruit.transform_device(X[c * rows:(c + 1) * rows], out=buf)
-            done = torch.cuda.Event()
-            done.record(cur)
-            with torch.cuda.stream(comm):
-                comm.wait_event(done)
-                dist.all_gather_into_tensor(full[c].view(world * rows, N_FEATS), buf)
-                free_ev[c % 2] = torch.cuda.Event()
-                free_ev[c % 2].record(comm)
-        cur.wait_stream(comm)
-
-    free_ev = [None, None]
+        if gather:
+            transform_sharded(compute, X, N_FEATS, chunks=n_chunks, out=out)
+        else:
+            compute(X, out)
 
     def barrier():
         if world > 1:
@@ -274,7 +257,7 @@ def run_ours(args):
     # ---- kernel-only timing of the dominant kernel + fp64 roof (rank 0) ----
     roofline = e2e = cpu = None
     if rank == 0:
-        kout = out if not gather else local_out[0]
+        kout = out[:S] if not gather else out[:rows]
         kX = X if not gather else X[:rows]
         ks = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -348,8 +331,9 @@ def run_ours(args):
             "config": workload_config(args),
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * n_chunks,
             "roofline": roofline, "cpu_baseline": cpu, "fit_seconds": fit_s,
-            "collective": ("nccl all_gather_into_tensor of the features, 8 row chunks "
-                           "overlapped with compute" if gather else "none"),
+            "collective": ("nccl all_gather_into_tensor of the [S, F] feature blocks in 8 row "
+                           "chunks on a side stream, overlapped with the kernels; every rank "
+                           "holds the assembled [N*S, F] matrix" if gather else "none"),
         }
         print(json.dumps(line))
     if world > 1:

@@ -1,0 +1,142 @@
+"""Series-sharded execution on several GPUs of one box.
+
+The hot path is embarrassingly parallel over series (every numba kernel of
+the reference is a ``prange`` over axis 0, e.g. fruits/iss/semiring.py:184),
+so the multi-GPU layout is: one process per GPU (``torch.distributed``, NCCL),
+rank ``r`` owns the contiguous rows ``[r*S, (r+1)*S)`` of the batch, the plan
+and the fitted thresholds (a few kB) are replicated, and the only exchange is
+one all-gather of the ``[S, F]`` feature blocks so that every rank ends up
+with the full feature matrix.  The gather runs per row chunk on a side stream
+and overlaps the kernels of the next chunk.
+
+Fit: the fit sample is drawn on rank 0 with the global numpy RNG (same draws
+as the reference, fruits/fruit.py:430-438), the owning ranks contribute the
+sampled rows, and every rank fits the same sample -- thresholds are identical
+on all ranks without any further exchange.
+"""
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n: int, world: int, rank: int):
+    """Contiguous row block ``[lo, hi)`` of rank ``rank`` (first ranks get the
+    remainder rows)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sync_numpy_rng(group=None) -> None:
+    """Give every rank rank 0's global numpy RNG state, so that all ranks draw
+    the same fit sample and the same PPV subsamples (the reference consumes
+    ``np.random`` in fit: fruits/fruit.py:434-437, fruits/sieving/implicit.py:104)."""
+    state = [np.random.get_state() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(state, 0, group=group)
+    np.random.set_state(state[0])
+
+
+def gather_fit_sample(X_local: torch.Tensor, n_total: int, fit_sample_size, group=None):
+    """Rows of the global batch that ``FruitSlice._select_fit_sample`` draws
+    (fruits/fruit.py:430-438), assembled on every rank.  ``X_local`` holds the
+    rows ``shard_rows(n_total, world, rank)``; the ranks must share one RNG
+    state (``sync_numpy_rng``), every rank makes the same draw."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if isinstance(fit_sample_size, int) and fit_sample_size == 1:
+        idx = np.array([np.random.randint(0, n_total)], dtype=np.int64)
+    else:
+        s = max(int(fit_sample_size * n_total), 1)
+        idx = np.random.choice(n_total, size=s, replace=False).astype(np.int64)
+    idx_t = torch.from_numpy(idx).to(X_local.device)
+    lo, hi = shard_rows(n_total, world, rank)
+    mine = (idx_t >= lo) & (idx_t < hi)
+    sample = torch.zeros((idx_t.numel(),) + tuple(X_local.shape[1:]), dtype=X_local.dtype,
+                         device=X_local.device)
+    sample[mine] = X_local.index_select(0, idx_t[mine] - lo)
+    # every sampled row is owned by exactly one rank: the sum assembles them
+    dist.all_reduce(sample, op=dist.ReduceOp.SUM, group=group)
+    return sample
+
+
+def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, group=None) -> None:
+    """``Fruit.fit`` on a row-sharded batch: every slice is fitted on the same
+    gathered sample on every rank, so the thresholds agree bit for bit."""
+    from . import _backend as be
+    from .cache import SharedSeedCache
+    if n_total is None:
+        sizes = torch.tensor([X_local.shape[0]], dtype=torch.int64, device=X_local.device)
+        dist.all_reduce(sizes, group=group)
+        n_total = int(sizes.item())
+    sync_numpy_rng(group)
+    for slc in fruit:
+        for iss in slc.get_iss():
+            w = iss.weighting
+            if w is not None and not getattr(w, "_on_prepared", True) and any(
+                    s.requires_fitting for s in slc.get_sieves()):
+                raise NotImplementedError(
+                    "sharded fit of sieves on L1/L2-weighted sums needs the raw-input cache "
+                    "of the whole batch (reference quirk: fruits/cache.py:97-112)")
+        sample = gather_fit_sample(X_local, n_total, slc.fit_sample_size, group)
+        try:
+            # the gathered rows ARE the sample: fit on all of them
+            slc._select_fit_sample = lambda X: X
+            slc._fit_device(be.to_device(sample), SharedSeedCache(sample))
+        finally:
+            del slc._select_fit_sample
+    fruit._fitted = True
+
+
+def transform_sharded(compute: Callable[[torch.Tensor, torch.Tensor], None],
+                      X_local: torch.Tensor, n_feats: int, chunks: int = 8, group=None,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """All ranks hold ``S`` rows; returns the assembled ``[world*S, n_feats]``
+    feature matrix (rank-major row order, identical on every rank).
+
+    ``compute(X_rows, out_rows)`` writes the features of a row block (e.g.
+    ``lambda x, o: fruit.transform_device(x, out=o)``).  The rows are processed
+    in ``chunks`` pieces; the all-gather of piece ``c`` runs on a side stream
+    while piece ``c+1`` is computed."""
+    world = dist.get_world_size(group)
+    S = X_local.shape[0]
+    dev = X_local.device
+    if out is None:
+        out = torch.empty((world * S, n_feats), dtype=torch.float64, device=dev)
+    if world == 1:
+        compute(X_local, out)
+        return out
+    chunks = max(1, min(chunks, S)) if S else 1
+    bounds = [shard_rows(S, chunks, c) for c in range(chunks)]
+    rows_max = max(hi - lo for lo, hi in bounds) if S else 0
+    use_cuda = dev.type == "cuda"
+    local = [torch.empty((rows_max, n_feats), dtype=torch.float64, device=dev) for _ in range(2)]
+    stage = [torch.empty((world, rows_max, n_feats), dtype=torch.float64, device=dev)
+             for _ in range(2)]
+    out3 = out.view(world, S, n_feats)
+    if use_cuda:
+        cur = torch.cuda.current_stream(dev)
+        comm = torch.cuda.Stream(device=dev)
+        free_ev = [None, None]
+    for c, (lo, hi) in enumerate(bounds):
+        b, rows = c % 2, hi - lo
+        if use_cuda and free_ev[b] is not None:
+            cur.wait_event(free_ev[b])
+        compute(X_local[lo:hi], local[b][:rows])
+        if use_cuda:
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                dist.all_gather_into_tensor(stage[b].view(world * rows_max, n_feats), local[b],
+                                            group=group)
+                out3[:, lo:hi].copy_(stage[b][:, :rows])
+                free_ev[b] = torch.cuda.Event()
+                free_ev[b].record(comm)
+        else:
+            dist.all_gather_into_tensor(stage[b].view(world * rows_max, n_feats), local[b],
+                                        group=group)
+            out3[:, lo:hi].copy_(stage[b][:, :rows])
+    if use_cuda:
+        cur.wait_stream(comm)
+    return out
