@@ -107,6 +107,14 @@ def lib() -> ctypes.CDLL:
         "fb_order_stats_workspace": ([i64], i64),
         "fb_order_stats": ([vp, i64, i64, i64, i64, vp, vp, vp, vp], i32),
         "fb_fp64_peak": ([vp, i32, i32, vp], i32),
+        "fb_jit_compile": ([ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(vp),
+                            ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t], i32),
+        "fb_jit_free": ([vp], None),
+        "fb_jit_load": ([ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp)], i32),
+        "fb_jit_unload": ([vp], i32),
+        "fb_jit_slice_features": ([vp, vp, ctypes.POINTER(FbBatch), vp, i64, vp, i64, vp, i64, i64,
+                                   i32, vp], i32),
+        "fb_exp_rows": ([vp, vp, i64, i64, ctypes.POINTER(ctypes.c_float), i32, vp], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -124,7 +132,8 @@ EXPORTED = [
     "fb_iss_materialize", "fb_increments", "fb_row_stats", "fb_standardize",
     "fb_lsum", "fb_nrm_scale", "fb_coquantile", "fb_pretransform",
     "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_order_stats_workspace",
-    "fb_order_stats", "fb_fp64_peak",
+    "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
+    "fb_jit_unload", "fb_jit_slice_features", "fb_exp_rows",
 ]
 
 

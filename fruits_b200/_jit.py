@@ -1,0 +1,890 @@
+"""Plan-specialised fused kernel: the word trie compiled to straight-line CUDA.
+
+The generic kernel of ``csrc/lns.cuh`` interprets the prefix trie at run time
+(one lane per node, parents passed through shared memory) and spends most of
+its issue slots on that interpretation.  This module *compiles* a slice --
+trie, semiring, weighting mode, sieve set -- into CUDA source in which
+
+* one thread owns one series and one *part* of the trie (a few dozen nodes
+  plus the ancestors they need); a warp is 32 series of the same part, so
+  control flow never diverges;
+* every running iterated sum and every sieve accumulator is a named register;
+  the only memory traffic of a time step is the read of ``x[t]`` from a
+  shared-memory tile that the CTA stages with ``cp.async``;
+* letter products are shared between siblings: ``P*x1*x1*x2`` reuses the
+  product ``P*x1*x1`` of the sibling letter ``[11]`` -- the reference
+  multiplies once per letter occurrence, dimensions ascending
+  (fruits/iss/semiring.py:114-120, :142-148), so every partial product of a
+  letter is the full product of a shorter letter and the result is bit
+  identical while one multiplication per node remains;
+* thresholds sit in constant memory and are folded into the compare
+  instructions.
+
+The floating point order of every emitted value is the reference's
+(fruits/iss/semiring.py:93-158 Reals, :282-338 Arctic): unweighted Reals and
+all Arctic results are bit-identical, weighted Reals differ only through
+``exp`` (computed on the device).  The source is compiled with NVRTC for
+sm_100a by ``libfruits_b200.so`` (``fb_jit_*`` in include/fruits_b200.h) and
+cached as a cubin next to the library.
+"""
+import ctypes
+import hashlib
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _backend as be
+
+JIT_VERSION = 5            # bump to invalidate cached cubins
+CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
+
+# threshold table columns (include/fruits_b200.h, FB_NTHR)
+_COL_U = {0: (0, 1), 1: (2, 3), 2: (4, 5)}
+_COL_PPV, _COL_MAX, _COL_MIN = 6, (8, 9), (10, 11)
+
+
+# ---------------------------------------------------------------------------
+# program: trie -> parts
+# ---------------------------------------------------------------------------
+
+@dataclass
+class SieveSet:
+    """Which accumulators an emitted node carries (from the feature list)."""
+    feats: list                     # [(FEAT_*, arg)]
+    cnt: tuple = (False, False, False)     # a unit (increment depth) is used
+    avg: tuple = (False, False, False)     # ... and its sum is needed
+    ppv: bool = False
+    mx: bool = False
+    mn: bool = False
+    hi: bool = False                # finite upper bounds possible
+    mmb: bool = False               # MAX/MIN restricted to (lo, hi]
+
+    @staticmethod
+    def make(feats, bounded_hi, bounded_mm) -> "SieveSet":
+        cnt, avg = [False] * 3, [False] * 3
+        ppv = mx = mn = False
+        for kind, arg in feats:
+            if kind in (be.FEAT_CNT, be.FEAT_AVG):
+                cnt[arg] = True
+                if kind == be.FEAT_AVG:
+                    avg[arg] = True
+            elif kind == be.FEAT_PPV:
+                ppv = True
+            elif kind == be.FEAT_MAX:
+                mx = True
+            elif kind == be.FEAT_MIN:
+                mn = True
+        return SieveSet(list(feats), tuple(cnt), tuple(avg), ppv, mx, mn,
+                        bool(bounded_hi), bool(bounded_mm))
+
+    def thr_cols(self) -> list:
+        cols = []
+        for k in range(3):
+            if self.cnt[k]:
+                cols.append(_COL_U[k][0])
+                if self.hi:
+                    cols.append(_COL_U[k][1])
+        if self.ppv:
+            cols.append(_COL_PPV)
+        if self.mx and self.mmb:
+            cols += list(_COL_MAX)
+        if self.mn and self.mmb:
+            cols += list(_COL_MIN)
+        return cols
+
+    # registers (32-bit) of sieve state per emitted node
+    def regs(self) -> int:
+        r = 0
+        ncnt = sum(self.cnt) + (1 if self.ppv else 0)
+        r += (ncnt + 1) // 2
+        r += 2 * sum(self.avg)
+        if self.cnt[2]:
+            r += 2          # previous first increment
+        r += 2 * (int(self.mx) + int(self.mn))
+        return r
+
+    # rough issue slots per emitted node and step
+    def cost(self) -> int:
+        c = 0
+        for k in range(3):
+            if self.cnt[k]:
+                c += 2 + (1 if self.hi else 0) + (1 if self.avg[k] else 0)
+        if self.cnt[1] or self.cnt[2]:
+            c += 1
+        if self.cnt[2]:
+            c += 2
+        if self.ppv:
+            c += 2
+        c += 3 * (int(self.mx) + int(self.mn))
+        if self.mmb:
+            c += 2 * (int(self.mx) + int(self.mn))
+        return c
+
+
+@dataclass
+class Part:
+    owned: list = field(default_factory=list)     # trie node ids whose features this part writes
+    snodes: list = field(default_factory=list)    # trie node ids with a running sum (owned + ancestors)
+    cost: int = 0
+    regs: int = 0
+
+
+def _occurrences(expo, dim_index):
+    """Letter -> [(used-dim index, is_division)] in the reference's order."""
+    occ = []
+    for d, e in enumerate(expo):
+        if e != 0:
+            occ += [(dim_index[d], e < 0)] * abs(e)
+    return tuple(occ)
+
+
+class Program:
+    """Partition of a trie into parts plus everything the emitter needs."""
+
+    def __init__(self, trie, semiring: int, weight_mode: int, sieves: SieveSet,
+                 reg_budget: int = 150, parts_multiple: int = 1) -> None:
+        self.trie = trie
+        self.semiring = semiring
+        self.weight_mode = weight_mode
+        self.sieves = sieves
+        self.reals = semiring == be.SEMIRING_REALS
+        self.used = trie.used_dims()
+        self.dim_index = {d: u for u, d in enumerate(self.used)}
+        nodes = trie.nodes
+        weighted = weight_mode != be.WEIGHT_NONE
+        self.alphas = sorted({n.alpha for n in nodes}) if weighted else []
+        self.aidx = {a: i for i, a in enumerate(self.alphas)}
+        self.has_children = [bool(n.children) for n in nodes]
+
+        # state registers of one running-sum node
+        def sregs(v, owned):
+            r = 2
+            if weight_mode == be.WEIGHT_NONTOTAL and nodes[v].children:
+                r += 2          # second accumulator C_k / arctic carry
+            if weight_mode == be.WEIGHT_TOTAL and owned:
+                r += 2          # previous output
+            return r + (sieves.regs() if owned else 0)
+
+        def scost(v, owned):
+            c = 2 + (2 if weighted else 0)
+            if not self.reals:
+                c += 1 + max(0, sum(1 for e in nodes[v].expo if e != 0) - 1)
+            return c + (sieves.cost() if owned else 0)
+
+        self._sregs, self._scost = sregs, scost
+
+        emitted = [v for v in trie.dfs() if nodes[v].emit >= 0]
+        # fewest parts the register budget allows, rounded up to whole CTAs;
+        # then the smallest cost cap that still needs no more parts than that
+        # (greedy filling of the DFS order is optimal for a given cap)
+        k = len(self._split(emitted, float("inf"), reg_budget))
+        k = -(-k // parts_multiple) * parts_multiple
+        lo, hi = 1.0, float(sum(self._scost(v, True) for v in emitted)) + 1.0
+        while hi - lo > 0.5:
+            mid = (lo + hi) / 2
+            if len(self._split(emitted, mid, reg_budget)) <= k:
+                hi = mid
+            else:
+                lo = mid
+        parts = self._split(emitted, hi, reg_budget)
+        while len(parts) % parts_multiple:
+            parts.append(Part())
+        self.parts = parts
+
+    def _chain(self, v):
+        out = []
+        while v >= 0:
+            out.append(v)
+            v = self.trie.nodes[v].parent
+        return out[::-1]
+
+    def _split(self, emitted, cap, reg_budget):
+        parts, cur, have = [], Part(), set()
+        for v in emitted:
+            need = [a for a in self._chain(v) if a not in have]
+            add_regs = sum(self._sregs(a, a == v) for a in need)
+            add_cost = sum(self._scost(a, a == v) for a in need)
+            if cur.owned and (cur.regs + add_regs > reg_budget or cur.cost + add_cost > cap):
+                parts.append(cur)
+                cur, have = Part(), set()
+                need = self._chain(v)
+                add_regs = sum(self._sregs(a, a == v) for a in need)
+                add_cost = sum(self._scost(a, a == v) for a in need)
+            for a in need:
+                cur.snodes.append(a)
+                have.add(a)
+            cur.owned.append(v)
+            cur.regs += add_regs
+            cur.cost += add_cost
+        if cur.owned:
+            parts.append(cur)
+        return parts
+
+
+# ---------------------------------------------------------------------------
+# emitter
+# ---------------------------------------------------------------------------
+
+def _dlit(x: float) -> str:
+    """C++ literal of a double (exact)."""
+    if x != x:
+        return "__longlong_as_double(0x7ff8000000000000LL)"
+    if x == float("inf"):
+        return "D_INF"
+    if x == float("-inf"):
+        return "D_NINF"
+    return float(x).hex()
+
+
+class Emitter:
+    """CUDA source of one slice program."""
+
+    def __init__(self, prog: Program, dims: list, ppc: int, gpc: int, shared_extra: bool,
+                 tt: int = 8) -> None:
+        """dims[u] = (raw_dim, inc) of used dimension u; ppc/gpc = parts and
+        series groups per CTA; shared_extra: the weighting rows are the same
+        for every series (Indices)."""
+        self.p = prog
+        self.dims = dims
+        self.ppc, self.gpc = ppc, gpc
+        self.tt = tt                 # time steps per shared-memory tile (even)
+        self.shared_extra = shared_extra
+        self.sv = prog.sieves
+        self.cols = self.sv.thr_cols()
+        self.ntc = len(self.cols)
+        self.colpos = {c: i for i, c in enumerate(self.cols)}
+        # distinct raw rows staged per series
+        self.raw_rows = sorted({r for r, _ in dims})
+        self.row_of = {r: i for i, r in enumerate(self.raw_rows)}
+        self.nrow = len(self.raw_rows)
+        # extra (weighting) rows: Reals: ep_a, em_a per alpha; Arctic: g
+        wm = prog.weight_mode
+        if wm == be.WEIGHT_NONE:
+            self.nextra = 0
+        elif prog.reals:
+            self.nextra = 2 * len(prog.alphas)
+        else:
+            self.nextra = 1
+
+    # -- names ---------------------------------------------------------------
+    def th(self, emit: int, col: int) -> str:
+        return f"TH[{emit * self.ntc + self.colpos[col]}]"
+
+    # -- one step of one part ------------------------------------------------
+    def step(self, part: Part, first: bool) -> list:
+        p, nodes = self.p, self.p.trie.nodes
+        L = []
+        sidx = {v: i for i, v in enumerate(part.snodes)}
+        owned = set(part.owned)
+        oidx = {v: i for i, v in enumerate(part.owned)}
+        wm = p.weight_mode
+        inset = set(part.snodes)
+        if p.reals:
+            # children of every parent that live in this part
+            groups = {}
+            for v in part.snodes:
+                groups.setdefault(nodes[v].parent, []).append(v)
+            # deepest parents first: a node is updated after its children read it
+            order = sorted(groups, key=lambda u: -(nodes[u].depth if u >= 0 else 0))
+            for u in order:
+                if u < 0:
+                    base = None
+                elif wm == be.WEIGHT_NONE:
+                    base = f"S[{sidx[u]}]"
+                else:
+                    a = p.aidx[nodes[u].alpha]
+                    acc = f"S[{sidx[u]}]" if wm == be.WEIGHT_TOTAL else f"A2[{sidx[u]}]"
+                    L.append(f"const double b{u} = __dmul_rn({acc}, em{a});")
+                    base = f"b{u}"
+                # product tree over the occurrences of the children's letters
+                prods = {}       # occ prefix -> variable
+
+                def prod(occ):
+                    if occ in prods:
+                        return prods[occ]
+                    (d, div) = occ[-1]
+                    x = f"x{d}"
+                    if len(occ) == 1:
+                        if base is None:
+                            # 1.0 * x is x; 1.0 / x needs the division
+                            name = x if not div else None
+                            if name is None:
+                                name = f"v{u if u >= 0 else 'r'}_{len(prods)}"
+                                L.append(f"const double {name} = __ddiv_rn(1.0, {x});")
+                        else:
+                            name = f"v{u}_{len(prods)}"
+                            op = "__ddiv_rn" if div else "__dmul_rn"
+                            L.append(f"const double {name} = {op}({base}, {x});")
+                    else:
+                        src = prod(occ[:-1])
+                        name = f"v{u if u >= 0 else 'r'}_{len(prods)}"
+                        op = "__ddiv_rn" if div else "__dmul_rn"
+                        L.append(f"const double {name} = {op}({src}, {x});")
+                    prods[occ] = name
+                    return name
+
+                kids = sorted(groups[u], key=lambda v: _occurrences(nodes[v].expo, p.dim_index))
+                vals = {}
+                for v in kids:
+                    occ = _occurrences(nodes[v].expo, p.dim_index)
+                    if not occ:
+                        # empty letter: the product is the base itself
+                        vals[v] = base if base is not None else "1.0"
+                    else:
+                        vals[v] = prod(occ)
+                for v in kids:
+                    self._update_reals(L, v, vals[v], sidx[v], v in owned, oidx.get(v), first)
+        else:
+            # arctic: parents first, children read the parent's new value
+            for v in part.snodes:
+                u = nodes[v].parent
+                if u < 0:
+                    base = "0.0"
+                elif wm == be.WEIGHT_NONE:
+                    base = f"S[{sidx[u]}]"
+                elif wm == be.WEIGHT_TOTAL:
+                    base = f"OP[{sidx[u]}]"
+                else:
+                    base = f"A2[{sidx[u]}]"
+                expr = base
+                for d, e in enumerate(nodes[v].expo):
+                    if e != 0:
+                        expr = f"fma({float(e)!r}, x{p.dim_index[d]}, {expr})"
+                L.append(f"const double w{v} = {expr};")
+                self._update_arctic(L, v, f"w{v}", sidx[v], v in owned, oidx.get(v), first)
+        return L
+
+    def _update_reals(self, L, v, val, si, is_owned, oi, first):
+        p = self.p
+        node = p.trie.nodes[v]
+        wm = p.weight_mode
+        S = f"S[{si}]"
+        if wm == be.WEIGHT_TOTAL:
+            a = p.aidx[node.alpha]
+            L.append(f"{S} = __dadd_rn({S}, __dmul_rn({val}, ep{a}));")
+            if is_owned:
+                L.append(f"const double o{v} = __dmul_rn({S}, em{a});")
+                L.append(f"const double q{v} = OP[{si}]; OP[{si}] = o{v};")
+                self._sieve(L, v, f"o{v}", f"q{v}", oi, first)
+        else:
+            if is_owned:
+                L.append(f"const double q{v} = {S};")
+            L.append(f"{S} = __dadd_rn({S}, {val});")
+            if wm == be.WEIGHT_NONTOTAL and node.children:
+                a = p.aidx[node.alpha]
+                L.append(f"A2[{si}] = __dadd_rn(A2[{si}], __dmul_rn({val}, ep{a}));")
+            if is_owned:
+                self._sieve(L, v, S, f"q{v}", oi, first)
+
+    def _update_arctic(self, L, v, val, si, is_owned, oi, first):
+        p = self.p
+        node = p.trie.nodes[v]
+        wm = p.weight_mode
+        S = f"S[{si}]"
+        mx = lambda a, b: f"(({b}) > ({a}) ? ({b}) : ({a}))"   # noqa: E731  keeps a on NaN
+        if wm == be.WEIGHT_TOTAL:
+            al = _dlit(float(node.alpha))
+            L.append(f"const double y{v} = fma(g0, {al}, {val});")
+            L.append(f"{S} = {mx(S, f'y{v}')};")
+            L.append(f"const double q{v} = OP[{si}];")
+            L.append(f"OP[{si}] = fma(-g0, {al}, {S});")
+            if is_owned:
+                self._sieve(L, v, f"OP[{si}]", f"q{v}", oi, first)
+        elif wm == be.WEIGHT_NONTOTAL:
+            u = node.parent
+            if u >= 0:
+                alp = _dlit(float(p.trie.nodes[u].alpha))
+                L.append(f"const double y{v} = fma(-g0, {alp}, {val});")
+            else:
+                L.append(f"const double y{v} = {val};")
+            if is_owned:
+                L.append(f"const double q{v} = {S};")
+            L.append(f"{S} = {mx(S, f'y{v}')};")
+            if node.children:
+                al = _dlit(float(node.alpha))
+                L.append(f"const double z{v} = fma(g0, {al}, y{v});")
+                L.append(f"A2[{si}] = {mx(f'A2[{si}]', f'z{v}')};")
+            if is_owned:
+                self._sieve(L, v, S, f"q{v}", oi, first)
+        else:
+            if is_owned:
+                L.append(f"const double q{v} = {S};")
+            L.append(f"{S} = {mx(S, val)};")
+            if is_owned:
+                self._sieve(L, v, S, f"q{v}", oi, first)
+
+    def _sieve(self, L, v, out, prev, oi, first):
+        """Feed the new value ``out`` (previous value ``prev``) of the owned
+        node with index ``oi`` to its accumulators."""
+        sv = self.sv
+        e = self.p.trie.nodes[v].emit
+        cregs = self._cnt_layout()
+
+        def unit(k, val):
+            reg, hi16 = cregs[("U", k)]
+            inc = "0x10000" if hi16 else "1"
+            outs = [f'"+r"(CN[{oi}][{reg}])']
+            if sv.avg[k]:
+                outs.append(f'"+d"(SM{k}[{oi}])')
+            iv = len(outs)                      # operand index of the value
+            ins = [f'"d"({val})', f'"d"({self.th(e, _COL_U[k][0])})']
+            asm = ["{ .reg .pred p;", f"setp.gt.f64 p, %{iv}, %{iv + 1};"]
+            if sv.hi:
+                ins.append(f'"d"({self.th(e, _COL_U[k][1])})')
+                asm.append(f"setp.le.and.f64 p, %{iv}, %{iv + 2}, p;")
+            asm.append(f"@p add.u32 %0, %0, {inc};")
+            if sv.avg[k]:
+                asm.append(f"@p add.rn.f64 %1, %1, %{iv};")
+            asm.append("}")
+            L.append('asm("' + " ".join(asm) + '" : ' + ", ".join(outs) + " : " + ", ".join(ins) + ");")
+
+        if sv.cnt[0]:
+            unit(0, out)
+        if sv.cnt[1] or sv.cnt[2]:
+            if first:
+                d1 = "0.0"
+            else:
+                L.append(f"const double d{v} = __dadd_rn({out}, -{prev});")
+                d1 = f"d{v}"
+            if sv.cnt[1]:
+                unit(1, d1)
+            if sv.cnt[2]:
+                if first:
+                    unit(2, "0.0")
+                    L.append(f"D1[{oi}] = 0.0;")
+                else:
+                    L.append(f"const double dd{v} = __dadd_rn({d1}, -D1[{oi}]); D1[{oi}] = {d1};")
+                    unit(2, f"dd{v}")
+        if sv.ppv:
+            reg, hi16 = cregs[("P", 0)]
+            inc = "0x10000" if hi16 else "1"
+            L.append('asm("{ .reg .pred p; setp.ge.f64 p, %1, %2; @p add.u32 %0, %0, ' + inc + '; }" : '
+                     f'"+r"(CN[{oi}][{reg}]) : "d"({out}), "d"({self.th(e, _COL_PPV)}));')
+        for on, arr, cmp_, cols in ((sv.mx, "MX", "gt", _COL_MAX), (sv.mn, "MN", "lt", _COL_MIN)):
+            if not on:
+                continue
+            asm = ["{ .reg .pred p;", f"setp.{cmp_}.f64 p, %1, %0;"]
+            ins = [f'"d"({out})']
+            if sv.mmb:
+                asm.append("setp.gt.and.f64 p, %1, %2, p;")
+                asm.append("setp.le.and.f64 p, %1, %3, p;")
+                ins += [f'"d"({self.th(e, cols[0])})', f'"d"({self.th(e, cols[1])})']
+            asm.append("selp.f64 %0, %1, %0, p; }")
+            L.append('asm("' + " ".join(asm) + f'" : "+d"({arr}[{oi}]) : ' + ", ".join(ins) + ");")
+
+    def _cnt_layout(self):
+        """16-bit counters packed two per register: {(kind, k): (reg, high half)}."""
+        keys = [("U", k) for k in range(3) if self.sv.cnt[k]]
+        if self.sv.ppv:
+            keys.append(("P", 0))
+        return {key: (i // 2, bool(i % 2)) for i, key in enumerate(keys)}
+
+    def n_cnt_regs(self) -> int:
+        return (len(self._cnt_layout()) + 1) // 2
+
+    # -- epilogue of one part --------------------------------------------------
+    def epilogue(self, part: Part) -> list:
+        p, sv = self.p, self.sv
+        nodes = p.trie.nodes
+        L = []
+        sidx = {v: i for i, v in enumerate(part.snodes)}
+        cregs = self._cnt_layout()
+        nf = len(sv.feats)
+
+        def count(oi, key):
+            reg, hi16 = cregs[key]
+            return f"(CN[{oi}][{reg}] >> 16)" if hi16 else f"(CN[{oi}][{reg}] & 0xffffu)"
+
+        for oi, v in enumerate(part.owned):
+            e = nodes[v].emit
+            endv = f"OP[{sidx[v]}]" if p.weight_mode == be.WEIGHT_TOTAL else f"S[{sidx[v]}]"
+            for f, (kind, arg) in enumerate(sv.feats):
+                if kind == be.FEAT_CNT:
+                    val = f"(double){count(oi, ('U', arg))}"
+                elif kind == be.FEAT_AVG:
+                    c = count(oi, ("U", arg))
+                    val = f"({c} ? __ddiv_rn(SM{arg}[{oi}], (double){c}) : 0.0)"
+                elif kind == be.FEAT_PPV:
+                    val = f"__ddiv_rn((double){count(oi, ('P', 0))}, (double)T)"
+                elif kind == be.FEAT_MAX:
+                    val = f"(MX[{oi}] == D_NINF ? 0.0 : MX[{oi}])"
+                elif kind == be.FEAT_MIN:
+                    val = f"(MN[{oi}] == D_INF ? 0.0 : MN[{oi}])"
+                else:
+                    val = endv
+                L.append(f"o[{e * nf + f}] = fin({val}, a.sanitize);")
+        return L
+
+    # -- whole kernel ------------------------------------------------------------
+    def source(self) -> str:
+        p, sv = self.p, self.sv
+        wm = p.weight_mode
+        ns = max(1, max(len(pt.snodes) for pt in p.parts))
+        no = max(1, max(len(pt.owned) for pt in p.parts))
+        need_first = sv.cnt[1] or sv.cnt[2]
+        ncr = max(1, self.n_cnt_regs())
+        nthr = max(1, len(p.trie.emits) * self.ntc)
+        du = len(p.used)
+        TT = self.tt
+        row = self.nrow * TT + 2           # doubles per series and tile
+        erow = self.nextra * TT + 2
+        per_series_extra = self.nextra and not self.shared_extra
+        src = []
+        A = src.append
+        A("// generated by fruits_b200/_jit.py -- do not edit")
+        A(f"#define TT {TT}")
+        A(f"#define PPC {self.ppc}")
+        A(f"#define GPC {self.gpc}")
+        A("#define NT (32 * PPC * GPC)")
+        A(f"#define NROW {self.nrow}")
+        A(f"#define ROW {row}")
+        A(f"#define NEXTRA {self.nextra}")
+        A(f"#define EROW {erow}")
+        A("#define D_INF __longlong_as_double(0x7ff0000000000000LL)")
+        A("#define D_NINF __longlong_as_double(0xfff0000000000000LL)")
+        A(f"__constant__ double TH[{nthr}];")
+        A("__constant__ int RAW[NROW] = {" + ", ".join(str(r) for r in self.raw_rows) + "};")
+        A("struct Args { const double *X; const double *E; double *out; long long n, d, t, e_ld, out_ld, col0; int sanitize; };")
+        A("__device__ __forceinline__ double fin(double v, int sanitize) {")
+        A("    if (!sanitize) return v;")
+        A("    if (v != v) return 0.0;")
+        A("    if (v == D_INF) return __longlong_as_double(0x7fefffffffffffffLL);")
+        A("    if (v == D_NINF) return __longlong_as_double(0xffefffffffffffffLL);")
+        A("    return v; }")
+        A("__device__ __forceinline__ void cp16(double *dst, const double *src) {")
+        A('    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
+        A("__device__ __forceinline__ void cp8(double *dst, const double *src) {")
+        A('    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
+        A('extern "C" __global__ void __launch_bounds__(NT, 1) fb_jit_slice(const Args a)')
+        A("{")
+        A("    extern __shared__ __align__(16) double smem[];")
+        A("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
+        A(f"    // consecutive CTAs work on the same series with different parts: the")
+        A(f"    // input tile is read from HBM once and hits L2 for the other parts")
+        A(f"    const int part = (int)(blockIdx.x % {len(p.parts) // self.ppc}u) * PPC + warp % PPC;")
+        A("    const int sg = warp / PPC;")
+        A(f"    const long long nbase = (long long)(blockIdx.x / {len(p.parts) // self.ppc}u) * (GPC * 32);")
+        A("    const int T = (int)a.t;")
+        A("    // tile buffers: [2][GPC*32 series][ROW] then the weighting rows")
+        A("    double *xbuf = smem;")
+        A("    double *ebuf = smem + 2 * GPC * 32 * ROW;")
+        A(f"    double S[{ns}];")
+        if wm == be.WEIGHT_NONTOTAL:
+            A(f"    double A2[{ns}];")
+        if wm == be.WEIGHT_TOTAL:
+            A(f"    double OP[{ns}];")
+        A(f"    unsigned CN[{no}][{ncr}];")
+        for k in range(3):
+            if sv.avg[k]:
+                A(f"    double SM{k}[{no}];")
+        if sv.cnt[2]:
+            A(f"    double D1[{no}];")
+        if sv.mx:
+            A(f"    double MX[{no}];")
+        if sv.mn:
+            A(f"    double MN[{no}];")
+        init = "0.0" if p.reals else "D_NINF"
+        A("#pragma unroll")
+        A(f"    for (int i = 0; i < {ns}; i++) {{ S[i] = {init};"
+          + (f" A2[i] = {init};" if wm == be.WEIGHT_NONTOTAL else "")
+          + (" OP[i] = 0.0;" if wm == be.WEIGHT_TOTAL else "") + " }")
+        A("#pragma unroll")
+        A(f"    for (int i = 0; i < {no}; i++) {{")
+        A("#pragma unroll")
+        A(f"        for (int j = 0; j < {ncr}; j++) CN[i][j] = 0u;")
+        for k in range(3):
+            if sv.avg[k]:
+                A(f"        SM{k}[i] = 0.0;")
+        if sv.cnt[2]:
+            A("        D1[i] = 0.0;")
+        if sv.mx:
+            A("        MX[i] = D_NINF;")
+        if sv.mn:
+            A("        MN[i] = D_INF;")
+        A("    }")
+        # previous raw values of the dimensions that are read as increments
+        inc_rows = sorted({self.row_of[r] for r, inc in self.dims if inc})
+        for r in inc_rows:
+            A(f"    double xp{r} = 0.0;")
+        # ---- staging ----
+        A("    const bool even = ((a.t & 1) == 0) && ((((unsigned long long)a.X) & 15) == 0);")
+        # slow path: any CTA shape / alignment (tail CTA, odd lengths)
+        A("    auto stage_slow = [&](int buf, int t0) {")
+        A("        const int nchunk = GPC * 32 * NROW * (TT / 2);")
+        A("        for (int c = threadIdx.x; c < nchunk; c += NT) {")
+        A("            const int k = c % (TT / 2), sr = c / (TT / 2);")
+        A("            const int r = sr % NROW, s = sr / NROW;")
+        A("            long long n = nbase + s; if (n >= a.n) n = a.n - 1;")
+        A("            const int t = t0 + 2 * k;")
+        A("            const double *g = a.X + ((size_t)n * a.d + RAW[r]) * (size_t)T + t;")
+        A("            double *d = xbuf + ((size_t)(buf * GPC * 32 + s)) * ROW + r * TT + 2 * k;")
+        A("            if (even) { if (t < T) cp16(d, g); }")
+        A("            else { if (t < T) cp8(d, g); if (t + 1 < T) cp8(d + 1, g + 1); }")
+        A("        }")
+        if per_series_extra:
+            A("        const int echunk = GPC * 32 * NEXTRA * (TT / 2);")
+            A("        const bool eeven = ((a.t & 1) == 0) && ((((unsigned long long)a.E) & 15) == 0) && ((a.e_ld & 1) == 0);")
+            A("        for (int c = threadIdx.x; c < echunk; c += NT) {")
+            A("            const int k = c % (TT / 2), sr = c / (TT / 2);")
+            A("            const int r = sr % NEXTRA, s = sr / NEXTRA;")
+            A("            const int t = t0 + 2 * k;")
+            A("            long long n = nbase + s; if (n >= a.n) n = a.n - 1;")
+            A("            const double *g = a.E + (size_t)n * a.e_ld + (size_t)r * T + t;")
+            A("            double *d = ebuf + ((size_t)(buf * GPC * 32 + s)) * EROW + r * TT + 2 * k;")
+            A("            if (eeven) { if (t < T) cp16(d, g); }")
+            A("            else { if (t < T) cp8(d, g); if (t + 1 < T) cp8(d + 1, g + 1); }")
+            A("        }")
+        A("    };")
+        # fast path: whole CTA inside the batch, 16-byte aligned rows; every
+        # thread copies the same (series, chunk) pattern each tile, so all
+        # offsets are compile-time multiples of T and D*T
+        ch = TT // 2
+        nt = 32 * self.ppc * self.gpc
+        fast_ok = nt % ch == 0 and (self.gpc * 32) % (nt // ch) == 0
+        sp = nt // ch if fast_ok else 1           # series covered per pass
+        passes = (self.gpc * 32) // sp if fast_ok else 0
+        A(f"    const bool fast = {'true' if fast_ok else 'false'} && even && (nbase + GPC * 32 <= a.n)"
+          + (" && ((((unsigned long long)a.E) & 15) == 0) && ((a.e_ld & 1) == 0)" if per_series_extra else "") + ";")
+        A(f"    const int fk = (threadIdx.x % {ch}) * 2, fs = threadIdx.x / {ch};")
+        A("    const double *fsrc = a.X + ((size_t)(nbase + fs) * a.d) * (size_t)T + fk;")
+        A("    double *fdst = xbuf + (size_t)fs * ROW + fk;")
+        A("    const size_t DT = (size_t)a.d * (size_t)T;")
+        if per_series_extra:
+            A("    const double *fesrc = a.E + (size_t)(nbase + fs) * a.e_ld + fk;")
+            A("    double *fedst = ebuf + (size_t)fs * EROW + fk;")
+        A("    auto stage_fast = [&](int buf, int t0) {")
+        A("        if (t0 + fk < T) {")
+        A("            const double *g = fsrc + t0;")
+        A("            double *d = fdst + (size_t)buf * (GPC * 32 * ROW);")
+        for j in range(passes):
+            for r, raw in enumerate(self.raw_rows):
+                A(f"            cp16(d + {j * sp} * ROW + {r} * TT, g + {j * sp} * DT + {raw} * (size_t)T);")
+        if per_series_extra:
+            A("            const double *ge = fesrc + t0;")
+            A("            double *de = fedst + (size_t)buf * (GPC * 32 * EROW);")
+            for j in range(passes):
+                for r in range(self.nextra):
+                    A(f"            cp16(de + {j * sp} * EROW + {r} * TT, ge + {j * sp} * (size_t)a.e_ld + {r} * (size_t)T);")
+        A("        }")
+        A("    };")
+        A("    auto stage = [&](int buf, int t0) {")
+        A("        if (fast) stage_fast(buf, t0); else stage_slow(buf, t0);")
+        if self.nextra and not per_series_extra:
+            A("        // weighting rows shared by all series")
+            A("        const bool eeven = ((a.t & 1) == 0) && ((((unsigned long long)a.E) & 15) == 0);")
+            A("        for (int c = threadIdx.x; c < NEXTRA * (TT / 2); c += NT) {")
+            A("            const int k = c % (TT / 2), r = c / (TT / 2);")
+            A("            const int t = t0 + 2 * k;")
+            A("            const double *g = a.E + (size_t)r * T + t;")
+            A("            double *d = ebuf + (size_t)buf * EROW + r * TT + 2 * k;")
+            A("            if (eeven) { if (t < T) cp16(d, g); }")
+            A("            else { if (t < T) cp8(d, g); if (t + 1 < T) cp8(d + 1, g + 1); }")
+            A("        }")
+        A('        asm volatile("cp.async.commit_group;" ::: "memory");')
+        A("    };")
+        A("    stage(0, 0);")
+        A("    int buf = 0;")
+        A("    for (int t0 = 0; t0 < T; t0 += TT, buf ^= 1) {")
+        A('        asm volatile("cp.async.wait_all;" ::: "memory");')
+        A("        __syncthreads();")
+        A("        if (t0 + TT < T) stage(buf ^ 1, t0 + TT);")
+        A("        const double *xs = xbuf + ((size_t)(buf * GPC * 32 + sg * 32 + lane)) * ROW;")
+        if self.nextra:
+            if per_series_extra:
+                A("        const double *es = ebuf + ((size_t)(buf * GPC * 32 + sg * 32 + lane)) * EROW;")
+            else:
+                A("        const double *es = ebuf + (size_t)buf * EROW;")
+        A("        const int tend = min(TT, T - t0);")
+        A("        int tt = 0;")
+        A("        switch (part) {")
+        for pi, part in enumerate(p.parts):
+            if not part.owned:
+                continue
+            A(f"        case {pi}: {{")
+            if need_first:
+                A("            if (t0 == 0) {")
+                for ln in self._loads(first=True) + self.step(part, True) + self._after(first=True):
+                    A("                " + ln)
+                A("                tt = 1;")
+                A("            }")
+            A("#pragma unroll 1")
+            A("            for (; tt < tend; tt++) {")
+            for ln in self._loads(first=False) + self.step(part, False) + self._after(first=False):
+                A("                " + ln)
+            A("            }")
+            A("        } break;")
+        A("        default: break;")
+        A("        }")
+        A("    }")
+        # ---- epilogue ----
+        A("    const long long ns_ = nbase + sg * 32 + lane;")
+        A("    if (ns_ < a.n) {")
+        A("        double *o = a.out + (size_t)ns_ * a.out_ld + a.col0;")
+        A("        switch (part) {")
+        for pi, part in enumerate(p.parts):
+            if not part.owned:
+                continue
+            A(f"        case {pi}: {{")
+            for ln in self.epilogue(part):
+                A("            " + ln)
+            A("        } break;")
+        A("        default: break;")
+        A("        }")
+        A("    }")
+        A("}")
+        del du
+        return "\n".join(src) + "\n"
+
+    def _loads(self, first: bool) -> list:
+        """Values of the current step: x{u} per used dimension, ep/em/g0."""
+        L = []
+        for r in range(self.nrow):
+            L.append(f"const double r{r} = xs[{r} * TT + tt];")
+        for u, (raw, inc) in enumerate(self.dims):
+            r = self.row_of[raw]
+            if inc:
+                L.append(f"const double x{u} = " + ("0.0;" if first else f"__dadd_rn(r{r}, -xp{r});"))
+            else:
+                L.append(f"const double x{u} = r{r};")
+        p = self.p
+        if p.weight_mode != be.WEIGHT_NONE:
+            if p.reals:
+                for a in range(len(p.alphas)):
+                    L.append(f"const double ep{a} = es[{2 * a} * TT + tt];")
+                    L.append(f"const double em{a} = es[{2 * a + 1} * TT + tt];")
+            else:
+                L.append("const double g0 = es[tt];")
+        return L
+
+    def _after(self, first: bool) -> list:
+        inc_rows = sorted({self.row_of[r] for r, inc in self.dims if inc})
+        return [f"xp{r} = r{r};" for r in inc_rows]
+
+    def smem_bytes(self) -> int:
+        row = self.nrow * self.tt + 2
+        erow = self.nextra * self.tt + 2
+        n = 2 * self.gpc * 32 * row
+        if self.nextra:
+            n += 2 * (erow if self.shared_extra else self.gpc * 32 * erow)
+        return n * 8
+
+
+# ---------------------------------------------------------------------------
+# run time: compile (NVRTC inside libfruits_b200.so), cache, load, launch
+# ---------------------------------------------------------------------------
+
+class FbJitGeometry(ctypes.Structure):
+    _fields_ = [("n_parts", ctypes.c_int32), ("parts_per_cta", ctypes.c_int32),
+                ("groups_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32)]
+
+
+DEFAULT_OPTS = {"budget": 150, "ppc": 1, "gpc": 8, "minb": 1, "unroll": 1, "tt": 16}
+
+
+def options() -> dict:
+    """Generator options; ``FRUITS_B200_JIT_OPTS="budget=150,ppc=4"`` overrides."""
+    opts = dict(DEFAULT_OPTS)
+    env = os.environ.get("FRUITS_B200_JIT_OPTS", "")
+    for item in filter(None, env.split(",")):
+        key, val = item.split("=")
+        if key not in opts:
+            raise ValueError(f"unknown JIT option {key!r}")
+        opts[key] = int(val)
+    return opts
+
+
+def options_key() -> tuple:
+    return tuple(sorted(options().items()))
+
+
+def enabled() -> bool:
+    return os.environ.get("FRUITS_B200_JIT", "1") != "0"
+
+
+def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
+             shared_extra: bool, opts: dict):
+    """-> (source, Emitter).  Raises NotImplementedError for plans the
+    generated kernel cannot hold (the caller then uses the generic kernel)."""
+    prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
+                   parts_multiple=opts["ppc"])
+    em = Emitter(prog, dims, opts["ppc"], opts["gpc"], shared_extra, opts["tt"])
+    if len(trie.emits) * em.ntc * 8 > 60 * 1024:
+        raise NotImplementedError("threshold table exceeds the constant bank")
+    if em.smem_bytes() > 200 * 1024:
+        raise NotImplementedError("input tile exceeds shared memory")
+    if len(prog.parts) // opts["ppc"] > 65535:
+        raise NotImplementedError("too many parts")
+    src = em.source()
+    src = src.replace("__launch_bounds__(NT, 1)", f"__launch_bounds__(NT, {opts['minb']})")
+    src = src.replace("#pragma unroll 1\n            for (; tt < tend; tt++)",
+                      f"#pragma unroll {opts['unroll']}\n            for (; tt < tend; tt++)")
+    return src, em
+
+
+def compile_source(src: str, name: str = "fb_jit_slice.cu") -> bytes:
+    """CUDA source -> sm_100a cubin through ``fb_jit_compile`` (NVRTC), with an
+    on-disk cache keyed by the source text."""
+    digest = hashlib.sha256((f"v{JIT_VERSION}\n" + src).encode()).hexdigest()[:24]
+    path = os.path.join(CACHE_DIR, digest + ".cubin")
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            return f.read()
+    L = be.lib()
+    cubin, size = ctypes.c_void_p(), ctypes.c_size_t()
+    log = ctypes.create_string_buffer(1 << 16)
+    rc = L.fb_jit_compile(src.encode(), name.encode(), ctypes.byref(cubin), ctypes.byref(size),
+                          log, len(log))
+    if rc != 0:
+        msg = L.fb_last_error().decode(errors="replace")
+        raise RuntimeError(f"JIT compilation failed: {msg}\n{log.value.decode(errors='replace')}")
+    data = ctypes.string_at(cubin.value, size.value)
+    L.fb_jit_free(cubin)
+    try:
+        os.makedirs(CACHE_DIR, exist_ok=True)
+        tmp = path + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            f.write(data)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return data
+
+
+class JitSlice:
+    """One loaded plan-specialised kernel."""
+
+    _loaded: dict = {}     # source digest -> JitSlice
+
+    def __init__(self, src: str, em: Emitter) -> None:
+        self.em = em
+        self.src = src
+        cubin = compile_source(src)
+        self._cubin = cubin
+        handle = ctypes.c_void_p()
+        be.check(be.lib().fb_jit_load(cubin, len(cubin), ctypes.byref(handle)))
+        self.handle = handle
+        self.geo = FbJitGeometry(len(em.p.parts), em.ppc, em.gpc, em.smem_bytes())
+        self.cols = list(em.cols)
+
+    @classmethod
+    def get(cls, trie, semiring, weight_mode, sieves, dims, shared_extra) -> "JitSlice":
+        src, em = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options())
+        key = hashlib.sha256(src.encode()).hexdigest()
+        obj = cls._loaded.get(key)
+        if obj is None:
+            obj = cls(src, em)
+            cls._loaded[key] = obj
+        return obj
+
+    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize) -> None:
+        """X[n, d, t] cuda float64; extra: weighting rows or None;
+        thr_compact: [n_emit * len(cols)] cuda float64."""
+        batch = be.FbBatch()
+        batch.X = X.data_ptr()
+        batch.n, batch.d, batch.t = X.shape
+        n_thr = 0 if thr_compact is None else thr_compact.numel()
+        be.check(be.lib().fb_jit_slice_features(
+            self.handle, ctypes.byref(self.geo), ctypes.byref(batch), be.ptr(extra), int(extra_ld),
+            be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0), int(sanitize),
+            be.stream_ptr()))

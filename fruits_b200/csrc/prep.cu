@@ -169,6 +169,26 @@ static inline unsigned grid_for(long long total, int block)
 
 using namespace fb;
 
+namespace fb {
+struct ExpAlphas { double a[FB_MAX_ALPHAS]; };
+// out[r][2a + s][t] = exp(+-alpha_a * g[r][t])   (fruits/iss/semiring.py:121-124, :150-157;
+// alpha is float32 in the reference and promoted to double in the product)
+__global__ void exp_rows_kernel(const double *__restrict__ g, double *__restrict__ out,
+                                long long rows, int t, ExpAlphas al, int na)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * t) return;
+    const long long r = i / t;
+    const int tt = (int)(i - r * t);
+    const double gv = g[i];
+    double *o = out + (size_t)r * (2 * na) * t + tt;
+    for (int a = 0; a < na; a++) {
+        o[(size_t)(2 * a) * t] = exp(gv * al.a[a]);
+        o[(size_t)(2 * a + 1) * t] = exp(-gv * al.a[a]);
+    }
+}
+}  // namespace fb
+
 extern "C" {
 
 int fb_increments(const double *X, const double *pad_src, double *out, int64_t rows, int64_t t,
@@ -222,6 +242,21 @@ int fb_nrm_scale(const double *in, double *out, int64_t rows, int64_t t, int rel
     if (rows == 0) return 0;
     nrm_scale_kernel<<<(unsigned)((rows * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         in, out, rows, (int)t, relative, scale);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_exp_rows(const double *g, double *out, int64_t rows, int64_t t, const float *alphas_h,
+                int n_alphas, void *stream)
+{
+    FB_REQUIRE(g && out && alphas_h && rows >= 0 && t >= 1, "bad arguments");
+    FB_REQUIRE(n_alphas >= 1 && n_alphas <= FB_MAX_ALPHAS, "n_alphas=%d out of range", n_alphas);
+    if (rows == 0) return 0;
+    fb::ExpAlphas al;
+    for (int a = 0; a < FB_MAX_ALPHAS; a++) al.a[a] = a < n_alphas ? (double)alphas_h[a] : 0.0;
+    const long long total = rows * t;
+    fb::exp_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        g, out, rows, (int)t, al, n_alphas);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

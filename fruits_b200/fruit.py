@@ -18,9 +18,11 @@ import numpy as np
 import torch
 
 from . import _backend as be
+from . import _jit
 from .cache import SharedSeedCache
 from .callback import AbstractCallback
 from .iss.iss import ISS
+from .iss.semiring import Reals
 from .preparation.abstract import Preparateur
 from .preparation.wrapper import NEW
 from .seed import Seed
@@ -609,13 +611,77 @@ class FruitSlice:
 
     def _transform_fused(self, X, cache, out, col0, sanitize) -> None:
         iss = self._iss[0]
-        L = be.lib()
         n, d, t = X.shape
         dims = self._fused_dims(d)
         if iss.max_dim() > len(dims):
             raise IndexError(
                 f"words use dimension {iss.max_dim()} but the prepared input has {len(dims)}")
+        if out.stride(1) != 1:
+            raise ValueError("feature matrix must be row-major")
         feats, bounded_hi, bounded_mm = self._fused_sieves()
+        if _jit.enabled():
+            try:
+                self._transform_jit(X, cache, out, col0, sanitize, dims, feats, bounded_hi,
+                                    bounded_mm)
+                return
+            except NotImplementedError:
+                pass      # plan too large for the specialised kernel: generic kernel below
+        self._transform_generic(X, out, col0, sanitize, dims, feats, bounded_hi, bounded_mm)
+
+    def _transform_jit(self, X, cache, out, col0, sanitize, dims, feats, bounded_hi,
+                       bounded_mm) -> None:
+        """Plan-specialised kernel (``_jit.py``): trie nodes and sieve state in
+        registers, one thread per series and trie part."""
+        iss = self._iss[0]
+        trie = iss.trie()
+        used = trie.used_dims()
+        lookup_src = X
+        if any(dims[u][2] for u in used):
+            # standardised dimensions: materialise the prepared input once
+            # (2 x 8 bytes per value against ~10^3 flop per value of ISS work)
+            X = self._prepare_device(X, cache, fit=False)
+            dims = [(u, 0, 0) for u in range(X.shape[1])]
+        jdims = [(dims[u][0], dims[u][1]) for u in used]
+        sieves = _jit.SieveSet.make(feats, bounded_hi, bounded_mm)
+        g, g_ld = iss._lookup(lookup_src)
+        wm = iss._weight_mode()
+        key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0, _jit.options_key())
+        memo = getattr(iss, "_jit_memo", None)
+        if memo is None or memo[0] is not trie:
+            memo = (trie, {})
+            iss._jit_memo = memo
+        kern = memo[1].get(key)
+        if kern is None:
+            kern = _jit.JitSlice.get(trie, iss.semiring._code, wm, sieves, jdims, g_ld == 0)
+            memo[1][key] = kern
+        thr = self._threshold_table(len(trie.emits))
+        thr_c = None
+        if kern.cols:
+            tkey = (id(thr), tuple(kern.cols))
+            if getattr(self, "_thr_compact", (None, None))[0] != tkey:
+                idx = torch.as_tensor(kern.cols, device=thr.device, dtype=torch.long)
+                self._thr_compact = (tkey, thr.index_select(1, idx).contiguous(), thr)
+            thr_c = self._thr_compact[1]
+        extra, extra_ld = None, 0
+        if wm != be.WEIGHT_NONE:
+            rows = 1 if g_ld == 0 else X.shape[0]
+            if isinstance(iss.semiring, Reals):
+                alphas = (ctypes.c_float * len(kern.em.p.alphas))(*kern.em.p.alphas)
+                extra = be.empty((rows, 2 * len(alphas), X.shape[2]))
+                be.check(be.lib().fb_exp_rows(g.data_ptr(), extra.data_ptr(), rows, X.shape[2],
+                                              alphas, len(alphas), be.stream_ptr()))
+                extra_ld = 0 if g_ld == 0 else 2 * len(alphas) * X.shape[2]
+            else:
+                extra = g
+                extra_ld = g_ld
+        kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize)
+
+    def _transform_generic(self, X, out, col0, sanitize, dims, feats, bounded_hi,
+                           bounded_mm) -> None:
+        """Generic trie-interpreting kernel (``csrc/lns.cuh``)."""
+        iss = self._iss[0]
+        L = be.lib()
+        n, d, t = X.shape
         sp = be.FbSievePlan()
         sp.n_feats = len(feats)
         for f, (kind, arg) in enumerate(feats):
@@ -643,8 +709,6 @@ class FruitSlice:
                 stats[:, ui, :] = st
         g, g_ld = iss._lookup(X)
         batch = iss.batch(X, g, g_ld, stats)
-        if out.stride(1) != 1:
-            raise ValueError("feature matrix must be row-major")
         be.check(L.fb_slice_features_ex(plan.byref(), ctypes.byref(batch), ctypes.byref(sp),
                                         out.data_ptr(), out.stride(0), col0, policy,
                                         int(sanitize), be.stream_ptr()))

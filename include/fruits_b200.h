@@ -20,6 +20,7 @@
 #ifndef FRUITS_B200_H
 #define FRUITS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -173,6 +174,48 @@ FB_API int fb_slice_features_ex(const fb_iss_plan *plan, const fb_batch *batch,
 FB_API int fb_slice_features(const fb_iss_plan *plan, const fb_batch *batch,
                              const fb_sieve_plan *sieves, double *out, int64_t out_ld,
                              int64_t col0, void *stream);
+
+/* -- plan-specialised kernels --
+ * The fastest form of the fused FruitSlice.transform: the host compiles the
+ * slice (word trie, semiring, weighting mode, sieve set) into CUDA source in
+ * which every trie node is a register of a thread (one thread = one series x
+ * one part of the trie; generator: fruits_b200/_jit.py).  The library
+ * compiles that source for sm_100a with NVRTC, loads the cubin and launches
+ * it.  Semantics are those of fb_slice_features_ex; the source contract is
+ *   extern "C" __global__ void fb_jit_slice(struct Args)   and
+ *   __constant__ double TH[]    (compact threshold table, see _jit.py).  */
+typedef struct fb_jit_kernel fb_jit_kernel;
+
+typedef struct fb_jit_geometry {
+    int32_t n_parts;         /* parts the trie was split into (multiple of parts_per_cta) */
+    int32_t parts_per_cta;   /* warps of one CTA working on the same 32 series */
+    int32_t groups_per_cta;  /* groups of 32 series per CTA */
+    int32_t smem_bytes;      /* dynamic shared memory of the generated kernel */
+} fb_jit_geometry;
+
+/* CUDA C++ source -> sm_100a cubin (malloc'ed, release with fb_jit_free).
+ * log (may be NULL) receives the compiler log.  Needs no GPU. */
+FB_API int fb_jit_compile(const char *src, const char *name, void **cubin, size_t *size,
+                          char *log, size_t log_cap);
+FB_API void fb_jit_free(void *p);
+FB_API int fb_jit_load(const void *cubin, size_t size, fb_jit_kernel **out);
+FB_API int fb_jit_unload(fb_jit_kernel *k);
+/* Fused FruitSlice.transform (fruits/fruit.py:498-553) with a generated kernel.
+ * extra: weighting rows [n or 1][rows][t] (Reals: exp(+a g), exp(-a g) per
+ * alpha; Arctic: g), extra_ld = row stride between series in elements, 0 if
+ * shared.  thr: device table of n_thr doubles copied into the kernel's
+ * constant bank on `stream` before the launch.  Launches of one kernel
+ * object must be issued on one stream at a time. */
+FB_API int fb_jit_slice_features(fb_jit_kernel *k, const fb_jit_geometry *geo,
+                                 const fb_batch *batch, const double *extra, int64_t extra_ld,
+                                 const double *thr, int64_t n_thr, double *out, int64_t out_ld,
+                                 int64_t col0, int sanitize, void *stream);
+
+/* fruits/iss/semiring.py:103-125, :138-158: exp(+alpha g), exp(-alpha g) rows
+ * of the exponential weighting for every distinct alpha:
+ * out[r][2a + s][t] = exp((s ? -1 : 1) * alpha[a] * g[r][t]),  r < rows. */
+FB_API int fb_exp_rows(const double *g, double *out, int64_t rows, int64_t t,
+                       const float *alphas_h, int n_alphas, void *stream);
 
 /* ISS.transform / batch_transform (fruits/iss/iss.py:118-185,
  * fruits/iss/semiring.py:93-201, :282-404): materialise every emitted

@@ -1,0 +1,47 @@
+"""Pre-compile the plan-specialised kernels of the benchmark / test pipelines.
+
+NVRTC needs no GPU, so this runs in the build container; the cubins land in
+``fruits_b200/lib/jit/`` (git-ignored, shipped to the GPU box with the tree)
+and the first ``transform`` on the box skips the compile.
+
+    python scripts/jit_warm.py [config ...]     # default: every config of tests/specs.py
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import fruits_b200 as fruits  # noqa: E402
+from fruits_b200 import _jit  # noqa: E402
+from fruits_b200.iss.weighting import Indices, Plateaus  # noqa: E402
+import specs  # noqa: E402
+
+SHAPES = {"C1_readme": 3, "C2_reduced": 1, "C3_general": 6, "C4_twi": 3, "C5_sweep": 3}
+
+
+def warm(name: str) -> None:
+    fruit = specs.build_fruit(fruits, specs.SPECS[name])
+    for si, slc in enumerate(fruit._slices):
+        iss = slc._iss[0]
+        feats, bhi, bmm = slc._fused_sieves()
+        dims = slc._fused_dims(SHAPES[name])
+        trie = iss.trie()
+        used = trie.used_dims()
+        if any(dims[u][2] for u in used):
+            dims = [(u, 0, 0) for u in range(len(dims))]
+        jdims = [(dims[u][0], dims[u][1]) for u in used]
+        shared = iss.weighting is None or isinstance(iss.weighting, (Indices, Plateaus))
+        t0 = time.time()
+        src, em = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
+                                _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options())
+        cubin = _jit.compile_source(src)
+        print(f"{name} slice {si}: {len(trie.nodes)} nodes, {len(em.p.parts)} parts, "
+              f"{len(cubin) // 1024} KB cubin, {time.time() - t0:.1f} s", flush=True)
+
+
+if __name__ == "__main__":
+    for cfg in (sys.argv[1:] or list(SHAPES)):
+        warm(cfg)
