@@ -269,6 +269,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         k_s = ks[0].elapsed_time(ks[1]) * 1e-3 / reps
         n_launch = kX.shape[0]
+        kname, klaunches, kern = fruit.get_slice(0)._last_launch
+        if kern is not None:
+            em = kern.em
+            kdesc = (f"{kname}: plan-specialised kernel, {klaunches} module launches per slice "
+                     f"({len([p for p in em.p.parts if p.owned])} trie parts, {32 * em.gpc} series "
+                     f"per CTA, tile {em.tt} steps); achieved = slice flops / sum of the "
+                     f"{klaunches} launch durations")
+        else:
+            kdesc = f"{kname}<Reals, unweighted, PolP> (generic trie interpreter)"
         achieved = FLOP_PER_SERIES * n_launch / k_s / 1e12
         # measured fp64 FMA peak (same clocks / power state as the run)
         sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -288,7 +297,7 @@ def run_ours(args):
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None,
-            "kernel": "fb::lns_kernel<8, Reals, unweighted, PolP>",
+            "kernel": kdesc, "launches_per_slice": klaunches,
             "kernel_ms": k_s * 1e3, "series_per_launch": n_launch,
             "flop_per_series": FLOP_PER_SERIES,
             "peak_source": "DFMA microbenchmark fb_fp64_peak measured in this run",
@@ -329,7 +338,8 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * n_chunks,
+            "clocks": clocks, "e2e": e2e,
+            "gpu_launches": args.steps * n_chunks * fruit.get_slice(0)._last_launch[1],
             "roofline": roofline, "cpu_baseline": cpu, "fit_seconds": fit_s,
             "collective": ("nccl all_gather_into_tensor of the [S, F] feature blocks in 8 row "
                            "chunks on a side stream, overlapped with the kernels; every rank "

@@ -30,13 +30,14 @@ cached as a cubin next to the library.
 import ctypes
 import hashlib
 import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
 import numpy as np
 
 from . import _backend as be
 
-JIT_VERSION = 5            # bump to invalidate cached cubins
+JIT_VERSION = 7            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -272,7 +273,7 @@ class Emitter:
         return f"TH[{emit * self.ntc + self.colpos[col]}]"
 
     # -- one step of one part ------------------------------------------------
-    def step(self, part: Part, first: bool) -> list:
+    def step(self, part: Part) -> list:
         p, nodes = self.p, self.p.trie.nodes
         L = []
         sidx = {v: i for i, v in enumerate(part.snodes)}
@@ -334,7 +335,7 @@ class Emitter:
                     else:
                         vals[v] = prod(occ)
                 for v in kids:
-                    self._update_reals(L, v, vals[v], sidx[v], v in owned, oidx.get(v), first)
+                    self._update_reals(L, v, vals[v], sidx[v], v in owned, oidx.get(v))
         else:
             # arctic: parents first, children read the parent's new value
             for v in part.snodes:
@@ -352,10 +353,10 @@ class Emitter:
                     if e != 0:
                         expr = f"fma({float(e)!r}, x{p.dim_index[d]}, {expr})"
                 L.append(f"const double w{v} = {expr};")
-                self._update_arctic(L, v, f"w{v}", sidx[v], v in owned, oidx.get(v), first)
+                self._update_arctic(L, v, f"w{v}", sidx[v], v in owned, oidx.get(v))
         return L
 
-    def _update_reals(self, L, v, val, si, is_owned, oi, first):
+    def _update_reals(self, L, v, val, si, is_owned, oi):
         p = self.p
         node = p.trie.nodes[v]
         wm = p.weight_mode
@@ -366,7 +367,7 @@ class Emitter:
             if is_owned:
                 L.append(f"const double o{v} = __dmul_rn({S}, em{a});")
                 L.append(f"const double q{v} = OP[{si}]; OP[{si}] = o{v};")
-                self._sieve(L, v, f"o{v}", f"q{v}", oi, first)
+                self._sieve(L, v, f"o{v}", f"q{v}", oi)
         else:
             if is_owned:
                 L.append(f"const double q{v} = {S};")
@@ -375,9 +376,9 @@ class Emitter:
                 a = p.aidx[node.alpha]
                 L.append(f"A2[{si}] = __dadd_rn(A2[{si}], __dmul_rn({val}, ep{a}));")
             if is_owned:
-                self._sieve(L, v, S, f"q{v}", oi, first)
+                self._sieve(L, v, S, f"q{v}", oi)
 
-    def _update_arctic(self, L, v, val, si, is_owned, oi, first):
+    def _update_arctic(self, L, v, val, si, is_owned, oi):
         p = self.p
         node = p.trie.nodes[v]
         wm = p.weight_mode
@@ -390,7 +391,7 @@ class Emitter:
             L.append(f"const double q{v} = OP[{si}];")
             L.append(f"OP[{si}] = fma(-g0, {al}, {S});")
             if is_owned:
-                self._sieve(L, v, f"OP[{si}]", f"q{v}", oi, first)
+                self._sieve(L, v, f"OP[{si}]", f"q{v}", oi)
         elif wm == be.WEIGHT_NONTOTAL:
             u = node.parent
             if u >= 0:
@@ -406,15 +407,15 @@ class Emitter:
                 L.append(f"const double z{v} = fma(g0, {al}, y{v});")
                 L.append(f"A2[{si}] = {mx(f'A2[{si}]', f'z{v}')};")
             if is_owned:
-                self._sieve(L, v, S, f"q{v}", oi, first)
+                self._sieve(L, v, S, f"q{v}", oi)
         else:
             if is_owned:
                 L.append(f"const double q{v} = {S};")
             L.append(f"{S} = {mx(S, val)};")
             if is_owned:
-                self._sieve(L, v, S, f"q{v}", oi, first)
+                self._sieve(L, v, S, f"q{v}", oi)
 
-    def _sieve(self, L, v, out, prev, oi, first):
+    def _sieve(self, L, v, out, prev, oi):
         """Feed the new value ``out`` (previous value ``prev``) of the owned
         node with index ``oi`` to its accumulators."""
         sv = self.sv
@@ -442,20 +443,14 @@ class Emitter:
         if sv.cnt[0]:
             unit(0, out)
         if sv.cnt[1] or sv.cnt[2]:
-            if first:
-                d1 = "0.0"
-            else:
-                L.append(f"const double d{v} = __dadd_rn({out}, -{prev});")
-                d1 = f"d{v}"
+            # (the very first step sees prev = 0 / -inf instead of the zero
+            # padding of the reference; fixup() repairs these units after it)
+            L.append(f"const double d{v} = __dadd_rn({out}, -{prev});")
             if sv.cnt[1]:
-                unit(1, d1)
+                unit(1, f"d{v}")
             if sv.cnt[2]:
-                if first:
-                    unit(2, "0.0")
-                    L.append(f"D1[{oi}] = 0.0;")
-                else:
-                    L.append(f"const double dd{v} = __dadd_rn({d1}, -D1[{oi}]); D1[{oi}] = {d1};")
-                    unit(2, f"dd{v}")
+                L.append(f"const double dd{v} = __dadd_rn(d{v}, -D1[{oi}]); D1[{oi}] = d{v};")
+                unit(2, f"dd{v}")
         if sv.ppv:
             reg, hi16 = cregs[("P", 0)]
             inc = "0x10000" if hi16 else "1"
@@ -472,6 +467,31 @@ class Emitter:
                 ins += [f'"d"({self.th(e, cols[0])})', f'"d"({self.th(e, cols[1])})']
             asm.append("selp.f64 %0, %1, %0, p; }")
             L.append('asm("' + " ".join(asm) + f'" : "+d"({arr}[{oi}]) : ' + ", ".join(ins) + ");")
+
+    def fixup(self, part: Part) -> list:
+        """After the step t = 0: the increments of the reference are zero
+        padded (fruits/sieving/increment.py:63-71, fruits/cache.py:8-13), so
+        the first value of every increment unit is 0.0, not y[0] - 0."""
+        sv = self.sv
+        nodes = self.p.trie.nodes
+        cregs = self._cnt_layout()
+        L = []
+        for oi, v in enumerate(part.owned):
+            e = nodes[v].emit
+            for k in (1, 2):
+                if not sv.cnt[k]:
+                    continue
+                reg, hi16 = cregs[("U", k)]
+                cond = f"(0.0 > {self.th(e, _COL_U[k][0])})"
+                if sv.hi:
+                    cond += f" && (0.0 <= {self.th(e, _COL_U[k][1])})"
+                keep, one = ("0x0000ffffu", "0x10000u") if hi16 else ("0xffff0000u", "1u")
+                L.append(f"CN[{oi}][{reg}] = (CN[{oi}][{reg}] & {keep}) | (({cond}) ? {one} : 0u);")
+                if sv.avg[k]:
+                    L.append(f"SM{k}[{oi}] = 0.0;")
+            if sv.cnt[2]:
+                L.append(f"D1[{oi}] = 0.0;")
+        return L
 
     def _cnt_layout(self):
         """16-bit counters packed two per register: {(kind, k): (reg, high half)}."""
@@ -517,11 +537,13 @@ class Emitter:
         return L
 
     # -- whole kernel ------------------------------------------------------------
-    def source(self) -> str:
+    def source(self, sel=None) -> str:
+        """Source of the kernel that evaluates the parts ``sel`` (all if None)."""
         p, sv = self.p, self.sv
+        parts = p.parts if sel is None else [p.parts[i] for i in sel]
         wm = p.weight_mode
-        ns = max(1, max(len(pt.snodes) for pt in p.parts))
-        no = max(1, max(len(pt.owned) for pt in p.parts))
+        ns = max(1, max(len(pt.snodes) for pt in parts))
+        no = max(1, max(len(pt.owned) for pt in parts))
         need_first = sv.cnt[1] or sv.cnt[2]
         ncr = max(1, self.n_cnt_regs())
         nthr = max(1, len(p.trie.emits) * self.ntc)
@@ -562,9 +584,9 @@ class Emitter:
         A("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
         A(f"    // consecutive CTAs work on the same series with different parts: the")
         A(f"    // input tile is read from HBM once and hits L2 for the other parts")
-        A(f"    const int part = (int)(blockIdx.x % {len(p.parts) // self.ppc}u) * PPC + warp % PPC;")
+        A(f"    const int part = (int)(blockIdx.x % {len(parts) // self.ppc}u) * PPC + warp % PPC;")
         A("    const int sg = warp / PPC;")
-        A(f"    const long long nbase = (long long)(blockIdx.x / {len(p.parts) // self.ppc}u) * (GPC * 32);")
+        A(f"    const long long nbase = (long long)(blockIdx.x / {len(parts) // self.ppc}u) * (GPC * 32);")
         A("    const int T = (int)a.t;")
         A("    // tile buffers: [2][GPC*32 series][ROW] then the weighting rows")
         A("    double *xbuf = smem;")
@@ -698,20 +720,21 @@ class Emitter:
         A("        const int tend = min(TT, T - t0);")
         A("        int tt = 0;")
         A("        switch (part) {")
-        for pi, part in enumerate(p.parts):
+        for pi, part in enumerate(parts):
             if not part.owned:
                 continue
             A(f"        case {pi}: {{")
-            if need_first:
-                A("            if (t0 == 0) {")
-                for ln in self._loads(first=True) + self.step(part, True) + self._after(first=True):
-                    A("                " + ln)
-                A("                tt = 1;")
-                A("            }")
             A("#pragma unroll 1")
             A("            for (; tt < tend; tt++) {")
-            for ln in self._loads(first=False) + self.step(part, False) + self._after(first=False):
+            A("                const bool is0 = (t0 + tt) == 0;")
+            for ln in self._loads() + self.step(part) + self._after():
                 A("                " + ln)
+            if need_first:
+                A("                if (is0) {")
+                A('                    asm volatile("// first step: zero padding of the increments");')
+                for ln in self.fixup(part):
+                    A("                    " + ln)
+                A("                }")
             A("            }")
             A("        } break;")
         A("        default: break;")
@@ -722,7 +745,7 @@ class Emitter:
         A("    if (ns_ < a.n) {")
         A("        double *o = a.out + (size_t)ns_ * a.out_ld + a.col0;")
         A("        switch (part) {")
-        for pi, part in enumerate(p.parts):
+        for pi, part in enumerate(parts):
             if not part.owned:
                 continue
             A(f"        case {pi}: {{")
@@ -736,7 +759,7 @@ class Emitter:
         del du
         return "\n".join(src) + "\n"
 
-    def _loads(self, first: bool) -> list:
+    def _loads(self) -> list:
         """Values of the current step: x{u} per used dimension, ep/em/g0."""
         L = []
         for r in range(self.nrow):
@@ -744,7 +767,7 @@ class Emitter:
         for u, (raw, inc) in enumerate(self.dims):
             r = self.row_of[raw]
             if inc:
-                L.append(f"const double x{u} = " + ("0.0;" if first else f"__dadd_rn(r{r}, -xp{r});"))
+                L.append(f"const double x{u} = is0 ? 0.0 : __dadd_rn(r{r}, -xp{r});")
             else:
                 L.append(f"const double x{u} = r{r};")
         p = self.p
@@ -757,7 +780,7 @@ class Emitter:
                 L.append("const double g0 = es[tt];")
         return L
 
-    def _after(self, first: bool) -> list:
+    def _after(self) -> list:
         inc_rows = sorted({self.row_of[r] for r, inc in self.dims if inc})
         return [f"xp{r} = r{r};" for r in inc_rows]
 
@@ -779,7 +802,7 @@ class FbJitGeometry(ctypes.Structure):
                 ("groups_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32)]
 
 
-DEFAULT_OPTS = {"budget": 150, "ppc": 1, "gpc": 8, "minb": 1, "unroll": 1, "tt": 16}
+DEFAULT_OPTS = {"budget": 150, "ppc": 1, "gpc": 8, "minb": 1, "unroll": 1, "tt": 16, "ppm": 4}
 
 
 def options() -> dict:
@@ -804,22 +827,40 @@ def enabled() -> bool:
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
              shared_extra: bool, opts: dict):
-    """-> (source, Emitter).  Raises NotImplementedError for plans the
-    generated kernel cannot hold (the caller then uses the generic kernel)."""
+    """-> ([(source, n_parts)], Emitter): one CUDA module per group of parts.
+    Raises NotImplementedError for plans the generated kernels cannot hold
+    (the caller then uses the generic kernel)."""
     prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                    parts_multiple=opts["ppc"])
-    em = Emitter(prog, dims, opts["ppc"], opts["gpc"], shared_extra, opts["tt"])
+    # largest tile (then most series per CTA) whose double buffer fits
+    em = None
+    for gpc, tt in ((opts["gpc"], opts["tt"]), (opts["gpc"], 8), (max(1, opts["gpc"] // 2), 8),
+                    (max(1, opts["gpc"] // 4), 8), (1, 4), (1, 2)):
+        cand = Emitter(prog, dims, opts["ppc"], gpc, shared_extra, tt)
+        if cand.smem_bytes() <= 200 * 1024:
+            em = cand
+            break
+    if em is None:
+        raise NotImplementedError("input tile exceeds shared memory")
     if len(trie.emits) * em.ntc * 8 > 60 * 1024:
         raise NotImplementedError("threshold table exceeds the constant bank")
-    if em.smem_bytes() > 200 * 1024:
-        raise NotImplementedError("input tile exceeds shared memory")
     if len(prog.parts) // opts["ppc"] > 65535:
         raise NotImplementedError("too many parts")
-    src = em.source()
-    src = src.replace("__launch_bounds__(NT, 1)", f"__launch_bounds__(NT, {opts['minb']})")
-    src = src.replace("#pragma unroll 1\n            for (; tt < tend; tt++)",
-                      f"#pragma unroll {opts['unroll']}\n            for (; tt < tend; tt++)")
-    return src, em
+    # one module per `ppm` parts: compile time grows faster than linearly with
+    # the size of a kernel and the modules compile in parallel
+    real = [i for i, pt in enumerate(prog.parts) if pt.owned]
+    per = max(opts["ppc"], (opts["ppm"] // opts["ppc"]) * opts["ppc"])
+    groups = [real[i:i + per] for i in range(0, len(real), per)]
+    srcs = []
+    for grp in groups:
+        while len(grp) % opts["ppc"]:
+            grp = grp + [next(i for i, pt in enumerate(prog.parts) if not pt.owned)]
+        src = em.source(grp)
+        src = src.replace("__launch_bounds__(NT, 1)", f"__launch_bounds__(NT, {opts['minb']})")
+        src = src.replace("#pragma unroll 1\n            for (; tt < tend; tt++)",
+                          f"#pragma unroll {opts['unroll']}\n            for (; tt < tend; tt++)")
+        srcs.append((src, len(grp)))
+    return srcs, em
 
 
 def compile_source(src: str, name: str = "fb_jit_slice.cu") -> bytes:
@@ -852,30 +893,45 @@ def compile_source(src: str, name: str = "fb_jit_slice.cu") -> bytes:
 
 
 class JitSlice:
-    """One loaded plan-specialised kernel."""
+    """The loaded plan-specialised kernels of one slice (one module per group
+    of trie parts, launched back to back on the same stream)."""
 
     _loaded: dict = {}     # source digest -> JitSlice
 
-    def __init__(self, src: str, em: Emitter) -> None:
+    def __init__(self, srcs: list, em: Emitter) -> None:
         self.em = em
-        self.src = src
-        cubin = compile_source(src)
-        self._cubin = cubin
-        handle = ctypes.c_void_p()
-        be.check(be.lib().fb_jit_load(cubin, len(cubin), ctypes.byref(handle)))
-        self.handle = handle
-        self.geo = FbJitGeometry(len(em.p.parts), em.ppc, em.gpc, em.smem_bytes())
+        self.srcs = srcs
+        workers = min(len(srcs), os.cpu_count() or 1, 16)
+        if workers > 1:
+            # fb_jit_compile releases the GIL (ctypes) and NVRTC is thread safe
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                cubins = list(ex.map(lambda sn: compile_source(sn[0]), srcs))
+        else:
+            cubins = [compile_source(src) for src, _ in srcs]
+        self.modules = []
+        for cubin, (_, n_parts) in zip(cubins, srcs):
+            handle = ctypes.c_void_p()
+            be.check(be.lib().fb_jit_load(cubin, len(cubin), ctypes.byref(handle)))
+            geo = FbJitGeometry(n_parts, em.ppc, em.gpc, em.smem_bytes())
+            self.modules.append((handle, geo))
         self.cols = list(em.cols)
 
     @classmethod
     def get(cls, trie, semiring, weight_mode, sieves, dims, shared_extra) -> "JitSlice":
-        src, em = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options())
-        key = hashlib.sha256(src.encode()).hexdigest()
+        srcs, em = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options())
+        h = hashlib.sha256()
+        for src, _ in srcs:
+            h.update(src.encode())
+        key = h.hexdigest()
         obj = cls._loaded.get(key)
         if obj is None:
-            obj = cls(src, em)
+            obj = cls(srcs, em)
             cls._loaded[key] = obj
         return obj
+
+    @property
+    def n_launches(self) -> int:
+        return len(self.modules)
 
     def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize) -> None:
         """X[n, d, t] cuda float64; extra: weighting rows or None;
@@ -884,7 +940,9 @@ class JitSlice:
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape
         n_thr = 0 if thr_compact is None else thr_compact.numel()
-        be.check(be.lib().fb_jit_slice_features(
-            self.handle, ctypes.byref(self.geo), ctypes.byref(batch), be.ptr(extra), int(extra_ld),
-            be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0), int(sanitize),
-            be.stream_ptr()))
+        L = be.lib()
+        for handle, geo in self.modules:
+            be.check(L.fb_jit_slice_features(
+                handle, ctypes.byref(geo), ctypes.byref(batch), be.ptr(extra), int(extra_ld),
+                be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0),
+                int(sanitize), be.stream_ptr()))

@@ -675,6 +675,7 @@ class FruitSlice:
                 extra = g
                 extra_ld = g_ld
         kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize)
+        self._last_launch = ("fb_jit_slice", kern.n_launches, kern)
 
     def _transform_generic(self, X, out, col0, sanitize, dims, feats, bounded_hi,
                            bounded_mm) -> None:
@@ -712,6 +713,7 @@ class FruitSlice:
         be.check(L.fb_slice_features_ex(plan.byref(), ctypes.byref(batch), ctypes.byref(sp),
                                         out.data_ptr(), out.stride(0), col0, policy,
                                         int(sanitize), be.stream_ptr()))
+        self._last_launch = ("fb::lns_kernel", 1, None)
 
     def _transform_composed(self, X, callbacks, cache, out, col0, sanitize) -> None:
         prepared = self._prepare_device(X, cache, fit=False, callbacks=callbacks)

@@ -9,6 +9,7 @@ and the first ``transform`` on the box skips the compile.
 import os
 import sys
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -35,11 +36,13 @@ def warm(name: str) -> None:
         jdims = [(dims[u][0], dims[u][1]) for u in used]
         shared = iss.weighting is None or isinstance(iss.weighting, (Indices, Plateaus))
         t0 = time.time()
-        src, em = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
-                                _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options())
-        cubin = _jit.compile_source(src)
+        srcs, em = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
+                                 _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options())
+        with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
+            cubins = list(ex.map(lambda sn: _jit.compile_source(sn[0]), srcs))
         print(f"{name} slice {si}: {len(trie.nodes)} nodes, {len(em.p.parts)} parts, "
-              f"{len(cubin) // 1024} KB cubin, {time.time() - t0:.1f} s", flush=True)
+              f"{len(srcs)} modules, {sum(map(len, cubins)) // 1024} KB cubin, "
+              f"{time.time() - t0:.1f} s", flush=True)
 
 
 if __name__ == "__main__":
