@@ -37,7 +37,7 @@ import numpy as np
 
 from . import _backend as be
 
-JIT_VERSION = 7            # bump to invalidate cached cubins
+JIT_VERSION = 10            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -189,6 +189,10 @@ class Program:
             else:
                 lo = mid
         parts = self._split(emitted, hi, reg_budget)
+        # work of the duplicated ancestors relative to the work of the trie itself
+        ideal = sum(self._scost(v, nodes[v].emit >= 0) for v in range(len(nodes)))
+        self.overhead = sum(pt.cost for pt in parts) / max(ideal, 1)
+        self.max_regs = max(pt.regs for pt in parts)
         while len(parts) % parts_multiple:
             parts.append(Part())
         self.parts = parts
@@ -719,25 +723,44 @@ class Emitter:
                 A("        const double *es = ebuf + (size_t)buf * EROW;")
         A("        const int tend = min(TT, T - t0);")
         A("        int tt = 0;")
+        if need_first:
+            A("        // the very first step runs on its own: the zero padding of the")
+            A("        // increments is repaired right after it (fixup)")
+            A("        bool fix = (t0 == 0);")
+            A("        int stop = fix ? 1 : tend;")
+        else:
+            A("        const int stop = tend;")
+        A("        for (;;) {")
         A("        switch (part) {")
         for pi, part in enumerate(parts):
             if not part.owned:
                 continue
             A(f"        case {pi}: {{")
             A("#pragma unroll 1")
-            A("            for (; tt < tend; tt++) {")
+            A("            for (; tt < stop; tt++) {")
             A("                const bool is0 = (t0 + tt) == 0;")
             for ln in self._loads() + self.step(part) + self._after():
                 A("                " + ln)
-            if need_first:
-                A("                if (is0) {")
-                A('                    asm volatile("// first step: zero padding of the increments");')
-                for ln in self.fixup(part):
-                    A("                    " + ln)
-                A("                }")
             A("            }")
             A("        } break;")
         A("        default: break;")
+        A("        }")
+        if need_first:
+            A("        if (!fix) break;")
+            A("        switch (part) {")
+            for pi, part in enumerate(parts):
+                if not part.owned:
+                    continue
+                A(f"        case {pi}: {{")
+                for ln in self.fixup(part):
+                    A("            " + ln)
+                A("        } break;")
+            A("        default: break;")
+            A("        }")
+            A("        stop = tend;")
+            A("        fix = false;")
+        else:
+            A("        break;")
         A("        }")
         A("    }")
         # ---- epilogue ----
@@ -802,7 +825,7 @@ class FbJitGeometry(ctypes.Structure):
                 ("groups_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32)]
 
 
-DEFAULT_OPTS = {"budget": 150, "ppc": 1, "gpc": 8, "minb": 1, "unroll": 1, "tt": 16, "ppm": 4}
+DEFAULT_OPTS = {"budget": 70, "ppc": 2, "gpc": 4, "minb": 2, "unroll": 2, "tt": 16, "ppm": 4}
 
 
 def options() -> dict:
@@ -821,8 +844,20 @@ def options_key() -> tuple:
     return tuple(sorted(options().items()))
 
 
-def enabled() -> bool:
-    return os.environ.get("FRUITS_B200_JIT", "1") != "0"
+def enabled(n_series: int = None) -> bool:
+    """``FRUITS_B200_JIT``: "0" never, "force" always, default: whenever the
+    batch is large enough to fill the GPU with one thread per series and trie
+    part (small batches are better served by the generic kernel, which runs
+    one lane per trie node)."""
+    mode = os.environ.get("FRUITS_B200_JIT", "1")
+    if mode == "0":
+        return False
+    if mode == "force" or n_series is None:
+        return True
+    return n_series >= MIN_SERIES
+
+
+MIN_SERIES = 4096          # below this the generic kernel is used (unless forced)
 
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
@@ -832,6 +867,16 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
     (the caller then uses the generic kernel)."""
     prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                    parts_multiple=opts["ppc"])
+    if ((prog.overhead > 1.25 or prog.max_regs > opts["budget"] + 20 or sieves.regs() > 6)
+            and "FRUITS_B200_JIT_OPTS" not in os.environ):
+        # deep or sieve-heavy tries: fewer, larger parts (one CTA per SM, 255 registers)
+        opts = dict(opts, budget=150, ppc=1, gpc=8, minb=1, unroll=1)
+        prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
+                       parts_multiple=opts["ppc"])
+    if prog.overhead > 1.6 or prog.max_regs > 190:
+        # long chains (e.g. arctic words of 24-48 letters): every part would
+        # recompute most of the chain -- the generic kernel is the better shape
+        raise NotImplementedError("trie too deep for the plan-specialised kernel")
     # largest tile (then most series per CTA) whose double buffer fits
     em = None
     for gpc, tt in ((opts["gpc"], opts["tt"]), (opts["gpc"], 8), (max(1, opts["gpc"] // 2), 8),
@@ -849,7 +894,8 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
     # one module per `ppm` parts: compile time grows faster than linearly with
     # the size of a kernel and the modules compile in parallel
     real = [i for i, pt in enumerate(prog.parts) if pt.owned]
-    per = max(opts["ppc"], (opts["ppm"] // opts["ppc"]) * opts["ppc"])
+    ppm = max(opts["ppm"], -(-len(real) // 32))      # at most ~32 modules (launches)
+    per = max(opts["ppc"], -(-ppm // opts["ppc"]) * opts["ppc"])
     groups = [real[i:i + per] for i in range(0, len(real), per)]
     srcs = []
     for grp in groups:
@@ -857,8 +903,8 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
             grp = grp + [next(i for i, pt in enumerate(prog.parts) if not pt.owned)]
         src = em.source(grp)
         src = src.replace("__launch_bounds__(NT, 1)", f"__launch_bounds__(NT, {opts['minb']})")
-        src = src.replace("#pragma unroll 1\n            for (; tt < tend; tt++)",
-                          f"#pragma unroll {opts['unroll']}\n            for (; tt < tend; tt++)")
+        src = src.replace("#pragma unroll 1\n            for (; tt < stop; tt++)",
+                          f"#pragma unroll {opts['unroll']}\n            for (; tt < stop; tt++)")
         srcs.append((src, len(grp)))
     return srcs, em
 
@@ -936,13 +982,51 @@ class JitSlice:
     def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize) -> None:
         """X[n, d, t] cuda float64; extra: weighting rows or None;
         thr_compact: [n_emit * len(cols)] cuda float64."""
+        import torch
         batch = be.FbBatch()
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape
         n_thr = 0 if thr_compact is None else thr_compact.numel()
         L = be.lib()
-        for handle, geo in self.modules:
+        main = torch.cuda.current_stream()
+        # modules are independent (disjoint feature columns): when one launch
+        # cannot fill the GPU for long, spread them over side streams
+        ctas = -(-X.shape[0] // (32 * self.em.gpc)) * max(g.n_parts // g.parts_per_cta
+                                                          for _, g in self.modules)
+        side = []
+        if len(self.modules) > 1 and ctas < 16 * _sm_count():
+            side = _side_streams(X.device, min(len(self.modules), 8))
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for st in side:
+                st.wait_event(fork)
+        for i, (handle, geo) in enumerate(self.modules):
+            st = side[i % len(side)] if side else main
             be.check(L.fb_jit_slice_features(
                 handle, ctypes.byref(geo), ctypes.byref(batch), be.ptr(extra), int(extra_ld),
                 be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0),
-                int(sanitize), be.stream_ptr()))
+                int(sanitize), st.cuda_stream))
+        for st in side:
+            join = torch.cuda.Event()
+            join.record(st)
+            main.wait_event(join)
+
+
+_streams: dict = {}
+_sms: list = []
+
+
+def _side_streams(device, k: int) -> list:
+    import torch
+    pool = _streams.setdefault(str(device), [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:k]
+
+
+def _sm_count() -> int:
+    if not _sms:
+        sm = ctypes.c_int()
+        be.check(be.lib().fb_device_info(ctypes.byref(sm), None, None, None))
+        _sms.append(sm.value)
+    return _sms[0]

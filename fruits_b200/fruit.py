@@ -619,7 +619,7 @@ class FruitSlice:
         if out.stride(1) != 1:
             raise ValueError("feature matrix must be row-major")
         feats, bounded_hi, bounded_mm = self._fused_sieves()
-        if _jit.enabled():
+        if _jit.enabled(n):
             try:
                 self._transform_jit(X, cache, out, col0, sanitize, dims, feats, bounded_hi,
                                     bounded_mm)
@@ -635,25 +635,30 @@ class FruitSlice:
         iss = self._iss[0]
         trie = iss.trie()
         used = trie.used_dims()
-        lookup_src = X
-        if any(dims[u][2] for u in used):
-            # standardised dimensions: materialise the prepared input once
-            # (2 x 8 bytes per value against ~10^3 flop per value of ISS work)
-            X = self._prepare_device(X, cache, fit=False)
-            dims = [(u, 0, 0) for u in range(X.shape[1])]
-        jdims = [(dims[u][0], dims[u][1]) for u in used]
+        # standardised dimensions: the prepared input is materialised once
+        # (2 x 8 bytes per value against ~10^3 flop per value of ISS work)
+        materialise = any(dims[u][2] for u in used)
+        jdims = [(u, 0) for u in used] if materialise else \
+            [(dims[u][0], dims[u][1]) for u in used]
         sieves = _jit.SieveSet.make(feats, bounded_hi, bounded_mm)
-        g, g_ld = iss._lookup(lookup_src)
+        g, g_ld = iss._lookup(X)
         wm = iss._weight_mode()
         key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0, _jit.options_key())
         memo = getattr(iss, "_jit_memo", None)
         if memo is None or memo[0] is not trie:
             memo = (trie, {})
             iss._jit_memo = memo
-        kern = memo[1].get(key)
-        if kern is None:
-            kern = _jit.JitSlice.get(trie, iss.semiring._code, wm, sieves, jdims, g_ld == 0)
-            memo[1][key] = kern
+        if key not in memo[1]:
+            try:
+                memo[1][key] = _jit.JitSlice.get(trie, iss.semiring._code, wm, sieves, jdims,
+                                                 g_ld == 0)
+            except NotImplementedError as exc:
+                memo[1][key] = exc          # remembered: planning is host work
+        kern = memo[1][key]
+        if isinstance(kern, NotImplementedError):
+            raise kern
+        if materialise:
+            X = self._prepare_device(X, cache, fit=False)
         thr = self._threshold_table(len(trie.emits))
         thr_c = None
         if kern.cols:

@@ -36,8 +36,13 @@ def warm(name: str) -> None:
         jdims = [(dims[u][0], dims[u][1]) for u in used]
         shared = iss.weighting is None or isinstance(iss.weighting, (Indices, Plateaus))
         t0 = time.time()
-        srcs, em = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
-                                 _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options())
+        try:
+            srcs, em = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
+                                     _jit.SieveSet.make(feats, bhi, bmm), jdims, shared,
+                                     _jit.options())
+        except NotImplementedError as exc:
+            print(f"{name} slice {si}: generic kernel ({exc})", flush=True)
+            continue
         with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
             cubins = list(ex.map(lambda sn: _jit.compile_source(sn[0]), srcs))
         print(f"{name} slice {si}: {len(trie.nodes)} nodes, {len(em.p.parts)} parts, "

@@ -426,3 +426,106 @@ def test_twi_full_length_subset():
     # slice 1 (arctic, columns 1533:) is bit-exact, slice 0 is L1-weighted
     assert_exact(res[pick][:, 1533:], ref[:, 1533:], "arctic slice")
     _assert_features_close(res[pick][:, :1533], ref[:, :1533], "weighted slice")
+
+
+# ---------------------------------------------------------------------------
+# (e) the plan-specialised kernel (fruits_b200/_jit.py).  Small batches take
+# the generic kernel by default, so these tests force the generated one.
+
+@pytest.fixture
+def force_jit(monkeypatch):
+    monkeypatch.setenv("FRUITS_B200_JIT", "force")
+
+
+def _routes(fruit):
+    return [getattr(slc, "_last_launch", (None,))[0] for slc in fruit._slices]
+
+
+@pytest.mark.parametrize("name", sorted(PIPE_CASES))
+def test_jit_pipeline_golden(name, golden_dir, force_jit):
+    g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
+    spec_name, n = PIPE_CASES[name]
+    X = specs.make_input(spec_name, n)
+    fruit = specs.build_fruit(fruits, specs.SPECS[spec_name])
+    np.random.seed(0)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    routes = _routes(fruit)
+    # every slice but the 48-letter arctic chains of C3 compiles to a generated kernel
+    want = ["fb_jit_slice", "fb::lns_kernel"] if name == "C3_general" else \
+        ["fb_jit_slice"] * len(routes)
+    assert routes == want, routes
+    if name in ("C1_readme", "C5_sweep"):
+        assert_exact(res, g["features"], name + " features")
+    else:
+        _assert_features_close(res, g["features"], name)
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1), (2, 3, 2), (33, 3, 15), (31, 3, 16), (70, 3, 17),
+                                   (5, 3, 33), (129, 3, 64), (300, 3, 301)])
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
+def test_jit_shapes_vs_generic_and_oracle(shape, semiring, force_jit, monkeypatch):
+    """Ragged batches (n not a multiple of the CTA, odd lengths, lengths below
+    and across the tile) through the generated kernel: bit-identical to the
+    generic kernel and to the oracle."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [3, 3]}, "mode": "extended",
+                                 "semiring": semiring}],
+                        "sieves": [["NPI", {"q": [0.4, 1.0]}], ["NPI", {"inc": 2}],
+                                   ["MPI", {"inc": 0}], ["PPV", {}], ["MAX", {}], ["MIN", {}],
+                                   ["END", {}]]}]}
+    X = np.random.default_rng(shape[0] + shape[2]).standard_normal(shape)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(1)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    monkeypatch.setenv("FRUITS_B200_JIT", "0")
+    gen = fruit.transform(X)
+    assert _routes(fruit) == ["fb::lns_kernel"]
+    assert_exact(res, gen, "generated vs generic kernel")
+    of = orc.OracleFruit(spec)
+    np.random.seed(1)
+    of.fit(X)
+    ref = of.transform(X)
+    mpi = np.zeros(ref.shape[1], dtype=bool)
+    mpi[2::7] = True                       # MPI means: summation order of numba fastmath
+    assert_exact(res[:, ~mpi], ref[:, ~mpi], "generated kernel vs oracle")
+    assert_close(res[:, mpi], ref[:, mpi], 1e-12, "MPI")
+
+
+def test_jit_bounded_quantile_intervals(force_jit):
+    """(lo, hi] intervals with finite upper bounds and bounded MAX/MIN."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [],
+                        "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended"}],
+                        "sieves": [["NPI", {"q": [0.2, 0.7]}], ["MAX", {"q": [0.1, 0.9]}],
+                                   ["MIN", {"q": [0.1, 0.9]}], ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(3).standard_normal((40, 2, 90)).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(2)
+    fruit.fit(X)
+    np.random.seed(2)
+    of.fit(X)
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    assert_exact(res, of.transform(X), "bounded intervals")
+
+
+def test_jit_large_batch_default_route():
+    """Large batches take the generated kernel without being forced."""
+    X = np.random.default_rng(8).standard_normal((6000, 3, 128))
+    fruit = specs.build_fruit(fruits, specs.SPECS["C5_sweep"])
+    np.random.seed(0)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    os.environ["FRUITS_B200_JIT"] = "0"
+    try:
+        gen = fruit.transform(X)
+    finally:
+        del os.environ["FRUITS_B200_JIT"]
+    assert_exact(res, gen, "generated vs generic kernel at 6000 series")
