@@ -247,6 +247,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    launches_per_call = fruit.get_slice(0)._last_launch[1]
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -272,10 +273,10 @@ def run_ours(args):
         kname, klaunches, kern = fruit.get_slice(0)._last_launch
         if kern is not None:
             em = kern.em
-            kdesc = (f"{kname}: plan-specialised kernel, {klaunches} module launches per slice "
-                     f"({len([p for p in em.p.parts if p.owned])} trie parts, {32 * em.gpc} series "
-                     f"per CTA, tile {em.tt} steps); achieved = slice flops / sum of the "
-                     f"{klaunches} launch durations")
+            kdesc = (f"{kname}: plan-specialised kernel, "
+                     f"{len([p for p in em.p.parts if p.owned])} trie parts compiled separately "
+                     f"and linked into one kernel, {32 * em.ppc * em.gpc} threads per CTA "
+                     f"({em.gpc} groups of 32 series x {em.ppc} parts), tile {em.tt} steps")
         else:
             kdesc = f"{kname}<Reals, unweighted, PolP> (generic trie interpreter)"
         achieved = FLOP_PER_SERIES * n_launch / k_s / 1e12
@@ -339,7 +340,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "clocks": clocks, "e2e": e2e,
-            "gpu_launches": args.steps * n_chunks * fruit.get_slice(0)._last_launch[1],
+            "gpu_launches": args.steps * n_chunks * launches_per_call,
             "roofline": roofline, "cpu_baseline": cpu, "fit_seconds": fit_s,
             "collective": ("nccl all_gather_into_tensor of the [S, F] feature blocks in 8 row "
                            "chunks on a side stream, overlapped with the kernels; every rank "

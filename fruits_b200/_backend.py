@@ -107,8 +107,11 @@ def lib() -> ctypes.CDLL:
         "fb_order_stats_workspace": ([i64], i64),
         "fb_order_stats": ([vp, i64, i64, i64, i64, vp, vp, vp, vp], i32),
         "fb_fp64_peak": ([vp, i32, i32, vp], i32),
-        "fb_jit_compile": ([ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(vp),
+        "fb_jit_compile": ([ctypes.c_char_p, ctypes.c_char_p, i32, i32, ctypes.POINTER(vp),
                             ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t], i32),
+        "fb_jit_link": ([ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32,
+                         ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p,
+                         ctypes.c_size_t], i32),
         "fb_jit_free": ([vp], None),
         "fb_jit_load": ([ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp)], i32),
         "fb_jit_unload": ([vp], i32),
@@ -133,7 +136,7 @@ EXPORTED = [
     "fb_lsum", "fb_nrm_scale", "fb_coquantile", "fb_pretransform",
     "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_order_stats_workspace",
     "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
-    "fb_jit_unload", "fb_jit_slice_features", "fb_exp_rows",
+    "fb_jit_unload", "fb_jit_slice_features", "fb_jit_link", "fb_exp_rows",
 ]
 
 

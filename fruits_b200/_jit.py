@@ -37,7 +37,7 @@ import numpy as np
 
 from . import _backend as be
 
-JIT_VERSION = 10            # bump to invalidate cached cubins
+JIT_VERSION = 12            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -541,21 +541,42 @@ class Emitter:
         return L
 
     # -- whole kernel ------------------------------------------------------------
-    def source(self, sel=None) -> str:
-        """Source of the kernel that evaluates the parts ``sel`` (all if None)."""
-        p, sv = self.p, self.sv
-        parts = p.parts if sel is None else [p.parts[i] for i in sel]
-        wm = p.weight_mode
-        ns = max(1, max(len(pt.snodes) for pt in parts))
-        no = max(1, max(len(pt.owned) for pt in parts))
-        need_first = sv.cnt[1] or sv.cnt[2]
-        ncr = max(1, self.n_cnt_regs())
+    def part_name(self, pi: int) -> str:
+        # padding parts (the part count is rounded up to whole groups) share one
+        # function that only takes part in the staging and the barriers
+        return f"fb_part_{pi}" if self.p.parts[pi].owned else "fb_part_idle"
+
+    def entry_source(self, minb: int) -> str:
+        """Translation unit of the kernel itself: the threshold table and the
+        dispatch of every warp to the device function of its trie part (the
+        parts are compiled separately, in parallel, and linked with nvJitLink)."""
+        p = self.p
+        npg = len(p.parts) // self.ppc
         nthr = max(1, len(p.trie.emits) * self.ntc)
-        du = len(p.used)
+        src = [self._common(), f"__constant__ double TH[{nthr}];"]
+        for name in sorted({self.part_name(pi) for pi in range(len(p.parts))}):
+            src.append(f'extern "C" __device__ void {name}(const Args a);')
+        src.append(f'extern "C" __global__ void __launch_bounds__(NT, {minb}) fb_jit_slice(const Args a)')
+        src.append("{")
+        src.append("    // consecutive CTAs work on the same series with different parts: the")
+        src.append("    // input tile is read from HBM once and hits L2 for the other parts")
+        src.append(f"    const int part = (int)(blockIdx.x % {npg}u) * PPC + (threadIdx.x >> 5) % PPC;")
+        src.append("    switch (part) {")
+        for pi, part in enumerate(p.parts):
+            if part.owned:
+                src.append(f"    case {pi}: {self.part_name(pi)}(a); break;")
+        if any(not part.owned for part in p.parts):
+            src.append("    default: fb_part_idle(a); break;")
+        else:
+            src.append("    default: break;")
+        src.append("    }")
+        src.append("}")
+        return "\n".join(src) + "\n"
+
+    def _common(self) -> str:
         TT = self.tt
         row = self.nrow * TT + 2           # doubles per series and tile
         erow = self.nextra * TT + 2
-        per_series_extra = self.nextra and not self.shared_extra
         src = []
         A = src.append
         A("// generated by fruits_b200/_jit.py -- do not edit")
@@ -569,9 +590,31 @@ class Emitter:
         A(f"#define EROW {erow}")
         A("#define D_INF __longlong_as_double(0x7ff0000000000000LL)")
         A("#define D_NINF __longlong_as_double(0xfff0000000000000LL)")
-        A(f"__constant__ double TH[{nthr}];")
-        A("__constant__ int RAW[NROW] = {" + ", ".join(str(r) for r in self.raw_rows) + "};")
         A("struct Args { const double *X; const double *E; double *out; long long n, d, t, e_ld, out_ld, col0; int sanitize; };")
+        return "\n".join(src)
+
+    def source(self, pi: int) -> str:
+        """Translation unit of one trie part: ``fb_part_<pi>`` runs the whole
+        time loop of the part for the 32 series of the calling warp."""
+        p, sv = self.p, self.sv
+        parts = [p.parts[pi]]
+        wm = p.weight_mode
+        ns = max(1, max(len(pt.snodes) for pt in parts))
+        no = max(1, max(len(pt.owned) for pt in parts))
+        need_first = sv.cnt[1] or sv.cnt[2]
+        ncr = max(1, self.n_cnt_regs())
+        nthr = max(1, len(p.trie.emits) * self.ntc)
+        du = len(p.used)
+        TT = self.tt
+        row = self.nrow * TT + 2           # doubles per series and tile
+        erow = self.nextra * TT + 2
+        per_series_extra = self.nextra and not self.shared_extra
+        src = [self._common()]
+        A = src.append
+        A(f"extern __constant__ double TH[{nthr}];")
+        A("__device__ __forceinline__ int raw_row(int r) { return "
+          + "".join(f"r == {i} ? {raw} : " for i, raw in enumerate(self.raw_rows[:-1]))
+          + f"{self.raw_rows[-1]}; }}")
         A("__device__ __forceinline__ double fin(double v, int sanitize) {")
         A("    if (!sanitize) return v;")
         A("    if (v != v) return 0.0;")
@@ -582,15 +625,13 @@ class Emitter:
         A('    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
         A("__device__ __forceinline__ void cp8(double *dst, const double *src) {")
         A('    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
-        A('extern "C" __global__ void __launch_bounds__(NT, 1) fb_jit_slice(const Args a)')
+        A(f'extern "C" __device__ __noinline__ void {self.part_name(pi)}(const Args a)')
         A("{")
         A("    extern __shared__ __align__(16) double smem[];")
         A("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
-        A(f"    // consecutive CTAs work on the same series with different parts: the")
-        A(f"    // input tile is read from HBM once and hits L2 for the other parts")
-        A(f"    const int part = (int)(blockIdx.x % {len(parts) // self.ppc}u) * PPC + warp % PPC;")
+        A("    const int part = 0;")
         A("    const int sg = warp / PPC;")
-        A(f"    const long long nbase = (long long)(blockIdx.x / {len(parts) // self.ppc}u) * (GPC * 32);")
+        A(f"    const long long nbase = (long long)(blockIdx.x / {len(p.parts) // self.ppc}u) * (GPC * 32);")
         A("    const int T = (int)a.t;")
         A("    // tile buffers: [2][GPC*32 series][ROW] then the weighting rows")
         A("    double *xbuf = smem;")
@@ -634,51 +675,56 @@ class Emitter:
         for r in inc_rows:
             A(f"    double xp{r} = 0.0;")
         # ---- staging ----
+        # Every group of 32 series is staged by its own PPC warps and synchronised
+        # with its own named barrier, so the groups of a CTA drift freely.
         A("    const bool even = ((a.t & 1) == 0) && ((((unsigned long long)a.X) & 15) == 0);")
-        # slow path: any CTA shape / alignment (tail CTA, odd lengths)
+        A("    const int gt = (warp % PPC) * 32 + lane;      // thread within the group")
+        A("    const long long gbase = nbase + sg * 32;       // first series of the group")
+        A("    double *gx = xbuf + (size_t)sg * 32 * ROW;     // + buf * GPC * 32 * ROW")
+        # slow path: any alignment, tail of the batch
         A("    auto stage_slow = [&](int buf, int t0) {")
-        A("        const int nchunk = GPC * 32 * NROW * (TT / 2);")
-        A("        for (int c = threadIdx.x; c < nchunk; c += NT) {")
+        A("        const int nchunk = 32 * NROW * (TT / 2);")
+        A("        for (int c = gt; c < nchunk; c += 32 * PPC) {")
         A("            const int k = c % (TT / 2), sr = c / (TT / 2);")
         A("            const int r = sr % NROW, s = sr / NROW;")
-        A("            long long n = nbase + s; if (n >= a.n) n = a.n - 1;")
+        A("            long long n = gbase + s; if (n >= a.n) n = a.n - 1;")
         A("            const int t = t0 + 2 * k;")
-        A("            const double *g = a.X + ((size_t)n * a.d + RAW[r]) * (size_t)T + t;")
-        A("            double *d = xbuf + ((size_t)(buf * GPC * 32 + s)) * ROW + r * TT + 2 * k;")
+        A("            const double *g = a.X + ((size_t)n * a.d + raw_row(r)) * (size_t)T + t;")
+        A("            double *d = gx + ((size_t)(buf * GPC * 32 + s)) * ROW + r * TT + 2 * k;")
         A("            if (even) { if (t < T) cp16(d, g); }")
         A("            else { if (t < T) cp8(d, g); if (t + 1 < T) cp8(d + 1, g + 1); }")
         A("        }")
         if per_series_extra:
-            A("        const int echunk = GPC * 32 * NEXTRA * (TT / 2);")
+            A("        const int echunk = 32 * NEXTRA * (TT / 2);")
             A("        const bool eeven = ((a.t & 1) == 0) && ((((unsigned long long)a.E) & 15) == 0) && ((a.e_ld & 1) == 0);")
-            A("        for (int c = threadIdx.x; c < echunk; c += NT) {")
+            A("        for (int c = gt; c < echunk; c += 32 * PPC) {")
             A("            const int k = c % (TT / 2), sr = c / (TT / 2);")
             A("            const int r = sr % NEXTRA, s = sr / NEXTRA;")
             A("            const int t = t0 + 2 * k;")
-            A("            long long n = nbase + s; if (n >= a.n) n = a.n - 1;")
+            A("            long long n = gbase + s; if (n >= a.n) n = a.n - 1;")
             A("            const double *g = a.E + (size_t)n * a.e_ld + (size_t)r * T + t;")
-            A("            double *d = ebuf + ((size_t)(buf * GPC * 32 + s)) * EROW + r * TT + 2 * k;")
+            A("            double *d = ebuf + ((size_t)(buf * GPC * 32 + sg * 32 + s)) * EROW + r * TT + 2 * k;")
             A("            if (eeven) { if (t < T) cp16(d, g); }")
             A("            else { if (t < T) cp8(d, g); if (t + 1 < T) cp8(d + 1, g + 1); }")
             A("        }")
         A("    };")
-        # fast path: whole CTA inside the batch, 16-byte aligned rows; every
+        # fast path: whole group inside the batch, 16-byte aligned rows; every
         # thread copies the same (series, chunk) pattern each tile, so all
         # offsets are compile-time multiples of T and D*T
         ch = TT // 2
-        nt = 32 * self.ppc * self.gpc
-        fast_ok = nt % ch == 0 and (self.gpc * 32) % (nt // ch) == 0
-        sp = nt // ch if fast_ok else 1           # series covered per pass
-        passes = (self.gpc * 32) // sp if fast_ok else 0
-        A(f"    const bool fast = {'true' if fast_ok else 'false'} && even && (nbase + GPC * 32 <= a.n)"
+        gthreads = 32 * self.ppc
+        fast_ok = gthreads % ch == 0 and 32 % (gthreads // ch) == 0
+        sp = gthreads // ch if fast_ok else 1     # series covered per pass
+        passes = 32 // sp if fast_ok else 0
+        A(f"    const bool fast = {'true' if fast_ok else 'false'} && even && (gbase + 32 <= a.n)"
           + (" && ((((unsigned long long)a.E) & 15) == 0) && ((a.e_ld & 1) == 0)" if per_series_extra else "") + ";")
-        A(f"    const int fk = (threadIdx.x % {ch}) * 2, fs = threadIdx.x / {ch};")
-        A("    const double *fsrc = a.X + ((size_t)(nbase + fs) * a.d) * (size_t)T + fk;")
-        A("    double *fdst = xbuf + (size_t)fs * ROW + fk;")
+        A(f"    const int fk = (gt % {ch}) * 2, fs = gt / {ch};")
+        A("    const double *fsrc = a.X + ((size_t)(gbase + fs) * a.d) * (size_t)T + fk;")
+        A("    double *fdst = gx + (size_t)fs * ROW + fk;")
         A("    const size_t DT = (size_t)a.d * (size_t)T;")
         if per_series_extra:
-            A("    const double *fesrc = a.E + (size_t)(nbase + fs) * a.e_ld + fk;")
-            A("    double *fedst = ebuf + (size_t)fs * EROW + fk;")
+            A("    const double *fesrc = a.E + (size_t)(gbase + fs) * a.e_ld + fk;")
+            A("    double *fedst = ebuf + (size_t)(sg * 32 + fs) * EROW + fk;")
         A("    auto stage_fast = [&](int buf, int t0) {")
         A("        if (t0 + fk < T) {")
         A("            const double *g = fsrc + t0;")
@@ -697,13 +743,13 @@ class Emitter:
         A("    auto stage = [&](int buf, int t0) {")
         A("        if (fast) stage_fast(buf, t0); else stage_slow(buf, t0);")
         if self.nextra and not per_series_extra:
-            A("        // weighting rows shared by all series")
+            A("        // weighting rows shared by all series (one copy per group)")
             A("        const bool eeven = ((a.t & 1) == 0) && ((((unsigned long long)a.E) & 15) == 0);")
-            A("        for (int c = threadIdx.x; c < NEXTRA * (TT / 2); c += NT) {")
+            A("        for (int c = gt; c < NEXTRA * (TT / 2); c += 32 * PPC) {")
             A("            const int k = c % (TT / 2), r = c / (TT / 2);")
             A("            const int t = t0 + 2 * k;")
             A("            const double *g = a.E + (size_t)r * T + t;")
-            A("            double *d = ebuf + (size_t)buf * EROW + r * TT + 2 * k;")
+            A("            double *d = ebuf + (size_t)(buf * GPC + sg) * EROW + r * TT + 2 * k;")
             A("            if (eeven) { if (t < T) cp16(d, g); }")
             A("            else { if (t < T) cp8(d, g); if (t + 1 < T) cp8(d + 1, g + 1); }")
             A("        }")
@@ -713,14 +759,15 @@ class Emitter:
         A("    int buf = 0;")
         A("    for (int t0 = 0; t0 < T; t0 += TT, buf ^= 1) {")
         A('        asm volatile("cp.async.wait_all;" ::: "memory");')
-        A("        __syncthreads();")
+        A("        // the PPC warps of this group (each inside its own part function)")
+        A('        asm volatile("bar.sync %0, %1;" :: "r"(sg + 1), "n"(32 * PPC) : "memory");')
         A("        if (t0 + TT < T) stage(buf ^ 1, t0 + TT);")
         A("        const double *xs = xbuf + ((size_t)(buf * GPC * 32 + sg * 32 + lane)) * ROW;")
         if self.nextra:
             if per_series_extra:
                 A("        const double *es = ebuf + ((size_t)(buf * GPC * 32 + sg * 32 + lane)) * EROW;")
             else:
-                A("        const double *es = ebuf + (size_t)buf * EROW;")
+                A("        const double *es = ebuf + (size_t)(buf * GPC + sg) * EROW;")
         A("        const int tend = min(TT, T - t0);")
         A("        int tt = 0;")
         if need_first:
@@ -812,7 +859,7 @@ class Emitter:
         erow = self.nextra * self.tt + 2
         n = 2 * self.gpc * 32 * row
         if self.nextra:
-            n += 2 * (erow if self.shared_extra else self.gpc * 32 * erow)
+            n += 2 * self.gpc * (erow if self.shared_extra else 32 * erow)
         return n * 8
 
 
@@ -825,7 +872,7 @@ class FbJitGeometry(ctypes.Structure):
                 ("groups_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32)]
 
 
-DEFAULT_OPTS = {"budget": 70, "ppc": 2, "gpc": 4, "minb": 2, "unroll": 2, "tt": 16, "ppm": 4}
+DEFAULT_OPTS = {"budget": 70, "ppc": 2, "gpc": 8, "minb": 1, "unroll": 2, "tt": 16}
 
 
 def options() -> dict:
@@ -862,15 +909,15 @@ MIN_SERIES = 4096          # below this the generic kernel is used (unless force
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
              shared_extra: bool, opts: dict):
-    """-> ([(source, n_parts)], Emitter): one CUDA module per group of parts.
-    Raises NotImplementedError for plans the generated kernels cannot hold
-    (the caller then uses the generic kernel)."""
+    """-> Generated: one translation unit per trie part plus the kernel that
+    dispatches to them.  Raises NotImplementedError for plans the generated
+    kernel cannot hold (the caller then uses the generic kernel)."""
     prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                    parts_multiple=opts["ppc"])
     if ((prog.overhead > 1.25 or prog.max_regs > opts["budget"] + 20 or sieves.regs() > 6)
             and "FRUITS_B200_JIT_OPTS" not in os.environ):
         # deep or sieve-heavy tries: fewer, larger parts (one CTA per SM, 255 registers)
-        opts = dict(opts, budget=150, ppc=1, gpc=8, minb=1, unroll=1)
+        opts = dict(opts, budget=150, ppc=1, gpc=8, minb=1, unroll=1)      # 256 threads x 255 registers
         prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                        parts_multiple=opts["ppc"])
     if prog.overhead > 1.6 or prog.max_regs > 190:
@@ -891,42 +938,77 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
         raise NotImplementedError("threshold table exceeds the constant bank")
     if len(prog.parts) // opts["ppc"] > 65535:
         raise NotImplementedError("too many parts")
-    # one module per `ppm` parts: compile time grows faster than linearly with
-    # the size of a kernel and the modules compile in parallel
-    real = [i for i, pt in enumerate(prog.parts) if pt.owned]
-    ppm = max(opts["ppm"], -(-len(real) // 32))      # at most ~32 modules (launches)
-    per = max(opts["ppc"], -(-ppm // opts["ppc"]) * opts["ppc"])
-    groups = [real[i:i + per] for i in range(0, len(real), per)]
+    minb = opts["minb"]
+    nt = 32 * em.ppc * em.gpc
+    # register file: 64K per SM, allocated per 4 warps, 8 registers granularity
+    warps = -(-(nt // 32) // 4) * 4
+    max_regs = min(255, (65536 // (warps * 32 * minb)) // 8 * 8)
     srcs = []
-    for grp in groups:
-        while len(grp) % opts["ppc"]:
-            grp = grp + [next(i for i, pt in enumerate(prog.parts) if not pt.owned)]
-        src = em.source(grp)
-        src = src.replace("__launch_bounds__(NT, 1)", f"__launch_bounds__(NT, {opts['minb']})")
-        src = src.replace("#pragma unroll 1\n            for (; tt < stop; tt++)",
-                          f"#pragma unroll {opts['unroll']}\n            for (; tt < stop; tt++)")
-        srcs.append((src, len(grp)))
-    return srcs, em
+    idle = [pi for pi, part in enumerate(prog.parts) if not part.owned][:1]
+    for pi, part in enumerate(prog.parts):
+        if part.owned or pi in idle:
+            src = em.source(pi)
+            src = src.replace("#pragma unroll 1\n            for (; tt < stop; tt++)",
+                              f"#pragma unroll {opts['unroll']}\n            for (; tt < stop; tt++)")
+            srcs.append(src)
+    return Generated(srcs, em.entry_source(minb), max_regs, em)
 
 
-def compile_source(src: str, name: str = "fb_jit_slice.cu") -> bytes:
-    """CUDA source -> sm_100a cubin through ``fb_jit_compile`` (NVRTC), with an
-    on-disk cache keyed by the source text."""
-    digest = hashlib.sha256((f"v{JIT_VERSION}\n" + src).encode()).hexdigest()[:24]
-    path = os.path.join(CACHE_DIR, digest + ".cubin")
-    if os.path.exists(path):
-        with open(path, "rb") as f:
-            return f.read()
+@dataclass
+class Generated:
+    parts: list          # source of one translation unit per trie part
+    entry: str           # source of the kernel (dispatch + threshold table)
+    max_regs: int        # register cap of the part functions
+    em: Emitter
+
+    def digest(self) -> str:
+        h = hashlib.sha256(f"v{JIT_VERSION} r{self.max_regs}\n".encode())
+        for src in self.parts + [self.entry]:
+            h.update(src.encode())
+            h.update(b"\0")
+        return h.hexdigest()[:24]
+
+
+def _nvrtc(src: str, name: str, relocatable: bool, max_regs: int) -> bytes:
     L = be.lib()
     cubin, size = ctypes.c_void_p(), ctypes.c_size_t()
     log = ctypes.create_string_buffer(1 << 16)
-    rc = L.fb_jit_compile(src.encode(), name.encode(), ctypes.byref(cubin), ctypes.byref(size),
-                          log, len(log))
+    rc = L.fb_jit_compile(src.encode(), name.encode(), int(relocatable), int(max_regs),
+                          ctypes.byref(cubin), ctypes.byref(size), log, len(log))
     if rc != 0:
         msg = L.fb_last_error().decode(errors="replace")
         raise RuntimeError(f"JIT compilation failed: {msg}\n{log.value.decode(errors='replace')}")
     data = ctypes.string_at(cubin.value, size.value)
     L.fb_jit_free(cubin)
+    return data
+
+
+def build_cubin(gen: Generated) -> bytes:
+    """Compile every part (NVRTC, in parallel threads: ctypes releases the
+    GIL and NVRTC is thread safe), link them with the entry kernel
+    (nvJitLink) and cache the loadable cubin on disk, keyed by the sources."""
+    path = os.path.join(CACHE_DIR, gen.digest() + ".cubin")
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            return f.read()
+    jobs = [(src, f"fb_part_{i}.cu", True, gen.max_regs) for i, src in enumerate(gen.parts)]
+    jobs.append((gen.entry, "fb_jit_slice.cu", True, 0))
+    workers = max(1, min(len(jobs), os.cpu_count() or 1, 32))
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        objs = list(ex.map(lambda j: _nvrtc(*j), jobs))
+    L = be.lib()
+    n = len(objs)
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(ctypes.c_char_p(o), ctypes.c_void_p).value
+                                   for o in objs])
+    sizes = (ctypes.c_size_t * n)(*[len(o) for o in objs])
+    out, size = ctypes.c_void_p(), ctypes.c_size_t()
+    log = ctypes.create_string_buffer(1 << 16)
+    rc = L.fb_jit_link(ptrs, sizes, n, ctypes.byref(out), ctypes.byref(size), log, len(log))
+    if rc != 0:
+        msg = L.fb_last_error().decode(errors="replace")
+        raise RuntimeError(f"JIT link failed: {msg}\n{log.value.decode(errors='replace')}")
+    data = ctypes.string_at(out.value, size.value)
+    L.fb_jit_free(out)
     try:
         os.makedirs(CACHE_DIR, exist_ok=True)
         tmp = path + f".tmp{os.getpid()}"
@@ -939,94 +1021,42 @@ def compile_source(src: str, name: str = "fb_jit_slice.cu") -> bytes:
 
 
 class JitSlice:
-    """The loaded plan-specialised kernels of one slice (one module per group
-    of trie parts, launched back to back on the same stream)."""
+    """The loaded plan-specialised kernel of one slice."""
 
     _loaded: dict = {}     # source digest -> JitSlice
 
-    def __init__(self, srcs: list, em: Emitter) -> None:
-        self.em = em
-        self.srcs = srcs
-        workers = min(len(srcs), os.cpu_count() or 1, 16)
-        if workers > 1:
-            # fb_jit_compile releases the GIL (ctypes) and NVRTC is thread safe
-            with ThreadPoolExecutor(max_workers=workers) as ex:
-                cubins = list(ex.map(lambda sn: compile_source(sn[0]), srcs))
-        else:
-            cubins = [compile_source(src) for src, _ in srcs]
-        self.modules = []
-        for cubin, (_, n_parts) in zip(cubins, srcs):
-            handle = ctypes.c_void_p()
-            be.check(be.lib().fb_jit_load(cubin, len(cubin), ctypes.byref(handle)))
-            geo = FbJitGeometry(n_parts, em.ppc, em.gpc, em.smem_bytes())
-            self.modules.append((handle, geo))
+    def __init__(self, gen: Generated) -> None:
+        self.em = gen.em
+        self.gen = gen
+        cubin = build_cubin(gen)
+        handle = ctypes.c_void_p()
+        be.check(be.lib().fb_jit_load(cubin, len(cubin), ctypes.byref(handle)))
+        self.handle = handle
+        em = gen.em
+        self.geo = FbJitGeometry(len(em.p.parts), em.ppc, em.gpc, em.smem_bytes())
         self.cols = list(em.cols)
 
     @classmethod
     def get(cls, trie, semiring, weight_mode, sieves, dims, shared_extra) -> "JitSlice":
-        srcs, em = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options())
-        h = hashlib.sha256()
-        for src, _ in srcs:
-            h.update(src.encode())
-        key = h.hexdigest()
+        gen = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options())
+        key = gen.digest()
         obj = cls._loaded.get(key)
         if obj is None:
-            obj = cls(srcs, em)
+            obj = cls(gen)
             cls._loaded[key] = obj
         return obj
 
-    @property
-    def n_launches(self) -> int:
-        return len(self.modules)
+    def n_launches(self, n_series: int = 0, length: int = 0) -> int:
+        return 1
 
     def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize) -> None:
         """X[n, d, t] cuda float64; extra: weighting rows or None;
         thr_compact: [n_emit * len(cols)] cuda float64."""
-        import torch
         batch = be.FbBatch()
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape
         n_thr = 0 if thr_compact is None else thr_compact.numel()
-        L = be.lib()
-        main = torch.cuda.current_stream()
-        # modules are independent (disjoint feature columns): when one launch
-        # cannot fill the GPU for long, spread them over side streams
-        ctas = -(-X.shape[0] // (32 * self.em.gpc)) * max(g.n_parts // g.parts_per_cta
-                                                          for _, g in self.modules)
-        side = []
-        if len(self.modules) > 1 and ctas < 16 * _sm_count():
-            side = _side_streams(X.device, min(len(self.modules), 8))
-            fork = torch.cuda.Event()
-            fork.record(main)
-            for st in side:
-                st.wait_event(fork)
-        for i, (handle, geo) in enumerate(self.modules):
-            st = side[i % len(side)] if side else main
-            be.check(L.fb_jit_slice_features(
-                handle, ctypes.byref(geo), ctypes.byref(batch), be.ptr(extra), int(extra_ld),
-                be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0),
-                int(sanitize), st.cuda_stream))
-        for st in side:
-            join = torch.cuda.Event()
-            join.record(st)
-            main.wait_event(join)
-
-
-_streams: dict = {}
-_sms: list = []
-
-
-def _side_streams(device, k: int) -> list:
-    import torch
-    pool = _streams.setdefault(str(device), [])
-    while len(pool) < k:
-        pool.append(torch.cuda.Stream(device=device))
-    return pool[:k]
-
-
-def _sm_count() -> int:
-    if not _sms:
-        sm = ctypes.c_int()
-        be.check(be.lib().fb_device_info(ctypes.byref(sm), None, None, None))
-        _sms.append(sm.value)
-    return _sms[0]
+        be.check(be.lib().fb_jit_slice_features(
+            self.handle, ctypes.byref(self.geo), ctypes.byref(batch), be.ptr(extra),
+            int(extra_ld), be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0),
+            int(sanitize), be.stream_ptr()))

@@ -680,7 +680,7 @@ class FruitSlice:
                 extra = g
                 extra_ld = g_ld
         kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize)
-        self._last_launch = ("fb_jit_slice", kern.n_launches, kern)
+        self._last_launch = ("fb_jit_slice", kern.n_launches(X.shape[0], X.shape[2]), kern)
 
     def _transform_generic(self, X, out, col0, sanitize, dims, feats, bounded_hi,
                            bounded_mm) -> None:

@@ -180,8 +180,10 @@ FB_API int fb_slice_features(const fb_iss_plan *plan, const fb_batch *batch,
  * slice (word trie, semiring, weighting mode, sieve set) into CUDA source in
  * which every trie node is a register of a thread (one thread = one series x
  * one part of the trie; generator: fruits_b200/_jit.py).  The library
- * compiles that source for sm_100a with NVRTC, loads the cubin and launches
- * it.  Semantics are those of fb_slice_features_ex; the source contract is
+ * compiles that source for sm_100a with NVRTC (one translation unit per trie
+ * part, in parallel), links the parts with nvJitLink, loads the cubin and
+ * launches it.  Semantics are those of fb_slice_features_ex; the source
+ * contract is
  *   extern "C" __global__ void fb_jit_slice(struct Args)   and
  *   __constant__ double TH[]    (compact threshold table, see _jit.py).  */
 typedef struct fb_jit_kernel fb_jit_kernel;
@@ -194,9 +196,15 @@ typedef struct fb_jit_geometry {
 } fb_jit_geometry;
 
 /* CUDA C++ source -> sm_100a cubin (malloc'ed, release with fb_jit_free).
- * log (may be NULL) receives the compiler log.  Needs no GPU. */
-FB_API int fb_jit_compile(const char *src, const char *name, void **cubin, size_t *size,
-                          char *log, size_t log_cap);
+ * relocatable != 0: a translation unit to be linked with fb_jit_link (the
+ * parts of a trie are compiled in parallel, thread-safe); max_registers > 0
+ * caps the registers per thread.  log (may be NULL) receives the compiler
+ * log.  Needs no GPU. */
+FB_API int fb_jit_compile(const char *src, const char *name, int relocatable, int max_registers,
+                          void **cubin, size_t *size, char *log, size_t log_cap);
+/* Link relocatable cubins into one loadable cubin (nvJitLink). */
+FB_API int fb_jit_link(const void *const *cubins, const size_t *sizes, int n, void **out,
+                       size_t *size, char *log, size_t log_cap);
 FB_API void fb_jit_free(void *p);
 FB_API int fb_jit_load(const void *cubin, size_t size, fb_jit_kernel **out);
 FB_API int fb_jit_unload(fb_jit_kernel *k);

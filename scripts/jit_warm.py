@@ -37,17 +37,16 @@ def warm(name: str) -> None:
         shared = iss.weighting is None or isinstance(iss.weighting, (Indices, Plateaus))
         t0 = time.time()
         try:
-            srcs, em = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
-                                     _jit.SieveSet.make(feats, bhi, bmm), jdims, shared,
-                                     _jit.options())
+            gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
+                                _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options())
         except NotImplementedError as exc:
             print(f"{name} slice {si}: generic kernel ({exc})", flush=True)
             continue
-        with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
-            cubins = list(ex.map(lambda sn: _jit.compile_source(sn[0]), srcs))
-        print(f"{name} slice {si}: {len(trie.nodes)} nodes, {len(em.p.parts)} parts, "
-              f"{len(srcs)} modules, {sum(map(len, cubins)) // 1024} KB cubin, "
-              f"{time.time() - t0:.1f} s", flush=True)
+        cubin = _jit.build_cubin(gen)
+        em = gen.em
+        print(f"{name} slice {si}: {len(trie.nodes)} nodes, {len(gen.parts)} parts, "
+              f"{32 * em.ppc * em.gpc} threads/CTA, <= {gen.max_regs} registers, "
+              f"{len(cubin) // 1024} KB cubin, {time.time() - t0:.1f} s", flush=True)
 
 
 if __name__ == "__main__":

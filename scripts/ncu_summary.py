@@ -35,17 +35,38 @@ for h, u, v in zip(hdr, units, vals):
         lines.append(f"| {h} | {v} | {u} |")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(src.splitlines()))
-shdr = srows[1]
-ix = {h: i for i, h in enumerate(shdr)}
-body = srows[2:]
-tot = sum(int(r[ix["# Samples"]]) for r in body)
-lines += ["", f"## hottest instructions ({len(body)} SASS instructions, {tot} samples)", "",
-          "| % samples | executed | smem wavefronts (actual/ideal) | SASS | top stall reasons |",
-          "|---|---|---|---|---|"]
+# the page lists every function of the module (the kernel and the device
+# functions it calls): "Kernel Name" line, column header, instructions
+body, func, ix, shdr = [], "", None, None
+for r in srows:
+    if not r:
+        continue
+    if r[0] == "Kernel Name":
+        func = r[1]
+    elif r[0] == "Address":
+        shdr = r
+        ix = {h: i for i, h in enumerate(shdr)}
+    elif ix is not None and len(r) >= len(shdr) - 1:
+        body.append((func, r))
+tot = sum(int(r[ix["# Samples"]]) for _, r in body)
+per_func = {}
+for f, r in body:
+    per_func[f] = per_func.get(f, 0) + int(r[ix["# Samples"]])
+lines += ["", f"## samples per function ({len(body)} SASS instructions, {tot} samples)", "",
+          "| function | % samples |", "|---|---|"]
+top = sorted(per_func.items(), key=lambda kv: -kv[1])
+for f, c in top[:12]:
+    lines.append(f"| {f} | {100 * c / max(tot, 1):.2f} |")
+if len(top) > 12:
+    rest = sum(c for _, c in top[12:])
+    lines.append(f"| ({len(top) - 12} more) | {100 * rest / max(tot, 1):.2f} |")
+lines += ["", "## hottest instructions", "",
+          "| % samples | function | executed | smem wavefronts (actual/ideal) | SASS | top stall reasons |",
+          "|---|---|---|---|---|---|"]
 stall_cols = [h for h in shdr if h.startswith("stall_") and "Not Issued" not in h]
-for r in sorted(body, key=lambda r: -int(r[ix["# Samples"]]))[:25]:
+for f, r in sorted(body, key=lambda fr: -int(fr[1][ix["# Samples"]]))[:25]:
     stalls = sorted(((int(r[ix[c]]), c[6:]) for c in stall_cols if r[ix[c]].isdigit()), reverse=True)[:2]
-    lines.append(f'| {100*int(r[ix["# Samples"]])/tot:.1f} | {r[ix["Instructions Executed"]]} | '
+    lines.append(f'| {100*int(r[ix["# Samples"]])/max(tot, 1):.2f} | {f} | {r[ix["Instructions Executed"]]} | '
                  f'{r[ix["L1 Wavefronts Shared"]]}/{r[ix["L1 Wavefronts Shared Ideal"]]} | '
                  f'`{r[ix["Source"]].strip()}` | ' + ", ".join(f"{n} {c}" for c, n in stalls) + " |")
 open(out, "w").write("\n".join(lines) + "\n")
