@@ -114,7 +114,10 @@ def cpu_reference(seconds: float, steps: int = 1, warmup: int = 0):
     from oracle import pipeline as orc
     from oracle.build import load_oracle
 
-    cores = int(load_oracle().fo_num_threads())
+    orc_lib = load_oracle()
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    orc_lib.fo_set_num_threads(len(os.sched_getaffinity(0)))
+    cores = int(orc_lib.fo_num_threads())
     spec = specs.SPECS["C5_sweep"]
     fitX = specs.make_input("C5_sweep", 64)
     of = orc.OracleFruit(spec)
@@ -295,9 +298,21 @@ def run_ours(args):
         peak = 3 * grid * 256 * iters * 64 * 2 / (ps[0].elapsed_time(ps[1]) * 1e-3) / 1e12
         peaks, how = measured_peaks()
         hbm = BYTES_PER_SERIES * n_launch / k_s / 1e9
+        # DRAM traffic of the kernel from the committed ncu capture, scaled to
+        # this launch (traffic is linear in the number of series)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if kern is not None and os.path.exists(tpath):
+            with open(tpath) as f:
+                tr = json.load(f)
+            traffic = ((tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["series_per_launch"]
+                       * n_launch)
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": traffic,
+            "traffic_note": ("dram__bytes_read+write of one ncu --set full capture "
+                             "(profiles/r01_traffic.json), scaled to series_per_launch; "
+                             f"algorithmic bytes per launch = {BYTES_PER_SERIES * n_launch}"),
             "kernel": kdesc, "launches_per_slice": klaunches,
             "kernel_ms": k_s * 1e3, "series_per_launch": n_launch,
             "flop_per_series": FLOP_PER_SERIES,
@@ -327,7 +342,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(hx.numel() * 8), "d2h_bytes_per_step": int(hf.numel() * 8),
                "series_per_step": E, "ms_per_step": e_s * 1e3,
                "note": "Fruit.transform(numpy pinned in, numpy pinned out); value scaled by n_gpus"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             rate, cores, sample, _ = cpu_reference(args.cpu_seconds)
             cpu = {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",
                    "sample": sample}

@@ -373,3 +373,14 @@ EXPORT int fo_num_threads(void)
     return 1;
 #endif
 }
+
+/* bench.py: use all host cores even when the launcher exported OMP_NUM_THREADS=1
+ * (torchrun does). */
+EXPORT void fo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -1,0 +1,107 @@
+"""Host side of the plan-specialised kernel (no GPU needed): partitioning of
+the trie, source generation, NVRTC compilation and nvJitLink linking through
+the C ABI."""
+import numpy as np
+import pytest
+
+import fruits_b200 as fruits
+import specs
+from fruits_b200 import _backend as be
+from fruits_b200 import _jit
+
+
+def _program(name, si=0, **kw):
+    fruit = specs.build_fruit(fruits, specs.SPECS[name])
+    slc = fruit._slices[si]
+    iss = slc._iss[0]
+    feats, bhi, bmm = slc._fused_sieves()
+    sieves = _jit.SieveSet.make(feats, bhi, bmm)
+    trie = iss.trie()
+    return trie, iss, sieves, _jit.Program(trie, iss.semiring._code, iss._weight_mode(), sieves, **kw)
+
+
+@pytest.mark.parametrize("name,si", [("C1_readme", 0), ("C2_reduced", 0), ("C4_twi", 0),
+                                     ("C5_sweep", 0)])
+@pytest.mark.parametrize("budget,mult", [(70, 2), (150, 1)])
+def test_partition_covers_every_emission_once(name, si, budget, mult):
+    trie, _, _, prog = _program(name, si, reg_budget=budget, parts_multiple=mult)
+    owned = [v for part in prog.parts for v in part.owned]
+    emitted = [v for v, n in enumerate(trie.nodes) if n.emit >= 0]
+    assert sorted(owned) == sorted(emitted)
+    assert len(prog.parts) % mult == 0
+    for part in prog.parts:
+        have = set(part.snodes)
+        assert set(part.owned) <= have
+        for v in part.snodes:                     # closed under parents, parents first
+            p = trie.nodes[v].parent
+            assert p < 0 or (p in have and part.snodes.index(p) < part.snodes.index(v))
+    assert 1.0 <= prog.overhead < 1.6
+
+
+def test_sweep_partition_is_balanced():
+    _, _, _, prog = _program("C5_sweep", reg_budget=70, parts_multiple=2)
+    costs = [p.cost for p in prog.parts if p.owned]
+    assert len(costs) == 50 and max(costs) <= 1.15 * (sum(costs) / len(costs))
+
+
+def test_deep_arctic_chain_is_left_to_the_generic_kernel():
+    trie, iss, sieves, _ = _program("C3_general", 1)
+    with pytest.raises(NotImplementedError):
+        _jit.generate(trie, iss.semiring._code, iss._weight_mode(), sieves,
+                      [(d, 0) for d in trie.used_dims()], True, _jit.options())
+
+
+def test_sibling_letters_share_products():
+    """One multiplication per node: [112] reuses the product of [11]."""
+    trie, iss, sieves, _ = _program("C5_sweep")
+    gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(), sieves,
+                        [(d, 0) for d in trie.used_dims()], True, _jit.options())
+    em = gen.em
+    muls = sum(sum(ln.count("__dmul_rn(") for ln in em.step(part)) for part in em.p.parts
+               if part.owned)
+    nodes = sum(len(part.snodes) for part in em.p.parts)
+    # the reference multiplies 684 times per step (plus duplicated ancestors); sharing
+    # leaves one product per node plus the few a part boundary separates from its sibling
+    assert muls <= 1.2 * nodes and muls < 684, (muls, nodes)
+    adds = sum(sum(1 for ln in em.step(part) if ln.startswith("S[")) for part in em.p.parts
+               if part.owned)
+    assert adds == nodes
+
+
+def test_compile_and_link_without_gpu(tmp_path, monkeypatch):
+    """README slice -> CUDA source -> NVRTC (one unit per part) -> nvJitLink."""
+    monkeypatch.setattr(_jit, "CACHE_DIR", str(tmp_path))
+    trie, iss, sieves, _ = _program("C1_readme")
+    gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(), sieves,
+                        [(d, 1) for d in trie.used_dims()], True, _jit.options())
+    assert len(gen.parts) >= 1 and "fb_jit_slice" in gen.entry
+    assert all("fb_part_" in src for src in gen.parts)
+    cubin = _jit.build_cubin(gen)
+    assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
+    assert (tmp_path / (gen.digest() + ".cubin")).exists()
+    assert _jit.build_cubin(gen) == cubin         # second call: disk cache
+    # same plan -> same digest; other preparateur descriptor -> other kernel
+    gen2 = _jit.generate(trie, iss.semiring._code, iss._weight_mode(), sieves,
+                         [(d, 0) for d in trie.used_dims()], True, _jit.options())
+    assert gen2.digest() != gen.digest()
+
+
+def test_compile_error_is_reported():
+    import ctypes
+    L = be.lib()
+    cubin, size = ctypes.c_void_p(), ctypes.c_size_t()
+    log = ctypes.create_string_buffer(4096)
+    rc = L.fb_jit_compile(b"this is not CUDA", b"bad.cu", 0, 0, ctypes.byref(cubin),
+                          ctypes.byref(size), log, len(log))
+    assert rc != 0 and b"nvrtc" in L.fb_last_error().lower()
+    assert b"error" in log.value.lower()
+
+
+def test_route_rule(monkeypatch):
+    monkeypatch.delenv("FRUITS_B200_JIT", raising=False)
+    assert not _jit.enabled(100) and _jit.enabled(_jit.MIN_SERIES)
+    monkeypatch.setenv("FRUITS_B200_JIT", "force")
+    assert _jit.enabled(1)
+    monkeypatch.setenv("FRUITS_B200_JIT", "0")
+    assert not _jit.enabled(10 ** 6)
+    assert np.isfinite(_jit.DEFAULT_OPTS["budget"])
