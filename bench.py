@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="assemble the features with NCCL instead of peer-memory pushes")
     return ap.parse_args()
 
 
@@ -221,14 +223,37 @@ def run_ours(args):
     from fruits_b200.parallel import transform_sharded
     # N > 1: every rank ends up with the assembled [N*S, F] feature matrix
     # (rank-major rows); the all-gather of row chunk c overlaps the kernel of c+1
-    out = torch.empty(((world if gather else 1) * S, N_FEATS), dtype=torch.float64, device=dev)
+    out = peer = None
+    collective = "none"
+    if gather and not args.nccl_gather:
+        try:
+            from fruits_b200.parallel import PeerGather
+            peer = PeerGather(S, N_FEATS)
+            out = peer.out
+            collective = ("every finished row chunk is pushed into the peers' feature matrices "
+                          "(symmetric NVLink peer memory, copy engines, 8 chunks overlapped with "
+                          "the kernels), one device-side barrier per step; every rank holds the "
+                          "assembled [N*S, F] matrix")
+        except Exception as exc:                      # no symmetric memory on this box
+            if rank == 0:
+                print(f"# PeerGather unavailable ({type(exc).__name__}: {exc}); NCCL all-gather",
+                      file=sys.stderr)
+            peer = None
+    if out is None:
+        out = torch.empty(((world if gather else 1) * S, N_FEATS), dtype=torch.float64,
+                          device=dev)
+        if gather:
+            collective = ("nccl all_gather_into_tensor of the [S, F] feature blocks in 8 row "
+                          "chunks on a side stream, overlapped with the kernels; every rank "
+                          "holds the assembled [N*S, F] matrix")
 
     def compute(x, o):
         fruit.transform_device(x, out=o)
 
     def step():
         if gather:
-            transform_sharded(compute, X, N_FEATS, chunks=n_chunks, out=out)
+            transform_sharded(compute, X, N_FEATS, chunks=n_chunks,
+                              out=peer if peer is not None else out)
         else:
             compute(X, out)
 
@@ -261,7 +286,7 @@ def run_ours(args):
     # ---- kernel-only timing of the dominant kernel + fp64 roof (rank 0) ----
     roofline = e2e = cpu = None
     if rank == 0:
-        kout = out[:S] if not gather else out[:rows]
+        kout = out[:S] if not gather else out[rank * S:rank * S + rows]
         kX = X if not gather else X[:rows]
         ks = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -357,9 +382,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e,
             "gpu_launches": args.steps * n_chunks * launches_per_call,
             "roofline": roofline, "cpu_baseline": cpu, "fit_seconds": fit_s,
-            "collective": ("nccl all_gather_into_tensor of the [S, F] feature blocks in 8 row "
-                           "chunks on a side stream, overlapped with the kernels; every rank "
-                           "holds the assembled [N*S, F] matrix" if gather else "none"),
+            "collective": collective,
         }
         print(json.dumps(line))
     if world > 1:

@@ -88,19 +88,81 @@ def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, gro
     fruit._fitted = True
 
 
+class PeerGather:
+    """Assembled feature matrix ``[world*S, n_feats]`` in NVLink peer memory.
+
+    The buffer is a symmetric allocation (``torch.distributed._symmetric_memory``):
+    every rank maps the buffers of all peers, so a rank *pushes* each finished
+    row chunk straight into its rows of every peer's matrix with plain
+    device-to-device copies.  Those run on the copy engines over NVLink 5 /
+    NVSwitch: no SM is taken from the feature kernel, there is no staging
+    buffer and no re-packing pass.  ``finish()`` is a device-side barrier over
+    all ranks, after which every rank holds the complete matrix.
+
+    Raises ``RuntimeError`` if symmetric memory is unavailable (the caller
+    then falls back to the NCCL all-gather)."""
+
+    def __init__(self, rows_per_rank: int, n_feats: int, group=None) -> None:
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.S, self.F = rows_per_rank, n_feats
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.out = symm.empty((self.world * rows_per_rank, n_feats), dtype=torch.float64,
+                              device=dev)
+        self.handle = symm.rendezvous(self.out, self.group)
+        shape = (self.world, rows_per_rank, n_feats)
+        self.peers = [self.handle.get_buffer(r, shape, torch.float64)
+                      for r in range(self.world)]
+        self.local = self.peers[self.rank]
+        self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(min(4, self.world - 1))]
+
+    def rows(self, lo: int, hi: int) -> torch.Tensor:
+        """This rank's rows ``[lo, hi)`` inside its own matrix (compute target)."""
+        return self.local[self.rank, lo:hi]
+
+    def push(self, lo: int, hi: int) -> None:
+        """Send rows ``[lo, hi)`` (already computed on the current stream) to all peers."""
+        cur = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(cur)
+        src = self.local[self.rank, lo:hi]
+        for i in range(1, self.world):
+            peer = (self.rank + i) % self.world          # staggered: no two ranks hit one peer
+            st = self.copy_streams[(i - 1) % len(self.copy_streams)]
+            st.wait_event(done)
+            with torch.cuda.stream(st):
+                self.peers[peer][self.rank, lo:hi].copy_(src, non_blocking=True)
+
+    def finish(self) -> torch.Tensor:
+        cur = torch.cuda.current_stream()
+        for st in self.copy_streams:
+            cur.wait_stream(st)
+        self.handle.barrier(channel=0)                   # all pushes of all ranks have landed
+        return self.out
+
+
 def transform_sharded(compute: Callable[[torch.Tensor, torch.Tensor], None],
                       X_local: torch.Tensor, n_feats: int, chunks: int = 8, group=None,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out=None) -> torch.Tensor:
     """All ranks hold ``S`` rows; returns the assembled ``[world*S, n_feats]``
     feature matrix (rank-major row order, identical on every rank).
 
     ``compute(X_rows, out_rows)`` writes the features of a row block (e.g.
     ``lambda x, o: fruit.transform_device(x, out=o)``).  The rows are processed
-    in ``chunks`` pieces; the all-gather of piece ``c`` runs on a side stream
-    while piece ``c+1`` is computed."""
+    in ``chunks`` pieces.  With ``out`` a :class:`PeerGather` every finished
+    piece is pushed to the peers by the copy engines while the next piece is
+    computed; otherwise the pieces are all-gathered with NCCL on a side
+    stream."""
     world = dist.get_world_size(group)
     S = X_local.shape[0]
     dev = X_local.device
+    if isinstance(out, PeerGather):
+        chunks = max(1, min(chunks, S)) if S else 1
+        for lo, hi in (shard_rows(S, chunks, c) for c in range(chunks)):
+            compute(X_local[lo:hi], out.rows(lo, hi))
+            out.push(lo, hi)
+        return out.finish()
     if out is None:
         out = torch.empty((world * S, n_feats), dtype=torch.float64, device=dev)
     if world == 1:
