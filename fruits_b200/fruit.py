@@ -428,6 +428,8 @@ class FruitSlice:
     def _is_fusable(self, n_dims: int, callbacks) -> bool:
         if callbacks or len(self._iss) != 1:
             return False
+        if not getattr(self._iss[0], "_fusable_iss", True):
+            return False          # e.g. CosWISS: sieved on materialised iterated sums
         w = self._iss[0].weighting
         if w is not None and getattr(w, "_on_prepared", False):
             return False

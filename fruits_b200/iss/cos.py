@@ -1,12 +1,150 @@
-"""Cosine-weighted ISS (reference: ``fruits/iss/cos.py``).
+"""Cosine weighted ISS (reference: ``fruits/iss/cos.py:184-351``).
 
-Listed as the first "next" row of SURVEY.md section 8(f): it is used by
-slices 2-3 of the reduced / general experiment fruits but is not part of the
-north-star hot path.  Not built yet -- constructing it raises."""
+``CosWISS`` is an ISS over the real semiring whose summands are weighted with
+``cos(pi |i-j| / (f (T-1)))**s`` for every pair of consecutive summation
+indices.  The power of the cosine of a difference expands into products of
+powers of ``sin`` and ``cos`` of the single indices (``_get_weightings``), so
+every expansion term is an ordinary iterated sum with extra per-level
+factors; ``csrc/cos.cu`` evaluates all terms of one word for all frequencies
+in one launch.  Emission order: word-major, frequency-minor.
+
+The randomised variants of the reference (``ffn_size``, ``dropout``) are out
+of scope and raise ``NotImplementedError``.
+"""
+import itertools
+from typing import Generator, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _backend as be
+from .iss import ISS
+from .words.word import SimpleWord, Word
 
 
-class CosWISS:
+class CosWISS(ISS):
+    """Args:
+        words: ``SimpleWord`` objects.
+        freqs: frequencies ``f``; one iterated sum per word and frequency.
+        exponent: exponent ``s`` of the cosine (default 2).
+        total_weighting: also weight the outermost sum.
+    """
 
-    def __init__(self, *args, **kwargs) -> None:
-        raise NotImplementedError(
-            "CosWISS is not built yet (SURVEY.md section 8(f), rank 1)")
+    _fusable_iss = False     # runs on materialised iterated sums (composed route)
+
+    def __init__(self, words: Sequence[Word], freqs: Sequence[float], exponent: int = 2,
+                 total_weighting: bool = False, ffn_size: Optional[int] = None,
+                 dropout: Optional[float] = None) -> None:
+        for word in words:
+            if not isinstance(word, SimpleWord):
+                raise ValueError("CosWISS only implemented for simple words")
+        if ffn_size is not None or dropout is not None:
+            raise NotImplementedError(
+                "the randomised CosWISS variants (ffn_size, dropout) are not built")
+        super().__init__(words)
+        self._total_weighting = total_weighting
+        self._freqs = freqs
+        self._exponent = exponent
+        self._ffn_size = ffn_size
+        self._dropout = dropout
+        self._tables: dict = {}
+
+    @property
+    def requires_fitting(self) -> bool:
+        return False
+
+    def n_iterated_sums(self) -> int:
+        return len(self._freqs) * len(self.words)
+
+    def trie(self):
+        raise NotImplementedError("CosWISS has no prefix trie")
+
+    # -- expansion table ---------------------------------------------------------
+    def _get_weightings(self, word: Word) -> np.ndarray:
+        """``[n_terms, 2p+1]`` int32: binomial coefficient product, then the
+        exponent of sin and of cos for every level (reference :265-287).  Like
+        the reference, only one decimal digit of every binomial coefficient
+        is used (exponents up to 4 are exact)."""
+        p = len(word) + 1 if self._total_weighting else len(word)
+        e = self._exponent
+        binom = [1]
+        for k in range(e):
+            binom.append(binom[-1] * (e - k) // (k + 1))
+        rows = np.zeros(((e + 1) ** (p - 1), 2 * p + 1), dtype=np.int32)
+        rows[:, 0] = 1
+        for c, comb in enumerate(itertools.product(range(e + 1), repeat=p - 1)):
+            for i, k in enumerate(comb):
+                rows[c, 0] *= int(str(binom[k])[0])
+                rows[c, 2 * i + 1] += int(str(e - k)[0])
+                rows[c, 2 * i + 3] += int(str(e - k)[0])
+                rows[c, 2 * i + 2] += int(str(k)[0])
+                rows[c, 2 * i + 4] += int(str(k)[0])
+        return rows
+
+    def _word_tables(self, index: int, dev):
+        key = (index, str(dev))
+        if key not in self._tables:
+            word = self.words[index]
+            mat = np.ascontiguousarray(np.array(list(word), dtype=np.int32))
+            wts = np.ascontiguousarray(self._get_weightings(word))
+            self._tables[key] = (torch.from_numpy(mat).to(dev), torch.from_numpy(wts).to(dev),
+                                 mat.shape, wts.shape)
+        return self._tables[key]
+
+    def _trig(self, X: torch.Tensor) -> torch.Tensor:
+        freqs = torch.tensor(np.asarray(self._freqs, dtype=np.float32), device=X.device)
+        trig = be.empty((len(self._freqs), 2, X.shape[2]))
+        be.check(be.lib().fb_cos_trig(freqs.data_ptr(), len(self._freqs), X.shape[2],
+                                      trig.data_ptr(), be.stream_ptr()))
+        return trig
+
+    # -- execution ---------------------------------------------------------------
+    def _lookup(self, X: torch.Tensor):
+        return None, 0
+
+    def materialize(self, X: torch.Tensor, emit_range=None, lookup=None) -> torch.Tensor:
+        """Iterated sums ``[emit_hi-emit_lo, n, t]`` (word-major, frequency-minor)."""
+        self._check_input(X)
+        X = X.contiguous()
+        n, d, t = X.shape
+        nf = len(self._freqs)
+        lo, hi = (0, self.n_iterated_sums()) if emit_range is None else emit_range
+        out = be.empty((hi - lo, n, t))
+        trig = self._trig(X)
+        L = be.lib()
+        for w in range(lo // nf, -(-hi // nf)):
+            mat, wts, mshape, wshape = self._word_tables(w, X.device)
+            first, last = w * nf, (w + 1) * nf
+            whole = first >= lo and last <= hi
+            dst = out[first - lo:last - lo] if whole else be.empty((nf, n, t))
+            be.check(L.fb_coswiss_word(X.data_ptr(), n, d, t, mat.data_ptr(), mshape[0],
+                                       mshape[1], trig.data_ptr(), nf, wts.data_ptr(),
+                                       wshape[0], wshape[1], dst.data_ptr(), be.stream_ptr()))
+            if not whole:
+                a, b = max(first, lo), min(last, hi)
+                out[a - lo:b - lo] = dst[a - first:b - first]
+        return out
+
+    def batch_transform(self, X, batch_size: int = 1) -> Generator:
+        """Yields the iterated sums of ``batch_size`` words at a time, each
+        word contributing one array per frequency (reference :289-333)."""
+        Xd = be.to_device(X)
+        nf = len(self._freqs)
+        i = 0
+        while i < len(self.words):
+            nb = min(batch_size, len(self.words) - i)
+            res = self.materialize(Xd, (i * nf, (i + nb) * nf))
+            yield res if isinstance(X, torch.Tensor) else res.cpu().numpy()
+            i += nb
+
+    def _copy(self) -> "CosWISS":
+        return CosWISS(freqs=self._freqs, words=self.words, exponent=self._exponent,
+                       total_weighting=self._total_weighting)
+
+    def _label(self, index: int) -> str:
+        d, r = divmod(index, len(self._freqs))
+        string = str(self.words[d])
+        string += f"!{self._freqs[r]} : ^{self._exponent}"
+        if self._total_weighting:
+            string += " : total"
+        return string

@@ -37,7 +37,7 @@ assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF)), ref.__f
 from oracle import pipeline as orc  # noqa: E402
 sys.path.append(os.path.join(ROOT, "tests"))
 import specs  # noqa: E402  (tests/specs.py)
-from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES,  # noqa: E402
+from cases import (COS_CASES, COS_PIPE_CASES, ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES,  # noqa: E402
                    make_iss_input, make_prep_input, make_sieve_input)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -193,9 +193,30 @@ def orc_thresholds(of):
     return np.concatenate(rows) if rows else np.zeros(0)
 
 
-def gen_pipelines():
+def gen_cos():
+    """Cosine weighted ISS: ISS cases and the
+    CosWISS slices of experiments/fruit_reduced.py."""
+    print("[coswiss]")
+    out = {}
+    for name, (desc, shape, kind) in COS_CASES.items():
+        X = make_iss_input(shape, kind)
+        iss = specs.build_iss(ref, desc)
+        r = iss.transform(X)
+        o = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+        check_close(o, r, f"coswiss {name}", rtol=1e-11)
+        assert iss.n_iterated_sums() == orc.n_iterated_sums(desc) == r.shape[0]
+        for i in (0, r.shape[0] - 1):
+            assert iss.label(i) == orc.iss_label(desc, i), (iss.label(i), orc.iss_label(desc, i))
+        out[name] = r
+        out[name + "_xsha"] = np.array(sha(X))
+        out[name + "_labels"] = np.array("|".join(iss.label(i) for i in range(r.shape[0])))
+    np.savez_compressed(os.path.join(GOLD, "cos.npz"), **out)
+    gen_pipelines(COS_PIPE_CASES)
+
+
+def gen_pipelines(cases=None):
     print("[pipelines]")
-    for name, (spec_name, n) in PIPE_CASES.items():
+    for name, (spec_name, n) in (PIPE_CASES if cases is None else cases).items():
         spec = specs.SPECS[spec_name]
         X = specs.make_input(spec_name, n)
         fruit = specs.build_fruit(ref, spec)
@@ -207,7 +228,8 @@ def gen_pipelines():
         of.fit(X)
         o = of.transform(X)
         assert fruit.nfeatures() == of.nfeatures() == r.shape[1]
-        weighted = any(i.get("weighting") for s in spec["slices"] for i in s["iss"])
+        weighted = any(i.get("weighting") or i.get("coswiss")
+                       for s in spec["slices"] for i in s["iss"])
         has_mpi = any(sv[0] == "MPI" for s in spec["slices"] for sv in s["sieves"])
         rt, ot = ref_thresholds(fruit), orc_thresholds(of)
         if weighted or has_mpi:

@@ -294,9 +294,76 @@ def iss_word(X, word: str, extended: int, semiring: str, weighting,
     return np.ascontiguousarray(np.swapaxes(res, 0, 1))
 
 
+def coswiss_weightings(n_letters: int, exponent: int, total: bool) -> np.ndarray:
+    """Expansion of ``cos(a-b)**exponent`` into products of powers of sines
+    and cosines (fruits/iss/cos.py:265-287): row = (binomial coefficient
+    product, sin/cos exponent of every level [, of the total weighting])."""
+    p = n_letters + 1 if total else n_letters
+    binom = [1]
+    for k in range(exponent):
+        binom.append(binom[-1] * (exponent - k) // (k + 1))
+    # term k of one factor: coefficient C(e, k), cos^(e-k) sin^k spread over two levels
+    rows = []
+    for comb in itertools.product(range(exponent + 1), repeat=p - 1):
+        w = np.zeros(2 * p + 1, dtype=np.int32)
+        w[0] = 1
+        for i, k in enumerate(comb):
+            w[0] *= binom[k]
+            w[2 * i + 1] += exponent - k
+            w[2 * i + 3] += exponent - k
+            w[2 * i + 2] += k
+            w[2 * i + 4] += k
+        rows.append(w)
+    return np.array(rows, dtype=np.int32).reshape(len(rows), 2 * p + 1)
+
+
+def coswiss_word(X, word: str, freqs, exponent: int, total: bool):
+    """``[n_freqs, n, t]`` cosine weighted iterated sums of one word
+    (fruits/iss/cos.py:16-49, :171-181), same operation order."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, d, t = X.shape
+    mat = parse_word(word)
+    p = mat.shape[0]
+    wts = coswiss_weightings(p, exponent, total)
+    out = np.zeros((len(freqs), n, t))
+    for f, freq in enumerate(freqs):
+        den = float(np.float32(freq)) * (t - 1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            arg = np.pi * np.arange(t) / den
+        sin_w, cos_w = np.sin(arg), np.cos(arg)
+        for row in wts:
+            tmp = np.ones((n, t))
+            for k in range(p):
+                if k > 0:
+                    tmp = np.roll(tmp, 1, axis=1)
+                    tmp[:, 0] = 0
+                for letter, occ in enumerate(mat[k]):
+                    for _ in range(abs(int(occ))):
+                        tmp = tmp * X[:, letter, :] if occ > 0 else tmp / X[:, letter, :]
+                for _ in range(row[2 * k + 1]):
+                    tmp = tmp * sin_w
+                for _ in range(row[2 * k + 2]):
+                    tmp = tmp * cos_w
+                tmp = np.cumsum(tmp, axis=1)
+            if total:
+                for _ in range(row[2 * p + 1]):
+                    tmp = tmp * sin_w
+                for _ in range(row[2 * p + 2]):
+                    tmp = tmp * cos_w
+            out[f] += row[0] * tmp
+    return out
+
+
 def iss_iter(X, iss, cache: RawCache):
     """Yield ``[n, t]`` arrays in emission order for one ISS description."""
     words = expand_words(iss["words"])
+    if iss.get("coswiss") is not None:
+        c = iss["coswiss"]
+        for w in words:      # word-major, frequency-minor (fruits/iss/cos.py:289-333)
+            out = coswiss_word(X, w, c["freqs"], c.get("exponent", 2), c.get("total", False))
+            for f in range(out.shape[0]):
+                yield out[f]
+        return
     extended = iss.get("mode", "single") == "extended"
     plan = cache_plan(words) if extended else [1] * len(words)
     alphas = iss.get("alphas")
@@ -310,6 +377,8 @@ def iss_iter(X, iss, cache: RawCache):
 
 def n_iterated_sums(iss):
     words = expand_words(iss["words"])
+    if iss.get("coswiss") is not None:
+        return len(words) * len(iss["coswiss"]["freqs"])
     if iss.get("mode", "single") == "extended":
         return sum(cache_plan(words))
     return len(words)
@@ -318,6 +387,11 @@ def n_iterated_sums(iss):
 def iss_label(iss, index):
     # fruits/iss/iss.py:195-204, fruits/iss/cache.py:55-66
     words = expand_words(iss["words"])
+    if iss.get("coswiss") is not None:
+        c = iss["coswiss"]
+        d, r = divmod(index, len(c["freqs"]))
+        return (f"{words[d]}!{c['freqs'][r]} : ^{c.get('exponent', 2)}"
+                + (" : total" if c.get("total", False) else ""))
     if iss.get("mode", "single") == "extended":
         plan = cache_plan(words)
         for i, w in enumerate(words):

@@ -45,6 +45,21 @@ ISS_CASES = {
 }
 
 
+COS_CASES = {
+    # cosine weighted ISS (reference: fruits/iss/cos.py)
+    "cos_e2": ({"words": ["[1]", "[1][2]", "[12][1]", "[1][2][11]"],
+                "coswiss": {"freqs": [0.25, 0.05], "exponent": 2}}, (4, 2, 70), "std"),
+    "cos_e1_total": ({"words": {"concat": [{"of_weight": [1, 2]}, {"of_weight": [2, 2]}]},
+                      "coswiss": {"freqs": [0.05, 0.15, 0.45], "exponent": 1, "total": True}},
+                     (3, 2, 64), "std"),
+    "cos_e3_total": ({"words": ["[2]", "[1][-1]", "[1][2][1]"],
+                      "coswiss": {"freqs": [0.3], "exponent": 3, "total": True}},
+                     (3, 2, 50), "uniform1"),
+    "cos_e4": ({"words": ["[1][1]", "[11][2]"],
+                "coswiss": {"freqs": [0.1, 0.7], "exponent": 4}}, (2, 2, 41), "normal"),
+}
+
+
 def make_iss_input(shape, kind, seed=7):
     rng = np.random.default_rng(seed)
     if kind == "normal":
@@ -127,5 +142,7 @@ PIPE_CASES = {
     "C4_twi": ("C4_twi", 8),
     "C5_sweep": ("C5_sweep", 32),
 }
+
+COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
 

@@ -66,6 +66,15 @@ SPECS = {
                   "semiring": "arctic"}],
          "sieves": [["NPI", {}], ["END", {}]], "fit_sample_size": 1.0},
     ]},
+    # experiments/fruit_reduced.py:52-68 (slices 2-3: cosine weighted ISS, exponents 1 and 2)
+    "C2_cos": {"slices": [
+        {"preps": [["NEW", ["INC", {}]], ["STD", {}]],
+         "iss": [{"words": {"concat": [{"of_weight": [1, 2]}, {"of_weight": [2, 2]},
+                                       {"of_weight": [3, 2]}]},
+                  "coswiss": {"freqs": [i / 20 for i in range(1, 11, 2)], "exponent": e,
+                              "total": True}}],
+         "sieves": _seven_sieves(), "fit_sample_size": 1.0}
+        for e in (1, 2)]},
     # throughput sweep (BASELINE.json configs[4])
     "C5_sweep": {"slices": [
         {"preps": [],
@@ -79,7 +88,7 @@ SPECS = {
 def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
-    shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512),
+    shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -135,6 +144,10 @@ def _sieve(mod, desc):
 
 def build_iss(mod, desc):
     words = _words(mod, desc["words"])
+    if desc.get("coswiss") is not None:
+        c = desc["coswiss"]
+        return mod.CosWISS(words=words, freqs=list(c["freqs"]), exponent=c.get("exponent", 2),
+                           total_weighting=c.get("total", False))
     if desc.get("alphas") is not None:
         for w, a in zip(words, desc["alphas"]):
             w.alpha = a

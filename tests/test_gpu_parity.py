@@ -529,3 +529,57 @@ def test_jit_large_batch_default_route():
     finally:
         del os.environ["FRUITS_B200_JIT"]
     assert_exact(res, gen, "generated vs generic kernel at 6000 series")
+
+
+# ---------------------------------------------------------------------------
+# (f) cosine weighted ISS (reference: fruits/iss/cos.py)
+
+@pytest.mark.parametrize("name", sorted(__import__("cases").COS_CASES))
+def test_coswiss_golden(name, golden_dir):
+    from cases import COS_CASES
+    g = np.load(os.path.join(golden_dir, "cos.npz"))
+    desc, shape, kind = COS_CASES[name]
+    X = make_iss_input(shape, kind)
+    iss = specs.build_iss(fruits, desc)
+    res = iss.transform(X)
+    assert res.shape == g[name].shape == (iss.n_iterated_sums(),) + (shape[0], shape[2])
+    assert_close(res, g[name], 1e-9, name)          # sin/cos: device libm vs host libm
+    assert "|".join(iss.label(i) for i in range(res.shape[0])) == str(g[name + "_labels"])
+    # batches of words, like FruitSlice iterates them
+    parts = list(iss.batch_transform(X, batch_size=1))
+    assert len(parts) == len(iss.words)
+    assert_exact(np.concatenate(parts), res, "batch_transform")
+    # brute force (reference tests/signature/test_cosine.py): word [1][2], exponent 1
+    if name == "cos_e2":
+        f, T = 0.25, shape[2]
+        w = np.cos(np.pi * (np.arange(T)[:, None] - np.arange(T)[None, :]) / (f * (T - 1))) ** 2
+        want = np.zeros((shape[0], T))
+        for t in range(T):
+            for j in range(1, t + 1):
+                want[:, t] += X[:, 1, j] * np.sum(X[:, 0, :j] * w[j, :j], axis=1)
+        np.testing.assert_allclose(res[2], want, rtol=1e-6, atol=1e-8)
+
+
+def test_coswiss_pipeline_golden(golden_dir):
+    """Slices 2-3 of experiments/fruit_reduced.py (CosWISS exponents 1 and 2, total)."""
+    g = np.load(os.path.join(golden_dir, "pipeline_C2_cos.npz"))
+    X = specs.make_input("C2_cos", 16)
+    fruit = specs.build_fruit(fruits, specs.SPECS["C2_cos"])
+    assert fruit.nfeatures() == int(g["nfeatures"]) == 2310
+    np.random.seed(0)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    assert_close(fitted_thresholds(fruit), g["thresholds"], 1e-9, "thresholds")
+    _assert_features_close(res, g["features"], "C2_cos")
+    labels = "|".join(fruit.label(i) for i in
+                      sorted(set(np.linspace(0, res.shape[1] - 1, 23).astype(int))))
+    assert labels == str(g["labels"])
+    assert fruit.summary() == str(g["summary"])
+
+
+def test_coswiss_unsupported_variants():
+    words = [fruits.words.SimpleWord("[1][2]")]
+    with pytest.raises(NotImplementedError):
+        fruits.CosWISS(words, freqs=[0.1], ffn_size=4)
+    with pytest.raises(NotImplementedError):
+        fruits.CosWISS(words, freqs=[0.1], dropout=0.2)

@@ -124,10 +124,11 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES))
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos"])
 def test_pipeline_golden(name, golden_dir):
+    from cases import COS_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
-    spec_name, n = PIPE_CASES[name]
+    spec_name, n = {**PIPE_CASES, **COS_PIPE_CASES}[name]
     spec = specs.SPECS[spec_name]
     X = specs.make_input(spec_name, n)
     assert sha(X) == str(g["xsha"])
@@ -144,3 +145,31 @@ def test_pipeline_golden(name, golden_dir):
         scale = np.maximum(np.abs(g["features"]), 1.0)
         bad = np.abs(res - g["features"]) > 1e-9 * scale
         assert bad.mean() < 1e-3, f"{bad.sum()} features beyond 1e-9"
+
+
+@pytest.mark.parametrize("name", sorted(__import__("cases").COS_CASES))
+def test_oracle_coswiss_matches_reference(name, golden_dir):
+    """Cosine weighted ISS (fruits/iss/cos.py) of the oracle vs the frozen reference."""
+    from cases import COS_CASES, make_iss_input
+    g = np.load(os.path.join(golden_dir, "cos.npz"))
+    desc, shape, kind = COS_CASES[name]
+    X = make_iss_input(shape, kind)
+    o = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    ref = g[name]
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=-1, keepdims=True))
+    assert o.shape == ref.shape and np.all(np.abs(o - ref) <= 1e-11 * scale)
+    labels = "|".join(orc.iss_label(desc, i) for i in range(ref.shape[0]))
+    assert labels == str(g[name + "_labels"])
+
+
+def test_coswiss_expansion_table():
+    # cos(a-b)^2 = sin^2 a sin^2 b + 2 sin a cos a sin b cos b + cos^2 a cos^2 b
+    w = orc.coswiss_weightings(2, 2, False)
+    assert w.tolist() == [[1, 2, 0, 2, 0], [2, 1, 1, 1, 1], [1, 0, 2, 0, 2]]
+    assert orc.coswiss_weightings(3, 2, True).shape == (27, 9)
+    import fruits_b200 as fruits
+    for n_letters, e, total in [(1, 1, True), (2, 3, False), (3, 2, True), (2, 4, True)]:
+        word = fruits.words.SimpleWord("[1]" * n_letters)
+        host = fruits.CosWISS([word], freqs=[0.1], exponent=e,
+                              total_weighting=total)._get_weightings(word)
+        assert np.array_equal(host, orc.coswiss_weightings(n_letters, e, total))
