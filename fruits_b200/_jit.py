@@ -37,7 +37,7 @@ import numpy as np
 
 from . import _backend as be
 
-JIT_VERSION = 12            # bump to invalidate cached cubins
+JIT_VERSION = 13            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -158,7 +158,8 @@ class Program:
         self.aidx = {a: i for i, a in enumerate(self.alphas)}
         self.has_children = [bool(n.children) for n in nodes]
 
-        # state registers of one running-sum node
+        # state registers of one running-sum node (a combination output --
+        # virtual node with a ``combo`` term list -- keeps its previous value)
         def sregs(v, owned):
             r = 2
             if weight_mode == be.WEIGHT_NONTOTAL and nodes[v].children:
@@ -168,6 +169,9 @@ class Program:
             return r + (sieves.regs() if owned else 0)
 
         def scost(v, owned):
+            combo = getattr(nodes[v], "combo", None)
+            if combo is not None:
+                return 1 + sum(1 + t[2] + t[4] for t in combo) + sieves.cost()
             c = 2 + (2 if weighted else 0)
             if not self.reals:
                 c += 1 + max(0, sum(1 for e in nodes[v].expo if e != 0) - 1)
@@ -198,6 +202,16 @@ class Program:
         self.parts = parts
 
     def _chain(self, v):
+        """Nodes ``v`` needs, parents first, ``v`` last."""
+        combo = getattr(self.trie.nodes[v], "combo", None)
+        if combo is not None:
+            seen, out = set(), []
+            for term in combo:
+                for a in self._chain(term[1]):
+                    if a not in seen:
+                        seen.add(a)
+                        out.append(a)
+            return out + [v]
         out = []
         while v >= 0:
             out.append(v)
@@ -246,12 +260,11 @@ class Emitter:
     """CUDA source of one slice program."""
 
     def __init__(self, prog: Program, dims: list, ppc: int, gpc: int, shared_extra: bool,
-                 tt: int = 8) -> None:
+                 tt: int = 8, n_shared_rows: int = 0) -> None:
         """dims[u] = (raw_dim, inc) of used dimension u; ppc/gpc = parts and
         series groups per CTA; shared_extra: the weighting rows are the same
         for every series (Indices)."""
         self.p = prog
-        self.dims = dims
         self.ppc, self.gpc = ppc, gpc
         self.tt = tt                 # time steps per shared-memory tile (even)
         self.shared_extra = shared_extra
@@ -259,13 +272,21 @@ class Emitter:
         self.cols = self.sv.thr_cols()
         self.ntc = len(self.cols)
         self.colpos = {c: i for i, c in enumerate(self.cols)}
+        # dims[u] = (raw_dim, inc) reads the series; ("row", r) reads the shared
+        # extra row r (e.g. the sin / cos rows of the cosine weighted ISS)
+        self.dims = [d if d[0] != "row" else None for d in dims]
+        self.row_dims = {u: d[1] for u, d in enumerate(dims) if d[0] == "row"}
+        dims = [d for d in dims if d[0] != "row"]
         # distinct raw rows staged per series
-        self.raw_rows = sorted({r for r, _ in dims})
+        self.raw_rows = sorted({r for r, _ in dims}) or [0]
         self.row_of = {r: i for i, r in enumerate(self.raw_rows)}
         self.nrow = len(self.raw_rows)
         # extra (weighting) rows: Reals: ep_a, em_a per alpha; Arctic: g
         wm = prog.weight_mode
-        if wm == be.WEIGHT_NONE:
+        if n_shared_rows:
+            assert wm == be.WEIGHT_NONE and shared_extra
+            self.nextra = n_shared_rows
+        elif wm == be.WEIGHT_NONE:
             self.nextra = 0
         elif prog.reals:
             self.nextra = 2 * len(prog.alphas)
@@ -289,7 +310,8 @@ class Emitter:
             # children of every parent that live in this part
             groups = {}
             for v in part.snodes:
-                groups.setdefault(nodes[v].parent, []).append(v)
+                if getattr(nodes[v], "combo", None) is None:
+                    groups.setdefault(nodes[v].parent, []).append(v)
             # deepest parents first: a node is updated after its children read it
             order = sorted(groups, key=lambda u: -(nodes[u].depth if u >= 0 else 0))
             for u in order:
@@ -340,6 +362,27 @@ class Emitter:
                         vals[v] = prod(occ)
                 for v in kids:
                     self._update_reals(L, v, vals[v], sidx[v], v in owned, oidx.get(v))
+            # combination outputs: sum of coeff * (running sum [* trailing factors])
+            # in term order (fruits/iss/cos.py:43-48); the previous value is kept in S
+            for v in part.snodes:
+                combo = getattr(nodes[v], "combo", None)
+                if combo is None:
+                    continue
+                L.append(f"double y{v} = 0.0;")
+                for ti, (coeff, node, sp, su, cp, cu) in enumerate(combo):
+                    term = f"S[{sidx[node]}]"
+                    if sp or cp:
+                        L.append(f"double z{v}_{ti} = {term};")
+                        for _ in range(sp):
+                            L.append(f"z{v}_{ti} = __dmul_rn(z{v}_{ti}, x{p.dim_index[su]});")
+                        for _ in range(cp):
+                            L.append(f"z{v}_{ti} = __dmul_rn(z{v}_{ti}, x{p.dim_index[cu]});")
+                        term = f"z{v}_{ti}"
+                    L.append(f"y{v} = fma({float(coeff)!r}, {term}, y{v});")
+                si = sidx[v]
+                L.append(f"const double q{v} = S[{si}]; S[{si}] = y{v};")
+                if v in owned:
+                    self._sieve(L, v, f"S[{si}]", f"q{v}", oidx[v])
         else:
             # arctic: parents first, children read the parent's new value
             for v in part.snodes:
@@ -671,7 +714,7 @@ class Emitter:
             A("        MN[i] = D_INF;")
         A("    }")
         # previous raw values of the dimensions that are read as increments
-        inc_rows = sorted({self.row_of[r] for r, inc in self.dims if inc})
+        inc_rows = sorted({self.row_of[d[0]] for d in self.dims if d is not None and d[1]})
         for r in inc_rows:
             A(f"    double xp{r} = 0.0;")
         # ---- staging ----
@@ -834,7 +877,11 @@ class Emitter:
         L = []
         for r in range(self.nrow):
             L.append(f"const double r{r} = xs[{r} * TT + tt];")
-        for u, (raw, inc) in enumerate(self.dims):
+        for u, dim in enumerate(self.dims):
+            if dim is None:                  # shared extra row (sin / cos of CosWISS)
+                L.append(f"const double x{u} = es[{self.row_dims[u]} * TT + tt];")
+                continue
+            raw, inc = dim
             r = self.row_of[raw]
             if inc:
                 L.append(f"const double x{u} = is0 ? 0.0 : __dadd_rn(r{r}, -xp{r});")
@@ -851,7 +898,7 @@ class Emitter:
         return L
 
     def _after(self) -> list:
-        inc_rows = sorted({self.row_of[r] for r, inc in self.dims if inc})
+        inc_rows = sorted({self.row_of[d[0]] for d in self.dims if d is not None and d[1]})
         return [f"xp{r} = r{r};" for r in inc_rows]
 
     def smem_bytes(self) -> int:
@@ -908,7 +955,7 @@ MIN_SERIES = 4096          # below this the generic kernel is used (unless force
 
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
-             shared_extra: bool, opts: dict):
+             shared_extra: bool, opts: dict, n_shared_rows: int = 0):
     """-> Generated: one translation unit per trie part plus the kernel that
     dispatches to them.  Raises NotImplementedError for plans the generated
     kernel cannot hold (the caller then uses the generic kernel)."""
@@ -928,7 +975,7 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
     em = None
     for gpc, tt in ((opts["gpc"], opts["tt"]), (opts["gpc"], 8), (max(1, opts["gpc"] // 2), 8),
                     (max(1, opts["gpc"] // 4), 8), (1, 4), (1, 2)):
-        cand = Emitter(prog, dims, opts["ppc"], gpc, shared_extra, tt)
+        cand = Emitter(prog, dims, opts["ppc"], gpc, shared_extra, tt, n_shared_rows)
         if cand.smem_bytes() <= 200 * 1024:
             em = cand
             break
@@ -1037,8 +1084,10 @@ class JitSlice:
         self.cols = list(em.cols)
 
     @classmethod
-    def get(cls, trie, semiring, weight_mode, sieves, dims, shared_extra) -> "JitSlice":
-        gen = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options())
+    def get(cls, trie, semiring, weight_mode, sieves, dims, shared_extra,
+            n_shared_rows: int = 0) -> "JitSlice":
+        gen = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options(),
+                       n_shared_rows)
         key = gen.digest()
         obj = cls._loaded.get(key)
         if obj is None:

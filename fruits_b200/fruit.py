@@ -621,13 +621,17 @@ class FruitSlice:
         if out.stride(1) != 1:
             raise ValueError("feature matrix must be row-major")
         feats, bounded_hi, bounded_mm = self._fused_sieves()
-        if _jit.enabled(n):
+        jit_only = getattr(iss, "_jit_only", False)
+        if _jit.enabled(n) or (jit_only and _jit.enabled()):
             try:
                 self._transform_jit(X, cache, out, col0, sanitize, dims, feats, bounded_hi,
                                     bounded_mm)
                 return
             except NotImplementedError:
-                pass      # plan too large for the specialised kernel: generic kernel below
+                pass      # plan too large for the specialised kernel: other route below
+        if jit_only:
+            self._transform_composed(X, [], cache, out, col0, sanitize)
+            return
         self._transform_generic(X, out, col0, sanitize, dims, feats, bounded_hi, bounded_mm)
 
     def _transform_jit(self, X, cache, out, col0, sanitize, dims, feats, bounded_hi,
@@ -635,13 +639,14 @@ class FruitSlice:
         """Plan-specialised kernel (``_jit.py``): trie nodes and sieve state in
         registers, one thread per series and trie part."""
         iss = self._iss[0]
-        trie = iss.trie()
+        trie, n_shared = iss._jit_trie(len(dims))
         used = trie.used_dims()
+        real = [u for u in used if u < len(dims)]
         # standardised dimensions: the prepared input is materialised once
         # (2 x 8 bytes per value against ~10^3 flop per value of ISS work)
-        materialise = any(dims[u][2] for u in used)
-        jdims = [(u, 0) for u in used] if materialise else \
-            [(dims[u][0], dims[u][1]) for u in used]
+        materialise = any(dims[u][2] for u in real)
+        jdims = [((u, 0) if materialise else (dims[u][0], dims[u][1])) if u < len(dims)
+                 else ("row", u - len(dims)) for u in used]
         sieves = _jit.SieveSet.make(feats, bounded_hi, bounded_mm)
         g, g_ld = iss._lookup(X)
         wm = iss._weight_mode()
@@ -653,7 +658,7 @@ class FruitSlice:
         if key not in memo[1]:
             try:
                 memo[1][key] = _jit.JitSlice.get(trie, iss.semiring._code, wm, sieves, jdims,
-                                                 g_ld == 0)
+                                                 g_ld == 0, n_shared)
             except NotImplementedError as exc:
                 memo[1][key] = exc          # remembered: planning is host work
         kern = memo[1][key]
@@ -670,7 +675,9 @@ class FruitSlice:
                 self._thr_compact = (tkey, thr.index_select(1, idx).contiguous(), thr)
             thr_c = self._thr_compact[1]
         extra, extra_ld = None, 0
-        if wm != be.WEIGHT_NONE:
+        if n_shared:
+            extra = iss._trig(X)              # CosWISS: sin / cos rows, shared by all series
+        elif wm != be.WEIGHT_NONE:
             rows = 1 if g_ld == 0 else X.shape[0]
             if isinstance(iss.semiring, Reals):
                 alphas = (ctypes.c_float * len(kern.em.p.alphas))(*kern.em.p.alphas)

@@ -30,7 +30,11 @@ class CosWISS(ISS):
         total_weighting: also weight the outermost sum.
     """
 
-    _fusable_iss = False     # runs on materialised iterated sums (composed route)
+    # In a FruitSlice the expansion is compiled into the plan-specialised kernel
+    # (``_jit_trie``); there is no generic fused kernel for it, so small batches
+    # and plans that do not fit run on materialised iterated sums.
+    _fusable_iss = True
+    _jit_only = True
 
     def __init__(self, words: Sequence[Word], freqs: Sequence[float], exponent: int = 2,
                  total_weighting: bool = False, ffn_size: Optional[int] = None,
@@ -57,7 +61,67 @@ class CosWISS(ISS):
         return len(self._freqs) * len(self.words)
 
     def trie(self):
-        raise NotImplementedError("CosWISS has no prefix trie")
+        raise NotImplementedError("CosWISS has no prefix trie of its own (see _jit_trie)")
+
+    def _jit_trie(self, n_dims: int):
+        """-> (trie, number of shared rows) for the kernel generator.
+
+        Every expansion term of every (word, frequency) pair is a word over the
+        input dimensions *augmented with the sin / cos rows of the frequency*:
+        level k multiplies by x^e, then sin^a, then cos^b -- the reference's
+        order, since the trig rows sort after the real dimensions.  The terms
+        form a prefix trie like any word list; the emitted value is the
+        combination ``sum_i coeff_i * S_i [* sin^a cos^b of the total
+        weighting]`` (a virtual node with a ``combo`` list)."""
+        from .._plan import Trie, _Node
+        key = ("jit", n_dims)
+        if key in self._tables:
+            return self._tables[key]
+        nf = len(self._freqs)
+
+        class _Term(list):
+            alpha = None
+
+        terms, owner = [], []
+        for w, word in enumerate(self.words):
+            mat = [list(int(x) for x in el) + [0] * (n_dims - len(el)) for el in word]
+            wts = self._get_weightings(word)
+            p = len(mat)
+            for f in range(nf):
+                for r, row in enumerate(wts):
+                    letters = []
+                    for k in range(p):
+                        trig = [0] * (2 * nf)
+                        trig[2 * f], trig[2 * f + 1] = int(row[2 * k + 1]), int(row[2 * k + 2])
+                        letters.append(mat[k] + trig)
+                    terms.append(_Term(letters))
+                    owner.append((w, f, r))
+        trie = Trie(terms, None, False)
+        term_node = list(trie.emits)
+        for node in trie.nodes:
+            node.emit = -1
+        trie.emits = []
+        i = 0
+        for w, word in enumerate(self.words):
+            wts = self._get_weightings(word)
+            p = len(word)
+            total = wts.shape[1] == 2 * p + 3
+            for f in range(nf):
+                combo = []
+                for row in wts:
+                    sp, cp = (int(row[2 * p + 1]), int(row[2 * p + 2])) if total else (0, 0)
+                    combo.append((int(row[0]), term_node[i], sp, n_dims + 2 * f,
+                                  cp, n_dims + 2 * f + 1))
+                    i += 1
+                # the marker exponents make the trig rows "used" dimensions
+                marker = [0] * (n_dims + 2 * nf)
+                marker[n_dims + 2 * f] = marker[n_dims + 2 * f + 1] = 1
+                node = _Node(-1, tuple(marker), 0.0, 1, len(trie.emits))
+                node.combo = combo
+                trie.nodes.append(node)
+                trie.emits.append(len(trie.nodes) - 1)
+        self._tables[key] = (trie, 2 * nf)
+        return self._tables[key]
 
     # -- expansion table ---------------------------------------------------------
     def _get_weightings(self, word: Word) -> np.ndarray:

@@ -81,6 +81,10 @@ class ISS(Seed):
             self._plan_memo = {}
         return self._trie_memo[1]
 
+    def _jit_trie(self, n_dims: int):
+        """-> (trie, number of shared extra rows) for the kernel generator."""
+        return self.trie(), 0
+
     def device_plan(self, rows_max: int, emit_range=None, dim_desc=None) -> DevicePlan:
         trie = self.trie()
         key = (rows_max, emit_range, None if dim_desc is None else tuple(dim_desc))

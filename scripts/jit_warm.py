@@ -20,7 +20,8 @@ from fruits_b200 import _jit  # noqa: E402
 from fruits_b200.iss.weighting import Indices, Plateaus  # noqa: E402
 import specs  # noqa: E402
 
-SHAPES = {"C1_readme": 3, "C2_reduced": 1, "C3_general": 6, "C4_twi": 3, "C5_sweep": 3}
+SHAPES = {"C1_readme": 3, "C2_reduced": 1, "C2_cos": 1, "C3_general": 6, "C4_twi": 3,
+          "C5_sweep": 3}
 
 
 def warm(name: str) -> None:
@@ -29,16 +30,18 @@ def warm(name: str) -> None:
         iss = slc._iss[0]
         feats, bhi, bmm = slc._fused_sieves()
         dims = slc._fused_dims(SHAPES[name])
-        trie = iss.trie()
+        trie, n_shared = iss._jit_trie(len(dims))
         used = trie.used_dims()
-        if any(dims[u][2] for u in used):
+        if any(dims[u][2] for u in used if u < len(dims)):
             dims = [(u, 0, 0) for u in range(len(dims))]
-        jdims = [(dims[u][0], dims[u][1]) for u in used]
+        jdims = [(dims[u][0], dims[u][1]) if u < len(dims) else ("row", u - len(dims))
+                 for u in used]
         shared = iss.weighting is None or isinstance(iss.weighting, (Indices, Plateaus))
         t0 = time.time()
         try:
             gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
-                                _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options())
+                                _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options(),
+                                n_shared)
         except NotImplementedError as exc:
             print(f"{name} slice {si}: generic kernel ({exc})", flush=True)
             continue

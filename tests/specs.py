@@ -85,10 +85,14 @@ SPECS = {
 }
 
 
+# the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
+SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
+
+
 def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
-    shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512),
+    shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]

@@ -575,6 +575,15 @@ def test_coswiss_pipeline_golden(golden_dir):
                       sorted(set(np.linspace(0, res.shape[1] - 1, 23).astype(int))))
     assert labels == str(g["labels"])
     assert fruit.summary() == str(g["summary"])
+    # the expansion is compiled into the plan-specialised kernel ...
+    assert _routes(fruit) == ["fb_jit_slice", "fb_jit_slice"]
+    # ... and agrees with the materialise + stand-alone sieves route
+    os.environ["FRUITS_B200_JIT"] = "0"
+    try:
+        composed = fruit.transform(X)
+    finally:
+        del os.environ["FRUITS_B200_JIT"]
+    _assert_features_close(res, composed, "generated kernel vs composed route")
 
 
 def test_coswiss_unsupported_variants():
