@@ -955,7 +955,7 @@ MIN_SERIES = 4096          # below this the generic kernel is used (unless force
 
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
-             shared_extra: bool, opts: dict, n_shared_rows: int = 0):
+             shared_extra: bool, opts: dict, n_shared_rows: int = 0, max_state_regs: int = 0):
     """-> Generated: one translation unit per trie part plus the kernel that
     dispatches to them.  Raises NotImplementedError for plans the generated
     kernel cannot hold (the caller then uses the generic kernel)."""
@@ -967,7 +967,8 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
         opts = dict(opts, budget=150, ppc=1, gpc=8, minb=1, unroll=1)      # 256 threads x 255 registers
         prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                        parts_multiple=opts["ppc"])
-    if prog.overhead > 1.6 or prog.max_regs > 190:
+    # (plans without another fused route -- CosWISS -- may spill a few sums to local memory)
+    if prog.overhead > 1.6 or prog.max_regs > (max_state_regs or 190):
         # long chains (e.g. arctic words of 24-48 letters): every part would
         # recompute most of the chain -- the generic kernel is the better shape
         raise NotImplementedError("trie too deep for the plan-specialised kernel")
@@ -1085,9 +1086,9 @@ class JitSlice:
 
     @classmethod
     def get(cls, trie, semiring, weight_mode, sieves, dims, shared_extra,
-            n_shared_rows: int = 0) -> "JitSlice":
+            n_shared_rows: int = 0, max_state_regs: int = 0) -> "JitSlice":
         gen = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options(),
-                       n_shared_rows)
+                       n_shared_rows, max_state_regs)
         key = gen.digest()
         obj = cls._loaded.get(key)
         if obj is None:

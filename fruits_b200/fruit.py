@@ -657,8 +657,10 @@ class FruitSlice:
             iss._jit_memo = memo
         if key not in memo[1]:
             try:
+                # a plan without another fused route may keep part of its sums in local memory
+                spill = 450 if getattr(iss, "_jit_only", False) else 0
                 memo[1][key] = _jit.JitSlice.get(trie, iss.semiring._code, wm, sieves, jdims,
-                                                 g_ld == 0, n_shared)
+                                                 g_ld == 0, n_shared, spill)
             except NotImplementedError as exc:
                 memo[1][key] = exc          # remembered: planning is host work
         kern = memo[1][key]

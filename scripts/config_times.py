@@ -17,7 +17,7 @@ import torch  # noqa: E402
 import fruits_b200 as fruits  # noqa: E402
 import specs  # noqa: E402
 
-SIZES = {"C1_readme": 200, "C2_reduced": 1000, "C2_cos": 1000, "C2_full": 1000, "C3_general": 10000,
+SIZES = {"C1_readme": 200, "C2_reduced": 1000, "C2_cos": 1000, "C2_full": 1000, "C3_cos": 10000, "C3_full": 10000, "C3_general": 10000,
          "C4_twi": 100000, "C5_sweep": 65536}
 
 

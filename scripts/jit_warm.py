@@ -20,8 +20,8 @@ from fruits_b200 import _jit  # noqa: E402
 from fruits_b200.iss.weighting import Indices, Plateaus  # noqa: E402
 import specs  # noqa: E402
 
-SHAPES = {"C1_readme": 3, "C2_reduced": 1, "C2_cos": 1, "C3_general": 6, "C4_twi": 3,
-          "C5_sweep": 3}
+SHAPES = {"C1_readme": 3, "C2_reduced": 1, "C2_cos": 1, "C3_general": 6, "C3_cos": 6,
+          "C4_twi": 3, "C5_sweep": 3}
 
 
 def warm(name: str) -> None:
@@ -41,7 +41,7 @@ def warm(name: str) -> None:
         try:
             gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
                                 _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options(),
-                                n_shared)
+                                n_shared, 450 if getattr(iss, "_jit_only", False) else 0)
         except NotImplementedError as exc:
             print(f"{name} slice {si}: generic kernel ({exc})", flush=True)
             continue

@@ -85,6 +85,16 @@ SPECS = {
 }
 
 
+# experiments/fruit_general.py:53-69 (slices 2-3: 115 words up to four letters)
+SPECS["C3_cos"] = {"slices": [
+    {"preps": [["NEW", ["INC", {}]], ["STD", {}]],
+     "iss": [{"words": {"concat": [{"of_weight": [w, 2]} for w in (1, 2, 3, 4)]},
+              "coswiss": {"freqs": [i / 20 for i in range(1, 11, 2)], "exponent": e,
+                          "total": True}}],
+     "sieves": _seven_sieves(), "fit_sample_size": 1.0}
+    for e in (1, 2)]}
+SPECS["C3_full"] = {"slices": SPECS["C3_general"]["slices"] + SPECS["C3_cos"]["slices"]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -93,6 +103,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]

@@ -592,3 +592,33 @@ def test_coswiss_unsupported_variants():
         fruits.CosWISS(words, freqs=[0.1], ffn_size=4)
     with pytest.raises(NotImplementedError):
         fruits.CosWISS(words, freqs=[0.1], dropout=0.2)
+
+
+def test_coswiss_four_letter_words_generated_kernel():
+    """Four-letter words with exponent 2 and the total weighting (81 expansion
+    terms, 120 running sums per word and frequency -- part of them live in
+    local memory): generated kernel vs the composed route vs the oracle."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": ["[1][2][1][2]", "[1][1][2]", "[2]", "[12][1][1][-2]"],
+                                 "coswiss": {"freqs": [0.05, 0.35], "exponent": 2, "total": True}}],
+                        "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MPI", {"inc": 0}], ["MAX", {}],
+                                   ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(21).random((37, 2, 53)) + 0.5
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(4)
+    fruit.fit(X)
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    os.environ["FRUITS_B200_JIT"] = "0"
+    try:
+        composed = fruit.transform(X)
+    finally:
+        del os.environ["FRUITS_B200_JIT"]
+    _assert_features_close(res, composed, "generated kernel vs composed route")
+    of = orc.OracleFruit(spec)
+    np.random.seed(4)
+    of.fit(X)
+    assert_close(fitted_thresholds(fruit), oracle_thresholds(of), 1e-9, "thresholds")
+    _assert_features_close(res, of.transform(X), "generated kernel vs oracle")
