@@ -21,10 +21,10 @@ FB_MAX_ALPHAS = 4
 FB_MAX_FEATS = 16
 FB_NTHR = 12
 
-SEMIRING_REALS, SEMIRING_ARCTIC = 0, 1
+SEMIRING_REALS, SEMIRING_ARCTIC, SEMIRING_BAYESIAN = 0, 1, 2
 WEIGHT_NONE, WEIGHT_TOTAL, WEIGHT_NONTOTAL = 0, 1, 2
 FEAT_CNT, FEAT_AVG, FEAT_PPV, FEAT_MAX, FEAT_MIN, FEAT_END = range(6)
-SIEVE_NPI, SIEVE_MPI, SIEVE_MAX, SIEVE_MIN, SIEVE_XPI, SIEVE_LPI, SIEVE_END = range(7)
+SIEVE_NPI, SIEVE_MPI, SIEVE_MAX, SIEVE_MIN, SIEVE_XPI, SIEVE_LPI, SIEVE_END, SIEVE_CUR = range(8)
 POLICY_MAT = 0
 
 # numpy view of `struct fb_slot` (16 bytes)
@@ -119,6 +119,7 @@ def lib() -> ctypes.CDLL:
                                    i32, vp], i32),
         "fb_cos_trig": ([vp, i32, i64, vp, vp], i32),
         "fb_coswiss_word": ([vp, i64, i64, i64, vp, i32, i32, vp, i32, vp, i32, i32, vp, vp], i32),
+        "fb_bayes_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, i32, i32, vp, vp], i32),
         "fb_exp_rows": ([vp, vp, i64, i64, ctypes.POINTER(ctypes.c_float), i32, vp], i32),
     }
     for name, (args, res) in sig.items():
@@ -139,6 +140,7 @@ EXPORTED = [
     "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_order_stats_workspace",
     "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
     "fb_jit_unload", "fb_jit_slice_features", "fb_jit_link", "fb_exp_rows", "fb_cos_trig", "fb_coswiss_word",
+    "fb_bayes_word",
 ]
 
 

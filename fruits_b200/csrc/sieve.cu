@@ -50,10 +50,13 @@ __global__ void pretransform_cumsum_kernel(const double *__restrict__ Y, double 
     }
 }
 
-enum { SV_NPI = 0, SV_MPI = 1, SV_MAX = 2, SV_MIN = 3, SV_XPI = 4, SV_LPI = 5, SV_END = 6 };
+enum { SV_NPI = 0, SV_MPI = 1, SV_MAX = 2, SV_MIN = 3, SV_XPI = 4, SV_LPI = 5, SV_END = 6,
+       SV_CUR = 7 };
 
 // fruits/sieving/segment.py:107-225 (MAX, MIN, END) and
-// fruits/sieving/increment.py:101-239 (NPI, MPI, XPI, LPI) backends.
+// fruits/sieving/increment.py:101-239 (NPI, MPI, XPI, LPI) backends;
+// fruits/sieving/segment.py:246-258 CUR: sum of the squares of the selected
+// values (the caller passes the second-order increments).
 // V[rows][ld]; cuts[rows][nc] (sorted, first column 0) or null = {0, t};
 // q[nq] thresholds; out[r*out_ld + col0 + j*(nq-1) + k].
 __global__ void segment_sieve_kernel(const double *__restrict__ V, long long ld,
@@ -94,13 +97,14 @@ __global__ void segment_sieve_kernel(const double *__restrict__ V, long long ld,
                 }
             } else {
                 int cnt = 0;
-                double sum = 0.0, mx = d_ninf(), mn = d_inf();
+                double sum = 0.0, sq = 0.0, mx = d_ninf(), mn = d_inf();
                 long long isum = 0;
                 for (long long s = lo + lane; s < hi; s += 32) {
                     const double v = x[s];
                     if (ql < v && v <= qh) {
                         cnt++;
                         sum += v;
+                        sq = __dadd_rn(sq, __dmul_rn(v, v));
                         isum += (s - lo);
                         mx = fmax(mx, v);
                         mn = fmin(mn, v);
@@ -110,6 +114,7 @@ __global__ void segment_sieve_kernel(const double *__restrict__ V, long long ld,
                 for (int sft = 16; sft; sft >>= 1) {
                     cnt += __shfl_xor_sync(0xffffffffu, cnt, sft);
                     sum += __shfl_xor_sync(0xffffffffu, sum, sft);
+                    sq += __shfl_xor_sync(0xffffffffu, sq, sft);
                     isum += __shfl_xor_sync(0xffffffffu, isum, sft);
                     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
                     mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, sft));
@@ -118,6 +123,7 @@ __global__ void segment_sieve_kernel(const double *__restrict__ V, long long ld,
                 else if (kind == SV_MPI) res = cnt ? sum / (double)cnt : 0.0;
                 else if (kind == SV_MAX) res = cnt ? mx : 0.0;
                 else if (kind == SV_MIN) res = cnt ? mn : 0.0;
+                else if (kind == SV_CUR) res = sq;
                 else res = cnt ? (double)isum / (double)cnt : 0.0;
             }
             if (lane == 0) o[j * (nq - 1) + k] = res;
@@ -125,7 +131,10 @@ __global__ void segment_sieve_kernel(const double *__restrict__ V, long long ld,
     }
 }
 
-// fruits/sieving/implicit.py:114-129 PPV._transform.
+// fruits/sieving/implicit.py:114-129 PPV._transform; with bit 1 of `segments`
+// set, :169-190 CPV._transform: 2 * #{s >= 1: in(x[s]) and not in(x[s-1])} / n,
+// n = t rounded up to an even number (the increments are zero-padded, so a
+// series that starts inside the set does not open a component).
 __global__ void ppv_kernel(const double *__restrict__ V, long long ld, const double *__restrict__ q,
                            int nq, int segments, double *__restrict__ out, long long out_ld,
                            long long col0, long long rows, int t)
@@ -134,19 +143,29 @@ __global__ void ppv_kernel(const double *__restrict__ V, long long ld, const dou
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
     const double *x = V + r * ld;
+    const bool cpv = (segments & 2) != 0;
+    segments &= 1;
     const int nf = segments ? nq - 1 : nq;
     for (int j = 0; j < nf; j++) {
         int c = 0;
-        if (segments) {
-            const double a = q[j], b = q[j + 1];
+        const double a = q[j], b = segments ? q[j + 1] : d_inf();
+        if (cpv) {
+            for (int s = 1 + lane; s < t; s += 32) {
+                const double u = x[s - 1], v = x[s];
+                const bool pu = segments ? (a <= u && u < b) : (u >= a);
+                const bool pv = segments ? (a <= v && v < b) : (v >= a);
+                c += (pv && !pu);
+            }
+        } else if (segments) {
             for (int s = lane; s < t; s += 32) c += (a <= x[s] && x[s] < b);
         } else {
-            const double a = q[j];
             for (int s = lane; s < t; s += 32) c += (x[s] >= a);
         }
 #pragma unroll
         for (int sft = 16; sft; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
-        if (lane == 0) out[r * out_ld + col0 + j] = (double)c / (double)t;
+        if (lane == 0)
+            out[r * out_ld + col0 + j] =
+                cpv ? (double)(2 * c) / (double)(t + (t & 1)) : (double)c / (double)t;
     }
 }
 
@@ -192,7 +211,7 @@ int fb_segment_sieve(const double *V, int64_t ld, const int64_t *cuts, int nc, c
                      int64_t t, void *stream)
 {
     FB_REQUIRE(V && q && out && rows >= 0 && t >= 1, "bad arguments");
-    FB_REQUIRE(nc >= 2 && nq >= 2 && kind >= SV_NPI && kind <= SV_END, "bad sieve description");
+    FB_REQUIRE(nc >= 2 && nq >= 2 && kind >= SV_NPI && kind <= SV_CUR, "bad sieve description");
     if (rows == 0) return 0;
     segment_sieve_kernel<<<(unsigned)((rows * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         V, ld, (const long long *)cuts, nc, q, nq, kind, out, out_ld, col0, rows, (int)t);

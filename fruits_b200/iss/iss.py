@@ -16,7 +16,7 @@ from .._plan import DevicePlan, Trie
 from ..cache import SharedSeedCache
 from ..seed import Seed
 from .cache import CachePlan
-from .semiring import Arctic, Reals, Semiring
+from .semiring import Arctic, Bayesian, Reals, Semiring
 from .weighting import Weighting
 from .words.word import SimpleWord, Word
 
@@ -35,7 +35,7 @@ class ISS(Seed):
         mode: ``ISSMode.SINGLE`` (one iterated sum per word) or
             ``ISSMode.EXTENDED`` (additionally every prefix of every word
             that was not already emitted by an earlier word).
-        semiring: ``Reals()`` (default) or ``Arctic()``.
+        semiring: ``Reals()`` (default), ``Arctic()`` or ``Bayesian()``.
         weighting: optional exponential weighting.
     """
 
@@ -49,7 +49,7 @@ class ISS(Seed):
         self.words = words
         self.mode = mode
         self.semiring = semiring if semiring is not None else Reals()
-        if not isinstance(self.semiring, (Reals, Arctic)):
+        if not isinstance(self.semiring, (Reals, Arctic, Bayesian)):
             raise NotImplementedError(
                 f"semiring {type(self.semiring).__name__} is not supported")
         self._cache_plan = CachePlan(self.words if mode == ISSMode.EXTENDED else [])
@@ -60,6 +60,11 @@ class ISS(Seed):
     @property
     def requires_fitting(self) -> bool:
         return False
+
+    @property
+    def _fusable_iss(self) -> bool:
+        # the Bayesian semiring has no trie kernel: sieved on materialised sums
+        return not isinstance(self.semiring, Bayesian)
 
     # -- plan ------------------------------------------------------------------
     def _weight_mode(self) -> int:
@@ -86,6 +91,8 @@ class ISS(Seed):
         return self.trie(), 0
 
     def device_plan(self, rows_max: int, emit_range=None, dim_desc=None) -> DevicePlan:
+        if isinstance(self.semiring, Bayesian):
+            raise NotImplementedError("the Bayesian semiring has no trie kernel")
         trie = self.trie()
         key = (rows_max, emit_range, None if dim_desc is None else tuple(dim_desc))
         plan = self._plan_memo.get(key)
@@ -142,6 +149,8 @@ class ISS(Seed):
         ``emit_range`` (all if None) on the device."""
         self._check_input(X)
         X = X.contiguous()
+        if isinstance(self.semiring, Bayesian):
+            return self._materialize_bayesian(X, emit_range, lookup)
         rows = be.lib().fb_slice_rows(be.POLICY_MAT)
         plan = self.device_plan(rows, emit_range)
         g, g_ld = self._lookup(X) if lookup is None else lookup
@@ -150,6 +159,41 @@ class ISS(Seed):
         batch = self.batch(X, g, g_ld)
         be.check(be.lib().fb_iss_materialize(plan.byref(), ctypes.byref(batch), out.data_ptr(),
                                              be.stream_ptr()))
+        return out
+
+    def _materialize_bayesian(self, X: torch.Tensor, emit_range, lookup) -> torch.Tensor:
+        """Word by word through ``fb_bayes_word`` (reference: iss.py:42-63 with
+        ``Bayesian.iterated_sum_fast``, semiring.py:530-566): word ``i`` emits
+        its last ``extended_i`` prefixes (all but those an earlier word emitted)."""
+        n, d, t = X.shape
+        g, g_ld = self._lookup(X) if lookup is None else lookup
+        lo, hi = (0, self.n_iterated_sums()) if emit_range is None else emit_range
+        out = be.empty((hi - lo, n, t))
+        tabs = self.__dict__.setdefault("_bayes_tables", {})
+        first = 0
+        for i, word in enumerate(self.words):
+            ext = (self._cache_plan.unique_el_depth(i) if self.mode == ISSMode.EXTENDED else 1)
+            last = first + ext
+            if ext > 0 and last > lo and first < hi:
+                key = (i, str(X.device), tuple(float(a) for a in word.alpha)
+                       if self.weighting is not None else None)
+                if key not in tabs:
+                    mat = np.ascontiguousarray(np.array(list(word), dtype=np.int32))
+                    alpha = (np.asarray(word.alpha, dtype=np.float32) if self.weighting is not None
+                             else np.zeros(len(mat), dtype=np.float32))
+                    tabs[key] = (torch.from_numpy(mat).to(X.device),
+                                 torch.from_numpy(np.ascontiguousarray(alpha)).to(X.device),
+                                 mat.shape)
+                mat, alpha, (p, md) = tabs[key]
+                whole = first >= lo and last <= hi
+                dst = out[first - lo:last - lo] if whole else be.empty((ext, n, t))
+                be.check(be.lib().fb_bayes_word(
+                    X.data_ptr(), n, d, t, mat.data_ptr(), p, md, alpha.data_ptr(), be.ptr(g),
+                    g_ld, self._weight_mode(), ext, dst.data_ptr(), be.stream_ptr()))
+                if not whole:
+                    a, b = max(first, lo), min(last, hi)
+                    out[a - lo:b - lo] = dst[a - first:b - first]
+            first = last
         return out
 
     def iter_chunks(self, X: torch.Tensor, max_bytes: int = 1 << 30):

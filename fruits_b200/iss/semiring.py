@@ -2,8 +2,9 @@
 
 On the GPU a semiring is only a tag that selects the instantiation of the ISS
 kernel (``csrc/lns.cuh``): ``Reals`` (:161-231, sum / product, the standard
-iterated sums) and ``Arctic`` (:341-457, max / plus).  ``Bayesian``
-(:461-601) and ``Arctic(argmax=True)`` are not part of the accelerated path.
+iterated sums) and ``Arctic`` (:341-457, max / plus); ``Bayesian``
+(:461-601, max / times) has its own scan kernel (``csrc/bayes.cu``).
+``Arctic(argmax=True)`` is not part of the accelerated path.
 """
 from abc import ABC
 
@@ -37,8 +38,8 @@ class Arctic(Semiring):
 
 
 class Bayesian(Semiring):
-    """Max-times semiring on [0, 1] (reference :461-601): listed as "next" in
-    SURVEY.md section 8(f), not built yet."""
-
-    def __init__(self) -> None:
-        raise NotImplementedError("the Bayesian semiring is not built yet")
+    """Max-times semiring on [0, 1] (reference :461-601): "sum" is the
+    maximum, "product" the multiplication.  Evaluated by a parallel running
+    maximum (``csrc/bayes.cu``); slices over this semiring are sieved on the
+    materialised iterated sums."""
+    _code = be.SEMIRING_BAYESIAN

@@ -1,5 +1,5 @@
 """Implicit sieves (reference: ``fruits/sieving/implicit.py``): ``PPV``
-(:11-153).  ``CPV`` (:156-213) is listed as "next" in SURVEY.md 8(f)."""
+(:11-153) and ``CPV`` (:156-213)."""
 __all__ = ["PPV", "CPV"]
 
 from typing import Union
@@ -18,6 +18,8 @@ class PPV(FeatureSieve):
     Args as in the reference (implicit.py:25-53): ``quantile`` (value or
     probability, or a list), ``constant`` (interpret as value), ``sample_size``
     (fraction of series used for the quantile), ``segments``."""
+
+    _mode = 0   # bit 1 of the kernel's mode word: connected components (CPV)
 
     def __init__(self, quantile: Union[list, float] = 0.5,
                  constant: Union[list, bool] = False, sample_size: float = 1.0,
@@ -98,7 +100,7 @@ class PPV(FeatureSieve):
         n, t = arr.shape
         q = be.to_device(np.array(self._q, dtype=np.float64))
         be.check(be.lib().fb_ppv(arr.data_ptr(), arr.stride(0), q.data_ptr(), len(self._q),
-                                 int(self._segments), out.data_ptr(), out.stride(0), col0,
+                                 int(self._segments) | self._mode, out.data_ptr(), out.stride(0), col0,
                                  n, t, be.stream_ptr()))
 
     def _fused(self):
@@ -129,8 +131,27 @@ class PPV(FeatureSieve):
 
 
 class CPV(PPV):
-    """Connected components of values above a quantile (reference :156-213):
-    not built yet."""
+    """Proportion of connected components of values ``>=`` a fitted quantile
+    (reference :156-213): the number of rising edges of the indicator
+    ``X >= q`` (a series that starts above ``q`` does not open one -- the
+    increments are zero-padded), times two, over the even-rounded length.
+    Arguments as :class:`PPV`."""
+    _mode = 2
 
-    def __init__(self, *args, **kwargs) -> None:
-        raise NotImplementedError("sieve CPV is not built yet")
+    def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
+        if not hasattr(self, "_q"):
+            raise RuntimeError("Missing call of CPV.fit()")
+        return super()._transform_device(X)
+
+    def _fused(self):
+        return None
+
+    def _copy(self) -> "CPV":
+        return CPV([x[0] for x in self._q_c_input], [x[1] for x in self._q_c_input],
+                   self._sample_size, self._segments)
+
+    def _summary(self) -> str:
+        return "C" + super()._summary()[1:]
+
+    def __str__(self) -> str:
+        return "C" + super().__str__()[1:]

@@ -1,7 +1,7 @@
 """Segment sieves (reference: ``fruits/sieving/segment.py``): the common
 base with cuts and quantile thresholds (:14-104) and ``MAX`` (:107-152),
-``MIN`` (:155-200), ``END`` (:203-225).  ``CUR``/``AVG``/``STD`` are listed as
-"next" in SURVEY.md section 8(f)."""
+``MIN`` (:155-200), ``END`` (:203-225), ``CUR`` (:228-274), ``AVG`` (:277-317),
+``STD`` (:320-358)."""
 __all__ = ["MAX", "MIN", "END", "CUR", "AVG", "STD"]
 
 from abc import ABC
@@ -193,17 +193,28 @@ class END(SegmentSieve):
         return ("END", 0) if self._default_cut() and len(self._q) == 2 else None
 
 
-def _next(name: str, ref: str):
-    class _Unsupported(SegmentSieve):
-        __doc__ = f"{name} (reference: {ref}) is not built yet (SURVEY.md section 8(f))."
+class CUR(SegmentSieve):
+    """Curvature (reference: segment.py:228-274): sum of the squared
+    second-order increments (zero-padded like ``_increments``) that lie in
+    ``(q_k, q_{k+1}]``, per cut segment.  As in the reference the thresholds
+    are fitted on the values themselves (``SegmentSieve._fit`` :66-75), not on
+    the increments they are later compared with."""
+    _kind = be.SIEVE_CUR
 
-        def __init__(self, *args, **kwargs) -> None:
-            raise NotImplementedError(f"sieve {name} is not built yet")
+    def _apply(self, arr: torch.Tensor, out: torch.Tensor, col0: int) -> None:
+        arr = arr.contiguous()
+        inc2 = torch.empty_like(arr)
+        be.check(be.lib().fb_pretransform(arr.data_ptr(), inc2.data_ptr(), arr.shape[0],
+                                          arr.shape[1], 2, be.stream_ptr()))
+        super()._apply(inc2, out, col0)
 
-    _Unsupported.__name__ = _Unsupported.__qualname__ = name
-    return _Unsupported
+
+class AVG(CUR):
+    """Reference :277-317.  Its ``_transform`` (:303-307) calls
+    ``CUR._backend``, so the reference's AVG *is* the curvature; a drop-in
+    returns what the reference returns."""
 
 
-CUR = _next("CUR", "segment.py:228-274")
-AVG = _next("AVG", "segment.py:277-317")
-STD = _next("STD", "segment.py:320-358")
+class STD(CUR):
+    """Reference :320-358; ``_transform`` (:346-350) calls ``CUR._backend``
+    as well (see :class:`AVG`)."""

@@ -36,6 +36,7 @@ extern "C" {
 /* fruits/iss/semiring.py: Reals (:161), Arctic (:341) */
 #define FB_SEMIRING_REALS   0
 #define FB_SEMIRING_ARCTIC  1
+#define FB_SEMIRING_BAYESIAN 2  /* fb_bayes_word only: not a trie-kernel semiring */
 /* fruits/iss/semiring.py:27-35: no weighting, Weighting.total True/False */
 #define FB_WEIGHT_NONE      0
 #define FB_WEIGHT_TOTAL     1
@@ -246,6 +247,16 @@ FB_API int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, con
                            const int32_t *weights, int n_terms, int ncols, double *out,
                            void *stream);
 
+/* fruits/iss/semiring.py:461-601 Bayesian semiring (max, times): iterated sums
+ * of ONE word (exponents word[p][md], device memory; alpha[p] float32, device
+ * memory) for all n series; the last `extended` prefixes are written to
+ * out[extended][n][t] (semiring.py:478-483).  weight_mode FB_WEIGHT_*: g is
+ * the weighting lookup (row stride g_ld, 0 = one row shared by all series).
+ * A parallel running maximum over time -- exact, the maximum is associative. */
+FB_API int fb_bayes_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word,
+                         int p, int md, const float *alpha, const double *g, int64_t g_ld,
+                         int weight_mode, int extended, double *out, void *stream);
+
 /* -- preparateurs, lookups, raw-input cache -- */
 
 /* fruits/cache.py:8-13 _increments on rows x t; pad_src != NULL keeps the
@@ -281,13 +292,15 @@ FB_API int fb_pretransform(const double *Y, double *out, int64_t rows, int64_t t
 #define FB_SIEVE_XPI 4
 #define FB_SIEVE_LPI 5
 #define FB_SIEVE_END 6
+#define FB_SIEVE_CUR 7   /* segment.py:228-274 (also what AVG :277-317 and STD :320-358 run) */
 /* fruits/sieving/segment.py:107-225, increment.py:101-239 backends on
  * V[rows][ld]; cuts[rows][nc] sorted with first column 0 (NULL: {0, t});
  * q[nq] sorted thresholds; out[r*out_ld + col0 + seg*(nq-1) + k]. */
 FB_API int fb_segment_sieve(const double *V, int64_t ld, const int64_t *cuts, int nc,
                             const double *q, int nq, int kind, double *out, int64_t out_ld,
                             int64_t col0, int64_t rows, int64_t t, void *stream);
-/* fruits/sieving/implicit.py:114-129 PPV._transform. */
+/* fruits/sieving/implicit.py:114-129 PPV._transform (segments = 0 / 1);
+ * segments | 2: :169-190 CPV._transform (connected components). */
 FB_API int fb_ppv(const double *V, int64_t ld, const double *q, int nq, int segments, double *out,
                   int64_t out_ld, int64_t col0, int64_t rows, int64_t t, void *stream);
 /* np.nan_to_num(a, nan=0.0) in place (fruits/fruit.py:172). */

@@ -250,13 +250,72 @@ static void arctic_single(const double *Z, const int32_t *word,
     }
 }
 
+/* fruits/iss/semiring.py:503-527 _total_weighted_bayesian_single */
+static void bayesian_total_single(const double *Z, const int32_t *word,
+                                  const float *alpha, const double *w,
+                                  int64_t p, int64_t md, int64_t t,
+                                  int64_t extended, double *result, double *tmp)
+{
+    for (int64_t j = 0; j < t; j++)
+        tmp[j] = 1.0;
+    for (int64_t k = 0; k < p; k++) {
+        double a = (double)alpha[k];
+        mul_letters(tmp, Z, word + k * md, md, t);
+        for (int64_t j = 0; j < t; j++)
+            tmp[j] = tmp[j] * exp(w[j] * a);
+        for (int64_t j = 1; j < t; j++)
+            tmp[j] = (tmp[j - 1] > tmp[j]) ? tmp[j - 1] : tmp[j];
+        if (p - k <= extended) {
+            double *r = result + (extended - (p - k)) * t;
+            for (int64_t j = 0; j < t; j++)
+                r[j] = tmp[j] * exp(-w[j] * a);
+        }
+        if (k < p - 1) {
+            for (int64_t j = 0; j < t; j++)
+                tmp[j] = tmp[j] * exp(-w[j] * a);
+        }
+    }
+}
+
+/* fruits/iss/semiring.py:466-495 _bayesian_single */
+static void bayesian_single(const double *Z, const int32_t *word,
+                            const float *alpha, const double *w, int64_t p,
+                            int64_t md, int64_t t, int64_t extended,
+                            double *result, double *tmp)
+{
+    for (int64_t j = 0; j < t; j++)
+        tmp[j] = 1.0;
+    for (int64_t k = 0; k < p; k++) {
+        mul_letters(tmp, Z, word + k * md, md, t);
+        if (k > 0) {
+            double a = (double)alpha[k - 1];
+            for (int64_t j = 0; j < t; j++)
+                tmp[j] = tmp[j] * exp(-w[j] * a);
+        }
+        if (p - k <= extended) {
+            double *r = result + (extended - (p - k)) * t;
+            if (t > 0)
+                r[0] = tmp[0];
+            for (int64_t j = 1; j < t; j++)
+                r[j] = (r[j - 1] > tmp[j]) ? r[j - 1] : tmp[j];
+        }
+        if (k < p - 1) {
+            double a = (double)alpha[k];
+            for (int64_t j = 0; j < t; j++)
+                tmp[j] = tmp[j] * exp(w[j] * a);
+            for (int64_t j = 1; j < t; j++)
+                tmp[j] = (tmp[j - 1] > tmp[j]) ? tmp[j - 1] : tmp[j];
+        }
+    }
+}
+
 /* fruits/iss/semiring.py:167-201 Reals._iterated_sum_fast and :354-404
  * Arctic._iterated_sum_fast: loop (prange) over series.
  *   X       [n, d, t]
  *   word    [p, md] (md <= d)
  *   lookup  [n, t]
  *   result  [n, extended, t]
- *   semiring: 0 reals, 1 arctic
+ *   semiring: 0 reals, 1 arctic, 2 bayesian (:530-566)
  */
 EXPORT void fo_iterated_sums(const double *X, const int32_t *word,
                              const float *alpha, const double *lookup,
@@ -278,11 +337,16 @@ EXPORT void fo_iterated_sums(const double *X, const int32_t *word,
                     reals_total_single(Z, word, alpha, w, p, md, t, extended, r, tmp);
                 else
                     reals_single(Z, word, alpha, w, p, md, t, extended, r, tmp);
-            } else {
+            } else if (semiring == 1) {
                 if (total)
                     arctic_total_single(Z, word, alpha, w, p, md, t, extended, r, tmp);
                 else
                     arctic_single(Z, word, alpha, w, p, md, t, extended, r, tmp);
+            } else {
+                if (total)
+                    bayesian_total_single(Z, word, alpha, w, p, md, t, extended, r, tmp);
+                else
+                    bayesian_single(Z, word, alpha, w, p, md, t, extended, r, tmp);
             }
         }
         free(tmp);
@@ -294,7 +358,8 @@ EXPORT void fo_iterated_sums(const double *X, const int32_t *word,
 /* q [nq] thresholds sorted; result [n, (nc-1)*(nq-1)].                 */
 /* kind: 0 NPI (increment.py:121-129), 1 MPI (:152-163),                */
 /*       2 MAX (segment.py:123-140), 3 MIN (:171-188),                  */
-/*       4 XPI (increment.py:184-199), 5 LPI (:217-239)                 */
+/*       4 XPI (increment.py:184-199), 5 LPI (:217-239),                */
+/*       6 CUR (segment.py:246-258; X = second-order increments)        */
 EXPORT void fo_segment_sieve(const double *X, const int64_t *cuts,
                              const double *q, double *result, int64_t n,
                              int64_t t, int64_t nc, int64_t nq, int kind)
@@ -310,7 +375,7 @@ EXPORT void fo_segment_sieve(const double *X, const int64_t *cuts,
             for (int64_t k = 0; k < nq - 1; k++) {
                 double ql = q[k], qh = q[k + 1];
                 int64_t cnt = 0, longest = 0, current = 0;
-                double sum = 0.0, idxsum = 0.0;
+                double sum = 0.0, idxsum = 0.0, sq = 0.0;
                 double mx = 0.0, mn = 0.0;
                 int have = 0;
                 for (int64_t s = lo; s < hi; s++) {
@@ -318,6 +383,7 @@ EXPORT void fo_segment_sieve(const double *X, const int64_t *cuts,
                     if (ql < v && v <= qh) {
                         cnt++;
                         sum = sum + v;
+                        sq = sq + v * v;
                         idxsum = idxsum + (double)(s - lo);
                         if (!have) { mx = v; mn = v; have = 1; }
                         else { if (v > mx) mx = v; if (v < mn) mn = v; }
@@ -334,6 +400,7 @@ EXPORT void fo_segment_sieve(const double *X, const int64_t *cuts,
                 case 2: r = have ? mx : 0.0; break;
                 case 3: r = have ? mn : 0.0; break;
                 case 4: r = cnt ? idxsum / (double)cnt : 0.0; break;
+                case 6: r = sq; break;
                 default: r = (double)longest; break;
                 }
                 result[i * nf + j * (nq - 1) + k] = r;
@@ -343,16 +410,29 @@ EXPORT void fo_segment_sieve(const double *X, const int64_t *cuts,
 }
 
 /* fruits/sieving/implicit.py:114-129 PPV._transform.
- * segments==0: count(X >= q_j)/t ; segments==1: count(q_{j-1} <= X < q_j)/t */
+ * segments==0: count(X >= q_j)/t ; segments==1: count(q_{j-1} <= X < q_j)/t
+ * segments|2: :169-190 CPV._transform -- 2 * #(rising edges of the indicator,
+ * zero-padded increments) / (t rounded up to even) */
 EXPORT void fo_ppv(const double *X, const double *q, double *result,
                    int64_t n, int64_t t, int64_t nq, int segments)
 {
+    const int cpv = (segments & 2) != 0;
+    segments &= 1;
     int64_t nf = segments ? nq - 1 : nq;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; i++) {
         const double *x = X + i * t;
         for (int64_t j = 0; j < nf; j++) {
             int64_t c = 0;
+            if (cpv) {
+                for (int64_t s = 1; s < t; s++) {
+                    int a = segments ? (q[j] <= x[s - 1] && x[s - 1] < q[j + 1]) : (x[s - 1] >= q[j]);
+                    int b = segments ? (q[j] <= x[s] && x[s] < q[j + 1]) : (x[s] >= q[j]);
+                    c += ((double)b - (double)a == 1.0);
+                }
+                result[i * nf + j] = (double)(2 * c) / (double)(t + (t & 1));
+                continue;
+            }
             if (segments) {
                 for (int64_t s = 0; s < t; s++)
                     c += (q[j] <= x[s] && x[s] < q[j + 1]);

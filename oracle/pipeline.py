@@ -290,7 +290,7 @@ def iss_word(X, word: str, extended: int, semiring: str, weighting,
     res = np.zeros((n, extended, t))
     load_oracle().fo_iterated_sums(
         _p(X), _p(mat), _p(a), _p(lk), _p(res), n, d, t, p, md, extended,
-        0 if semiring == "reals" else 1, 1 if total else 0)
+        {"reals": 0, "arctic": 1, "bayesian": 2}[semiring], 1 if total else 0)
     return np.ascontiguousarray(np.swapaxes(res, 0, 1))
 
 
@@ -414,7 +414,10 @@ def iterate_iss(X, iss_list, cache, idx=0):
 # ---------------------------------------------------------------------------
 # sieves
 
-_SEGMENT_KINDS = {"NPI": 0, "MPI": 1, "MAX": 2, "MIN": 3, "XPI": 4, "LPI": 5}
+# AVG and STD run CUR's backend in the reference (fruits/sieving/segment.py:303-307, :346-350)
+_SEGMENT_KINDS = {"NPI": 0, "MPI": 1, "MAX": 2, "MIN": 3, "XPI": 4, "LPI": 5,
+                  "CUR": 6, "AVG": 6, "STD": 6}
+_IMPLICIT = ("PPV", "CPV")
 _INCREMENT_SIEVES = ("NPI", "MPI", "XPI", "LPI")
 
 
@@ -423,7 +426,7 @@ class OracleSieve:
         self.name, args = desc
         args = dict(args)
         self.args = args
-        if self.name == "PPV":
+        if self.name in _IMPLICIT:
             q = args.get("quantile", 0.5)
             c = args.get("constant", False)
             q = q if isinstance(q, list) else [q]
@@ -445,12 +448,12 @@ class OracleSieve:
 
     # -- bookkeeping -------------------------------------------------------
     def nfeatures(self):
-        if self.name == "PPV":
+        if self.name in _IMPLICIT:
             return len(self.q_c) - 1 if self.segments else len(self.q_c)
         return len(self.cut) * (len(self.q) - 1)
 
     def requires_fitting(self):
-        if self.name == "PPV":
+        if self.name in _IMPLICIT:
             return True
         return any(q not in (-1, 0, 1) for q in self.q)
 
@@ -468,7 +471,7 @@ class OracleSieve:
         return np.ascontiguousarray(arr)
 
     def fit(self, X):
-        if self.name == "PPV":
+        if self.name in _IMPLICIT:
             # fruits/sieving/implicit.py:99-112
             self.fitted_q = [x[0] for x in self.q_c]
             for i, q in enumerate(list(self.fitted_q)):
@@ -517,11 +520,11 @@ class OracleSieve:
         lib = load_oracle()
         X = np.ascontiguousarray(X, dtype=np.float64)
         n, t = X.shape
-        if self.name == "PPV":
+        if self.name in _IMPLICIT:
             q = np.ascontiguousarray(np.array(self.fitted_q, dtype=np.float64))
             res = np.zeros((n, self.nfeatures()))
             lib.fo_ppv(_p(X), _p(q), _p(res), n, t, len(q),
-                       1 if self.segments else 0)
+                       (1 if self.segments else 0) | (2 if self.name == "CPV" else 0))
             return res
         if not self.requires_fitting():
             self.unfitted_quantiles()
@@ -536,12 +539,17 @@ class OracleSieve:
             return res
         q = np.ascontiguousarray(self.quantiles, dtype=np.float64)
         res = np.zeros((n, self.nfeatures()))
+        if _SEGMENT_KINDS[self.name] == 6:
+            # fruits/sieving/segment.py:246-249: cuts and thresholds of X applied to
+            # the second-order increments
+            arr = np.ascontiguousarray(
+                increments(increments(arr[:, np.newaxis, :], 1), 1)[:, 0, :])
         lib.fo_segment_sieve(_p(arr), _p(cuts), _p(q), _p(res), n, t,
                              cuts.shape[1], len(q), _SEGMENT_KINDS[self.name])
         return res
 
     def label(self, index):
-        if self.name == "PPV":
+        if self.name in _IMPLICIT:
             return "PPV"
         r, m = divmod(index, len(self.q) - 1)
         lab = f"{self.name}!{self.cut[r]}![{self.q[m]}, {self.q[m + 1]}]"

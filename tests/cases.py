@@ -42,6 +42,21 @@ ISS_CASES = {
                          "semiring": "arctic",
                          "weighting": ["L1", {"total": True}]},
                         (3, 2, 60), "walk"),
+    # Bayesian (max, times) semiring, SURVEY.md section 8(f) rank 2
+    "bayes_w3d2_ext": ({"words": {"of_weight": [3, 2]}, "mode": "extended",
+                        "semiring": "bayesian"}, (5, 2, 300), "unit"),
+    "bayes_single": ({"words": ["[1][2][1]", "[2]", "[12][1]"], "mode": "single",
+                      "semiring": "bayesian"}, (4, 2, 70), "unit"),
+    "bayes_neg": ({"words": ["[-1][2]", "[1][-2-2][1]", "[11][2]"], "mode": "extended",
+                   "semiring": "bayesian"}, (3, 2, 257), "uniform1"),
+    "bayes_indices": ({"words": ["[1][1]", "[1][2][1]"], "mode": "extended",
+                       "semiring": "bayesian", "weighting": ["Indices", {"scale": 3}]},
+                      (3, 2, 60), "unit"),
+    "bayes_L1_total": ({"words": ["[1][1]", "[1][2][1]"], "mode": "extended",
+                        "semiring": "bayesian",
+                        "weighting": ["L1", {"total": True, "scale": 2}],
+                        "alphas": [[0.5, 1.0], [1.0, 0.25, 2.0]]},
+                       (3, 2, 600), "unit"),
 }
 
 
@@ -68,6 +83,8 @@ def make_iss_input(shape, kind, seed=7):
         return rng.standard_normal(shape).cumsum(axis=2)
     if kind == "uniform1":
         return rng.random(shape) + 0.5
+    if kind == "unit":
+        return rng.random(shape)
     if kind == "std":
         x = rng.standard_normal(shape).cumsum(axis=2)
         return (x - x.mean(axis=2, keepdims=True)) / x.std(axis=2, keepdims=True)
@@ -100,7 +117,20 @@ SIEVE_CASES = {
     "ppv_multi": ["PPV", {"quantile": [0.2, 0.0, 0.9],
                           "constant": [False, True, False]}],
     "ppv_segments": ["PPV", {"quantile": [0.2, 0.5, 0.9], "segments": True}],
+    # SURVEY.md section 8(f) rank 2
+    "cur_default": ["CUR", {}],
+    "cur_q_cuts": ["CUR", {"cut": [12, 0.6, -1], "q": [-1.0, 0.4, 1.0]}],
+    "avg_default": ["AVG", {}],                      # runs CUR's backend in the reference
+    "std_q": ["STD", {"q": [0.3, 1.0]}],             # so does STD
+    "cpv_default": ["CPV", {}],
+    "cpv_multi": ["CPV", {"quantile": [0.2, 0.0, 0.9],
+                          "constant": [False, True, False]}],
+    "cpv_segments": ["CPV", {"quantile": [0.2, 0.5, 0.9], "segments": True}],
 }
+
+# sieves whose value is a floating-point sum (order unspecified under numba fastmath)
+SUMMING_SIEVES = ("MPI", "XPI", "CUR", "AVG", "STD")
+IMPLICIT_SIEVES = ("PPV", "CPV")
 
 
 

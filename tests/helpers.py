@@ -49,6 +49,6 @@ def oracle_thresholds(of):
     for slc in of.slices:
         for sieves in slc.sieves_extended:
             for sv in sieves:
-                q = sv.fitted_q if sv.name == "PPV" else sv.quantiles
+                q = sv.fitted_q if sv.name in ("PPV", "CPV") else sv.quantiles
                 rows.append(np.asarray(q, dtype=np.float64).ravel())
     return np.concatenate(rows) if rows else np.zeros(0)

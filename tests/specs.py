@@ -145,7 +145,8 @@ def _weighting(mod, desc):
 
 def _semiring(mod, name):
     return {"reals": mod.iss.semiring.Reals,
-            "arctic": mod.iss.semiring.Arctic}[name]()
+            "arctic": mod.iss.semiring.Arctic,
+            "bayesian": mod.iss.semiring.Bayesian}[name]()
 
 
 def _sieve(mod, desc):

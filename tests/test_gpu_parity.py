@@ -18,7 +18,7 @@ import torch
 
 import fruits_b200 as fruits
 import specs
-from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, make_iss_input,
+from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, make_iss_input,
                    make_prep_input, make_sieve_input)
 from helpers import (assert_close, assert_exact, fitted_thresholds, oracle_thresholds,
                      rowmax_rel_err)
@@ -39,6 +39,7 @@ def _need_gpu():
 
 
 def _exact_iss(desc):
+    # (weighted Bayesian sums multiply by exp(): device vs host libm)
     return desc.get("weighting") is None or desc.get("semiring") == "arctic"
 
 
@@ -66,9 +67,9 @@ def test_sieve_golden(name, golden_dir):
     np.random.seed(3)
     sv.fit(Y)
     res = sv.transform(Y)
-    thr = sv._q if SIEVE_CASES[name][0] == "PPV" else sv._quantiles
+    thr = sv._q if SIEVE_CASES[name][0] in IMPLICIT_SIEVES else sv._quantiles
     assert_exact(np.array(thr, dtype=np.float64), g[name + "_thr"], name + " thresholds")
-    if SIEVE_CASES[name][0] in ("MPI", "XPI"):
+    if SIEVE_CASES[name][0] in SUMMING_SIEVES:
         assert_close(res, g[name], 1e-12, name)
     else:
         assert_exact(res, g[name], name)
@@ -622,3 +623,84 @@ def test_coswiss_four_letter_words_generated_kernel():
     of.fit(X)
     assert_close(fitted_thresholds(fruit), oracle_thresholds(of), 1e-9, "thresholds")
     _assert_features_close(res, of.transform(X), "generated kernel vs oracle")
+
+
+# ---------------------------------------------------------------------------
+# Bayesian semiring, CUR / AVG / STD, CPV
+
+def test_bayesian_slice_with_curvature_and_components():
+    """A slice over the Bayesian semiring (scan kernel, sieved on materialised
+    sums) with the rank-2 sieves, against the oracle; thresholds bit-exact,
+    counts bit-exact, curvature sums within 1e-12."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [],
+                        "iss": [{"words": {"of_weight": [3, 2]}, "mode": "extended",
+                                 "semiring": "bayesian"}],
+                        "sieves": [["NPI", {"q": [0.4, 1.0]}], ["CPV", {"quantile": [0.3, 0.8]}],
+                                   ["CUR", {"cut": [0.5, -1], "q": [-1.0, 0.5, 1.0]}],
+                                   ["MAX", {}], ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(17).random((23, 2, 333))
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(5)
+    fruit.fit(X)
+    np.random.seed(5)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    res, ref = fruit.transform(X), of.transform(X)
+    assert res.shape == ref.shape == (23, fruit.nfeatures())
+    nf = sum(s.nfeatures() for s in fruit.get_slice().get_sieves())
+    cur_cols = np.zeros(res.shape[1], dtype=bool)
+    for e in range(res.shape[1] // nf):
+        cur_cols[e * nf + 3:e * nf + 7] = True       # NPI 1, CPV 2, CUR 4, MAX 1, END 1
+    assert_exact(res[:, ~cur_cols], ref[:, ~cur_cols], "counts / max / end")
+    assert_close(res[:, cur_cols], ref[:, cur_cols], 1e-12, "curvature")
+
+
+def test_bayesian_batch_transform_and_ragged_lengths():
+    """Partial emission ranges and lengths around the scan tile (256)."""
+    from oracle import pipeline as orc
+    desc = {"words": ["[1][2][1]", "[1][2]", "[2][2][1][1]", "[1]"], "mode": "extended",
+            "semiring": "bayesian"}
+    for T in (1, 2, 255, 256, 257, 700):
+        X = np.random.default_rng(T).random((3, 2, T)) + 0.25
+        iss = specs.build_iss(fruits, desc)
+        ref = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+        assert_exact(iss.transform(X), ref, f"T={T}")
+        parts = list(iss.batch_transform(X, batch_size=3))
+        assert_exact(np.concatenate(parts, axis=0), ref, f"batches T={T}")
+
+
+def test_rank2_sieves_large_rows_property():
+    """CUR == sum of squared second differences, CPV == rising edges, on
+    20,000 rows (no oracle needed: closed forms in numpy)."""
+    Y = np.random.default_rng(3).standard_normal((20000, 96)).cumsum(axis=1)
+    cur = fruits.sieving.CUR()
+    cur.fit(Y)
+    d1 = np.diff(Y, axis=1, prepend=Y[:, :1]); d1[:, 0] = 0.0
+    d2 = np.diff(d1, axis=1, prepend=d1[:, :1]); d2[:, 0] = 0.0
+    assert_close(cur.transform(Y)[:, 0], (d2 ** 2).sum(axis=1), 1e-12, "CUR")
+    cpv = fruits.sieving.CPV(quantile=0.0, constant=True)
+    cpv.fit(Y)
+    ind = (Y >= 0.0).astype(np.int8)
+    edges = ((ind[:, 1:] - ind[:, :-1]) == 1).sum(axis=1)
+    assert_exact(cpv.transform(Y)[:, 0], 2 * edges / 96, "CPV")
+
+
+def test_corbeille_fruitify_on_ucr_layout(tmp_path):
+    """The reference's experiment harness (fruitify / fruitify_all) against the
+    GPU path on a synthetic dataset in the UCR .txt layout: two well separated
+    classes must be classified, the CSV must be written."""
+    import corbeille
+    from test_host_api import _write_ucr
+    rng = np.random.default_rng(1)
+    _write_ucr(str(tmp_path), "Gamma", rng, n_train=40, n_test=30, length=64)
+    fruit = specs.build_fruit(fruits, specs.SPECS["C2_reduced"])
+    data = corbeille.data.load(str(tmp_path / "Gamma"))
+    np.random.seed(0)
+    seconds, acc = corbeille.fruitify(data, fruit)
+    assert seconds > 0 and 0.5 <= acc <= 1.0
+    df = corbeille.fruitify_all(str(tmp_path), fruit, output_csv=str(tmp_path / "res.csv"))
+    assert list(df.columns) == ["Dataset", "Accuracy", "Time"] and df["Dataset"][0] == "Gamma"
+    assert (tmp_path / "res.csv").exists()

@@ -210,3 +210,51 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(be.FbBatch) == 56
     assert ctypes.sizeof(be.FbSievePlan) == 4 + 4 * 16 * 2 + 4 + 8
     assert ctypes.sizeof(be.FbIssPlan) == 8 * 4 + 4 * 4 + 7 * 16 + 3 * 8
+
+
+# ---------------------------------------------------------------------------
+# caller side: UCR .txt loader of the harness
+
+def _write_ucr(root, name, rng, n_train=12, n_test=7, length=40, comma=False, nan=False):
+    import os
+    os.makedirs(os.path.join(root, name))
+    out = {}
+    for split, n in (("TRAIN", n_train), ("TEST", n_test)):
+        y = rng.integers(1, 3, size=n)
+        X = rng.standard_normal((n, length)).cumsum(axis=1) + y[:, None]
+        if nan:
+            X[0, 0] = np.nan
+            X[1, 5:8] = np.nan
+            X[2, -1] = np.nan
+        raw = np.concatenate([y[:, None].astype(float), X], axis=1)
+        np.savetxt(os.path.join(root, name, f"{name}_{split}.txt"), raw,
+                   delimiter="," if comma else "  ")
+        out[split] = (X, y)
+    return out
+
+
+def test_corbeille_loader(tmp_path):
+    import corbeille
+    rng = np.random.default_rng(0)
+    a = _write_ucr(str(tmp_path), "Alpha", rng)
+    b = _write_ucr(str(tmp_path), "Beta", rng, comma=True, nan=True)
+    Xtr, ytr, Xte, yte = corbeille.data.load(str(tmp_path / "Alpha") + "/")
+    assert Xtr.shape == (12, 1, 40) and Xte.shape == (7, 1, 40)
+    assert Xtr.dtype == np.float64 and ytr.dtype == np.int32
+    np.testing.assert_allclose(Xtr[:, 0], a["TRAIN"][0])
+    np.testing.assert_array_equal(yte, a["TEST"][1])
+    # NaNs: forward fill, 0 at the first step (reference data.py:125-147)
+    Xtr, _, _, _ = corbeille.data.load(str(tmp_path / "Beta"))
+    src = b["TRAIN"][0]
+    assert not np.isnan(Xtr).any()
+    assert Xtr[0, 0, 0] == 0.0
+    np.testing.assert_allclose(Xtr[1, 0, 5:8], src[1, 4])
+    np.testing.assert_allclose(Xtr[2, 0, -1], src[2, -2])
+    kept = corbeille.data.load(str(tmp_path / "Beta"), keep_nan=True)[0]
+    assert np.isnan(kept[1, 0, 5:8]).all()
+    assert corbeille.data.replace_nan(kept, 7.0)[1, 0, 6] == 7.0
+    names = [d[0] for d in corbeille.data.load_all(str(tmp_path))]
+    assert names == ["Alpha", "Beta"]
+    assert [d[0] for d in corbeille.data.load_all(str(tmp_path), datasets=["Beta"])] == ["Beta"]
+    with pytest.raises(NotImplementedError):
+        corbeille.data.load(str(tmp_path / "Alpha"), univariate=False)
