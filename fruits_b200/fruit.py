@@ -273,6 +273,11 @@ class Fruit:
         return self.get_slice(index)
 
 
+# iterated sums materialised per fit chunk (the pre-transformed copies and the
+# select workspace come on top: ~3x this in HBM)
+_FIT_CHUNK_BYTES = 2 << 30
+
+
 class FruitSlice:
     """One slice of a Fruit: preparateurs -> ISS -> sieves
     (reference: fruit.py:280-686, same methods)."""
@@ -497,7 +502,7 @@ class FruitSlice:
         over ``[chunk, n_fit * t]`` instead of one np.quantile per sieve."""
         iss = self._iss[0]
         n, _, t = prepared.shape
-        for _, chunk in iss.iter_chunks(prepared, max_bytes=1 << 29):
+        for _, chunk in iss.iter_chunks(prepared, max_bytes=_FIT_CHUNK_BYTES):
             G = chunk.shape[0]
             copies = [[sieve.copy() for sieve in self._sieves] for _ in range(G)]
             # replay the reference's RNG consumption: node-major, sieve order

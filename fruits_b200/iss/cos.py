@@ -166,9 +166,11 @@ class CosWISS(ISS):
     def _lookup(self, X: torch.Tensor):
         return None, 0
 
-    def materialize(self, X: torch.Tensor, emit_range=None, lookup=None) -> torch.Tensor:
+    def materialize(self, X: torch.Tensor, emit_range=None, lookup=None,
+                    trusted: bool = False) -> torch.Tensor:
         """Iterated sums ``[emit_hi-emit_lo, n, t]`` (word-major, frequency-minor)."""
-        self._check_input(X)
+        if not trusted:
+            self._check_input(X)
         X = X.contiguous()
         n, d, t = X.shape
         nf = len(self._freqs)

@@ -78,7 +78,11 @@ class ISS(Seed):
                 if self.weighting is not None else None,
                 self.mode, self.semiring._code, self._weight_mode())
 
-    def trie(self) -> Trie:
+    def trie(self, trusted: bool = False) -> Trie:
+        """``trusted``: the caller validated the memo in this call already
+        (chunk loops), skip rebuilding the signature of every word."""
+        if trusted and self._trie_memo is not None:
+            return self._trie_memo[1]
         sig = self._signature()
         if self._trie_memo is None or self._trie_memo[0] != sig:
             plan = self._cache_plan._plan if self.mode == ISSMode.EXTENDED else None
@@ -90,10 +94,11 @@ class ISS(Seed):
         """-> (trie, number of shared extra rows) for the kernel generator."""
         return self.trie(), 0
 
-    def device_plan(self, rows_max: int, emit_range=None, dim_desc=None) -> DevicePlan:
+    def device_plan(self, rows_max: int, emit_range=None, dim_desc=None,
+                    trusted: bool = False) -> DevicePlan:
         if isinstance(self.semiring, Bayesian):
             raise NotImplementedError("the Bayesian semiring has no trie kernel")
-        trie = self.trie()
+        trie = self.trie(trusted)
         key = (rows_max, emit_range, None if dim_desc is None else tuple(dim_desc))
         plan = self._plan_memo.get(key)
         if plan is None:
@@ -103,7 +108,12 @@ class ISS(Seed):
         return plan
 
     def max_dim(self) -> int:
-        return max(len(el) for w in self.words for el in w)
+        memo = self.__dict__.get("_max_dim_memo")
+        if memo is None or memo[0] is not self.words or memo[1] != len(self.words):
+            memo = (self.words, len(self.words),
+                    max(len(el) for w in self.words for el in w))
+            self._max_dim_memo = memo
+        return memo[2]
 
     def n_iterated_sums(self) -> int:
         """Number of iterated sums ``transform`` returns (reference :135-150)."""
@@ -144,15 +154,18 @@ class ISS(Seed):
         b.stats = be.ptr(stats)
         return b
 
-    def materialize(self, X: torch.Tensor, emit_range=None, lookup=None) -> torch.Tensor:
+    def materialize(self, X: torch.Tensor, emit_range=None, lookup=None,
+                    trusted: bool = False) -> torch.Tensor:
         """Iterated sums ``[emit_hi-emit_lo, n, t]`` of the emissions in
-        ``emit_range`` (all if None) on the device."""
-        self._check_input(X)
+        ``emit_range`` (all if None) on the device.  ``trusted``: input and
+        plan memo were validated by the caller (second and later chunks)."""
+        if not trusted:
+            self._check_input(X)
         X = X.contiguous()
         if isinstance(self.semiring, Bayesian):
             return self._materialize_bayesian(X, emit_range, lookup)
         rows = be.lib().fb_slice_rows(be.POLICY_MAT)
-        plan = self.device_plan(rows, emit_range)
+        plan = self.device_plan(rows, emit_range, trusted=trusted)
         g, g_ld = self._lookup(X) if lookup is None else lookup
         out = be.empty((plan.n_emit, X.shape[0], X.shape[2]))
         import ctypes
@@ -206,7 +219,7 @@ class ISS(Seed):
         for lo in range(0, n_emit, step):
             hi = min(n_emit, lo + step)
             rng = None if (lo == 0 and hi == n_emit) else (lo, hi)
-            yield lo, self.materialize(X, rng, lookup)
+            yield lo, self.materialize(X, rng, lookup, trusted=lo > 0)
 
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         return self.materialize(X)
