@@ -88,6 +88,121 @@ __global__ void __launch_bounds__(128) coswiss_kernel(const CosParams P)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Term-parallel form (used whenever the word has at most COS_P_MAX letters):
+// one CTA owns one series and a group of frequencies, one THREAD owns one
+// expansion term of one frequency and keeps its p running sums in registers.
+// Time is walked in tiles of COS_TT steps: phase 1, every thread advances its
+// term and leaves y_term[t] in shared memory; phase 2, one thread per
+// (frequency, t) adds the terms IN THE REFERENCE'S ORDER (term 0 first, fma
+// like numba's contraction) and writes the row coalesced.  Same operations in
+// the same order as coswiss_kernel, so the bits are the same.
+constexpr int COS_TT = 32;
+constexpr int COS_P_MAX = 6;
+
+template <int P>
+__global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, int fpc)
+{
+    extern __shared__ double sm[];
+    const int T = (int)Q.t, dw = Q.dw, nt = Q.n_terms;
+    const long long n = blockIdx.x;
+    const int f0 = blockIdx.y * fpc;
+    const int nf = min(fpc, Q.n_freq - f0);
+    double *xs = sm;                                  // [dw][COS_TT]
+    double *tr = xs + dw * COS_TT;                    // [fpc][2][COS_TT]
+    double *ys = tr + fpc * 2 * COS_TT;               // [fpc * n_terms][COS_TT + 1]
+    const int task = threadIdx.x;
+    const bool live = task < nf * nt;
+    const int fl = live ? task / nt : 0, term = live ? task - fl * nt : 0;
+    const bool total = Q.ncols == 2 * P + 3;
+    // exponents of this thread's term: sin / cos per level (+ the total weighting)
+    int ea[P + 1], eb[P + 1];
+    double coeff = 0.0;
+    {
+        const int *w = Q.weights + term * Q.ncols;
+#pragma unroll
+        for (int k = 0; k < P; k++) { ea[k] = w[2 * k + 1]; eb[k] = w[2 * k + 2]; }
+        ea[P] = total ? w[2 * P + 1] : 0;
+        eb[P] = total ? w[2 * P + 2] : 0;
+        coeff = (double)w[0];
+    }
+    (void)coeff;
+    double S[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) S[k] = 0.0;
+    const double *Xn = Q.X + (size_t)n * Q.d * T;
+    for (int t0 = 0; t0 < T; t0 += COS_TT) {
+        const int tn = min(COS_TT, T - t0);
+        __syncthreads();                              // phase 2 of the previous tile is done
+        for (int i = threadIdx.x; i < dw * COS_TT; i += blockDim.x) {
+            const int d = i / COS_TT, tt = i - d * COS_TT;
+            xs[i] = tt < tn ? Xn[(size_t)d * T + t0 + tt] : 0.0;
+        }
+        for (int i = threadIdx.x; i < nf * 2 * COS_TT; i += blockDim.x) {
+            const int r = i / COS_TT, tt = i - r * COS_TT;      // r = 2 * f_local + {0 sin, 1 cos}
+            tr[i] = tt < tn ? Q.trig[(size_t)(2 * f0 + r) * T + t0 + tt] : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+            const double *sw = tr + (2 * fl) * COS_TT, *cw = sw + COS_TT;
+            double *yo = ys + (size_t)task * (COS_TT + 1);
+            for (int tt = 0; tt < tn; tt++) {
+                const double s = sw[tt], c = cw[tt];
+                // last level first: level k reads the sum of level k-1 at t-1
+#pragma unroll
+                for (int k = P - 1; k >= 0; k--) {
+                    double tmp = k > 0 ? S[k - 1] : 1.0;
+                    const int *e = Q.word + k * dw;
+                    for (int d = 0; d < dw; d++) {
+                        const int occ = e[d];
+                        const double x = xs[d * COS_TT + tt];
+                        for (int r = 0; r < occ; r++) tmp = __dmul_rn(tmp, x);
+                        for (int r = 0; r < -occ; r++) tmp = __ddiv_rn(tmp, x);
+                    }
+                    for (int r = 0; r < ea[k]; r++) tmp = __dmul_rn(tmp, s);
+                    for (int r = 0; r < eb[k]; r++) tmp = __dmul_rn(tmp, c);
+                    S[k] = __dadd_rn(S[k], tmp);
+                }
+                double y = S[P - 1];
+                for (int r = 0; r < ea[P]; r++) y = __dmul_rn(y, s);
+                for (int r = 0; r < eb[P]; r++) y = __dmul_rn(y, c);
+                yo[tt] = y;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nf * COS_TT; i += blockDim.x) {
+            const int f = i / COS_TT, tt = i - f * COS_TT;
+            if (tt < tn) {
+                const double *yi = ys + (size_t)f * nt * (COS_TT + 1) + tt;
+                double result = 0.0;
+                for (int j = 0; j < nt; j++)
+                    result = fma((double)Q.weights[j * Q.ncols], yi[(size_t)j * (COS_TT + 1)], result);
+                Q.out[((size_t)(f0 + f) * Q.n + n) * T + t0 + tt] = result;
+            }
+        }
+    }
+}
+
+template <int P>
+static int coswiss_terms_launch(const CosParams &Q, cudaStream_t st)
+{
+    // frequencies per CTA: as many as fit 1024 threads
+    const int fpc = max(1, min(Q.n_freq, 1024 / Q.n_terms));
+    const int threads = ((fpc * Q.n_terms + 31) / 32) * 32;
+    const size_t smem = sizeof(double) * ((size_t)Q.dw * COS_TT + (size_t)fpc * 2 * COS_TT +
+                                          (size_t)fpc * Q.n_terms * (COS_TT + 1));
+    auto kern = coswiss_terms_kernel<P>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)Q.n, (unsigned)((Q.n_freq + fpc - 1) / fpc));
+    kern<<<grid, threads, smem, st>>>(Q, fpc);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -114,14 +229,32 @@ int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int3
                "word uses %d dimensions, the input has %lld (at most %d supported)", dw,
                (long long)d, COS_MAX_DIMS);
     FB_REQUIRE(ncols == 2 * p + 1 || ncols == 2 * p + 3, "weight table has %d columns", ncols);
-    if ((long long)n_terms * p > COS_MAX_SUMS)
-        return set_err(FB_ENOSUP, "CosWISS expansion too large: %d terms x %d letters (max %d)",
-                       n_terms, p, COS_MAX_SUMS);
     if (n == 0) return 0;
     CosParams P;
     P.X = X; P.trig = trig; P.word = word; P.weights = weights; P.out = out;
     P.n = n; P.d = d; P.t = t;
     P.p = p; P.dw = dw; P.n_freq = n_freq; P.n_terms = n_terms; P.ncols = ncols;
+    // term-parallel kernel: short words whose tile of term values fits shared memory
+    bool terms_ok = p <= COS_P_MAX && n_terms <= 1024 && n < (1LL << 31);
+    if (terms_ok) {
+        const int fpc = max(1, min(n_freq, 1024 / n_terms));
+        const size_t smem = sizeof(double) * ((size_t)dw * COS_TT + (size_t)fpc * 2 * COS_TT +
+                                              (size_t)fpc * n_terms * (COS_TT + 1));
+        terms_ok = smem <= 200 * 1024;
+    }
+    if (terms_ok) {
+        switch (p) {
+        case 1: return coswiss_terms_launch<1>(P, (cudaStream_t)stream);
+        case 2: return coswiss_terms_launch<2>(P, (cudaStream_t)stream);
+        case 3: return coswiss_terms_launch<3>(P, (cudaStream_t)stream);
+        case 4: return coswiss_terms_launch<4>(P, (cudaStream_t)stream);
+        case 5: return coswiss_terms_launch<5>(P, (cudaStream_t)stream);
+        default: return coswiss_terms_launch<6>(P, (cudaStream_t)stream);
+        }
+    }
+    if ((long long)n_terms * p > COS_MAX_SUMS)
+        return set_err(FB_ENOSUP, "CosWISS expansion too large: %d terms x %d letters (max %d)",
+                       n_terms, p, COS_MAX_SUMS);
     const long long tasks = n * n_freq;
     coswiss_kernel<<<(unsigned)((tasks + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
     FB_CUDA(cudaGetLastError());

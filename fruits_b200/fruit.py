@@ -502,7 +502,27 @@ class FruitSlice:
         over ``[chunk, n_fit * t]`` instead of one np.quantile per sieve."""
         iss = self._iss[0]
         n, _, t = prepared.shape
-        for _, chunk in iss.iter_chunks(prepared, max_bytes=_FIT_CHUNK_BYTES):
+        n_emit = iss.n_iterated_sums()
+        # multi-GPU fit (parallel.fit_sharded): every rank holds the whole fit
+        # sample and fits its contiguous share of the iterated sums; the fitted
+        # sieve copies (a few numbers each) are exchanged afterwards
+        shard = getattr(self, "_fit_shard", None)
+        first, last = (0, n_emit) if shard is None else shard[0](n_emit)
+        has_ppv = any(isinstance(sv, PPV) for sv in self._sieves)
+
+        def skip_draws(lo, hi):
+            # keep the global numpy RNG in step with the reference (and with the
+            # other ranks) for the iterated sums this rank does not fit
+            if has_ppv:
+                for _ in range(lo, hi):
+                    for sv in self._sieves:
+                        if isinstance(sv, PPV):
+                            sv._draw(n)
+
+        skip_draws(0, first)
+        local = []
+        for _, chunk in iss.iter_chunks(prepared, max_bytes=_FIT_CHUNK_BYTES,
+                                        emit_range=None if shard is None else (first, last)):
             G = chunk.shape[0]
             copies = [[sieve.copy() for sieve in self._sieves] for _ in range(G)]
             # replay the reference's RNG consumption: node-major, sieve order
@@ -547,10 +567,14 @@ class FruitSlice:
                 else:
                     for e in range(G):
                         copies[e][si]._fit_device(chunk[e])
-            for row in copies:
-                for sv in row:
-                    sv._cache = cache
-            self._sieves_extended.extend(copies)
+            local.extend(copies)
+        skip_draws(last, n_emit)
+        if shard is not None:
+            local = shard[1](local)          # all ranks' copies in emission order
+        for row in local:
+            for sv in row:
+                sv._cache = cache
+        self._sieves_extended.extend(local)
 
     # -- transform -------------------------------------------------------------------
     def transform(self, X, callbacks: Optional[list] = None,

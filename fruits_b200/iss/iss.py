@@ -209,17 +209,18 @@ class ISS(Seed):
             first = last
         return out
 
-    def iter_chunks(self, X: torch.Tensor, max_bytes: int = 1 << 30):
-        """Yield ``(emit_lo, tensor[g, n, t])`` over all emissions, at most
-        ``max_bytes`` per chunk."""
+    def iter_chunks(self, X: torch.Tensor, max_bytes: int = 1 << 30, emit_range=None):
+        """Yield ``(emit_lo, tensor[g, n, t])`` over all emissions (or those in
+        ``emit_range``), at most ``max_bytes`` per chunk."""
         n_emit = self.n_iterated_sums()
+        first, last = (0, n_emit) if emit_range is None else emit_range
         per = X.shape[0] * X.shape[2] * 8
         step = max(1, min(n_emit, max_bytes // max(per, 1)))
         lookup = self._lookup(X.contiguous())
-        for lo in range(0, n_emit, step):
-            hi = min(n_emit, lo + step)
+        for lo in range(first, last, step):
+            hi = min(last, lo + step)
             rng = None if (lo == 0 and hi == n_emit) else (lo, hi)
-            yield lo, self.materialize(X, rng, lookup, trusted=lo > 0)
+            yield lo, self.materialize(X, rng, lookup, trusted=lo > first)
 
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         return self.materialize(X)

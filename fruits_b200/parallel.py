@@ -11,8 +11,10 @@ and overlaps the kernels of the next chunk.
 
 Fit: the fit sample is drawn on rank 0 with the global numpy RNG (same draws
 as the reference, fruits/fruit.py:430-438), the owning ranks contribute the
-sampled rows, and every rank fits the same sample -- thresholds are identical
-on all ranks without any further exchange.
+sampled rows, and the iterated sums are split over the ranks: a threshold is a
+quantile over the WHOLE sample of one iterated sum, so rank r materialises and
+selects its share of the iterated sums and the fitted sieves (a few numbers
+each) are all-gathered -- thresholds are identical on all ranks.
 """
 from typing import Callable, Optional
 
@@ -60,9 +62,15 @@ def gather_fit_sample(X_local: torch.Tensor, n_total: int, fit_sample_size, grou
     return sample
 
 
-def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, group=None) -> None:
-    """``Fruit.fit`` on a row-sharded batch: every slice is fitted on the same
-    gathered sample on every rank, so the thresholds agree bit for bit."""
+def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, group=None,
+                shard_nodes: bool = True) -> None:
+    """``Fruit.fit`` on a row-sharded batch.  The fit sample is gathered on
+    every rank (quantiles are global over the sample, fruits/sieving/segment.py:66-75);
+    with ``shard_nodes`` the iterated sums of a slice are split over the ranks
+    -- each rank selects the thresholds of its share through the whole sample
+    and the fitted sieves are exchanged -- otherwise every rank fits everything.
+    Either way the thresholds are bit-identical on all ranks and equal to a
+    single-GPU fit."""
     from . import _backend as be
     from .cache import SharedSeedCache
     if n_total is None:
@@ -79,12 +87,24 @@ def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, gro
                     "sharded fit of sieves on L1/L2-weighted sums needs the raw-input cache "
                     "of the whole batch (reference quirk: fruits/cache.py:97-112)")
         sample = gather_fit_sample(X_local, n_total, slc.fit_sample_size, group)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+        def exchange(copies):
+            parts = [None] * world
+            dist.all_gather_object(parts, copies, group=group)
+            return [row for part in parts for row in part]
+
         try:
-            # the gathered rows ARE the sample: fit on all of them
+            # the gathered rows ARE the sample: fit on all of them; the iterated
+            # sums (each needs the whole sample for its quantiles) are split over
+            # the ranks, the fitted thresholds exchanged
             slc._select_fit_sample = lambda X: X
+            if world > 1 and shard_nodes:
+                slc._fit_shard = (lambda n_emit: shard_rows(n_emit, world, rank), exchange)
             slc._fit_device(be.to_device(sample), SharedSeedCache(sample))
         finally:
             del slc._select_fit_sample
+            slc.__dict__.pop("_fit_shard", None)
     fruit._fitted = True
 
 

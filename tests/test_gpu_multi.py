@@ -65,3 +65,65 @@ def test_two_gpu_sharded_transform(mode):
     for rank, same, shape in results:
         assert shape == (9000, 2225)
         assert same, f"rank {rank}: assembled matrix differs from the single-GPU transform"
+
+
+def _fit_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import fruits_b200 as fruits
+    from fruits_b200.parallel import fit_sharded, shard_rows
+    from helpers import fitted_thresholds
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [3, 2]}, "mode": "extended"}],
+                        "sieves": [["NPI", {"q": [0.3, 1.0]}], ["PPV", {"sample_size": 0.5}],
+                                   ["MPI", {"q": [0.2, 0.7], "inc": 2}], ["END", {}]],
+                        "fit_sample_size": 0.6},
+                       {"iss": [{"words": ["[1][2]", "[2][1][1]", "[1]"], "mode": "extended",
+                                 "semiring": "arctic"}],
+                        "sieves": [["MAX", {"q": [-1.0, 0.5]}], ["NPI", {"q": [0.5, 1.0]}]],
+                        "fit_sample_size": 1.0}]}
+    n = 301
+    X = np.random.default_rng(8).standard_normal((n, 2, 120)).cumsum(axis=2)
+    lo, hi = shard_rows(n, world, rank)
+    Xl = torch.from_numpy(X[lo:hi]).to(dev)
+    np.random.seed(40 + rank)                # different states: rank 0's is broadcast
+    if rank == 0:
+        np.random.seed(40)
+    fruit = specs.build_fruit(fruits, spec)
+    fit_sharded(fruit, Xl, n)
+    after = np.random.random()
+    single = specs.build_fruit(fruits, spec)
+    np.random.seed(40)
+    single.fit(torch.from_numpy(X).to(dev))
+    after_single = np.random.random()
+    same = bool(np.array_equal(fitted_thresholds(fruit), fitted_thresholds(single)))
+    feats = bool(torch.equal(fruit.transform_device(Xl), single.transform_device(Xl)))
+    q.put((rank, same, feats, after == after_single, len(fitted_thresholds(fruit))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_fit_splits_iterated_sums():
+    """fit_sharded: each rank fits its share of the iterated sums on the whole
+    gathered sample; thresholds, features and the consumption of the global
+    numpy RNG equal a single-GPU fit of the whole batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, same, feats, rng_ok, n_thr in results:
+        assert n_thr > 0
+        assert same, f"rank {rank}: thresholds differ from the single-GPU fit"
+        assert feats, f"rank {rank}: features differ"
+        assert rng_ok, f"rank {rank}: numpy RNG consumed differently"
