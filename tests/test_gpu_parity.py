@@ -704,3 +704,42 @@ def test_corbeille_fruitify_on_ucr_layout(tmp_path):
     df = corbeille.fruitify_all(str(tmp_path), fruit, output_csv=str(tmp_path / "res.csv"))
     assert list(df.columns) == ["Dataset", "Accuracy", "Time"] and df["Dataset"][0] == "Gamma"
     assert (tmp_path / "res.csv").exists()
+
+
+@pytest.mark.parametrize("n", [40, 4100])          # generic kernel / generated kernel
+def test_degenerate_values_match_the_oracle(n):
+    """Division by zero under negative exponents (inf, nan), overflow to +-inf,
+    constant series, STD of a constant series: nan / inf propagate through the
+    sums, the sieves and np.nan_to_num exactly as in the reference (means
+    within the summation-order tolerance)."""
+    from oracle import pipeline as orc
+    sieves = [["NPI", {"q": [0.5, 1.0]}], ["MPI", {}], ["PPV", {}], ["MAX", {}], ["MIN", {}],
+              ["END", {}]]
+    spec = {"slices": [
+        {"preps": [], "iss": [{"words": ["[-1]", "[1][-1]", "[-11][2]", "[2][-2][1]", "[1][2]"],
+                               "mode": "extended"}], "sieves": sieves, "fit_sample_size": 1.0},
+        {"preps": [], "iss": [{"words": ["[1][2]", "[-1][2][1]", "[11]"], "mode": "extended",
+                               "semiring": "arctic"}], "sieves": sieves, "fit_sample_size": 1.0},
+        {"preps": [["STD", {}]], "iss": [{"words": ["[1]", "[1][2]"], "mode": "extended"}],
+         "sieves": sieves, "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(2).standard_normal((n, 2, 64))
+    X[1, 0, 10] = 0.0
+    X[2, 0, 0] = 0.0
+    X[3, 1, 5:9] = 0.0
+    X[4] = 1.5
+    X[5, 0, 20] = 1e200
+    X[6, 0, 20] = -1e200
+    X[7, 1, 3] = 1e308
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(1)
+    fruit.fit(X)
+    np.random.seed(1)
+    with np.errstate(all="ignore"):
+        of.fit(X)
+        ref = of.transform(X)
+    res = fruit.transform(X)
+    assert not np.isnan(res).any()                   # fruit.py:172
+    with np.errstate(all="ignore"):
+        same = (res == ref) | (np.abs(res - ref) <= 1e-12 * np.maximum(np.abs(ref), 1.0))
+    assert same.all(), f"{(~same).sum()} of {same.size} differ, first {np.argwhere(~same)[:3]}"
