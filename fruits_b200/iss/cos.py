@@ -146,14 +146,24 @@ class CosWISS(ISS):
         return rows
 
     def _word_tables(self, index: int, dev):
-        key = (index, str(dev))
+        """Exponent matrix and expansion table of word ``index`` on the device.
+        All words are uploaded together on first use (one copy, not two per
+        word: every small pageable copy is a synchronisation)."""
+        key = ("tables", str(dev))
         if key not in self._tables:
-            word = self.words[index]
-            mat = np.ascontiguousarray(np.array(list(word), dtype=np.int32))
-            wts = np.ascontiguousarray(self._get_weightings(word))
-            self._tables[key] = (torch.from_numpy(mat).to(dev), torch.from_numpy(wts).to(dev),
-                                 mat.shape, wts.shape)
-        return self._tables[key]
+            mats = [np.ascontiguousarray(np.array(list(w), dtype=np.int32)) for w in self.words]
+            wtss = [np.ascontiguousarray(self._get_weightings(w)) for w in self.words]
+            flat = np.concatenate([a.ravel() for pair in zip(mats, wtss) for a in pair])
+            blob = torch.from_numpy(flat).to(dev)
+            views, off = [], 0
+            for mat, wts in zip(mats, wtss):
+                m = blob[off:off + mat.size]
+                off += mat.size
+                w = blob[off:off + wts.size]
+                off += wts.size
+                views.append((m, w, mat.shape, wts.shape))
+            self._tables[key] = views
+        return self._tables[key][index]
 
     def _trig(self, X: torch.Tensor) -> torch.Tensor:
         freqs = torch.tensor(np.asarray(self._freqs, dtype=np.float32), device=X.device)

@@ -37,7 +37,7 @@ assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF)), ref.__f
 from oracle import pipeline as orc  # noqa: E402
 sys.path.append(os.path.join(ROOT, "tests"))
 import specs  # noqa: E402  (tests/specs.py)
-from cases import (COS_CASES, COS_PIPE_CASES, ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES,  # noqa: E402
+from cases import (COS_CASES, COS_PIPE_CASES, ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap,  # noqa: E402
                    make_iss_input, make_prep_input, make_sieve_input)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -138,19 +138,19 @@ def gen_sieves():
         np.random.seed(3)
         sv.fit(Y)
         r = sv.transform(Y)
-        o = orc.OracleSieve(desc)
+        o = orc.make_sieve(desc)
         np.random.seed(3)
         o.fit(Y)
         oo = o.transform(Y, orc.RawCache(raw))
-        if desc[0] in SUMMING_SIEVES:
+        if sieve_kind(desc) in SUMMING_SIEVES:
             check_close(oo, r, f"sieve {name}", rtol=1e-13)
         else:
             check_equal(oo, r, f"sieve {name}")
         out[name] = r
-        if desc[0] in IMPLICIT_SIEVES:
-            out[name + "_thr"] = np.array(sv._q, dtype=np.float64)
+        if sieve_kind(desc) in IMPLICIT_SIEVES:
+            out[name + "_thr"] = np.array(unwrap(sv)._q, dtype=np.float64)
         else:
-            out[name + "_thr"] = np.array(sv._quantiles, dtype=np.float64)
+            out[name + "_thr"] = np.array(unwrap(sv)._quantiles, dtype=np.float64)
     np.savez_compressed(os.path.join(GOLD, "sieves.npz"), **out)
 
 

@@ -421,6 +421,51 @@ _IMPLICIT = ("PPV", "CPV")
 _INCREMENT_SIEVES = ("NPI", "MPI", "XPI", "LPI")
 
 
+class OracleWrapper:
+    """fruits/sieving/wrapper.py: INC (:9-64) / INT (:67-104).  The wrapped
+    sieve runs through its public fit / transform, i.e. with a cache of its
+    own built from the wrapped input (fruits/seed.py:26-51)."""
+
+    def __init__(self, desc):
+        self.name, args = desc
+        self.args = dict(args)
+        self.inner = make_sieve(self.args["sieve"])
+        self.depth = self.args.get("depth", 1)
+        self.shift = self.args.get("shift", 1)
+
+    def nfeatures(self):
+        return self.inner.nfeatures()
+
+    def requires_fitting(self):
+        return self.inner.requires_fitting()
+
+    def _wrapped(self, X):
+        if self.name == "INT":
+            return np.cumsum(X, axis=1)
+        inc = X[:, np.newaxis, :]
+        for _ in range(self.depth):          # wrapper.py:44-45: always from X
+            inc = increments(X[:, np.newaxis, :], self.shift)
+        return np.ascontiguousarray(inc[:, 0, :])
+
+    def fit(self, X):
+        self.inner.fit(self._wrapped(X))
+
+    def transform(self, X, cache=None):
+        W = self._wrapped(X)
+        return self.inner.transform(W, RawCache(W[:, np.newaxis, :]))
+
+    @property
+    def quantiles(self):
+        return self.inner.quantiles
+
+    def label(self, index):
+        return f"{self.name} of {self.inner.label(index)}"
+
+
+def make_sieve(desc):
+    return OracleWrapper(desc) if desc[0] in ("INC", "INT") else OracleSieve(desc)
+
+
 class OracleSieve:
     def __init__(self, desc):
         self.name, args = desc
@@ -564,7 +609,7 @@ class OracleSieve:
 class OracleSlice:
     def __init__(self, spec):
         self.spec = spec
-        self.sieves = [OracleSieve(s) for s in spec["sieves"]]
+        self.sieves = [make_sieve(s) for s in spec["sieves"]]
         self.sieves_extended = []
         self.fit_sample_size = spec.get("fit_sample_size", 1)
 
@@ -594,7 +639,7 @@ class OracleSlice:
             return
         self.sieves_extended = []
         for itsum in iterate_iss(prepared, self.spec["iss"], cache):
-            copies = [OracleSieve([s.name, s.args]) for s in self.sieves]
+            copies = [make_sieve([s.name, s.args]) for s in self.sieves]
             for s in copies:
                 s.fit(itsum)
             self.sieves_extended.append(copies)

@@ -126,6 +126,13 @@ SIEVE_CASES = {
     "cpv_multi": ["CPV", {"quantile": [0.2, 0.0, 0.9],
                           "constant": [False, True, False]}],
     "cpv_segments": ["CPV", {"quantile": [0.2, 0.5, 0.9], "segments": True}],
+    # sieve wrappers (fruits/sieving/wrapper.py)
+    "inc_of_max": ["INC", {"sieve": ["MAX", {"q": [-1.0, 0.5, 1.0]}]}],
+    "inc_shift3_of_npi": ["INC", {"sieve": ["NPI", {"q": [0.3, 1.0], "inc": 0}], "depth": 2,
+                                  "shift": 3}],
+    "inc_of_npi_cocut": ["INC", {"sieve": ["NPI", {"cut": [0.5, -1]}]}],
+    "int_of_end": ["INT", {"sieve": ["END", {"cut": [7, -1]}]}],
+    "int_of_ppv": ["INT", {"sieve": ["PPV", {"quantile": [0.4]}]}],
 }
 
 # sieves whose value is a floating-point sum (order unspecified under numba fastmath)
@@ -176,3 +183,17 @@ PIPE_CASES = {
 COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
 
+
+
+def sieve_kind(desc) -> str:
+    """Name of the innermost sieve of a (possibly wrapped) sieve description."""
+    while desc[0] in ("INC", "INT"):
+        desc = desc[1]["sieve"]
+    return desc[0]
+
+
+def unwrap(sieve):
+    """Innermost sieve object (product, reference: ``_sieve``; oracle: ``inner``)."""
+    while hasattr(sieve, "_sieve") or hasattr(sieve, "inner"):
+        sieve = getattr(sieve, "_sieve", None) or sieve.inner
+    return sieve

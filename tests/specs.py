@@ -152,6 +152,9 @@ def _semiring(mod, name):
 def _sieve(mod, desc):
     name, args = desc
     args = dict(args)
+    if name in ("INC", "INT"):           # sieve wrappers (fruits/sieving/wrapper.py)
+        args["sieve"] = _sieve(mod, args["sieve"])
+        return getattr(mod.sieving, name)(**args)
     for key in ("q", "cut"):
         if isinstance(args.get(key), list):
             args[key] = tuple(args[key])

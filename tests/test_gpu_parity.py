@@ -18,7 +18,7 @@ import torch
 
 import fruits_b200 as fruits
 import specs
-from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, make_iss_input,
+from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, make_iss_input,
                    make_prep_input, make_sieve_input)
 from helpers import (assert_close, assert_exact, fitted_thresholds, oracle_thresholds,
                      rowmax_rel_err)
@@ -67,9 +67,10 @@ def test_sieve_golden(name, golden_dir):
     np.random.seed(3)
     sv.fit(Y)
     res = sv.transform(Y)
-    thr = sv._q if SIEVE_CASES[name][0] in IMPLICIT_SIEVES else sv._quantiles
+    kind = sieve_kind(SIEVE_CASES[name])
+    thr = unwrap(sv)._q if kind in IMPLICIT_SIEVES else unwrap(sv)._quantiles
     assert_exact(np.array(thr, dtype=np.float64), g[name + "_thr"], name + " thresholds")
-    if SIEVE_CASES[name][0] in SUMMING_SIEVES:
+    if kind in SUMMING_SIEVES:
         assert_close(res, g[name], 1e-12, name)
     else:
         assert_exact(res, g[name], name)
@@ -743,3 +744,27 @@ def test_degenerate_values_match_the_oracle(n):
     with np.errstate(all="ignore"):
         same = (res == ref) | (np.abs(res - ref) <= 1e-12 * np.maximum(np.abs(ref), 1.0))
     assert same.all(), f"{(~same).sum()} of {same.size} differ, first {np.argwhere(~same)[:3]}"
+
+
+def test_sieve_wrappers_in_a_slice():
+    """INC / INT sieve wrappers (fruits/sieving/wrapper.py) inside a fruit:
+    composed route vs the oracle, thresholds and features bit-exact."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended"}],
+                        "sieves": [["INC", {"sieve": ["NPI", {"q": [0.3, 1.0], "inc": 0}],
+                                            "shift": 2}],
+                                   ["INT", {"sieve": ["MAX", {"q": [-1.0, 0.6]}]}],
+                                   ["INC", {"sieve": ["END", {"cut": [9, -1]}], "depth": 0}],
+                                   ["NPI", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(12).standard_normal((19, 2, 77)).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(6)
+    fruit.fit(X)
+    np.random.seed(6)
+    of.fit(X)
+    assert fruit.nfeatures() == of.nfeatures()
+    assert_exact(fruit.transform(X), of.transform(X), "wrapped sieves")
+    assert fruit.get_slice().get_sieves()[0].label(0).startswith("INC of NPI")
