@@ -768,3 +768,72 @@ def test_sieve_wrappers_in_a_slice():
     assert fruit.nfeatures() == of.nfeatures()
     assert_exact(fruit.transform(X), of.transform(X), "wrapped sieves")
     assert fruit.get_slice().get_sieves()[0].label(0).startswith("INC of NPI")
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json full sizes (one GPU's share): size-independent properties
+
+def test_sweep_full_shard_size():
+    """C5 at the size bench.py times (524,288 series x 3 x 1024, generated on
+    the device like the bench does): sampled rows equal the oracle bit for
+    bit, the run is deterministic, a chunk transformed on its own gives the
+    same rows (row independence), and the feature ranges hold everywhere."""
+    from oracle import pipeline as orc
+    n = 524288
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    spec = specs.SPECS["C5_sweep"]
+    gen = torch.Generator("cuda").manual_seed(1234)
+    X = torch.randn((n, 3, 1024), dtype=torch.float64, device="cuda", generator=gen)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(0)
+    fruit.fit(X)
+    out = fruit.transform_device(X)
+    assert out.shape == (n, 2225) and bool(torch.isfinite(out).all())
+    checksum = out.sum(dim=0)
+    again = fruit.transform_device(X)
+    assert bool(torch.equal(again, out)), "two runs differ"
+    del again
+    lo = 300000
+    part = fruit.transform_device(X[lo:lo + 70000])
+    assert bool(torch.equal(part, out[lo:lo + 70000])), "rows depend on their batch"
+    del part
+    pick = torch.tensor(sorted(np.random.default_rng(1).choice(n, 40, replace=False).tolist())
+                        + [0, n - 1], device="cuda")
+    Xs = X.index_select(0, pick).cpu().numpy()
+    np.random.seed(0)
+    fit_row = np.random.randint(0, n)                 # the draw fit() made (fruit.py:434)
+    of = orc.OracleFruit(spec)
+    np.random.seed(0)
+    of.fit(X[fit_row:fit_row + 1].cpu().numpy())      # randint(0, 1) == 0: the same row
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    assert_exact(out.index_select(0, pick).cpu().numpy(), of.transform(Xs), "sampled rows")
+    f = out.view(n, 445, 5)
+    assert bool((f[..., 0] == f[..., 0].round()).all()) and float(f[..., 0].min()) >= 0
+    assert float(f[..., 0].max()) <= 1024 and float(f[..., 1].min()) >= 0
+    assert float(f[..., 1].max()) <= 1
+    assert bool((f[..., 3] <= f[..., 4]).all()) and bool((f[..., 4] <= f[..., 2]).all())
+    assert bool(torch.isfinite(checksum).all())
+
+
+def test_twi_full_size():
+    """C4 at full size (100,000 x 3 x 2048): sampled rows against the oracle
+    (arctic slice bit-exact, L1-weighted slice within 1e-9), determinism."""
+    from oracle import pipeline as orc
+    spec = specs.SPECS["C4_twi"]
+    X = specs.make_input("C4_twi")
+    assert X.shape == (100000, 3, 2048)
+    Xd = torch.from_numpy(X).cuda()
+    fruit = specs.build_fruit(fruits, spec)
+    fruit.fit(Xd)
+    out = fruit.transform_device(Xd)
+    assert out.shape == (100000, 1725)
+    assert bool(torch.equal(fruit.transform_device(Xd), out))
+    pick = np.array([0, 1, 31, 32, 4097, 50000, 99999])
+    of = orc.OracleFruit(spec)
+    of.fit(X[pick])
+    ref = of.transform(X[pick])
+    res = out[torch.from_numpy(pick).cuda()].cpu().numpy()
+    assert_exact(res[:, 1533:], ref[:, 1533:], "arctic slice")
+    _assert_features_close(res[:, :1533], ref[:, :1533], "weighted slice")
