@@ -106,6 +106,9 @@ def lib() -> ctypes.CDLL:
         "fb_nan_to_num": ([vp, i64, vp], i32),
         "fb_order_stats_workspace": ([i64], i64),
         "fb_order_stats": ([vp, i64, i64, i64, i64, vp, vp, vp, vp], i32),
+        "fb_order_stats_multi_workspace": ([i64, i32], i64),
+        "fb_order_stats_multi": ([vp, i64, i64, i64, i64, i32, ctypes.POINTER(ctypes.c_int32),
+                                  ctypes.POINTER(ctypes.c_int64), vp, vp, vp, vp, vp], i32),
         "fb_fp64_peak": ([vp, i32, i32, vp], i32),
         "fb_jit_compile": ([ctypes.c_char_p, ctypes.c_char_p, i32, i32, ctypes.POINTER(vp),
                             ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t], i32),
@@ -140,7 +143,7 @@ EXPORTED = [
     "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_order_stats_workspace",
     "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
     "fb_jit_unload", "fb_jit_slice_features", "fb_jit_link", "fb_exp_rows", "fb_cos_trig", "fb_coswiss_word",
-    "fb_bayes_word",
+    "fb_bayes_word", "fb_order_stats_multi_workspace", "fb_order_stats_multi",
 ]
 
 

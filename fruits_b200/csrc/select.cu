@@ -162,6 +162,333 @@ __global__ void sel_out_kernel(const SelState *__restrict__ st, int P, unsigned 
     hi[p] = b;
 }
 
+// ---------------------------------------------------------------------------
+// Multi-selection form used by fit (fb_order_stats_multi): S selections
+// (increment depth 0..2 of the rows, rank k) of P problems in THREE reads of
+// the data instead of nine per selection plus the materialised increments:
+//   pass 0   histogram of key bits 63..52 (sign + exponent), all selections
+//   pass 1   histogram of bits 51..40 inside the chosen bucket
+//   pass 2   compaction: keys of the chosen 24-bit bucket go to a candidate
+//            list, the smallest key above the bucket and the NaN count are
+//            tracked on the way
+//   finish   one CTA per (problem, selection) resolves the remaining 40 bits
+//            on the candidate list (a few thousand keys, L2 resident)
+// The increments (fruits/cache.py:8-13, zero padded per row of length t) are
+// formed while the values are read.  A bucket that does not fit the candidate
+// list (many equal values) is reported as not done; the caller then takes the
+// eight-pass path for that selection.
+constexpr int SEL2_BINS = 4096;
+constexpr int SEL2_MAXSEL = 4;
+constexpr int SEL2_CAP = 1 << 16;
+
+struct Sel2State {
+    unsigned long long prefix;      // decided key bits (top aligned)
+    unsigned long long rank;        // remaining rank inside the bucket
+    unsigned long long bucket;      // keys in the chosen bucket
+    unsigned long long min_above;   // smallest key above the 24-bit bucket
+    unsigned long long n_nan;
+    unsigned int n_cand;
+    int done;
+};
+
+struct Sel2Args {
+    const double *V;
+    long long ldp, M;
+    int t, n_sel;
+    int inc[SEL2_MAXSEL];
+    unsigned long long k[SEL2_MAXSEL];
+};
+
+__device__ __forceinline__ double sel2_pick(const double val[3], int inc)
+{
+    return inc == 0 ? val[0] : (inc == 1 ? val[1] : val[2]);
+}
+
+// value of selection depth `inc` at flat index i (row position pos)
+__device__ __forceinline__ void sel2_values(const double *v, long long i, int pos, int max_inc,
+                                            double out[3])
+{
+    const double v0 = v[i];
+    out[0] = v0;
+    out[1] = 0.0;
+    out[2] = 0.0;
+    if (max_inc >= 1) {
+        const double vm1 = pos >= 1 ? v[i - 1] : 0.0;
+        const double d1 = pos >= 1 ? __dadd_rn(v0, -vm1) : 0.0;
+        out[1] = d1;
+        if (max_inc >= 2) {
+            const double vm2 = pos >= 2 ? v[i - 2] : 0.0;
+            const double d1m = pos >= 2 ? __dadd_rn(vm1, -vm2) : 0.0;
+            out[2] = pos >= 1 ? __dadd_rn(d1, -d1m) : 0.0;
+        }
+    }
+}
+
+__global__ void sel2_init_kernel(Sel2State *st, unsigned *hist, int n_states, Sel2Args a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_states) {
+        st[i].prefix = 0;
+        st[i].rank = a.k[i % a.n_sel];
+        st[i].bucket = 0;
+        st[i].min_above = ~0ULL;
+        st[i].n_nan = 0;
+        st[i].n_cand = 0;
+        st[i].done = 0;
+    }
+    for (long long j = i; j < (long long)n_states * SEL2_BINS; j += (long long)gridDim.x * blockDim.x)
+        hist[j] = 0;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS) sel2_hist_kernel(Sel2Args a, const Sel2State *st,
+                                                              unsigned *hist)
+{
+    extern __shared__ unsigned sh2[];                 // [n_sel][SEL2_BINS]
+    const int p = blockIdx.y, S = a.n_sel;
+    for (int j = threadIdx.x; j < S * SEL2_BINS; j += SEL_THREADS) sh2[j] = 0;
+    __syncthreads();
+    const double *v = a.V + p * a.ldp;
+    int max_inc = 0;
+    unsigned long long pre[SEL2_MAXSEL];
+    // pass 0: neighbouring values share sign and exponent, so a thread counts
+    // runs of equal bins in registers and touches shared memory once per run
+    int run_bin[SEL2_MAXSEL];
+    unsigned run_len[SEL2_MAXSEL];
+#pragma unroll
+    for (int s = 0; s < SEL2_MAXSEL; s++) {
+        run_bin[s] = 0;
+        run_len[s] = 0;
+        pre[s] = 0;
+        if (s < S) {
+            max_inc = max(max_inc, a.inc[s]);
+            pre[s] = st[p * S + s].prefix >> 52;
+        }
+    }
+    const long long base = (long long)blockIdx.x * SEL_THREADS * SEL_ITEMS;
+    // row position of the first element, advanced by SEL_THREADS per iteration
+    int pos = (int)((base + threadIdx.x) % a.t);
+    const int step = SEL_THREADS % a.t;
+#pragma unroll 2
+    for (int it = 0; it < SEL_ITEMS; it++) {
+        const long long i = base + (long long)it * SEL_THREADS + threadIdx.x;
+        const int cur = pos;
+        pos += step;
+        if (pos >= a.t) pos -= a.t;
+        if (i < a.M) {
+            double val[3];
+            sel2_values(v, i, cur, max_inc, val);
+#pragma unroll
+            for (int s = 0; s < SEL2_MAXSEL; s++)
+                if (s < S) {
+                    const unsigned long long key = order_key(sel2_pick(val, a.inc[s]));
+                    if (PASS == 0) {
+                        const int b = (int)(key >> 52);
+                        if (b == run_bin[s]) {
+                            run_len[s]++;
+                        } else {
+                            if (run_len[s]) atomicAdd(&sh2[s * SEL2_BINS + run_bin[s]], run_len[s]);
+                            run_bin[s] = b;
+                            run_len[s] = 1;
+                        }
+                    } else if ((key >> 52) == pre[s])
+                        atomicAdd(&sh2[s * SEL2_BINS + (int)((key >> 40) & (SEL2_BINS - 1))], 1u);
+                }
+        }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int s = 0; s < SEL2_MAXSEL; s++)
+            if (s < S && run_len[s]) atomicAdd(&sh2[s * SEL2_BINS + run_bin[s]], run_len[s]);
+    }
+    __syncthreads();
+    unsigned *h = hist + (size_t)p * S * SEL2_BINS;
+    for (int j = threadIdx.x; j < S * SEL2_BINS; j += SEL_THREADS) {
+        const unsigned c = sh2[j];
+        if (c) atomicAdd(&h[j], c);
+    }
+}
+
+// one warp per (problem, selection): the bin that holds the remaining rank
+__global__ void sel2_scan_kernel(Sel2State *st, unsigned *hist, int n_states, int shift)
+{
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= n_states) return;
+    unsigned *h = hist + (size_t)q * SEL2_BINS;
+    constexpr int PER = SEL2_BINS / 32;
+    unsigned long long sum = 0;
+    for (int i = 0; i < PER; i++) sum += h[lane * PER + i];
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl += o;
+    }
+    const unsigned long long excl = incl - sum;
+    const unsigned long long rank = st[q].rank;
+    if (rank >= excl && rank < incl) {
+        unsigned long long acc = excl;
+        int b = 0;
+        for (int i = 0; i < PER; i++) {
+            const unsigned long long c = h[lane * PER + i];
+            if (rank < acc + c) { b = i; break; }
+            acc += c;
+        }
+        st[q].prefix |= (unsigned long long)(lane * PER + b) << shift;
+        st[q].rank = rank - acc;
+        st[q].bucket = h[lane * PER + b];
+    }
+    __syncwarp();
+    for (int i = 0; i < PER; i++) h[lane * PER + i] = 0;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) sel2_compact_kernel(Sel2Args a, Sel2State *st,
+                                                                 unsigned long long *cand)
+{
+    const int p = blockIdx.y, S = a.n_sel;
+    const double *v = a.V + p * a.ldp;
+    int max_inc = 0;
+    unsigned long long pre[SEL2_MAXSEL], mab[SEL2_MAXSEL], nn[SEL2_MAXSEL];
+    bool fits[SEL2_MAXSEL];
+#pragma unroll
+    for (int s = 0; s < SEL2_MAXSEL; s++) {
+        mab[s] = ~0ULL;
+        nn[s] = 0;
+        fits[s] = false;
+        pre[s] = 0;
+        if (s < S) {
+            max_inc = max(max_inc, a.inc[s]);
+            pre[s] = st[p * S + s].prefix >> 40;
+            fits[s] = st[p * S + s].bucket <= (unsigned long long)SEL2_CAP;
+        }
+    }
+    const long long base = (long long)blockIdx.x * SEL_THREADS * SEL_ITEMS;
+    // row position of the first element, advanced by SEL_THREADS per iteration
+    int pos = (int)((base + threadIdx.x) % a.t);
+    const int step = SEL_THREADS % a.t;
+#pragma unroll 2
+    for (int it = 0; it < SEL_ITEMS; it++) {
+        const long long i = base + (long long)it * SEL_THREADS + threadIdx.x;
+        const int cur = pos;
+        pos += step;
+        if (pos >= a.t) pos -= a.t;
+        if (i < a.M) {
+            double val[3];
+            sel2_values(v, i, cur, max_inc, val);
+#pragma unroll
+            for (int s = 0; s < SEL2_MAXSEL; s++)
+                if (s < S) {
+                    const double x = sel2_pick(val, a.inc[s]);
+                    const unsigned long long key = order_key(x);
+                    const unsigned long long top = key >> 40;
+                    if (x != x) nn[s]++;
+                    if (top == pre[s]) {
+                        if (fits[s]) {
+                            const unsigned idx = atomicAdd(&st[p * S + s].n_cand, 1u);
+                            if (idx < (unsigned)SEL2_CAP)
+                                cand[((size_t)(p * S + s)) * SEL2_CAP + idx] = key;
+                        }
+                    } else if (top > pre[s] && key < mab[s]) {
+                        mab[s] = key;
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < SEL2_MAXSEL; s++)
+        if (s < S) {
+            unsigned long long m = mab[s], c = nn[s];
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, sft);
+                m = o < m ? o : m;
+                c += __shfl_xor_sync(0xffffffffu, c, sft);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                if (m != ~0ULL) atomicMin(&st[p * S + s].min_above, m);
+                if (c) atomicAdd(&st[p * S + s].n_nan, c);
+            }
+        }
+}
+
+// one CTA per (problem, selection): the remaining 40 bits on the candidate list
+__global__ void __launch_bounds__(256) sel2_finish_kernel(Sel2State *st, const unsigned long long *cand,
+                                                        Sel2Args a, double *lo, double *hi, int *done)
+{
+    __shared__ unsigned h[256];
+    __shared__ unsigned long long s_prefix, s_rank;
+    __shared__ unsigned long long red_min[8], red_cnt[8];
+    const int q = blockIdx.x;
+    const int s = q % a.n_sel;
+    Sel2State &S = st[q];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (S.bucket > (unsigned long long)SEL2_CAP) {
+        if (threadIdx.x == 0) { done[q] = 0; lo[q] = nan; hi[q] = nan; }
+        return;
+    }
+    const unsigned n = S.n_cand;
+    const unsigned long long *c = cand + (size_t)q * SEL2_CAP;
+    if (threadIdx.x == 0) { s_prefix = S.prefix; s_rank = S.rank; }
+    __syncthreads();
+    for (int shift = 32; shift >= 0; shift -= 8) {
+        h[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned long long himask = ~0ULL << (shift + 8);
+        const unsigned long long prefix = s_prefix;
+        for (unsigned i = threadIdx.x; i < n; i += 256) {
+            const unsigned long long key = c[i];
+            if ((key & himask) == prefix) atomicAdd(&h[(key >> shift) & 255], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long acc = 0, rank = s_rank;
+            int b = 0;
+            for (; b < 256; b++) {
+                if (rank < acc + h[b]) break;
+                acc += h[b];
+            }
+            s_prefix = prefix | ((unsigned long long)b << shift);
+            s_rank = rank - acc;
+        }
+        __syncthreads();
+    }
+    // successor of x_(k): another copy of the same key, the next candidate, or
+    // the smallest key above the bucket
+    const unsigned long long keyk = s_prefix;
+    unsigned long long cle = 0, mgt = ~0ULL;
+    for (unsigned i = threadIdx.x; i < n; i += 256) {
+        const unsigned long long key = c[i];
+        if (key <= keyk) cle++;
+        else if (key < mgt) mgt = key;
+    }
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) {
+        cle += __shfl_xor_sync(0xffffffffu, cle, sft);
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, mgt, sft);
+        mgt = o < mgt ? o : mgt;
+    }
+    if ((threadIdx.x & 31) == 0) { red_cnt[threadIdx.x >> 5] = cle; red_min[threadIdx.x >> 5] = mgt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cle = 0; mgt = ~0ULL;
+        for (int w = 0; w < 8; w++) { cle += red_cnt[w]; mgt = red_min[w] < mgt ? red_min[w] : mgt; }
+        // rank of x_(k) inside the bucket is S.rank (24-bit level); x_(k+1) equals
+        // x_(k) when more copies of the key follow
+        const unsigned long long r24 = S.rank;
+        double a_ = key_value(keyk), b_ = a_;
+        if (a.k[s] + 1 < (unsigned long long)a.M) {
+            if (r24 + 1 < cle) b_ = a_;
+            else if (mgt != ~0ULL) b_ = key_value(mgt);
+            else b_ = key_value(S.min_above);
+        }
+        if (S.n_nan) { a_ = nan; b_ = nan; }
+        lo[q] = a_;
+        hi[q] = b_;
+        done[q] = 1;
+    }
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -197,6 +524,65 @@ int fb_order_stats(const double *V, int64_t ldp, int64_t P, int64_t M, int64_t k
     }
     sel_final_kernel<<<grid, SEL_THREADS, 0, st>>>(V, ldp, M, state);
     sel_out_kernel<<<(Pi + 127) / 128, 128, 0, st>>>(state, Pi, (unsigned long long)k, M, lo, hi);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+int64_t fb_order_stats_multi_workspace(int64_t P, int n_sel)
+{
+    const int64_t ns = P * n_sel;
+    return (int64_t)(((ns * sizeof(Sel2State) + 255) / 256) * 256 + ns * SEL2_BINS * sizeof(unsigned) +
+                     ns * (int64_t)SEL2_CAP * sizeof(unsigned long long) + 256);
+}
+
+/* n_sel selections of every one of the P problems (V + p*ldp, M doubles, rows
+ * of length t): selection s looks at the inc[s]-fold zero-padded increments
+ * of the rows (0 = the values) and returns the order statistics x_(k[s]) and
+ * x_(min(k[s]+1, M-1)) in lo/hi[p*n_sel + s]; done[p*n_sel + s] = 0 if the
+ * selection must be repeated with fb_order_stats (too many equal values). */
+int fb_order_stats_multi(const double *V, int64_t ldp, int64_t P, int64_t M, int64_t t, int n_sel,
+                         const int32_t *inc, const int64_t *k, double *lo, double *hi, int32_t *done,
+                         void *work, void *stream)
+{
+    FB_REQUIRE(V && inc && k && lo && hi && done && work, "null argument");
+    FB_REQUIRE(P >= 0 && M >= 1 && t >= 1 && M % t == 0, "bad sizes P=%lld M=%lld t=%lld",
+               (long long)P, (long long)M, (long long)t);
+    FB_REQUIRE(n_sel >= 1 && n_sel <= SEL2_MAXSEL, "1..%d selections per call", SEL2_MAXSEL);
+    FB_REQUIRE(P <= 65535 && t < (1LL << 31), "too many problems in one call (%lld)", (long long)P);
+    if (P == 0) return 0;
+    Sel2Args a;
+    a.V = V; a.ldp = ldp; a.M = M; a.t = (int)t; a.n_sel = n_sel;
+    for (int s = 0; s < SEL2_MAXSEL; s++) { a.inc[s] = 0; a.k[s] = 0; }
+    for (int s = 0; s < n_sel; s++) {
+        FB_REQUIRE(inc[s] >= 0 && inc[s] <= 2, "increment depth %d (0..2 here)", inc[s]);
+        FB_REQUIRE(k[s] >= 0 && k[s] < M, "bad rank %lld", (long long)k[s]);
+        a.inc[s] = inc[s];
+        a.k[s] = (unsigned long long)k[s];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ns = (int)P * n_sel;
+    Sel2State *state = (Sel2State *)work;
+    unsigned *hist = (unsigned *)((char *)work + ((ns * sizeof(Sel2State) + 255) / 256) * 256);
+    unsigned long long *cand = (unsigned long long *)(hist + (size_t)ns * SEL2_BINS);
+    sel2_init_kernel<<<(ns * 64 + 255) / 256, 256, 0, st>>>(state, hist, ns, a);
+    const long long per_cta = (long long)SEL_THREADS * SEL_ITEMS;
+    dim3 grid((unsigned)((M + per_cta - 1) / per_cta), (unsigned)P);
+    const size_t smem = (size_t)n_sel * SEL2_BINS * sizeof(unsigned);
+    static bool configured = false;
+    if (!configured) {
+        FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
+        FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
+        configured = true;
+    }
+    sel2_hist_kernel<0><<<grid, SEL_THREADS, smem, st>>>(a, state, hist);
+    sel2_scan_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(state, hist, ns, 52);
+    sel2_hist_kernel<1><<<grid, SEL_THREADS, smem, st>>>(a, state, hist);
+    sel2_scan_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(state, hist, ns, 40);
+    sel2_compact_kernel<<<grid, SEL_THREADS, 0, st>>>(a, state, cand);
+    sel2_finish_kernel<<<ns, 256, 0, st>>>(state, cand, a, lo, hi, done);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -26,7 +26,7 @@ from .iss.semiring import Reals
 from .preparation.abstract import Preparateur
 from .preparation.wrapper import NEW
 from .seed import Seed
-from .sieving.abstract import FeatureSieve, quantile_rows
+from .sieving.abstract import FeatureSieve, quantile_multi, quantile_rows
 from .sieving.implicit import PPV
 from .sieving.segment import SegmentSieve
 
@@ -538,10 +538,27 @@ class FruitSlice:
                                       sv._pre_transform_device(flat)).reshape(G, n * t)
                 return key, pre_cache[key]
 
+            # every (increment depth, probability) this chunk needs, selected
+            # together in three reads of the chunk (fb_order_stats_multi)
+            pairs = []
+            for sv in self._sieves:
+                if isinstance(sv, PPV):
+                    if max(int(sv._sample_size * n), 1) == n:
+                        pairs += [(0, q) for q, const in sv._q_c_input if not const]
+                elif isinstance(sv, SegmentSieve) and 0 <= sv._inc <= 2:
+                    pairs += [(sv._inc, q) for q in sv._q if q not in (1.0, -1.0, 0)]
+            pairs = sorted(set(pairs))
+            if pairs:
+                q_cache.update({pair: vals for pair, vals in
+                                quantile_multi(chunk.reshape(G, n * t), t, pairs).items()
+                                if vals is not None})
+
             def quant(sv, q):
-                key, V = pretransformed(sv)
+                key = sv._inc if isinstance(sv, SegmentSieve) else 0
                 if (key, q) not in q_cache:
-                    q_cache[(key, q)] = quantile_rows(V, q)
+                    # other depths (cumulative sums, > 2) and buckets of equal values
+                    # too large for the candidate list: select on the materialised rows
+                    q_cache[(key, q)] = quantile_rows(pretransformed(sv)[1], q)
                 return q_cache[(key, q)]
 
             for si, sieve in enumerate(self._sieves):

@@ -313,6 +313,17 @@ FB_API int64_t fb_order_stats_workspace(int64_t P);
 FB_API int fb_order_stats(const double *V, int64_t ldp, int64_t P, int64_t M, int64_t k,
                           double *lo, double *hi, void *work, void *stream);
 
+/* The same for n_sel (<= 4) selections per problem in three reads of the
+ * data: selection s ranks the inc[s]-fold zero-padded increments (0..2; 0 =
+ * the values) of the rows of length t (IncrementSieve._pre_transform,
+ * increment.py:63-71, formed on the fly) and returns x_(k[s]), x_(k[s]+1) in
+ * lo/hi[p*n_sel + s].  done[p*n_sel + s] = 0: more equal values than the
+ * candidate list holds, repeat that selection with fb_order_stats. */
+FB_API int64_t fb_order_stats_multi_workspace(int64_t P, int n_sel);
+FB_API int fb_order_stats_multi(const double *V, int64_t ldp, int64_t P, int64_t M, int64_t t,
+                                int n_sel, const int32_t *inc, const int64_t *k, double *lo,
+                                double *hi, int32_t *done, void *work, void *stream);
+
 /* -- measurement -- */
 /* fp64 FMA microbenchmark (grid x 256 threads x iters*64 DFMA each; out holds
  * grid*256 doubles): the measured fp64 roof bench.py reports against. */

@@ -837,3 +837,69 @@ def test_twi_full_size():
     res = out[torch.from_numpy(pick).cuda()].cpu().numpy()
     assert_exact(res[:, 1533:], ref[:, 1533:], "arctic slice")
     _assert_features_close(res[:, :1533], ref[:, :1533], "weighted slice")
+
+
+def _np_increments(V, t, inc):
+    rows = V.reshape(V.shape[0], -1, t).copy()
+    for _ in range(inc):
+        d = np.zeros_like(rows)
+        d[..., 1:] = rows[..., 1:] - rows[..., :-1]
+        rows = d
+    return rows.reshape(V.shape[0], -1)
+
+
+@pytest.mark.parametrize("t,n", [(1, 700), (2, 513), (37, 300), (256, 40), (1000, 9), (50, 4000)])
+def test_order_stats_multi_matches_numpy(t, n):
+    """fb_order_stats_multi (three reads for up to four selections, increments
+    formed on the fly) == np.quantile of the materialised increments, bit for
+    bit: ties, zeros, negative values, huge values, a NaN problem."""
+    from fruits_b200.sieving.abstract import quantile_multi
+    rng = np.random.default_rng(t * 1000 + n)
+    P = 5
+    V = rng.standard_normal((P, n * t)).cumsum(axis=1)
+    V[1] = np.round(V[1])                      # many ties
+    V[2, ::7] = 0.0                            # (fewer than the candidate list holds)
+    V[3] *= 1e150
+    V[4, (n * t) // 2] = np.nan
+    pairs = [(0, 0.5), (1, 0.5), (2, 0.3), (1, 0.999), (0, 0.0), (2, 1.0), (0, 0.123)]
+    got = quantile_multi(torch.from_numpy(V).cuda(), t, pairs)
+    for inc, q in pairs:
+        ref = np.quantile(_np_increments(V, t, inc), q, axis=1)
+        res = got[(inc, q)]
+        if res is None:
+            # legitimate only if some problem has more keys in the quantile's 24-bit
+            # bucket (sign, exponent, 12 mantissa bits) than the candidate list holds
+            A = _np_increments(V, t, inc)
+            lower = np.quantile(A, q, axis=1, method="lower")
+            top = A.view(np.uint64) >> np.uint64(40)
+            big = [(top[p] == (np.float64(lower[p]).view(np.uint64) >> np.uint64(40))).sum()
+                   for p in range(P) if not np.isnan(lower[p])]
+            assert max(big) > 65536, (inc, q, big)
+            continue
+        assert_exact(res, ref, f"inc={inc} q={q} t={t}")
+
+
+def test_order_stats_multi_reports_large_buckets():
+    """More equal values at the quantile than the candidate list holds: the
+    selection is reported as not done and fit takes the eight-pass path."""
+    from fruits_b200.sieving.abstract import quantile_multi, quantile_rows
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal((2, 400 * 500))
+    V[0, :150000] = 0.25                       # the median bucket holds 150,000 keys
+    Vd = torch.from_numpy(V).cuda()
+    got = quantile_multi(Vd, 500, [(0, 0.5), (0, 0.999)])
+    assert got[(0, 0.5)] is None
+    assert_exact(got[(0, 0.999)], np.quantile(V, 0.999, axis=1), "unaffected selection")
+    assert_exact(quantile_rows(Vd, 0.5), np.quantile(V, 0.5, axis=1), "eight-pass path")
+    # through fit: constant rows make the increments' median bucket huge
+    spec = {"slices": [{"iss": [{"words": ["[1]"], "mode": "single"}],
+                        "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MPI", {"q": [0.2, 0.8], "inc": 0}]],
+                        "fit_sample_size": 1.0}]}
+    from oracle import pipeline as orc
+    X = rng.standard_normal((700, 1, 200))
+    X[:500] = 0.0
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    fruit.fit(X)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
