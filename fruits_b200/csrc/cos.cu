@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, 
     double *xs = sm;                                  // [dw][COS_TT]
     double *tr = xs + dw * COS_TT;                    // [fpc][2][COS_TT]
     double *ys = tr + fpc * 2 * COS_TT;               // [fpc * n_terms][COS_TT + 1]
+    double *cf = ys + (size_t)fpc * nt * (COS_TT + 1);   // [n_terms] binomial coefficients
+    for (int j = threadIdx.x; j < nt; j += blockDim.x) cf[j] = (double)Q.weights[j * Q.ncols];
     const int task = threadIdx.x;
     const bool live = task < nf * nt;
     const int fl = live ? task / nt : 0, term = live ? task - fl * nt : 0;
@@ -127,6 +129,23 @@ __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, 
         coeff = (double)w[0];
     }
     (void)coeff;
+    // the letters of the word as packed factor lists (4 bits per occurrence:
+    // dimension, bit 3 = division), the same for every thread of the CTA
+    unsigned long long ops[P];
+    int cnt[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        ops[k] = 0;
+        cnt[k] = 0;
+        for (int d = 0; d < dw; d++) {
+            const int occ = Q.word[k * dw + d];
+            const int m = occ < 0 ? -occ : occ;
+            for (int r = 0; r < m && cnt[k] < 16; r++) {
+                ops[k] |= (unsigned long long)(d | (occ < 0 ? 8 : 0)) << (4 * cnt[k]);
+                cnt[k]++;
+            }
+        }
+    }
     double S[P];
 #pragma unroll
     for (int k = 0; k < P; k++) S[k] = 0.0;
@@ -152,12 +171,10 @@ __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, 
 #pragma unroll
                 for (int k = P - 1; k >= 0; k--) {
                     double tmp = k > 0 ? S[k - 1] : 1.0;
-                    const int *e = Q.word + k * dw;
-                    for (int d = 0; d < dw; d++) {
-                        const int occ = e[d];
-                        const double x = xs[d * COS_TT + tt];
-                        for (int r = 0; r < occ; r++) tmp = __dmul_rn(tmp, x);
-                        for (int r = 0; r < -occ; r++) tmp = __ddiv_rn(tmp, x);
+                    unsigned long long o = ops[k];
+                    for (int j = 0; j < cnt[k]; j++, o >>= 4) {
+                        const double x = xs[(int)(o & 7) * COS_TT + tt];
+                        tmp = (o & 8) ? __ddiv_rn(tmp, x) : __dmul_rn(tmp, x);
                     }
                     for (int r = 0; r < ea[k]; r++) tmp = __dmul_rn(tmp, s);
                     for (int r = 0; r < eb[k]; r++) tmp = __dmul_rn(tmp, c);
@@ -176,7 +193,7 @@ __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, 
                 const double *yi = ys + (size_t)f * nt * (COS_TT + 1) + tt;
                 double result = 0.0;
                 for (int j = 0; j < nt; j++)
-                    result = fma((double)Q.weights[j * Q.ncols], yi[(size_t)j * (COS_TT + 1)], result);
+                    result = fma(cf[j], yi[(size_t)j * (COS_TT + 1)], result);
                 Q.out[((size_t)(f0 + f) * Q.n + n) * T + t0 + tt] = result;
             }
         }
@@ -190,7 +207,7 @@ static int coswiss_terms_launch(const CosParams &Q, cudaStream_t st)
     const int fpc = max(1, min(Q.n_freq, 1024 / Q.n_terms));
     const int threads = ((fpc * Q.n_terms + 31) / 32) * 32;
     const size_t smem = sizeof(double) * ((size_t)Q.dw * COS_TT + (size_t)fpc * 2 * COS_TT +
-                                          (size_t)fpc * Q.n_terms * (COS_TT + 1));
+                                          (size_t)fpc * Q.n_terms * (COS_TT + 1) + Q.n_terms);
     auto kern = coswiss_terms_kernel<P>;
     static size_t configured = 0;
     if (smem > configured) {
@@ -220,8 +237,8 @@ int fb_cos_trig(const float *freqs, int n_freq, int64_t t, double *trig, void *s
 }
 
 int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word, int p,
-                    int dw, const double *trig, int n_freq, const int32_t *weights, int n_terms,
-                    int ncols, double *out, void *stream)
+                    int dw, int max_occ, const double *trig, int n_freq, const int32_t *weights,
+                    int n_terms, int ncols, double *out, void *stream)
 {
     FB_REQUIRE(X && word && trig && weights && out, "null argument");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && p >= 1 && n_freq >= 1 && n_terms >= 1, "bad shape");
@@ -235,11 +252,12 @@ int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int3
     P.n = n; P.d = d; P.t = t;
     P.p = p; P.dw = dw; P.n_freq = n_freq; P.n_terms = n_terms; P.ncols = ncols;
     // term-parallel kernel: short words whose tile of term values fits shared memory
-    bool terms_ok = p <= COS_P_MAX && n_terms <= 1024 && n < (1LL << 31);
+    bool terms_ok = p <= COS_P_MAX && n_terms <= 1024 && n < (1LL << 31) && dw <= 8 &&
+                    max_occ <= 16;
     if (terms_ok) {
         const int fpc = max(1, min(n_freq, 1024 / n_terms));
         const size_t smem = sizeof(double) * ((size_t)dw * COS_TT + (size_t)fpc * 2 * COS_TT +
-                                              (size_t)fpc * n_terms * (COS_TT + 1));
+                                              (size_t)fpc * n_terms * (COS_TT + 1) + n_terms);
         terms_ok = smem <= 200 * 1024;
     }
     if (terms_ok) {

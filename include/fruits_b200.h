@@ -239,11 +239,12 @@ FB_API int fb_iss_materialize(const fb_iss_plan *plan, const fb_batch *batch, do
  * trig[f][1][t] = cos(...); freqs is a DEVICE array of float32. */
 FB_API int fb_cos_trig(const float *freqs, int n_freq, int64_t t, double *trig, void *stream);
 /* _coswiss (fruits/iss/cos.py:16-49, :171-181) for one word: out[f][n][t].
- * word: device int32 [p][dw] exponent matrix, weights: device int32
+ * word: device int32 [p][dw] exponent matrix (max_occ = the largest number of
+ * occurrences in one letter, sum_d |word[k][d]|), weights: device int32
  * [n_terms][ncols] table of CosWISS._get_weightings (:265-287; ncols = 2p+1,
  * or 2p+3 with the total weighting). */
 FB_API int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word,
-                           int p, int dw, const double *trig, int n_freq,
+                           int p, int dw, int max_occ, const double *trig, int n_freq,
                            const int32_t *weights, int n_terms, int ncols, double *out,
                            void *stream);
 
