@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-multicast", action="store_true",
+                    help="N > 1: copy-engine pushes instead of NVSwitch multicast stores")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="assemble the features with NCCL instead of peer-memory pushes")
     return ap.parse_args()
@@ -230,12 +232,19 @@ def run_ours(args):
     if gather and not args.nccl_gather:
         try:
             from fruits_b200.parallel import PeerGather
-            peer = PeerGather(S, N_FEATS)
+            peer = PeerGather(S, N_FEATS, multicast=not args.no_multicast)
             out = peer.out
-            collective = ("every finished row chunk is pushed into the peers' feature matrices "
-                          "(symmetric NVLink peer memory, copy engines, 8 chunks overlapped with "
-                          "the kernels), one device-side barrier per step; every rank holds the "
-                          "assembled [N*S, F] matrix")
+            if peer.fused:
+                n_chunks = 1
+                collective = ("fused into the feature kernel: its stores go through the NVSwitch "
+                              "multicast mapping (NVLS) of the symmetric [N*S, F] matrices, so "
+                              "every feature lands in the matrix of every rank as it is written; "
+                              "one device-side barrier per step, no copy or collective kernel")
+            else:
+                collective = ("every finished row chunk is pushed into the peers' feature "
+                              "matrices (symmetric NVLink peer memory, copy engines, 8 chunks "
+                              "overlapped with the kernels), one device-side barrier per step; "
+                              "every rank holds the assembled [N*S, F] matrix")
         except Exception as exc:                      # no symmetric memory on this box
             if rank == 0:
                 print(f"# PeerGather unavailable ({type(exc).__name__}: {exc}); NCCL all-gather",
@@ -248,6 +257,8 @@ def run_ours(args):
             collective = ("nccl all_gather_into_tensor of the [S, F] feature blocks in 8 row "
                           "chunks on a side stream, overlapped with the kernels; every rank "
                           "holds the assembled [N*S, F] matrix")
+
+    rows = S // n_chunks
 
     def compute(x, o):
         fruit.transform_device(x, out=o)

@@ -260,13 +260,14 @@ class Emitter:
     """CUDA source of one slice program."""
 
     def __init__(self, prog: Program, dims: list, ppc: int, gpc: int, shared_extra: bool,
-                 tt: int = 8, n_shared_rows: int = 0) -> None:
+                 tt: int = 8, n_shared_rows: int = 0, stage: int = 1) -> None:
         """dims[u] = (raw_dim, inc) of used dimension u; ppc/gpc = parts and
         series groups per CTA; shared_extra: the weighting rows are the same
         for every series (Indices)."""
         self.p = prog
         self.ppc, self.gpc = ppc, gpc
         self.tt = tt                 # time steps per shared-memory tile (even)
+        self.stage = stage
         self.shared_extra = shared_extra
         self.sv = prog.sieves
         self.cols = self.sv.thr_cols()
@@ -580,7 +581,50 @@ class Emitter:
                     val = f"(MN[{oi}] == D_INF ? 0.0 : MN[{oi}])"
                 else:
                     val = endv
-                L.append(f"o[{e * nf + f}] = fin({val}, a.sanitize);")
+                L.append((e * nf + f, f"fin({val}, a.sanitize)"))
+        return L
+
+    def staging_width(self) -> int:
+        """Doubles per series row of a warp's staging area in the epilogue (the
+        tile buffers of its group, free once the time loop is over), or 0 if
+        the features are stored directly."""
+        if not self.stage or self.ppc not in (1, 2, 4):
+            return 0
+        row = self.nrow * self.tt + 2
+        sw = row if self.ppc <= 2 else row // 2
+        if sw % 2 == 0:
+            sw -= 1                      # odd stride: conflict-free column writes
+        return sw if sw >= 5 else 0
+
+    def epilogue_code(self, part: Part) -> list:
+        """Store the features of one part.  Staged form: every lane puts its
+        values into shared memory, then the warp writes the 32 rows with
+        consecutive lanes on consecutive columns -- full sectors instead of one
+        8-byte piece per lane, which matters most when ``a.out`` is the
+        NVSwitch multicast mapping (every store becomes a packet to all GPUs)."""
+        vals = sorted(self.epilogue(part))
+        sw = self.staging_width()
+        if not sw:
+            return (["if (ns_ < a.n) {",
+                     "    double *o = a.out + (size_t)ns_ * a.out_ld + a.col0;"]
+                    + [f"    o[{col}] = {expr};" for col, expr in vals] + ["}"])
+        L = []
+        i = 0
+        while i < len(vals):
+            j = i + 1
+            while j < len(vals) and j - i < sw - 1 and vals[j][0] == vals[j - 1][0] + 1:
+                j += 1
+            for k in range(i, j):
+                L.append(f"stg[lane * {sw} + {k - i}] = {vals[k][1]};")
+            L.append("__syncwarp();")
+            L.append("#pragma unroll 1")
+            L.append("for (int r = 0; r < 32; r++) {")
+            L.append("    if (nrow0 + r >= a.n) break;")
+            L.append(f"    double *orow = a.out + (size_t)(nrow0 + r) * a.out_ld + a.col0 + {vals[i][0]};")
+            L.append(f"    for (int e = lane; e < {j - i}; e += 32) orow[e] = stg[r * {sw} + e];")
+            L.append("}")
+            L.append("__syncwarp();")
+            i = j
         return L
 
     # -- whole kernel ------------------------------------------------------------
@@ -855,18 +899,25 @@ class Emitter:
         A("    }")
         # ---- epilogue ----
         A("    const long long ns_ = nbase + sg * 32 + lane;")
-        A("    if (ns_ < a.n) {")
-        A("        double *o = a.out + (size_t)ns_ * a.out_ld + a.col0;")
-        A("        switch (part) {")
+        A("    const long long nrow0 = nbase + sg * 32;        // first series of this warp")
+        if self.staging_width():
+            # all warps of the group are done with the tile buffers: reuse them
+            A('    asm volatile("bar.sync %0, %1;" :: "r"(sg + 1), "n"(32 * PPC) : "memory");')
+            if self.ppc <= 2:
+                A("    double *stg = xbuf + ((size_t)((warp % PPC) * GPC * 32 + sg * 32)) * ROW;")
+            else:
+                A("    double *stg = xbuf + ((size_t)(((warp % PPC) / 2) * GPC * 32 + sg * 32)) * ROW"
+                  " + ((warp % PPC) % 2) * 16 * ROW;")
+        A("    (void)ns_; (void)nrow0;")
+        A("    switch (part) {")
         for pi, part in enumerate(parts):
             if not part.owned:
                 continue
-            A(f"        case {pi}: {{")
-            for ln in self.epilogue(part):
-                A("            " + ln)
-            A("        } break;")
-        A("        default: break;")
-        A("        }")
+            A(f"    case {pi}: {{")
+            for ln in self.epilogue_code(part):
+                A("        " + ln)
+            A("    } break;")
+        A("    default: break;")
         A("    }")
         A("}")
         del du
@@ -919,7 +970,8 @@ class FbJitGeometry(ctypes.Structure):
                 ("groups_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32)]
 
 
-DEFAULT_OPTS = {"budget": 70, "ppc": 2, "gpc": 8, "minb": 1, "unroll": 2, "tt": 16}
+DEFAULT_OPTS = {"budget": 70, "ppc": 2, "gpc": 8, "minb": 1, "unroll": 2, "tt": 16,
+                "stage": 1}        # epilogue: features through shared memory, coalesced rows
 
 
 def options() -> dict:
@@ -976,7 +1028,8 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
     em = None
     for gpc, tt in ((opts["gpc"], opts["tt"]), (opts["gpc"], 8), (max(1, opts["gpc"] // 2), 8),
                     (max(1, opts["gpc"] // 4), 8), (1, 4), (1, 2)):
-        cand = Emitter(prog, dims, opts["ppc"], gpc, shared_extra, tt, n_shared_rows)
+        cand = Emitter(prog, dims, opts["ppc"], gpc, shared_extra, tt, n_shared_rows,
+                       opts.get("stage", 1))
         if cand.smem_bytes() <= 200 * 1024:
             em = cand
             break

@@ -23,6 +23,20 @@ import torch
 import torch.distributed as dist
 
 
+class _DevicePointer:
+    """``__cuda_array_interface__`` of a raw device address (float64, C order)."""
+
+    def __init__(self, ptr: int, shape: tuple) -> None:
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape),
+                                         "typestr": "<f8", "version": 2, "strides": None}
+
+
+def _wrap_device_pointer(ptr: int, shape: tuple, device) -> torch.Tensor:
+    """Zero-copy tensor over ``ptr`` (used for the multicast mapping, which
+    torch does not hand out as a tensor)."""
+    return torch.as_tensor(_DevicePointer(ptr, shape), device=device)
+
+
 def shard_rows(n: int, world: int, rank: int):
     """Contiguous row block ``[lo, hi)`` of rank ``rank`` (first ranks get the
     remainder rows)."""
@@ -122,8 +136,10 @@ class PeerGather:
     Raises ``RuntimeError`` if symmetric memory is unavailable (the caller
     then falls back to the NCCL all-gather)."""
 
-    def __init__(self, rows_per_rank: int, n_feats: int, group=None) -> None:
+    def __init__(self, rows_per_rank: int, n_feats: int, group=None,
+                 multicast: bool = True) -> None:
         import torch.distributed._symmetric_memory as symm
+        from torch._C._autograd import DeviceType
         self.group = dist.group.WORLD if group is None else group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.S, self.F = rows_per_rank, n_feats
@@ -136,6 +152,28 @@ class PeerGather:
                       for r in range(self.world)]
         self.local = self.peers[self.rank]
         self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(min(4, self.world - 1))]
+        # NVSwitch multicast mapping of the same buffers (NVLS): a plain store to this
+        # address is replicated by the switch into the matrix of EVERY rank, so the
+        # feature kernel itself performs the all-gather (see ``multicast_rows``)
+        self.mc_ptr = 0
+        if multicast and self.world > 1:
+            try:
+                if self.handle.has_multicast_support(DeviceType.CUDA, dev.index):
+                    self.mc_ptr = int(self.handle.multicast_ptr)
+            except Exception:
+                self.mc_ptr = 0
+
+    @property
+    def fused(self) -> bool:
+        """True if the kernels can store straight into all ranks' matrices."""
+        return self.mc_ptr != 0
+
+    def multicast_rows(self, lo: int, hi: int) -> torch.Tensor:
+        """Write-only view of this rank's rows ``[lo, hi)`` in the multicast
+        address space: every store lands in the same rows of the matrix of
+        every rank (own included).  Must never be read."""
+        offset = ((self.rank * self.S + lo) * self.F) * 8
+        return _wrap_device_pointer(self.mc_ptr + offset, (hi - lo, self.F), self.out.device)
 
     def rows(self, lo: int, hi: int) -> torch.Tensor:
         """This rank's rows ``[lo, hi)`` inside its own matrix (compute target)."""
@@ -178,6 +216,12 @@ def transform_sharded(compute: Callable[[torch.Tensor, torch.Tensor], None],
     S = X_local.shape[0]
     dev = X_local.device
     if isinstance(out, PeerGather):
+        if out.fused:
+            # the kernels store through the NVSwitch multicast mapping: compute and
+            # all-gather are one launch, nothing is left to overlap
+            if S:
+                compute(X_local, out.multicast_rows(0, S))
+            return out.finish()
         chunks = max(1, min(chunks, S)) if S else 1
         for lo, hi in (shard_rows(S, chunks, c) for c in range(chunks)):
             compute(X_local[lo:hi], out.rows(lo, hi))

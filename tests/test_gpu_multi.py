@@ -36,7 +36,14 @@ def _worker(rank, world, port, mode, q):
     np.random.seed(3)
     fit_sharded(fruit, Xl, world * S)
     nf = fruit.nfeatures()
-    out = PeerGather(S, nf) if mode == "peer" else None
+    out = None
+    if mode in ("peer", "multicast"):
+        out = PeerGather(S, nf, multicast=(mode == "multicast"))
+        if mode == "multicast" and not out.fused:
+            q.put((rank, None, None))          # no NVLS on this box
+            dist.barrier()
+            dist.destroy_process_group()
+            return
     for _ in range(2):                      # the second pass reuses the peer buffers
         res = transform_sharded(lambda x, o: fruit.transform_device(x, out=o), Xl, nf,
                                 chunks=3, out=out)
@@ -48,7 +55,7 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer", "nccl"])
+@pytest.mark.parametrize("mode", ["multicast", "peer", "nccl"])
 def test_two_gpu_sharded_transform(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -62,6 +69,8 @@ def test_two_gpu_sharded_transform(mode):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    if any(same is None for _, same, _ in results):
+        pytest.skip("no NVSwitch multicast support on this box")
     for rank, same, shape in results:
         assert shape == (9000, 2225)
         assert same, f"rank {rank}: assembled matrix differs from the single-GPU transform"
