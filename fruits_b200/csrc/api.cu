@@ -21,7 +21,8 @@ int set_err(int code, const char *fmt, ...)
     return code;
 }
 
-static int fill_params(LnsParams &p, const fb_iss_plan *plan, const fb_batch *b, int rmax)
+static int fill_params(LnsParams &p, const fb_iss_plan *plan, const fb_batch *b, int rmax,
+                       long long t_max = 65535)
 {
     FB_REQUIRE(plan && b, "null plan or batch");
     FB_REQUIRE(plan->n_rows >= 1 && plan->n_rows <= rmax,
@@ -32,8 +33,9 @@ static int fill_params(LnsParams &p, const fb_iss_plan *plan, const fb_batch *b,
                plan->n_alphas);
     FB_REQUIRE(plan->max_depth >= 1 && plan->max_depth <= FB_RING - 64,
                "word length %d not supported (max %d)", plan->max_depth, FB_RING - 64);
-    FB_REQUIRE(b->t >= 1 && b->t < 65536, "series length %lld not supported (1..65535)",
-               (long long)b->t);
+    // (the sieving policies pack two 16-bit counters per register)
+    FB_REQUIRE(b->t >= 1 && b->t <= t_max, "series length %lld not supported (1..%lld)",
+               (long long)b->t, t_max);
     FB_REQUIRE(b->n >= 0 && b->d >= 1, "bad batch shape");
     FB_REQUIRE(plan->weight_mode == FB_WEIGHT_NONE || b->g != nullptr,
                "weighted ISS needs a lookup table");
@@ -88,7 +90,7 @@ int fb_device_info(int *sm_count, int *cc_major, int *cc_minor, int *smem_optin)
 int fb_iss_materialize(const fb_iss_plan *plan, const fb_batch *batch, double *out, void *stream)
 {
     LnsParams p;
-    int rc = fill_params(p, plan, batch, RMAX_MAT);
+    int rc = fill_params(p, plan, batch, RMAX_MAT, (1LL << 30));
     if (rc) return rc;
     FB_REQUIRE(out != nullptr, "null output");
     p.out = out;

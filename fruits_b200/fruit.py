@@ -430,9 +430,12 @@ class FruitSlice:
             return None
         return feats, bounded_hi, bounded_mm
 
-    def _is_fusable(self, n_dims: int, callbacks) -> bool:
+    def _is_fusable(self, n_dims: int, callbacks, length: int = 0) -> bool:
         if callbacks or len(self._iss) != 1:
             return False
+        if length >= 65536:
+            return False          # the fused kernels count in 16 bits: long series are sieved
+                                  # on materialised iterated sums (same results)
         if not getattr(self._iss[0], "_fusable_iss", True):
             return False          # e.g. CosWISS: sieved on materialised iterated sums
         w = self._iss[0].weighting
@@ -652,7 +655,7 @@ class FruitSlice:
             iss._cache = cache
         if X.shape[0] == 0:
             return
-        if self._is_fusable(X.shape[1], callbacks):
+        if self._is_fusable(X.shape[1], callbacks, X.shape[2]):
             self._transform_fused(X.contiguous(), cache, out, col0, sanitize)
         else:
             self._transform_composed(X, callbacks or [], cache, out, col0, sanitize)
@@ -678,7 +681,12 @@ class FruitSlice:
         if jit_only:
             self._transform_composed(X, [], cache, out, col0, sanitize)
             return
-        self._transform_generic(X, out, col0, sanitize, dims, feats, bounded_hi, bounded_mm)
+        try:
+            self._transform_generic(X, out, col0, sanitize, dims, feats, bounded_hi, bounded_mm)
+        except NotImplementedError:
+            # e.g. words over more distinct dimensions than one kernel block stages:
+            # materialise (in pieces) and sieve with the stand-alone kernels
+            self._transform_composed(X, [], cache, out, col0, sanitize)
 
     def _transform_jit(self, X, cache, out, col0, sanitize, dims, feats, bounded_hi,
                        bounded_mm) -> None:

@@ -88,6 +88,7 @@ class ISS(Seed):
             plan = self._cache_plan._plan if self.mode == ISSMode.EXTENDED else None
             self._trie_memo = (sig, Trie(self.words, plan, self.weighting is not None))
             self._plan_memo = {}
+            self._piece_memo = {}
         return self._trie_memo[1]
 
     def _jit_trie(self, n_dims: int):
@@ -106,6 +107,41 @@ class ISS(Seed):
             plan = DevicePlan(sub, self.semiring._code, self._weight_mode(), rows_max, dim_desc)
             self._plan_memo[key] = plan
         return plan
+
+    def _dim_pieces(self, emit_range, trusted: bool = False) -> list:
+        """Split ``emit_range`` (None = all) into consecutive emission ranges
+        whose sub-tries reference at most ``FB_MAX_USED_DIMS`` distinct input
+        dimensions each (one range if the whole already does)."""
+        trie = self.trie(trusted)
+        lo, hi = (0, len(trie.emits)) if emit_range is None else emit_range
+        memo = self.__dict__.setdefault("_piece_memo", {})
+        key = (id(trie), lo, hi)
+        if key in memo:
+            return memo[key]
+
+        def dims_of(v, acc):
+            while v >= 0:
+                n = trie.nodes[v]
+                acc.update(d for d, e in enumerate(n.expo) if e != 0)
+                v = n.parent
+            return acc
+
+        pieces, start, used = [], lo, set()
+        for e in range(lo, hi):
+            need = dims_of(trie.emits[e], set())
+            if len(need) > be.FB_MAX_USED_DIMS:
+                raise NotImplementedError(
+                    f"one word references {len(need)} distinct dimensions; the kernel "
+                    f"supports {be.FB_MAX_USED_DIMS}")
+            if len(used | need) > be.FB_MAX_USED_DIMS:
+                pieces.append((start, e))
+                start, used = e, set()
+            used |= need
+        pieces.append((start, hi))
+        if len(pieces) == 1:
+            pieces = [emit_range]
+        memo[key] = pieces
+        return pieces
 
     def max_dim(self) -> int:
         memo = self.__dict__.get("_max_dim_memo")
@@ -165,6 +201,13 @@ class ISS(Seed):
         if isinstance(self.semiring, Bayesian):
             return self._materialize_bayesian(X, emit_range, lookup)
         rows = be.lib().fb_slice_rows(be.POLICY_MAT)
+        pieces = self._dim_pieces(emit_range, trusted)
+        if len(pieces) > 1:
+            # the emissions reference more distinct dimensions than one launch
+            # stages: consecutive emission ranges, each within the limit
+            g_lookup = self._lookup(X) if lookup is None else lookup
+            return torch.cat([self.materialize(X, piece, g_lookup, trusted=True)
+                              for piece in pieces], dim=0)
         plan = self.device_plan(rows, emit_range, trusted=trusted)
         g, g_ld = self._lookup(X) if lookup is None else lookup
         out = be.empty((plan.n_emit, X.shape[0], X.shape[2]))

@@ -903,3 +903,45 @@ def test_order_stats_multi_reports_large_buckets():
     fruit.fit(X)
     of.fit(X)
     assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+
+
+def test_series_longer_than_the_16_bit_counters():
+    """T >= 65536: the fused kernels pack their counters in 16 bits, such
+    series take the materialise + stand-alone sieve route; same numbers."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": ["[1]", "[1][2]", "[2][1][1]"], "mode": "extended"}],
+                        "sieves": [["NPI", {"q": [0.5, 1.0]}], ["PPV", {}], ["MAX", {}], ["MIN", {}],
+                                   ["END", {}]],
+                        "fit_sample_size": 1}]}
+    X = np.random.default_rng(3).standard_normal((3, 2, 70001)) * 0.01
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(2)
+    fruit.fit(X)
+    np.random.seed(2)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    res = fruit.transform(X)
+    assert res[:, 0].max() > 0                      # NPI counts beyond 16 bits are possible
+    assert_exact(res, of.transform(X), "long series")
+
+
+def test_words_over_many_dimensions():
+    """of_weight(2, 12): 90 words over 12 input dimensions -- more distinct
+    dimensions than one kernel block stages; ISS.transform and a fruit must
+    still equal the oracle bit for bit."""
+    from oracle import pipeline as orc
+    desc = {"words": {"of_weight": [2, 12]}, "mode": "extended"}
+    X = np.random.default_rng(4).standard_normal((6, 12, 40))
+    ref = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    assert_exact(specs.build_iss(fruits, desc).transform(X), ref, "iss over 12 dimensions")
+    spec = {"slices": [{"preps": [], "iss": [desc],
+                        "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MAX", {}], ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    fruit.fit(X)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    assert_exact(fruit.transform(X), of.transform(X), "features over 12 dimensions")
