@@ -1003,7 +1003,13 @@ def enabled(n_series: int = None) -> bool:
     return n_series >= MIN_SERIES
 
 
-MIN_SERIES = 4096          # below this the generic kernel is used (unless forced)
+MIN_SERIES = 4096          # from this batch size on a slice is compiled (seconds, cached on disk)
+MIN_SERIES_CACHED = 1024   # ... and from this size on an already compiled kernel is used:
+                           # it beats the generic kernel from ~1,000 series (scripts/crossover.py)
+
+
+class NotCompiled(NotImplementedError):
+    """The generated kernel of a plan exists neither in memory nor on disk."""
 
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
@@ -1142,9 +1148,17 @@ class JitSlice:
             n_shared_rows: int = 0, max_state_regs: int = 0) -> "JitSlice":
         gen = generate(trie, semiring, weight_mode, sieves, dims, shared_extra, options(),
                        n_shared_rows, max_state_regs)
+        return cls.load(gen)
+
+    @classmethod
+    def load(cls, gen: Generated, cached_only: bool = False) -> "JitSlice":
+        """The loaded kernel of ``gen``; with ``cached_only`` only if it is
+        already in memory or compiled on disk (else ``NotCompiled``)."""
         key = gen.digest()
         obj = cls._loaded.get(key)
         if obj is None:
+            if cached_only and not os.path.exists(os.path.join(CACHE_DIR, key + ".cubin")):
+                raise NotCompiled(key)
             obj = cls(gen)
             cls._loaded[key] = obj
         return obj

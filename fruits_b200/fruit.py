@@ -671,13 +671,17 @@ class FruitSlice:
             raise ValueError("feature matrix must be row-major")
         feats, bounded_hi, bounded_mm = self._fused_sieves()
         jit_only = getattr(iss, "_jit_only", False)
-        if _jit.enabled(n) or (jit_only and _jit.enabled()):
+        compile_ok = _jit.enabled(n) or (jit_only and _jit.enabled())
+        # mid-size batches: the generated kernel only if it has been compiled already
+        cached_ok = not compile_ok and n >= _jit.MIN_SERIES_CACHED and _jit.enabled()
+        if compile_ok or cached_ok:
             try:
                 self._transform_jit(X, cache, out, col0, sanitize, dims, feats, bounded_hi,
-                                    bounded_mm)
+                                    bounded_mm, cached_only=cached_ok)
                 return
             except NotImplementedError:
-                pass      # plan too large for the specialised kernel: other route below
+                pass      # plan too large for the specialised kernel (or not compiled and
+                          # the batch too small to pay for it): other route below
         if jit_only:
             self._transform_composed(X, [], cache, out, col0, sanitize)
             return
@@ -689,7 +693,7 @@ class FruitSlice:
             self._transform_composed(X, [], cache, out, col0, sanitize)
 
     def _transform_jit(self, X, cache, out, col0, sanitize, dims, feats, bounded_hi,
-                       bounded_mm) -> None:
+                       bounded_mm, cached_only: bool = False) -> None:
         """Plan-specialised kernel (``_jit.py``): trie nodes and sieve state in
         registers, one thread per series and trie part."""
         iss = self._iss[0]
@@ -709,15 +713,26 @@ class FruitSlice:
         if memo is None or memo[0] is not trie:
             memo = (trie, {})
             iss._jit_memo = memo
-        if key not in memo[1]:
+        kern = memo[1].get(key)
+        if kern == "not compiled":
+            if cached_only:
+                raise _jit.NotCompiled("not compiled")
+            kern = None                     # a large batch pays for the compilation
+        if kern is None:
             try:
                 # a plan without another fused route may keep part of its sums in local memory
                 spill = 450 if getattr(iss, "_jit_only", False) else 0
-                memo[1][key] = _jit.JitSlice.get(trie, iss.semiring._code, wm, sieves, jdims,
-                                                 g_ld == 0, n_shared, spill)
+                gen = _jit.generate(trie, iss.semiring._code, wm, sieves, jdims, g_ld == 0,
+                                    _jit.options(), n_shared, spill)
             except NotImplementedError as exc:
                 memo[1][key] = exc          # remembered: planning is host work
-        kern = memo[1][key]
+                raise
+            try:
+                kern = _jit.JitSlice.load(gen, cached_only)
+            except _jit.NotCompiled:
+                memo[1][key] = "not compiled"      # do not plan again on every call
+                raise
+            memo[1][key] = kern
         if isinstance(kern, NotImplementedError):
             raise kern
         if materialise:

@@ -945,3 +945,40 @@ def test_words_over_many_dimensions():
     of.fit(X)
     assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
     assert_exact(fruit.transform(X), of.transform(X), "features over 12 dimensions")
+
+
+def test_mid_size_batches_use_a_compiled_kernel_only_if_it_exists(monkeypatch):
+    """1,024 <= n < 4,096: the generated kernel is used when its cubin is in
+    memory or on disk, never compiled for such a batch; identical numbers on
+    either route."""
+    from fruits_b200 import _jit
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": ["[1]", "[1][2]", "[2][2][1]", "[1][1][1]"],
+                                 "mode": "extended"}],
+                        "sieves": [["NPI", {"q": [0.37, 1.0]}], ["MAX", {}], ["END", {}]],
+                        "fit_sample_size": 1}]}
+    X = np.random.default_rng(31).standard_normal((5000, 2, 48))
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(1)
+    fruit.fit(X)
+    compiled = []
+    real_init = _jit.JitSlice.__init__
+
+    def spy(self, gen):
+        compiled.append(gen.digest())
+        real_init(self, gen)
+
+    monkeypatch.setattr(_jit.JitSlice, "__init__", spy)
+    monkeypatch.setattr(_jit.JitSlice, "_loaded", {})
+    monkeypatch.setattr(_jit, "CACHE_DIR", "/nonexistent-jit-cache")
+    small = fruit.transform(X[:2000])                 # nothing compiled yet: generic kernel
+    assert _routes(fruit) == ["fb::lns_kernel"] and not compiled
+    big = fruit.transform(X)                          # 5,000 series: compiled now
+    assert _routes(fruit) == ["fb_jit_slice"] and len(compiled) == 1
+    again = fruit.transform(X[:2000])                 # ... and reused for the mid-size batch
+    assert _routes(fruit) == ["fb_jit_slice"] and len(compiled) == 1
+    assert_exact(again, small, "generated vs generic kernel")
+    assert_exact(big[:2000], small, "row independence")
+    tiny = fruit.transform(X[:500])                   # below the crossover: generic kernel
+    assert _routes(fruit) == ["fb::lns_kernel"]
+    assert_exact(tiny, small[:500], "small batch")
