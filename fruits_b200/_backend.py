@@ -121,7 +121,7 @@ def lib() -> ctypes.CDLL:
         "fb_jit_slice_features": ([vp, vp, ctypes.POINTER(FbBatch), vp, i64, vp, i64, vp, i64, i64,
                                    i32, vp], i32),
         "fb_cos_trig": ([vp, i32, i64, vp, vp], i32),
-        "fb_coswiss_word": ([vp, i64, i64, i64, vp, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp], i32),
+        "fb_coswiss_word": ([vp, i64, i64, i64, vp, i32, i32, i32, i32, vp, i32, vp, i32, i32, vp, vp], i32),
         "fb_bayes_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, i32, i32, vp, vp], i32),
         "fb_exp_rows": ([vp, vp, i64, i64, ctypes.POINTER(ctypes.c_float), i32, vp], i32),
     }

@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(128) coswiss_kernel(const CosParams P)
 constexpr int COS_TT = 32;
 constexpr int COS_P_MAX = 6;
 
-template <int P>
+// EMAX: upper bound of the sin / cos exponents of a level (2 * exponent of the
+// cosine); the multiplications are unrolled and predicated instead of looped
+// (a loop iteration costs ~8 instructions around one DMUL).
+template <int P, int EMAX>
 __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, int fpc)
 {
     extern __shared__ double sm[];
@@ -172,17 +175,30 @@ __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, 
                 for (int k = P - 1; k >= 0; k--) {
                     double tmp = k > 0 ? S[k - 1] : 1.0;
                     unsigned long long o = ops[k];
-                    for (int j = 0; j < cnt[k]; j++, o >>= 4) {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {            // most letters: 1-3 occurrences
+                        if (j < cnt[k]) {
+                            const double x = xs[(int)(o & 7) * COS_TT + tt];
+                            if (o & 8) tmp = __ddiv_rn(tmp, x);
+                            else tmp = __dmul_rn(tmp, x);
+                            o >>= 4;
+                        }
+                    }
+                    for (int j = 3; j < cnt[k]; j++, o >>= 4) {
                         const double x = xs[(int)(o & 7) * COS_TT + tt];
                         tmp = (o & 8) ? __ddiv_rn(tmp, x) : __dmul_rn(tmp, x);
                     }
-                    for (int r = 0; r < ea[k]; r++) tmp = __dmul_rn(tmp, s);
-                    for (int r = 0; r < eb[k]; r++) tmp = __dmul_rn(tmp, c);
+#pragma unroll
+                    for (int r = 0; r < EMAX; r++) if (r < ea[k]) tmp = __dmul_rn(tmp, s);
+#pragma unroll
+                    for (int r = 0; r < EMAX; r++) if (r < eb[k]) tmp = __dmul_rn(tmp, c);
                     S[k] = __dadd_rn(S[k], tmp);
                 }
                 double y = S[P - 1];
-                for (int r = 0; r < ea[P]; r++) y = __dmul_rn(y, s);
-                for (int r = 0; r < eb[P]; r++) y = __dmul_rn(y, c);
+#pragma unroll
+                for (int r = 0; r < EMAX; r++) if (r < ea[P]) y = __dmul_rn(y, s);
+#pragma unroll
+                for (int r = 0; r < EMAX; r++) if (r < eb[P]) y = __dmul_rn(y, c);
                 yo[tt] = y;
             }
         }
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(1024) coswiss_terms_kernel(const CosParams Q, 
     }
 }
 
-template <int P>
+template <int P, int EMAX>
 static int coswiss_terms_launch(const CosParams &Q, cudaStream_t st)
 {
     // frequencies per CTA: as many as fit 1024 threads
@@ -208,7 +224,7 @@ static int coswiss_terms_launch(const CosParams &Q, cudaStream_t st)
     const int threads = ((fpc * Q.n_terms + 31) / 32) * 32;
     const size_t smem = sizeof(double) * ((size_t)Q.dw * COS_TT + (size_t)fpc * 2 * COS_TT +
                                           (size_t)fpc * Q.n_terms * (COS_TT + 1) + Q.n_terms);
-    auto kern = coswiss_terms_kernel<P>;
+    auto kern = coswiss_terms_kernel<P, EMAX>;
     static size_t configured = 0;
     if (smem > configured) {
         FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -237,8 +253,8 @@ int fb_cos_trig(const float *freqs, int n_freq, int64_t t, double *trig, void *s
 }
 
 int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word, int p,
-                    int dw, int max_occ, const double *trig, int n_freq, const int32_t *weights,
-                    int n_terms, int ncols, double *out, void *stream)
+                    int dw, int max_occ, int max_exp, const double *trig, int n_freq,
+                    const int32_t *weights, int n_terms, int ncols, double *out, void *stream)
 {
     FB_REQUIRE(X && word && trig && weights && out, "null argument");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && p >= 1 && n_freq >= 1 && n_terms >= 1, "bad shape");
@@ -253,7 +269,7 @@ int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int3
     P.p = p; P.dw = dw; P.n_freq = n_freq; P.n_terms = n_terms; P.ncols = ncols;
     // term-parallel kernel: short words whose tile of term values fits shared memory
     bool terms_ok = p <= COS_P_MAX && n_terms <= 1024 && n < (1LL << 31) && dw <= 8 &&
-                    max_occ <= 16;
+                    max_occ <= 16 && max_exp <= 8;
     if (terms_ok) {
         const int fpc = max(1, min(n_freq, 1024 / n_terms));
         const size_t smem = sizeof(double) * ((size_t)dw * COS_TT + (size_t)fpc * 2 * COS_TT +
@@ -261,14 +277,20 @@ int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int3
         terms_ok = smem <= 200 * 1024;
     }
     if (terms_ok) {
+        cudaStream_t st = (cudaStream_t)stream;
+#define FB_COS_CASE(PP)                                                              \
+    case PP:                                                                         \
+        return max_exp <= 2 ? coswiss_terms_launch<PP, 2>(P, st)                     \
+                            : (max_exp <= 4 ? coswiss_terms_launch<PP, 4>(P, st)     \
+                                            : coswiss_terms_launch<PP, 8>(P, st));
         switch (p) {
-        case 1: return coswiss_terms_launch<1>(P, (cudaStream_t)stream);
-        case 2: return coswiss_terms_launch<2>(P, (cudaStream_t)stream);
-        case 3: return coswiss_terms_launch<3>(P, (cudaStream_t)stream);
-        case 4: return coswiss_terms_launch<4>(P, (cudaStream_t)stream);
-        case 5: return coswiss_terms_launch<5>(P, (cudaStream_t)stream);
-        default: return coswiss_terms_launch<6>(P, (cudaStream_t)stream);
+            FB_COS_CASE(1) FB_COS_CASE(2) FB_COS_CASE(3) FB_COS_CASE(4) FB_COS_CASE(5)
+        default:
+            return max_exp <= 2 ? coswiss_terms_launch<6, 2>(P, st)
+                                : (max_exp <= 4 ? coswiss_terms_launch<6, 4>(P, st)
+                                                : coswiss_terms_launch<6, 8>(P, st));
         }
+#undef FB_COS_CASE
     }
     if ((long long)n_terms * p > COS_MAX_SUMS)
         return set_err(FB_ENOSUP, "CosWISS expansion too large: %d terms x %d letters (max %d)",

@@ -161,7 +161,8 @@ class CosWISS(ISS):
                 off += mat.size
                 w = blob[off:off + wts.size]
                 off += wts.size
-                views.append((m, w, mat.shape + (int(np.abs(mat).sum(axis=1).max()),), wts.shape))
+                views.append((m, w, mat.shape + (int(np.abs(mat).sum(axis=1).max()),
+                                           int(wts[:, 1:].max(initial=0))), wts.shape))
             self._tables[key] = views
         return self._tables[key][index]
 
@@ -194,7 +195,8 @@ class CosWISS(ISS):
             whole = first >= lo and last <= hi
             dst = out[first - lo:last - lo] if whole else be.empty((nf, n, t))
             be.check(L.fb_coswiss_word(X.data_ptr(), n, d, t, mat.data_ptr(), mshape[0],
-                                       mshape[1], mshape[2], trig.data_ptr(), nf, wts.data_ptr(),
+                                       mshape[1], mshape[2], mshape[3], trig.data_ptr(), nf,
+                                       wts.data_ptr(),
                                        wshape[0], wshape[1], dst.data_ptr(), be.stream_ptr()))
             if not whole:
                 a, b = max(first, lo), min(last, hi)

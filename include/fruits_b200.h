@@ -242,11 +242,11 @@ FB_API int fb_cos_trig(const float *freqs, int n_freq, int64_t t, double *trig, 
  * word: device int32 [p][dw] exponent matrix (max_occ = the largest number of
  * occurrences in one letter, sum_d |word[k][d]|), weights: device int32
  * [n_terms][ncols] table of CosWISS._get_weightings (:265-287; ncols = 2p+1,
- * or 2p+3 with the total weighting). */
+ * or 2p+3 with the total weighting; max_exp = its largest sin / cos exponent). */
 FB_API int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word,
-                           int p, int dw, int max_occ, const double *trig, int n_freq,
-                           const int32_t *weights, int n_terms, int ncols, double *out,
-                           void *stream);
+                           int p, int dw, int max_occ, int max_exp, const double *trig,
+                           int n_freq, const int32_t *weights, int n_terms, int ncols,
+                           double *out, void *stream);
 
 /* fruits/iss/semiring.py:461-601 Bayesian semiring (max, times): iterated sums
  * of ONE word (exponents word[p][md], device memory; alpha[p] float32, device
