@@ -510,7 +510,8 @@ class FruitSlice:
         # sample and fits its contiguous share of the iterated sums; the fitted
         # sieve copies (a few numbers each) are exchanged afterwards
         shard = getattr(self, "_fit_shard", None)
-        first, last = (0, n_emit) if shard is None else shard[0](n_emit)
+        first, last = (0, n_emit) if shard is None else shard[0](
+            n_emit, getattr(iss, "_emit_costs", lambda: None)())
         has_ppv = any(isinstance(sv, PPV) for sv in self._sieves)
 
         def skip_draws(lo, hi):

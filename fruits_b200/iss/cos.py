@@ -63,6 +63,15 @@ class CosWISS(ISS):
     def trie(self):
         raise NotImplementedError("CosWISS has no prefix trie of its own (see _jit_trie)")
 
+    def _emit_costs(self) -> list:
+        """Relative cost of every emitted sum (expansion terms x letters of its
+        word): lets a multi-GPU fit give every rank the same amount of work."""
+        costs = []
+        for word in self.words:
+            p = len(word) + 1 if self._total_weighting else len(word)
+            costs += [float((self._exponent + 1) ** (p - 1) * len(word))] * len(self._freqs)
+        return costs
+
     def _jit_trie(self, n_dims: int):
         """-> (trie, number of shared rows) for the kernel generator.
 

@@ -45,6 +45,21 @@ def shard_rows(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_by_cost(n: int, costs, world: int, rank: int):
+    """Contiguous block ``[lo, hi)`` of ``n`` items for ``rank`` such that the
+    blocks carry about the same total cost (``costs[i]`` per item; None = equal
+    costs, i.e. ``shard_rows``)."""
+    if costs is None:
+        return shard_rows(n, world, rank)
+    csum = np.concatenate([[0.0], np.cumsum(np.asarray(costs, dtype=np.float64))])
+    bounds = [int(np.searchsorted(csum, csum[-1] * r / world, side="left")) for r in range(world)]
+    bounds.append(n)
+    bounds = [min(max(b, 0), n) for b in bounds]
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds[rank], bounds[rank + 1]
+
+
 def sync_numpy_rng(group=None) -> None:
     """Give every rank rank 0's global numpy RNG state, so that all ranks draw
     the same fit sample and the same PPV subsamples (the reference consumes
@@ -114,7 +129,8 @@ def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, gro
             # the ranks, the fitted thresholds exchanged
             slc._select_fit_sample = lambda X: X
             if world > 1 and shard_nodes:
-                slc._fit_shard = (lambda n_emit: shard_rows(n_emit, world, rank), exchange)
+                slc._fit_shard = (lambda n_emit, costs: shard_by_cost(n_emit, costs, world, rank),
+                                  exchange)
             slc._fit_device(be.to_device(sample), SharedSeedCache(sample))
         finally:
             del slc._select_fit_sample

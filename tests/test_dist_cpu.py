@@ -81,3 +81,19 @@ def test_gloo_world2_gather_and_fit_sample():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results == [(0, True), (1, True)]
+
+
+def test_shard_by_cost_balances_contiguous_blocks():
+    from fruits_b200.parallel import shard_by_cost
+    costs = [1] * 10 + [27] * 10 + [81] * 10
+    for world in (1, 2, 3, 4, 8):
+        blocks = [shard_by_cost(30, costs, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == 30
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        loads = [sum(costs[lo:hi]) for lo, hi in blocks]
+        assert max(loads) <= sum(costs) / world + max(costs)
+    assert shard_by_cost(7, None, 3, 1) == shard_rows(7, 3, 1)
+    # more ranks than items: empty blocks are allowed, coverage is not lost
+    blocks = [shard_by_cost(2, [5, 5], 4, r) for r in range(4)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == 2
+    assert sum(hi - lo for lo, hi in blocks) == 2
