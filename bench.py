@@ -388,6 +388,21 @@ def run_ours(args):
                "h2d_bytes_per_step": int(hx.numel() * 8), "d2h_bytes_per_step": int(hf.numel() * 8),
                "series_per_step": E, "ms_per_step": e_s * 1e3,
                "note": "Fruit.transform(numpy pinned in, numpy pinned out); value scaled by n_gpus"}
+        # the same call with ordinary (pageable) numpy arrays, as a caller of the
+        # reference passes them: pinned staging ring + copy threads inside transform
+        Ep = min(E, 65536)
+        px = np.array(hx_np[:Ep])
+        pf = np.empty((Ep, N_FEATS))
+        fruit.transform(px, out=pf)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            fruit.transform(px, out=pf)
+        torch.cuda.synchronize()
+        e2e["pageable"] = {"value": world * Ep / ((time.perf_counter() - t0) / 2),
+                           "unit": "series/s", "series_per_step": Ep,
+                           "note": "plain numpy arrays in and out (host memcpy bound)"}
+        del px, pf
         if not args.no_cpu_baseline and world == 1:
             rate, cores, sample, _ = cpu_reference(args.cpu_seconds)
             cpu = {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _backend as be
+from . import _hoststage as hs
 from . import _jit
 from .cache import SharedSeedCache
 from .callback import AbstractCallback
@@ -105,7 +106,9 @@ class Fruit:
     def _transform_host(self, X, callbacks, cache, out):
         """Host input: stream row chunks through the GPU so that the upload of
         chunk i+1 and the download of chunk i-1 overlap the kernels of chunk i
-        (three streams, two device buffers per direction)."""
+        (three streams, two device buffers per direction).  Pageable arrays --
+        what a caller of the reference passes -- go through a ring of pinned
+        staging buffers that copy threads fill and drain (``_hoststage``)."""
         Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(self._check_host(X)))
         if Xh.dtype != torch.float64:
@@ -134,37 +137,65 @@ class Fruit:
         xb = [torch.empty((rows,) + tuple(Xh.shape[1:]), dtype=torch.float64, device=dev)
               for _ in range(2)]
         fb = [torch.empty((rows, nf), dtype=torch.float64, device=dev) for _ in range(2)]
-        x_ready, x_free, f_ready, f_free = [None] * 2, [None] * 2, [None] * 2, [None] * 2
+        # pageable arrays go through pinned staging buffers filled / drained by copy
+        # threads (_hoststage); pinned arrays are the DMA source / target themselves
+        stage_in, stage_out = not Xh.is_pinned(), not oh.is_pinned()
+        pin_in = [hs.pinned(f"in{b}", (rows,) + tuple(Xh.shape[1:])) for b in range(2)] \
+            if stage_in else None
+        pin_out = [hs.pinned(f"out{b}", (rows, nf)) for b in range(2)] if stage_out else None
         starts = list(range(0, n, rows))
+        nchunks = len(starts)
+        span = [(lo, min(n, lo + rows)) for lo in starts]
+        x_free, f_free = [None] * 2, [None] * 2          # device buffers reusable (events)
+        h2d_done, d2h_done = [None] * nchunks, [None] * nchunks
+        fill = [None] * nchunks                           # futures: user array -> pin_in
+        drain = [[] for _ in range(2)]                    # futures: pin_out -> user array
 
-        def upload(i):
-            b, lo = i % 2, starts[i]
-            hi = min(n, lo + rows)
+        def start_fill(i):
+            if stage_in and i < nchunks:
+                b, (lo, hi) = i % 2, span[i]
+                if i >= 2:
+                    h2d_done[i - 2].synchronize()         # the DMA has read pin_in[b]
+                fill[i] = hs.copy_rows(pin_in[b][:hi - lo], Xh[lo:hi])
+
+        def start_drain(i):
+            if stage_out and 0 <= i < nchunks:
+                b, (lo, hi) = i % 2, span[i]
+                d2h_done[i].synchronize()
+                drain[b] = hs.copy_rows(oh[lo:hi], pin_out[b][:hi - lo])
+
+        start_fill(0)
+        for i, (lo, hi) in enumerate(span):
+            b = i % 2
+            if stage_in:
+                hs.finish(fill[i])
             with torch.cuda.stream(up):
                 if x_free[b] is not None:
                     up.wait_event(x_free[b])
-                xb[b][:hi - lo].copy_(Xh[lo:hi], non_blocking=True)
-                x_ready[b] = torch.cuda.Event()
-                x_ready[b].record(up)
-
-        upload(0)
-        for i, lo in enumerate(starts):
-            b, hi = i % 2, min(n, lo + rows)
-            if i + 1 < len(starts):
-                upload(i + 1)
-            main.wait_event(x_ready[b])
+                src = pin_in[b][:hi - lo] if stage_in else Xh[lo:hi]
+                xb[b][:hi - lo].copy_(src, non_blocking=True)
+                h2d_done[i] = torch.cuda.Event()
+                h2d_done[i].record(up)
+            start_fill(i + 1)                             # host copy overlaps the queued GPU work
+            main.wait_event(h2d_done[i])
             if f_free[b] is not None:
                 main.wait_event(f_free[b])
             self.transform_device(xb[b][:hi - lo], None, None, out=fb[b][:hi - lo])
             x_free[b] = torch.cuda.Event()
             x_free[b].record(main)
-            f_ready[b] = torch.cuda.Event()
-            f_ready[b].record(main)
+            if stage_out:
+                hs.finish(drain[b])                       # pin_out[b] (chunk i-2) has been copied out
             with torch.cuda.stream(down):
-                down.wait_event(f_ready[b])
-                oh[lo:hi].copy_(fb[b][:hi - lo], non_blocking=True)
-                f_free[b] = torch.cuda.Event()
-                f_free[b].record(down)
+                down.wait_event(x_free[b])
+                dst = pin_out[b][:hi - lo] if stage_out else oh[lo:hi]
+                dst.copy_(fb[b][:hi - lo], non_blocking=True)
+                d2h_done[i] = torch.cuda.Event()
+                d2h_done[i].record(down)
+                f_free[b] = d2h_done[i]
+            start_drain(i - 1)                            # blocks until chunk i-1 has landed
+        start_drain(nchunks - 1)
+        for b in range(2):
+            hs.finish(drain[b])
         main.wait_stream(down)
         main.synchronize()
         return out
