@@ -23,7 +23,16 @@ class SharedSeedCache:
 
     def __init__(self, X=None) -> None:
         self._cache = {CacheType.COQUANTILE: {}, CacheType.ISS: {}}
-        self._input = None if X is None else self._as3d(be.to_device(X))
+        # uploaded on first use: most pipelines never ask the cache for anything,
+        # and fit only needs the fit sample on the device
+        self._source = X
+        self._uploaded = None
+
+    @property
+    def _input(self):
+        if self._uploaded is None and self._source is not None:
+            self._uploaded = self._as3d(be.to_device(self._source))
+        return self._uploaded
 
     @staticmethod
     def _as3d(X: torch.Tensor) -> torch.Tensor:

@@ -81,11 +81,26 @@ class Fruit:
 
     def fit(self, X, cache: Optional[SharedSeedCache] = None) -> None:
         """Fits all slices (reference: fruit.py:121-136)."""
-        Xd = be.to_device(X)
+        Xd = X if self._fit_from_host(X) else be.to_device(X)
         cache_ = SharedSeedCache(Xd) if cache is None else cache
         for slc in self._slices:
             slc._fit_device(Xd, cache_)
         self._fitted = True
+
+    def _fit_from_host(self, X) -> bool:
+        """A host array whose fit samples are a small part of it stays on the
+        host: only the sampled rows are uploaded (the default ``fit_sample_size``
+        is one series)."""
+        if isinstance(X, torch.Tensor) or not isinstance(X, np.ndarray) or X.ndim != 3:
+            return False
+        if X.dtype != np.float64:
+            return False                   # be.to_device raises the reference's TypeError
+        n = X.shape[0]
+        for slc in self._slices:
+            fs = slc.fit_sample_size
+            if not (isinstance(fs, int) and fs == 1) and max(int(fs * n), 1) * 4 > n:
+                return False
+        return n > 0
 
     def transform(self, X, callbacks: Optional[list] = None,
                   cache: Optional[SharedSeedCache] = None, out=None):
@@ -397,13 +412,16 @@ class FruitSlice:
         if not self._sieves:
             raise RuntimeError("No feature sieves given")
 
-    def _select_fit_sample(self, X: torch.Tensor) -> torch.Tensor:
-        # same draws from the global numpy RNG as the reference (fruit.py:430-438)
+    def _select_fit_sample(self, X) -> torch.Tensor:
+        """Rows to fit on, on the device (``X``: device tensor or host array).
+        Same draws from the global numpy RNG as the reference (fruit.py:430-438)."""
         if isinstance(self.fit_sample_size, int) and self.fit_sample_size == 1:
             ind = np.random.randint(0, X.shape[0])
-            return X[ind:ind+1, :, :]
+            return be.to_device(X[ind:ind+1, :, :])
         s = max(int(self.fit_sample_size * X.shape[0]), 1)
         indices = np.random.choice(X.shape[0], size=s, replace=False)
+        if not isinstance(X, torch.Tensor):
+            return be.to_device(X[indices])
         idx = torch.as_tensor(indices, device=X.device, dtype=torch.long)
         return X.index_select(0, idx)
 
@@ -505,7 +523,7 @@ class FruitSlice:
     def _fit_device(self, X: torch.Tensor, cache: Optional[SharedSeedCache] = None) -> None:
         self._compile()
         self._thr_memo = None
-        if X.dim() != 3:
+        if len(X.shape) != 3:
             raise ValueError("input must have shape (n_series, n_dimensions, length)")
         if cache is None:
             cache = SharedSeedCache(X)
