@@ -24,36 +24,28 @@ class PPV(FeatureSieve):
     def __init__(self, quantile: Union[list, float] = 0.5,
                  constant: Union[list, bool] = False, sample_size: float = 1.0,
                  segments: bool = False) -> None:
-        if isinstance(quantile, list):
-            if not isinstance(constant, list):
-                constant = [constant for _ in range(len(quantile))]
-            elif len(quantile) != len(constant):
-                raise ValueError("If 'quantile' is a list, then 'constant' "
-                                 "also has to be a list of same length or "
-                                 "a single boolean.")
-            for q, c in zip(quantile, constant):
-                if not c and not 0 <= q <= 1:
-                    raise ValueError("If 'constant' is set to False, "
-                                     "'quantile' has to be a value in [0,1]")
+        many = isinstance(quantile, list)
+        qs = list(quantile) if many else [quantile]
+        if isinstance(constant, list):
+            if many and len(constant) != len(qs):
+                raise ValueError("'quantile' and 'constant' must be lists of the same length "
+                                 "(or 'constant' a single boolean)")
+            if not many and len(constant) > 1:
+                raise ValueError("a single 'quantile' takes a single boolean 'constant'")
+            cs = list(constant)
         else:
-            quantile = [quantile]
-            if isinstance(constant, list):
-                if len(constant) > 1:
-                    raise ValueError("'constant' has to be a single boolean"
-                                     "if 'quantile' is a single float")
-            else:
-                constant = [constant]
-        if segments:
-            self._q_c_input = sorted(zip(list(set(quantile)), constant),
-                                     key=lambda x: x[0])
-        else:
-            self._q_c_input = list(zip(quantile, constant))
+            cs = [constant] * len(qs)
+        if many and any(not c and not 0 <= q <= 1 for q, c in zip(qs, cs)):
+            raise ValueError("a 'quantile' that is not 'constant' is a probability in [0, 1]")
         if not 0 < sample_size <= 1:
             raise ValueError("'sample_size' has to be a float in (0, 1]")
+        if segments and len(qs) == 1:
+            raise ValueError("'segments' needs a list of at least two quantiles")
+        # segments: distinct quantiles in ascending order, paired with the flags
+        # in their given order (reference :84-86)
+        self._q_c_input = (sorted(zip(list(set(qs)), cs), key=lambda qc: qc[0]) if segments
+                           else list(zip(qs, cs)))
         self._sample_size = sample_size
-        if segments and len(quantile) == 1:
-            raise ValueError("If 'segments' is set to `True` then 'quantile'"
-                             "has to be a list of length >= 2.")
         self._segments = segments
 
     def _nfeatures(self) -> int:
