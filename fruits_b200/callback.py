@@ -3,7 +3,8 @@
 Callbacks receive the prepared data, every iterated sum and every block of
 sieved features as host arrays.  That is incompatible with keeping the
 iterated sums in registers, so a transform with callbacks runs on the
-materialising (non-fused) route.
+materialising (non-fused) route: every hook costs a device-to-host copy of
+what it is shown.
 """
 from abc import ABC
 
@@ -11,21 +12,23 @@ import numpy as np
 
 
 class AbstractCallback(ABC):
+    """Subclass and override what you need; every hook defaults to a no-op.
+    The arrays are fresh host copies (float64), safe to keep."""
 
     def on_next_slice(self) -> None:
-        """Called every time the next FruitSlice starts."""
+        """A new ``FruitSlice`` starts (before its preparateurs run)."""
 
     def on_preparateur(self, X: np.ndarray) -> None:
-        """Called after each preparateur with the prepared data."""
+        """``X[n, d', t]``: the data after one more preparateur of the slice."""
 
     def on_preparation_end(self, X: np.ndarray) -> None:
-        """Called once after the last preparateur."""
+        """``X[n, d', t]``: the fully prepared input of the slice's ISS."""
 
     def on_iterated_sum(self, X: np.ndarray) -> None:
-        """Called for every iterated sum."""
+        """``X[n, t]``: one iterated sum, in emission order."""
 
     def on_sieve(self, X: np.ndarray) -> None:
-        """Called after each use of a feature sieve."""
+        """The feature columns one sieve produced for the current iterated sum."""
 
     def on_sieving_end(self, X: np.ndarray) -> None:
-        """Called once at the end of the feature calculation."""
+        """``X[n, nfeatures]``: all features of the slice."""
