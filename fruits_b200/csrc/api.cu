@@ -94,6 +94,7 @@ int fb_iss_materialize(const fb_iss_plan *plan, const fb_batch *batch, double *o
     if (rc) return rc;
     FB_REQUIRE(out != nullptr, "null output");
     p.out = out;
+    p.mat_stage = plan->n_emit <= LNS_STAGE_ROWS;      // few rows: staged 256-byte row writes
     return lns_run_mat(p, plan->semiring, plan->weight_mode, (cudaStream_t)stream);
 }
 

@@ -59,6 +59,7 @@ struct LnsParams {
     long long n, d, t, g_ld, out_ld, col0;
     int n_blocks, n_rows, n_emit, du, na, max_depth, n_feats, sanitize;
     int any_inc, any_std;
+    int mat_stage;               // materialise through the staged row writer
     float alphas[FB_MAX_ALPHAS];
     fb_dim dims[FB_MAX_USED_DIMS];
     int feat_kind[FB_MAX_FEATS];
@@ -81,10 +82,18 @@ struct Policy {
 };
 
 // doubles of shared memory one warp needs
-__host__ __device__ inline int lns_warp_doubles(int rmax, int du, int na, bool weighted)
+// materialising policy with at most LNS_STAGE_ROWS emitted sums per plan (fit
+// chunks, small word lists): the values of a tile are staged per emitted row
+// and written as 256-byte row segments instead of one 8-byte store per lane
+constexpr int LNS_STAGE_ROWS = 32;
+constexpr int LNS_STAGE_LD = LNS_TILE + 1;
+
+__host__ __device__ inline int lns_warp_doubles(int rmax, int du, int na, bool weighted,
+                                                bool stage = false)
 {
     int n = (du + 1) * RS + rmax * 32 + 8;
     if (weighted) n += (1 + 2 * na) * RS;
+    if (stage) n += LNS_STAGE_ROWS * LNS_STAGE_LD + LNS_STAGE_ROWS / 2;   // values + skews (int)
     return n;
 }
 
@@ -147,11 +156,18 @@ lns_kernel(const LnsParams P)
     const int nrows = P.n_rows;
 
     extern __shared__ double smem[];
-    double *xs = smem + (size_t)warp * lns_warp_doubles(RMAX, du, na, WEIGHTED);
+    // (only the small instantiations: the 16-row one has no registers to spare)
+    constexpr bool CAN_STAGE = POL::MAT && RMAX <= 4;
+    const bool STAGE = CAN_STAGE && P.mat_stage;
+    double *xs = smem + (size_t)warp * lns_warp_doubles(RMAX, du, na, WEIGHTED, STAGE);
     double *pub = xs + (du + 1) * RS;       // [RMAX*32] + identity at [RMAX*32]
     double *gs = pub + RMAX * 32 + 8;         // [RING]           (weighted only)
     double *ep = gs + RS;                   // [na][RING] exp(+alpha g)
     double *em = ep + na * RS;              // [na][RING] exp(-alpha g)
+    // staging area behind everything else of this warp
+    double *stg = xs + lns_warp_doubles(RMAX, du, na, WEIGHTED, false);
+    int *stg_skew = (int *)(stg + LNS_STAGE_ROWS * LNS_STAGE_LD);
+    unsigned stg_own = 0;        // emitted rows this warp produces
     const uint32_t xs_a = smem_addr(xs), pub_a = smem_addr(pub);
     const uint32_t gs_a = smem_addr(gs), ep_a = smem_addr(ep);
     const uint32_t em_off = (uint32_t)na * RS * 8;   // em = ep + em_off
@@ -180,6 +196,7 @@ lns_kernel(const LnsParams P)
     double d1p[POL::U2 ? RMAX : 1];
     double mx[POL::MAX ? RMAX : 1], mn[POL::MIN ? RMAX : 1];
     long long matoff[POL::MAT ? RMAX : 1];
+    int erow[CAN_STAGE ? RMAX : 1];
 
     const fb_slot *slots = P.slots + (size_t)blk * nrows * 32;
     const uint32_t pubmask = P.row_pub[blk];
@@ -208,6 +225,7 @@ lns_kernel(const LnsParams P)
         if (POL::MAX) { mx[j] = d_ninf(); if (POL::MMB) { mxl[j] = 0; mxh[j] = 0; } }
         if (POL::MIN) { mn[j] = d_inf(); if (POL::MMB) { mnl[j] = 0; mnh[j] = 0; } }
         if (POL::MAT) matoff[j] = -1;
+        if (CAN_STAGE) erow[j] = -1;
         if (j < nrows) {
             const fb_slot sl = slots[j * 32 + lane];
             let[j] = sl.letter_lo;
@@ -238,7 +256,13 @@ lns_kernel(const LnsParams P)
                 meta[j] = ((sl.depth ? sl.depth - 1 : 0) & 255) | ((sl.aidx & 3) << 8) | (paidx << 10);
             if (WEIGHTED) eo[j] = ep_a + (uint32_t)(sl.aidx & 3) * RS * 8;
             if (sl.emit >= 0) {
-                if (POL::MAT) matoff[j] = ((long long)sl.emit * P.n + n) * T;
+                if (POL::MAT) {
+                    matoff[j] = ((long long)sl.emit * P.n + n) * T;
+                    if (CAN_STAGE && STAGE) {
+                        erow[j] = sl.emit;
+                        stg_skew[sl.emit] = REALS ? 0 : (sl.depth ? sl.depth - 1 : 0);
+                    }
+                }
                 if (!POL::MAT) {
                     const double *th = P.thr + (size_t)sl.emit * FB_NTHR;
                     if (POL::U0) { thr0l[j] = th[0]; if (POL::HI) thr0h[j] = th[1]; }
@@ -251,6 +275,15 @@ lns_kernel(const LnsParams P)
             }
         }
     }
+
+    if (STAGE) {
+        unsigned mine = 0;
+#pragma unroll
+        for (int j = 0; j < RMAX; j++)
+            if (CAN_STAGE && erow[j] >= 0) mine |= 1u << erow[j];
+        stg_own = __reduce_or_sync(0xffffffffu, mine);
+    }
+    (void)stg_own; (void)stg_skew; (void)stg;
 
     // identity of the semiring's product for root-level slots
     if (lane < 8) pub[RMAX * 32 + lane] = REALS ? 1.0 : 0.0;
@@ -449,8 +482,11 @@ lns_kernel(const LnsParams P)
             }
             // -- consume the value --
             if (POL::MAT) {
-                if (active && matoff[j] >= 0)
+                if (CAN_STAGE && STAGE) {
+                    if (active && erow[j] >= 0) stg[erow[j] * LNS_STAGE_LD + (s & (LNS_TILE - 1))] = out;
+                } else if (active && matoff[j] >= 0) {
                     P.out[matoff[j] + (REALS ? s : s - (meta[j] & 255))] = out;
+                }
             } else {
                 if (POL::U0) {
                     bool sel = out > thr0l[j];
@@ -519,6 +555,19 @@ lns_kernel(const LnsParams P)
         }
 #pragma unroll 1
         for (; ss < send; ss++) step(std::false_type{}, s0_ + ss);
+        if (STAGE) {
+            // the tile of every emitted row this warp owns: lane = step of the tile,
+            // i.e. consecutive time steps of one row -> one 256-byte segment
+            __syncwarp();
+#pragma unroll 1
+            for (unsigned rem = stg_own; rem; rem &= rem - 1) {
+                const int e = __ffs(rem) - 1;
+                const int t = s0_ + lane - stg_skew[e];
+                if (lane < send && t >= 0 && t < T)
+                    P.out[((long long)e * P.n + n) * T + t] = stg[e * LNS_STAGE_LD + lane];
+            }
+            __syncwarp();
+        }
         if (have_next) stage_tile(tnext);
         __syncwarp();
     }
@@ -575,7 +624,8 @@ int lns_launch(const LnsParams &p, cudaStream_t stream)
 {
     auto kern = lns_kernel<RMAX, SEMI, WM, POL>;
     size_t smem = (size_t)LNS_WARPS *
-                  lns_warp_doubles(RMAX, p.du, p.na, WM != FB_WEIGHT_NONE) * sizeof(double);
+                  lns_warp_doubles(RMAX, p.du, p.na, WM != FB_WEIGHT_NONE,
+                                   POL::MAT && RMAX <= 4 && p.mat_stage) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
         FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
