@@ -197,3 +197,52 @@ def unwrap(sieve):
     while hasattr(sieve, "_sieve") or hasattr(sieve, "inner"):
         sieve = getattr(sieve, "_sieve", None) or sieve.inner
     return sieve
+
+
+# Known answers of the reference's own sieve tests, as data: (sieve description,
+# row block of KAT_X the sieve is applied to, expected features).  Sources:
+# tests/sieving/test_explicit.py:11-165 (MAX :11-40, MIN :43-72, END :75-97,
+# NPI :100-137, MPI :140-148, XPI :151-159, LPI :162-170) and
+# tests/sieving/test_implicit.py:12-74 (PPV, CPV) of the reference checkout.
+KAT_X = np.array([
+    [[-4., .8, 0., 5., -3.], [2., 1., 0., 0., -7.]],
+    [[5., 8., 2., 6., 0.], [-5., -1., -4., -.5, -8.]],
+])
+
+SIEVE_KATS = [
+    (["MAX", {}], 0, [[5], [2]]),
+    (["MAX", {"cut": 3}], 0, [[0.8], [2]]),
+    (["MAX", {"cut": 0.5}], 0, [[5], [2]]),
+    (["MAX", {"cut": [-1, 3, 1]}], 0, [[-4, 0.8, 5], [2, 1, 0]]),
+    (["MAX", {"cut": [-1, 0.2, 0.7, 0.5]}], 0, [[-4, 5, 0, -3], [2, 0, 0, -7]]),
+    (["MIN", {}], 1, [[0], [-8]]),
+    (["MIN", {"cut": 3}], 0, [[-4], [0]]),
+    (["MIN", {"cut": 0.5}], 1, [[2], [-5]]),
+    (["MIN", {"cut": [-1, 3, 1]}], 1, [[5, 2, 0], [-5, -4, -8]]),
+    (["MIN", {"cut": [-1, 0.2, 0.7, 0.5]}], 1, [[5, 2, 6, 0], [-5, -4, 0, -8]]),
+    (["END", {}], 0, [[-3], [-7]]),
+    (["END", {"cut": 0.2}], 0, [[-4], [0]]),
+    (["END", {"cut": [1, 0.2, 0.8, 4, -1]}], 0, [[-4, -4, 5, 5, -3], [2, 0, 0, 0, -7]]),
+    (["NPI", {}], 0, [[2], [0]]),
+    (["NPI", {"cut": 3}], 0, [[1], [0]]),
+    (["NPI", {"cut": 0.5}], 1, [[1], [2]]),
+    (["NPI", {"cut": [-1, 3, 1]}], 1, [[0, 1, 1], [0, 1, 1]]),
+    (["NPI", {"cut": [-1, 0.2, 0.7, 0.5]}], 1, [[1, 0, 1, 0], [1, 1, 0, 0]]),
+    (["MPI", {}], 0, [[4.9], [0]]),
+    (["MPI", {}], 1, [[3.5], [3.75]]),
+    (["XPI", {}], 0, [[2], [0]]),
+    (["XPI", {}], 1, [[2], [2]]),
+    (["LPI", {}], 0, [[1], [0]]),
+    (["LPI", {}], 1, [[1], [1]]),
+    (["PPV", {"quantile": 0, "constant": True}], 0, [[3 / 5], [4 / 5]]),
+    (["PPV", {"quantile": 0.5, "constant": False, "sample_size": 1}], 1, [[1], [0]]),
+    (["CPV", {"quantile": 0, "constant": True}], 0, [[1 / 3], [0.0]]),
+    (["PPV", {"quantile": [0.5, 0.1, 0.7], "constant": False, "sample_size": 1}], 1,
+     [[1., 1., 3 / 5], [0., 4 / 5, 0.]]),
+    (["PPV", {"quantile": [0.5, 0.1, 0.7], "constant": False, "sample_size": 1,
+              "segments": True}], 1, [[0., 2 / 5], [4 / 5, 0.]]),
+    (["PPV", {"quantile": [-5, 0, 2], "constant": True, "sample_size": 1}], 1,
+     [[1., 1., 4 / 5], [4 / 5, 0., 0.]]),
+    (["PPV", {"quantile": [0, -5, 2], "constant": True, "sample_size": 1, "segments": True}], 1,
+     [[0., 1 / 5], [4 / 5, 0.]]),
+]

@@ -18,7 +18,7 @@ import torch
 
 import fruits_b200 as fruits
 import specs
-from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, make_iss_input,
+from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, KAT_X, SIEVE_KATS, make_iss_input,
                    make_prep_input, make_sieve_input)
 from helpers import (assert_close, assert_exact, fitted_thresholds, oracle_thresholds,
                      rowmax_rel_err)
@@ -982,3 +982,14 @@ def test_mid_size_batches_use_a_compiled_kernel_only_if_it_exists(monkeypatch):
     tiny = fruit.transform(X[:500])                   # below the crossover: generic kernel
     assert _routes(fruit) == ["fb::lns_kernel"]
     assert_exact(tiny, small[:500], "small batch")
+
+
+@pytest.mark.parametrize("kat", range(len(SIEVE_KATS)))
+def test_reference_kat_sieve_table(kat):
+    """Known answers of the reference's own sieve tests (data in cases.py)
+    through the stand-alone seed API of the product."""
+    desc, block, want = SIEVE_KATS[kat]
+    sv = specs._sieve(fruits, desc)
+    np.random.seed(0)
+    got = sv.fit_transform(KAT_X[block])
+    np.testing.assert_allclose(got, np.array(want, dtype=float), rtol=1e-12, atol=1e-15)

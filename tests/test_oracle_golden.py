@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import specs
-from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, make_iss_input,
+from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, KAT_X, SIEVE_KATS, make_iss_input,
                    make_prep_input, make_sieve_input)
 from helpers import assert_close, assert_exact, oracle_thresholds
 from oracle import pipeline as orc
@@ -174,3 +174,52 @@ def test_coswiss_expansion_table():
         host = fruits.CosWISS([word], freqs=[0.1], exponent=e,
                               total_weighting=total)._get_weightings(word)
         assert np.array_equal(host, orc.coswiss_weightings(n_letters, e, total))
+
+
+@pytest.mark.parametrize("kat", range(len(SIEVE_KATS)))
+def test_reference_kat_sieve_table(kat):
+    """The oracle reproduces the known answers of the reference's own sieve
+    tests (tests/sieving/test_explicit.py, test_implicit.py; data in cases.py).
+    A sieve applied stand-alone builds its cache from its own input
+    (fruits/seed.py:26-51), so coquantile cuts refer to the sieved rows."""
+    desc, block, want = SIEVE_KATS[kat]
+    Y = KAT_X[block]
+    sv = orc.make_sieve(desc)
+    np.random.seed(0)
+    sv.fit(Y)
+    got = sv.transform(Y, orc.RawCache(Y[:, np.newaxis, :]))
+    np.testing.assert_allclose(got, np.array(want, dtype=float), rtol=1e-12, atol=1e-15)
+
+
+def _indices_lookup(t, scale=50):
+    # fruits/iss/weighting.py:100-110: NRM(arange(1..T)/T) * scale
+    base = np.arange(1, t + 1) / t
+    return (base - base.min()) / (base.max() - base.min()) * scale
+
+
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
+def test_two_letter_word_against_brute_force(semiring):
+    """Definition check independent of any implementation (the reference does
+    the same in tests/signature/test_weighting.py): the iterated sum of
+    ``[1][2]`` is a double sum / maximum over index pairs, with the weighting
+    ``exp(alpha (g(i) - g(j)))`` (reals) or ``+ alpha (g(i) - g(j))`` (arctic)
+    between the two indices."""
+    rng = np.random.default_rng(8)
+    n, t = 3, 23
+    X = rng.standard_normal((n, 2, t))
+    for weighting in (None, ["Indices", {"scale": 3}]):
+        desc = {"words": ["[1][2]"], "mode": "single", "semiring": semiring,
+                "weighting": weighting, "alphas": [[0.7, 1.0]] if weighting else None}
+        got = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))[0]
+        g = _indices_lookup(t, 3) if weighting else np.zeros(t)
+        a0 = np.float64(np.float32(0.7)) if weighting else 0.0
+        want = np.zeros((n, t))
+        for s in range(n):
+            for T in range(t):
+                if semiring == "reals":
+                    want[s, T] = sum(X[s, 0, i] * X[s, 1, j] * np.exp(a0 * (g[i] - g[j]))
+                                     for j in range(T + 1) for i in range(j))
+                else:
+                    want[s, T] = max(X[s, 0, i] + X[s, 1, j] + a0 * (g[i] - g[j])
+                                     for j in range(T + 1) for i in range(j + 1))
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
