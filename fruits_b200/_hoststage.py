@@ -7,13 +7,16 @@ the throughput of pinned buffers.  This module keeps a small ring of pinned
 staging buffers per process (allocated once: page-locking is slow) and copies
 between user memory and the ring with several threads (numpy releases the GIL
 in its copy loops), so that the copies overlap the DMA transfers and the
-kernels of the neighbouring chunks.  Nothing here touches the numerics.
+kernels of the neighbouring chunks.  Nothing here touches the numerics.  Like
+the reference API the ring is not re-entrant: one ``transform`` at a time per
+process.
 """
 import os
 from concurrent.futures import ThreadPoolExecutor, wait
 
 import torch
 
+WORKERS = max(2, min(8, os.cpu_count() or 2))
 _POOL = None
 _PINNED: dict = {}
 
@@ -21,8 +24,7 @@ _PINNED: dict = {}
 def pool() -> ThreadPoolExecutor:
     global _POOL
     if _POOL is None:
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, os.cpu_count() or 2)),
-                                   thread_name_prefix="fruits-b200-copy")
+        _POOL = ThreadPoolExecutor(max_workers=WORKERS, thread_name_prefix="fruits-b200-copy")
     return _POOL
 
 
@@ -43,8 +45,7 @@ def copy_rows(dst, src) -> list:
     """``dst[...] = src`` (same shape, first axis = rows) split over the copy
     threads; returns the futures."""
     n = dst.shape[0]
-    workers = pool()._max_workers
-    step = max(1, -(-n // workers))
+    step = max(1, -(-n // WORKERS))
     d, s = _as_numpy(dst), _as_numpy(src)
     return [pool().submit(_copy, d[lo:lo + step], s[lo:lo + step]) for lo in range(0, n, step)]
 
