@@ -258,3 +258,16 @@ def test_corbeille_loader(tmp_path):
     assert [d[0] for d in corbeille.data.load_all(str(tmp_path), datasets=["Beta"])] == ["Beta"]
     with pytest.raises(NotImplementedError):
         corbeille.data.load(str(tmp_path / "Alpha"), univariate=False)
+
+
+def test_copy_threads_copy_rows():
+    """Host staging helper: the row blocks of the copy threads tile the array."""
+    from fruits_b200 import _hoststage as hs
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 8, 1000):
+        src = rng.random((n, 3, 5))
+        dst = np.zeros_like(src)
+        hs.finish(hs.copy_rows(dst, src))
+        np.testing.assert_array_equal(dst, src)
+    with pytest.raises(ValueError):
+        hs.finish(hs.copy_rows(np.zeros((4, 2)), np.zeros((4, 3))))
