@@ -37,7 +37,7 @@ assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF)), ref.__f
 from oracle import pipeline as orc  # noqa: E402
 sys.path.append(os.path.join(ROOT, "tests"))
 import specs  # noqa: E402  (tests/specs.py)
-from cases import (COS_CASES, COS_PIPE_CASES, ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap,  # noqa: E402
+from cases import (COS_CASES, COS_PIPE_CASES, EXTRA_PIPE_CASES, ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap,  # noqa: E402
                    make_iss_input, make_prep_input, make_sieve_input)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -176,6 +176,7 @@ def ref_thresholds(fruit):
     for slc in fruit:
         for sieves in slc._sieves_extended:
             for sv in sieves:
+                sv = unwrap(sv)                      # sieve wrappers: the wrapped sieve's
                 q = getattr(sv, "_quantiles", None)
                 if q is None:
                     q = getattr(sv, "_q", [])
@@ -188,6 +189,7 @@ def orc_thresholds(of):
     for slc in of.slices:
         for sieves in slc.sieves_extended:
             for sv in sieves:
+                sv = unwrap(sv)
                 q = sv.fitted_q if sv.name in ("PPV", "CPV") else sv.quantiles
                 rows.append(np.asarray(q, dtype=np.float64).ravel())
     return np.concatenate(rows) if rows else np.zeros(0)
@@ -214,6 +216,12 @@ def gen_cos():
     gen_pipelines(COS_PIPE_CASES)
 
 
+def gen_extra():
+    """Pipelines of the rank 2-3 components (Bayesian semiring, CUR / CPV / XPI /
+    LPI, sieve wrappers, chained ISS)."""
+    gen_pipelines(EXTRA_PIPE_CASES)
+
+
 def gen_pipelines(cases=None):
     print("[pipelines]")
     for name, (spec_name, n) in (PIPE_CASES if cases is None else cases).items():
@@ -230,7 +238,8 @@ def gen_pipelines(cases=None):
         assert fruit.nfeatures() == of.nfeatures() == r.shape[1]
         weighted = any(i.get("weighting") or i.get("coswiss")
                        for s in spec["slices"] for i in s["iss"])
-        has_mpi = any(sv[0] == "MPI" for s in spec["slices"] for sv in s["sieves"])
+        has_mpi = any(sieve_kind(sv) in SUMMING_SIEVES for s in spec["slices"]
+                      for sv in s["sieves"])
         rt, ot = ref_thresholds(fruit), orc_thresholds(of)
         if weighted or has_mpi:
             check_close(ot, rt, f"thresholds {name}", rtol=1e-11)

@@ -1,6 +1,8 @@
 """Comparison helpers shared by the oracle and GPU parity tests."""
 import numpy as np
 
+from cases import unwrap
+
 
 def assert_exact(got, ref, what=""):
     got, ref = np.asarray(got), np.asarray(ref)
@@ -37,6 +39,7 @@ def fitted_thresholds(fruit):
     for slc in fruit:
         for sieves in slc._sieves_extended:
             for sv in sieves:
+                sv = unwrap(sv)                      # sieve wrappers: the wrapped sieve's
                 q = getattr(sv, "_quantiles", None)
                 if q is None:
                     q = getattr(sv, "_q", [])
@@ -49,6 +52,7 @@ def oracle_thresholds(of):
     for slc in of.slices:
         for sieves in slc.sieves_extended:
             for sv in sieves:
+                sv = unwrap(sv)
                 q = sv.fitted_q if sv.name in ("PPV", "CPV") else sv.quantiles
                 rows.append(np.asarray(q, dtype=np.float64).ravel())
     return np.concatenate(rows) if rows else np.zeros(0)

@@ -95,6 +95,22 @@ SPECS["C3_cos"] = {"slices": [
     for e in (1, 2)]}
 SPECS["C3_full"] = {"slices": SPECS["C3_general"]["slices"] + SPECS["C3_cos"]["slices"]}
 
+# SURVEY.md section 8(f) ranks 2-3 in one fruit: a Bayesian slice with rank-2
+# sieves and wrappers, a slice with two chained ISS (fruits/fruit.py:440-454)
+SPECS["R_mixed"] = {"slices": [
+    {"preps": [],
+     "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended", "semiring": "bayesian"}],
+     "sieves": [["NPI", {"q": [0.4, 1.0]}], ["CPV", {"quantile": [0.3, 0.8]}],
+                ["CUR", {"cut": [9, -1], "q": [-1.0, 0.5, 1.0]}],
+                ["INC", {"sieve": ["MAX", {"q": [-1.0, 0.6]}]}],
+                ["INT", {"sieve": ["END", {}]}], ["LPI", {}], ["END", {}]],
+     "fit_sample_size": 1.0},
+    {"preps": [["INC", {}]],
+     "iss": [{"words": ["[1]", "[1][2]"], "mode": "extended"},
+             {"words": ["[1]", "[1][1]"], "mode": "single", "semiring": "arctic"}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["XPI", {}], ["MIN", {}], ["END", {"cut": [5, -1]}]],
+     "fit_sample_size": 0.5}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -103,7 +119,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
-              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -112,6 +128,8 @@ def make_input(name: str, n: int = None) -> np.ndarray:
         return np.random.default_rng(0).random((N, D, T))[:n]
     if name == "C5_sweep":
         return np.random.default_rng(1234).standard_normal((n, D, T))
+    if name == "R_mixed":
+        return np.random.default_rng(42).random((n, D, T)) + 0.1
     return np.random.default_rng(0).standard_normal((n, D, T)).cumsum(axis=2)
 
 

@@ -125,11 +125,11 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos"])
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed"])
 def test_pipeline_golden(name, golden_dir):
-    from cases import COS_PIPE_CASES
+    from cases import COS_PIPE_CASES, EXTRA_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
-    spec_name, n = {**PIPE_CASES, **COS_PIPE_CASES}[name]
+    spec_name, n = {**PIPE_CASES, **COS_PIPE_CASES, **EXTRA_PIPE_CASES}[name]
     spec = specs.SPECS[spec_name]
     X = specs.make_input(spec_name, n)
     assert sha(X) == str(g["xsha"])
