@@ -2,6 +2,7 @@
 
     python scripts/jit_sweep.py --compile "budget=100,ppc=1" "budget=60,minb=2" ...   (no GPU: fills the cubin cache)
     python scripts/jit_sweep.py --run N "budget=100,ppc=1" ...                        (GPU: ms / series per second each)
+    ... --config C4_twi                                                               (another configuration)
 """
 import os
 import sys
@@ -22,11 +23,16 @@ def _compile(opt: str, config: str = "C5_sweep"):
 
 
 def main() -> None:
+    config = "C5_sweep"
+    if "--config" in sys.argv:
+        i = sys.argv.index("--config")
+        config = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     mode = sys.argv[1]
     if mode == "--compile":
         opts = sys.argv[2:]
         with ProcessPoolExecutor(max_workers=min(8, len(opts))) as ex:
-            for opt, dt in ex.map(_compile, opts):
+            for opt, dt in ex.map(_compile, opts, [config] * len(opts)):
                 print(f"compiled [{opt}] in {dt:.1f} s", flush=True)
         return
     n = int(sys.argv[2])
@@ -35,8 +41,11 @@ def main() -> None:
     import torch
     import fruits_b200 as fruits
     import specs
-    X = torch.randn((n, 3, 1024), dtype=torch.float64, device="cuda",
+    shape = {"C5_sweep": (3, 1024), "C4_twi": (3, 2048), "C3_general": (6, 1024)}[config]
+    X = torch.randn((n,) + shape, dtype=torch.float64, device="cuda",
                     generator=torch.Generator("cuda").manual_seed(1234))
+    if config != "C5_sweep":
+        X = X.cumsum(dim=2)
     first = None
     for opt in opts:
         os.environ["FRUITS_B200_JIT_OPTS"] = opt
@@ -45,7 +54,7 @@ def main() -> None:
             os.environ["FRUITS_B200_JIT_OPTS"] = ""
         else:
             os.environ["FRUITS_B200_JIT"] = "1"
-        fruit = specs.build_fruit(fruits, specs.SPECS["C5_sweep"])
+        fruit = specs.build_fruit(fruits, specs.SPECS[config])
         np.random.seed(0)
         fruit.fit(X[:64])
         out = torch.empty((n, fruit.nfeatures()), dtype=torch.float64, device="cuda")
