@@ -41,7 +41,7 @@ def main() -> None:
     import torch
     import fruits_b200 as fruits
     import specs
-    shape = {"C5_sweep": (3, 1024), "C4_twi": (3, 2048), "C3_general": (6, 1024)}[config]
+    shape = {"C5_sweep": (3, 1024), "C4_twi": (3, 2048), "C3_general": (6, 1024), "C3_cos": (6, 1024)}[config]
     X = torch.randn((n,) + shape, dtype=torch.float64, device="cuda",
                     generator=torch.Generator("cuda").manual_seed(1234))
     if config != "C5_sweep":
