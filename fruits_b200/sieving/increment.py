@@ -35,7 +35,9 @@ class IncrementSieve(SegmentSieve):
 
     def _copy(self):
         # like the reference (:83-84) the copy drops coquantile_norm
-        return self.__class__(self._cut, self._q, self._inc)
+        new = super()._copy()
+        new._inc = self._inc
+        return new
 
     def __str__(self) -> str:
         return f"{self.__class__.__name__}({self._cut}, {self._q}, {self._inc})"

@@ -129,7 +129,12 @@ class SegmentSieve(FeatureSieve, ABC):
         return len(self._cut) * (len(self._q) - 1)
 
     def _copy(self):
-        return self.__class__(self._cut, self._q)
+        # == self.__class__(self._cut, self._q) (the copy does not keep the
+        # coquantile norm, as in the reference), without re-running the argument
+        # checks: fit makes one copy of every sieve per iterated sum
+        new = object.__new__(self.__class__)
+        new._cut, new._q, new._coquantile_norm = self._cut, self._q, "L2"
+        return new
 
     def __str__(self) -> str:
         return f"{self.__class__.__name__}({self._cut}, {self._q})"
