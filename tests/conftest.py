@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The tests load ``libfruits_b200.so``; build it if the tree is fresh
+    (``__graft_entry__.build()`` does the same; nvcc needs no GPU)."""
+    from fruits_b200 import _backend, build
+    if not os.path.exists(_backend.LIB_PATH) and os.path.exists(build.NVCC):
+        build.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
