@@ -105,3 +105,39 @@ def test_route_rule(monkeypatch):
     monkeypatch.setenv("FRUITS_B200_JIT", "0")
     assert not _jit.enabled(10 ** 6)
     assert np.isfinite(_jit.DEFAULT_OPTS["budget"])
+
+
+@pytest.mark.parametrize("name,si,ppc,tt,ndims", [("C5_sweep", 0, 2, 16, 3), ("C4_twi", 0, 1, 16, 3),
+                                                  ("C2_reduced", 0, 1, 8, 2), ("C1_readme", 1, 4, 16, 3)])
+def test_staged_epilogue_writes_every_feature_column_once(name, si, ppc, tt, ndims):
+    """The epilogue stages a warp's features in the group's tile buffers and
+    writes them in chunks of consecutive columns: every feature column of every
+    owned node exactly once, every chunk inside the staging row."""
+    import re
+    trie, iss, sieves, prog = _program(name, si, reg_budget=70, parts_multiple=ppc)
+    dims = [(d, 0) for d in trie.used_dims()]
+    em = _jit.Emitter(prog, dims, ppc, 8, True, tt)
+    sw = em.staging_width()
+    row = em.nrow * tt + 2
+    assert 5 <= sw <= (row if ppc <= 2 else row // 2) and sw % 2 == 1
+    nf = len(sieves.feats)
+    written = []
+    for part in prog.parts:
+        if not part.owned:
+            continue
+        code = em.epilogue_code(part)
+        slots = [int(m.group(1)) for ln in code for m in [re.match(r"stg\[lane \* \d+ \+ (\d+)\]", ln)] if m]
+        assert max(slots) < sw - 1
+        starts = [int(m.group(1)) for ln in code
+                  for m in [re.search(r"a\.col0 \+ (\d+);", ln)] if m]
+        counts = [int(m.group(1)) for ln in code for m in [re.search(r"e < (\d+); e \+= 32", ln)] if m]
+        assert len(starts) == len(counts) and sum(counts) == len(slots) == len(part.owned) * nf
+        for c0, cnt in zip(starts, counts):
+            written += list(range(c0, c0 + cnt))
+    assert sorted(written) == list(range(len(trie.emits) * nf))
+    # without staging: one direct store per feature
+    em0 = _jit.Emitter(prog, dims, ppc, 8, True, tt, stage=0)
+    assert em0.staging_width() == 0
+    direct = [ln for part in prog.parts if part.owned for ln in em0.epilogue_code(part)
+              if ln.strip().startswith("o[")]
+    assert len(direct) == len(trie.emits) * nf
