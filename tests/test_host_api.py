@@ -271,3 +271,23 @@ def test_copy_threads_copy_rows():
         np.testing.assert_array_equal(dst, src)
     with pytest.raises(ValueError):
         hs.finish(hs.copy_rows(np.zeros((4, 2)), np.zeros((4, 3))))
+
+
+def test_emission_ranges_respect_the_dimension_limit():
+    """Words over more dimensions than one launch stages are materialised in
+    consecutive emission ranges, each within the limit (ISS._dim_pieces)."""
+    from fruits_b200 import _backend as be
+    iss = fruits.ISS(fruits.words.of_weight(2, 12), mode=fruits.ISSMode.EXTENDED)
+    trie = iss.trie()
+    pieces = iss._dim_pieces(None)
+    assert len(pieces) > 1 and pieces[0][0] == 0 and pieces[-1][1] == len(trie.emits)
+    assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    for lo, hi in pieces:
+        assert len(trie.subset(lo, hi).used_dims()) <= be.FB_MAX_USED_DIMS
+    sub = iss._dim_pieces((3, 40))
+    assert sub[0][0] == 3 and sub[-1][1] == 40
+    small = fruits.ISS(fruits.words.of_weight(3, 3), mode=fruits.ISSMode.EXTENDED)
+    assert small._dim_pieces(None) == [None] and small._dim_pieces((2, 9)) == [(2, 9)]
+    wide = fruits.ISS([fruits.words.SimpleWord("[12345678]")])
+    with pytest.raises(NotImplementedError):
+        wide._dim_pieces(None)
