@@ -72,6 +72,10 @@ COS_CASES = {
                      (3, 2, 50), "uniform1"),
     "cos_e4": ({"words": ["[1][1]", "[11][2]"],
                 "coswiss": {"freqs": [0.1, 0.7], "exponent": 4}}, (2, 2, 41), "normal"),
+    # four letters with the total weighting: 81 expansion terms (the C3 slices)
+    "cos_e2_total_4letters": ({"words": ["[1][2][1][2]", "[2][1][1][-2]"],
+                               "coswiss": {"freqs": [0.05, 0.45], "exponent": 2, "total": True}},
+                              (3, 2, 40), "uniform1"),
 }
 
 
