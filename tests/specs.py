@@ -111,6 +111,18 @@ SPECS["R_mixed"] = {"slices": [
      "sieves": [["NPI", {"q": [0.5, 1.0]}], ["XPI", {}], ["MIN", {}], ["END", {"cut": [5, -1]}]],
      "fit_sample_size": 0.5}]}
 
+# order in which fit consumes the global numpy RNG (fruits/fruit.py:430-438, then per
+# iterated sum and non-constant PPV quantile fruits/sieving/implicit.py:103-108)
+SPECS["R_rng"] = {"slices": [
+    {"preps": [["INC", {}]],
+     "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended"}],
+     "sieves": [["PPV", {"quantile": [0.3, 0.0, 0.8], "constant": [False, True, False],
+                         "sample_size": 0.5}], ["NPI", {"q": [0.4, 1.0]}], ["END", {}]],
+     "fit_sample_size": 0.7},
+    {"iss": [{"words": ["[1][2]", "[2]"], "mode": "single", "semiring": "arctic"}],
+     "sieves": [["PPV", {"sample_size": 0.25}], ["MAX", {"q": [-1.0, 0.5]}]],
+     "fit_sample_size": 1}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -119,7 +131,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
-              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -130,6 +142,8 @@ def make_input(name: str, n: int = None) -> np.ndarray:
         return np.random.default_rng(1234).standard_normal((n, D, T))
     if name == "R_mixed":
         return np.random.default_rng(42).random((n, D, T)) + 0.1
+    if name == "R_rng":
+        return np.random.default_rng(43).standard_normal((n, D, T)).cumsum(axis=2)
     return np.random.default_rng(0).standard_normal((n, D, T)).cumsum(axis=2)
 
 

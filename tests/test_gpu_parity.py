@@ -995,18 +995,24 @@ def test_reference_kat_sieve_table(kat):
     np.testing.assert_allclose(got, np.array(want, dtype=float), rtol=1e-12, atol=1e-15)
 
 
-def test_mixed_rank2_pipeline_golden(golden_dir):
-    """Frozen output of the real reference for a fruit with a Bayesian slice
-    (rank-2 sieves, sieve wrappers) and a slice of two chained ISS."""
-    g = np.load(os.path.join(golden_dir, "pipeline_R_mixed.npz"))
-    X = specs.make_input("R_mixed", 40)
-    fruit = specs.build_fruit(fruits, specs.SPECS["R_mixed"])
+@pytest.mark.parametrize("name", ["R_mixed", "R_rng"])
+def test_extra_pipeline_golden(name, golden_dir):
+    """Frozen outputs of the real reference: ``R_mixed`` -- a Bayesian slice
+    (rank-2 sieves, sieve wrappers) and a slice of two chained ISS; ``R_rng``
+    -- fractional fit samples and PPV subsamples, i.e. the order in which fit
+    consumes the global numpy RNG."""
+    g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
+    X = specs.make_input(name)
+    fruit = specs.build_fruit(fruits, specs.SPECS[name])
     assert fruit.nfeatures() == int(g["nfeatures"])
     np.random.seed(0)
     fruit.fit(X)
     res = fruit.transform(X)
     assert_exact(fitted_thresholds(fruit), g["thresholds"], "thresholds")
-    assert_close(res, g["features"], 1e-12, "features")      # CUR: summation order
+    if name == "R_rng":
+        assert_exact(res, g["features"], "features")
+    else:
+        assert_close(res, g["features"], 1e-12, "features")      # CUR: summation order
     labels = "|".join(fruit.label(i) for i in
                       sorted(set(np.linspace(0, res.shape[1] - 1, 23).astype(int))))
     assert labels == str(g["labels"])

@@ -125,7 +125,7 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed"])
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng"])
 def test_pipeline_golden(name, golden_dir):
     from cases import COS_PIPE_CASES, EXTRA_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
