@@ -226,6 +226,12 @@ def apply_prep(prep, X, state=None):
         if args is None:
             return np.concatenate((X, X), axis=1)
         return np.concatenate((X, apply_prep(args, X)), axis=1)
+    if name == "DIM":
+        # fruits/preparation/wrapper.py:37-43: the chosen dimensions (in the given
+        # order) transformed and appended behind the untouched ones
+        dims = args["dim"] if isinstance(args["dim"], (list, tuple)) else [args["dim"]]
+        inner = apply_prep(args["preparateur"], np.ascontiguousarray(X[:, list(dims), :]))
+        return np.concatenate((np.delete(X, list(dims), axis=1), inner), axis=1)
     raise NotImplementedError(name)
 
 

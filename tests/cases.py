@@ -165,6 +165,8 @@ PREP_CASES = {
     "nrm": ["NRM", {}],
     "new_inc": ["NEW", ["INC", {}]],
     "new_none": ["NEW", None],
+    "dim_inc": ["DIM", {"preparateur": ["INC", {}], "dim": 1}],
+    "dim_std_reordered": ["DIM", {"preparateur": ["STD", {}], "dim": [2, 0]}],
 }
 
 

@@ -165,6 +165,8 @@ def _prep(mod, desc):
     name, args = desc
     if name == "NEW":
         return mod.preparation.NEW(None if args is None else _prep(mod, args))
+    if name == "DIM":
+        return mod.preparation.DIM(_prep(mod, args["preparateur"]), args["dim"])
     return getattr(mod.preparation, name)(**args)
 
 
