@@ -291,3 +291,25 @@ def test_emission_ranges_respect_the_dimension_limit():
     wide = fruits.ISS([fruits.words.SimpleWord("[12345678]")])
     with pytest.raises(NotImplementedError):
         wide._dim_pieces(None)
+
+
+@pytest.mark.parametrize("script,n_slices,n_features", [("fruit_reduced", 4, 4431),
+                                                        ("fruit_general", 4, 20167),
+                                                        ("fruit_twi", 2, 1725)])
+def test_reference_experiment_scripts_build_unchanged(script, n_slices, n_features):
+    """The reference's own experiment definitions (experiments/fruit_*.py) run
+    unmodified against the ``fruits`` alias of this repository and describe the
+    same feature space.  Needs the reference checkout (build container only)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.environ.get("FRUITS_REF", "/root/reference"), "experiments",
+                        script + ".py")
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not available")
+    import fruits as alias
+    assert alias.Fruit is fruits.Fruit
+    spec = importlib.util.spec_from_file_location("ref_" + script, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert isinstance(mod.fruit, fruits.Fruit)
+    assert len(mod.fruit) == n_slices and mod.fruit.nfeatures() == n_features
