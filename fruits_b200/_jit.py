@@ -33,7 +33,6 @@ import os
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
-import numpy as np
 
 from . import _backend as be
 

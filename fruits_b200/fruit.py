@@ -21,7 +21,6 @@ from . import _backend as be
 from . import _hoststage as hs
 from . import _jit
 from .cache import SharedSeedCache
-from .callback import AbstractCallback
 from .iss.iss import ISS
 from .iss.semiring import Reals
 from .preparation.abstract import Preparateur

@@ -8,7 +8,6 @@ implement ``_fit_device`` / ``_transform_device`` on device tensors.
 from abc import ABC, abstractmethod
 from typing import TypeVar
 
-import numpy as np
 import torch
 
 from . import _backend as be
