@@ -12,6 +12,7 @@ array kernels of ``csrc/sieve.cu``.  There is no CPU route.
 """
 import ctypes
 import inspect
+import os
 from typing import Callable, Generator, Literal, Optional, Union
 
 import numpy as np
@@ -20,6 +21,7 @@ import torch
 from . import _backend as be
 from . import _hoststage as hs
 from . import _jit
+from . import _jit_chain
 from .cache import SharedSeedCache
 from .iss.iss import ISS
 from .iss.semiring import Reals
@@ -723,6 +725,11 @@ class FruitSlice:
         compile_ok = _jit.enabled(n) or (jit_only and _jit.enabled())
         # mid-size batches: the generated kernel only if it has been compiled already
         cached_ok = not compile_ok and n >= _jit.MIN_SERIES_CACHED and _jit.enabled()
+        if not compile_ok and _jit.enabled() and self._chain_first(iss, len(dims)):
+            # the chain kernel runs one lane per trie node like the generic kernel, so
+            # it pays from small batches on (one translation unit, ~1 s of NVRTC)
+            compile_ok = n >= _jit_chain.MIN_SERIES
+            cached_ok = not compile_ok and n >= _jit_chain.MIN_SERIES_CACHED
         if compile_ok or cached_ok:
             try:
                 self._transform_jit(X, cache, out, col0, sanitize, dims, feats, bounded_hi,
@@ -741,6 +748,14 @@ class FruitSlice:
             # materialise (in pieces) and sieve with the stand-alone kernels
             self._transform_composed(X, [], cache, out, col0, sanitize)
 
+    @staticmethod
+    def _chain_first(iss, n_dims: int) -> bool:
+        if os.environ.get("FRUITS_B200_CHAIN", "1") == "0":
+            return False
+        trie, n_shared = iss._jit_trie(n_dims)
+        return (not n_shared and _jit_chain.suitable(trie, iss.semiring._code, iss._weight_mode())
+                and _jit_chain.chain_like(trie))
+
     def _transform_jit(self, X, cache, out, col0, sanitize, dims, feats, bounded_hi,
                        bounded_mm, cached_only: bool = False) -> None:
         """Plan-specialised kernel (``_jit.py``): trie nodes and sieve state in
@@ -757,33 +772,62 @@ class FruitSlice:
         sieves = _jit.SieveSet.make(feats, bounded_hi, bounded_mm)
         g, g_ld = iss._lookup(X)
         wm = iss._weight_mode()
-        key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0, _jit.options_key())
+        # unweighted Arctic plans: the lane-per-node chain kernel (``_jit_chain.py``) first
+        # for chain-like tries (the alternating-sign words), else as the second choice
+        mode = os.environ.get("FRUITS_B200_CHAIN", "1")
+        kinds = ["slice"]
+        if mode != "0" and not n_shared and _jit_chain.suitable(trie, iss.semiring._code, wm):
+            first = mode == "force" or _jit_chain.chain_like(trie)
+            kinds = ["chain", "slice"] if first else ["slice", "chain"]
+        base_key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0)
         memo = getattr(iss, "_jit_memo", None)
         if memo is None or memo[0] is not trie:
             memo = (trie, {})
             iss._jit_memo = memo
-        kern = memo[1].get(key)
-        if kern == "not compiled":
-            if cached_only:
-                raise _jit.NotCompiled("not compiled")
-            kern = None                     # a large batch pays for the compilation
-        if kern is None:
+
+        def kernel_of(kind):
+            chain = kind == "chain"
+            key = base_key + ((kind, tuple(sorted(_jit_chain.options().items()))) if chain
+                              else (kind, _jit.options_key()))
+            kern = memo[1].get(key)
+            if kern == "not compiled":
+                if cached_only:
+                    raise _jit.NotCompiled("not compiled")
+                kern = None                     # a large batch pays for the compilation
+            if kern is None:
+                try:
+                    if chain:
+                        gen = _jit_chain.generate(trie, iss.semiring._code, wm, sieves, jdims)
+                    else:
+                        # a plan without another fused route may keep part of its sums
+                        # in local memory
+                        spill = 450 if getattr(iss, "_jit_only", False) else 0
+                        gen = _jit.generate(trie, iss.semiring._code, wm, sieves, jdims,
+                                            g_ld == 0, _jit.options(), n_shared, spill)
+                except NotImplementedError as exc:
+                    memo[1][key] = exc          # remembered: planning is host work
+                    raise
+                try:
+                    kern = (_jit_chain.JitChain if chain else _jit.JitSlice).load(gen, cached_only)
+                except _jit.NotCompiled:
+                    memo[1][key] = "not compiled"      # do not plan again on every call
+                    raise
+                memo[1][key] = kern
+            if isinstance(kern, NotImplementedError):
+                raise kern
+            if chain and not kern.fits(X.shape[2]):
+                raise NotImplementedError("series too long for the chain kernel's staging")
+            return kern
+
+        kern = None
+        for kind in kinds:
             try:
-                # a plan without another fused route may keep part of its sums in local memory
-                spill = 450 if getattr(iss, "_jit_only", False) else 0
-                gen = _jit.generate(trie, iss.semiring._code, wm, sieves, jdims, g_ld == 0,
-                                    _jit.options(), n_shared, spill)
-            except NotImplementedError as exc:
-                memo[1][key] = exc          # remembered: planning is host work
-                raise
-            try:
-                kern = _jit.JitSlice.load(gen, cached_only)
-            except _jit.NotCompiled:
-                memo[1][key] = "not compiled"      # do not plan again on every call
-                raise
-            memo[1][key] = kern
-        if isinstance(kern, NotImplementedError):
-            raise kern
+                kern = kernel_of(kind)
+                break
+            except NotImplementedError:
+                if kind == kinds[-1]:
+                    raise
+        chain = kind == "chain"
         if materialise:
             X = self._prepare_device(X, cache, fit=False)
         thr = self._threshold_table(len(trie.emits))
@@ -809,7 +853,8 @@ class FruitSlice:
                 extra = g
                 extra_ld = g_ld
         kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize)
-        self._last_launch = ("fb_jit_slice", kern.n_launches(X.shape[0], X.shape[2]), kern)
+        self._last_launch = ("fb_jit_chain" if chain else "fb_jit_slice",
+                             kern.n_launches(X.shape[0], X.shape[2]), kern)
 
     def _transform_generic(self, X, out, col0, sanitize, dims, feats, bounded_hi,
                            bounded_mm) -> None:

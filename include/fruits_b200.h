@@ -220,6 +220,25 @@ FB_API int fb_jit_slice_features(fb_jit_kernel *k, const fb_jit_geometry *geo,
                                  const double *thr, int64_t n_thr, double *out, int64_t out_ld,
                                  int64_t col0, int sanitize, void *stream);
 
+/* Lane-per-node form for deep Arctic tries (generator: fruits_b200/_jit_chain.py):
+ * the 24-48-letter alternating-sign chains of experiments/fruit_reduced.py:42-49
+ * and fruit_general.py:42-51 (fruits/iss/semiring.py:314-338).  One warp owns one
+ * series and one block of the trie, lanes are skewed in time by their depth and
+ * hand the parent value on with a warp shuffle; the prepared series is staged
+ * whole in shared memory.  Same source contract (fb_jit_slice, TH) and the same
+ * semantics as fb_jit_slice_features.  FB_ENOSUP if the series does not fit
+ * the shared-memory staging. */
+typedef struct fb_jit_chain_geometry {
+    int32_t blocks_per_series; /* warps working on the same series (trie blocks) */
+    int32_t series_per_cta;
+    int32_t rows_staged;       /* prepared dimensions staged per series */
+    int32_t pad;               /* zero padding on both sides of a staged row (> max depth) */
+} fb_jit_chain_geometry;
+FB_API int fb_jit_chain_features(fb_jit_kernel *k, const fb_jit_chain_geometry *geo,
+                                 const fb_batch *batch, const double *thr, int64_t n_thr,
+                                 double *out, int64_t out_ld, int64_t col0, int sanitize,
+                                 void *stream);
+
 /* fruits/iss/semiring.py:103-125, :138-158: exp(+alpha g), exp(-alpha g) rows
  * of the exponential weighting for every distinct alpha:
  * out[r][2a + s][t] = exp((s ? -1 : 1) * alpha[a] * g[r][t]),  r < rows. */

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import fruits_b200 as fruits  # noqa: E402
-from fruits_b200 import _jit  # noqa: E402
+from fruits_b200 import _jit, _jit_chain  # noqa: E402
 from fruits_b200.iss.weighting import Indices, Plateaus  # noqa: E402
 import specs  # noqa: E402
 
@@ -38,6 +38,19 @@ def warm(name: str) -> None:
                  for u in used]
         shared = iss.weighting is None or isinstance(iss.weighting, (Indices, Plateaus))
         t0 = time.time()
+        sieves = _jit.SieveSet.make(feats, bhi, bmm)
+        if (not n_shared and _jit_chain.suitable(trie, iss.semiring._code, iss._weight_mode())
+                and _jit_chain.chain_like(trie)):
+            genc = _jit_chain.generate(trie, iss.semiring._code, iss._weight_mode(), sieves, jdims)
+            path = os.path.join(_jit.CACHE_DIR, genc.digest() + ".cubin")
+            if not os.path.exists(path):
+                os.makedirs(_jit.CACHE_DIR, exist_ok=True)
+                with open(path, "wb") as f:
+                    f.write(_jit._nvrtc(genc.source, "fb_jit_chain.cu", False, genc.max_regs))
+            print(f"{name} slice {si}: {len(trie.nodes)} nodes, chain kernel, "
+                  f"{len(genc.em.p.blocks)} blocks x {genc.em.p.rows} rows, "
+                  f"{genc.em.spc} series/CTA, {time.time() - t0:.1f} s", flush=True)
+            continue
         try:
             gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
                                 _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options(),

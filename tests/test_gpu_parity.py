@@ -453,9 +453,10 @@ def test_jit_pipeline_golden(name, golden_dir, force_jit):
     fruit.fit(X)
     res = fruit.transform(X)
     routes = _routes(fruit)
-    # every slice but the 48-letter arctic chains of C3 compiles to a generated kernel
-    want = ["fb_jit_slice", "fb::lns_kernel"] if name == "C3_general" else \
-        ["fb_jit_slice"] * len(routes)
+    # every slice compiles to a generated kernel: the unweighted arctic slices to
+    # the lane-per-node chain kernel, everything else to the thread-per-series one
+    arctic = [slc["iss"][0].get("semiring") == "arctic" for slc in specs.SPECS[spec_name]["slices"]]
+    want = ["fb_jit_chain" if a else "fb_jit_slice" for a in arctic]
     assert routes == want, routes
     if name in ("C1_readme", "C5_sweep"):
         assert_exact(res, g["features"], name + " features")
@@ -468,8 +469,9 @@ def test_jit_pipeline_golden(name, golden_dir, force_jit):
 @pytest.mark.parametrize("semiring", ["reals", "arctic"])
 def test_jit_shapes_vs_generic_and_oracle(shape, semiring, force_jit, monkeypatch):
     """Ragged batches (n not a multiple of the CTA, odd lengths, lengths below
-    and across the tile) through the generated kernel: bit-identical to the
+    and across the tile) through the generated kernels: bit-identical to the
     generic kernel and to the oracle."""
+    monkeypatch.setenv("FRUITS_B200_CHAIN", "force")     # (bushy arctic tries prefer fb_jit_slice)
     from oracle import pipeline as orc
     spec = {"slices": [{"preps": [["INC", {}]],
                         "iss": [{"words": {"of_weight": [3, 3]}, "mode": "extended",
@@ -482,7 +484,13 @@ def test_jit_shapes_vs_generic_and_oracle(shape, semiring, force_jit, monkeypatc
     np.random.seed(1)
     fruit.fit(X)
     res = fruit.transform(X)
-    assert _routes(fruit) == ["fb_jit_slice"]
+    assert _routes(fruit) == ["fb_jit_chain" if semiring == "arctic" else "fb_jit_slice"]
+    if semiring == "arctic":
+        # the same plan through the thread-per-series kernel
+        monkeypatch.setenv("FRUITS_B200_CHAIN", "0")
+        res2 = fruit.transform(X)
+        assert _routes(fruit) == ["fb_jit_slice"]
+        assert_exact(res, res2, "chain kernel vs thread-per-series kernel")
     monkeypatch.setenv("FRUITS_B200_JIT", "0")
     gen = fruit.transform(X)
     assert _routes(fruit) == ["fb::lns_kernel"]

@@ -8,6 +8,7 @@ import fruits_b200 as fruits
 import specs
 from fruits_b200 import _backend as be
 from fruits_b200 import _jit
+from fruits_b200 import _jit_chain
 
 
 def _program(name, si=0, **kw):
@@ -44,11 +45,58 @@ def test_sweep_partition_is_balanced():
     assert len(costs) == 50 and max(costs) <= 1.15 * (sum(costs) / len(costs))
 
 
-def test_deep_arctic_chain_is_left_to_the_generic_kernel():
+def test_deep_arctic_chain_is_not_for_the_thread_per_series_kernel():
     trie, iss, sieves, _ = _program("C3_general", 1)
     with pytest.raises(NotImplementedError):
         _jit.generate(trie, iss.semiring._code, iss._weight_mode(), sieves,
                       [(d, 0) for d in trie.used_dims()], True, _jit.options())
+
+
+@pytest.mark.parametrize("name,si,blocks,slots", [("C2_reduced", 1, 2, 188), ("C3_general", 1, 4, 380),
+                                                  ("C4_twi", 1, 1, 96)])
+def test_chain_layout_of_the_arctic_slices(name, si, blocks, slots):
+    """Lane-per-node layout (fruits_b200/_jit_chain.py): every emission owned
+    once, blocks closed under ancestors, parents before children, and the
+    alternating-sign chains wire almost every parent to the previous row of
+    the same lane (no instruction) or to the rotation shuffle."""
+    trie, iss, sieves, _ = _program(name, si)
+    prog = _jit_chain.ChainProgram(trie, sieves, 3)
+    assert len(prog.blocks) == blocks and prog.n_slots == slots
+    owned = [sl.node for b in prog.blocks for sl in b if sl.owned]
+    assert sorted(owned) == sorted(v for v, n in enumerate(trie.nodes) if n.emit >= 0)
+    irregular = 0
+    for b in prog.blocks:
+        assert len(b) <= 96
+        pos = {}
+        for i, sl in enumerate(b):
+            par = trie.nodes[sl.node].parent
+            assert (par < 0 and sl.parent == -1) or pos[par] == sl.parent
+            pos[sl.node] = i
+            irregular += sl.parent >= 0 and sl.parent != i - 1
+    assert irregular <= len(prog.blocks) * 2
+    assert prog.max_skew == trie.max_depth - 1
+    node_w, pair_w, irr_w = prog.tables()
+    assert len(node_w) == len(pair_w) == len(irr_w) == blocks * 3 * 32
+    emits = sorted(w & 0xffff for w in node_w if w & 0xffff != 0xffff)
+    assert emits == list(range(len(trie.emits)))
+
+
+def test_chain_kernel_compiles_without_gpu(tmp_path, monkeypatch):
+    """C2 slice 1 (188-node arctic trie, seven sieves) -> CUDA source -> NVRTC."""
+    monkeypatch.setattr(_jit, "CACHE_DIR", str(tmp_path))
+    trie, iss, sieves, _ = _program("C2_reduced", 1)
+    gen = _jit_chain.generate(trie, iss.semiring._code, iss._weight_mode(), sieves,
+                              [(0, 0), (0, 1)])
+    assert "fb_jit_slice" in gen.source and "__shfl_sync" in gen.source
+    cubin = _jit._nvrtc(gen.source, "fb_jit_chain.cu", False, gen.max_regs)
+    assert cubin[:4] == b"\x7fELF"
+    # a masked copy of the step body for pipeline fill / drain and an unmasked one
+    assert gen.source.count("for (; s <") == 3
+    # Reals and weighted plans keep their routes
+    trie0, iss0, sieves0, _ = _program("C2_reduced", 0)
+    assert not _jit_chain.suitable(trie0, iss0.semiring._code, iss0._weight_mode())
+    with pytest.raises(NotImplementedError):
+        _jit_chain.generate(trie0, iss0.semiring._code, iss0._weight_mode(), sieves0, [(0, 0)])
 
 
 def test_sibling_letters_share_products():
