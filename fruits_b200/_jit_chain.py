@@ -40,7 +40,7 @@ from dataclasses import dataclass
 from . import _backend as be
 from . import _jit
 
-CHAIN_VERSION = 1
+CHAIN_VERSION = 2
 MIN_SERIES = 512           # from this batch size on a chain kernel is compiled (cached on disk)
 MIN_SERIES_CACHED = 16     # ... and from this size on an already compiled one is used
 
@@ -316,7 +316,7 @@ class ChainEmitter:
                 L.append(f"const bool fst{r} = tl{r} == 0;")
             expr = par
             for j in range(p.npairs[r]):
-                expr = f"fma(e{r}_{j}, smem[x{r}_{j} + s], {expr})"
+                expr = f"fma(e{r}_{j}, *xp{r}_{j}, {expr})"
             L.append(f"const double w{r} = {expr};")
             L.append(f"const double q{r} = S{r};")
             if masked:
@@ -324,6 +324,9 @@ class ChainEmitter:
             else:
                 L.append(f"S{r} = (w{r} > S{r}) ? w{r} : S{r};")      # keeps S on NaN like the reference's loop
             self._sieve(L, r, f"S{r}", f"q{r}", masked)
+        for r in range(R):
+            for j in range(p.npairs[r]):
+                L.append(f"xp{r}_{j}++;")
         return L
 
     def epilogue(self, r: int) -> list:
@@ -435,7 +438,7 @@ class ChainEmitter:
             for j in range(p.npairs[r]):
                 A(f"    const unsigned pw{r}_{j} = PAIR[((blk * R + {r}) * 32 + lane) * {npmax} + {j}];")
                 A(f"    const double e{r}_{j} = (double)(int)(signed char)(pw{r}_{j} >> 8);")
-                A(f"    const int x{r}_{j} = (sl * NROW + (int)(pw{r}_{j} & 0xffu)) * XLD + PAD - skew{r};")
+                A(f"    const double *xp{r}_{j} = smem + ((sl * NROW + (int)(pw{r}_{j} & 0xffu)) * XLD + PAD - skew{r});")
             for qi in range(len(p.irregular[r])):
                 A(f"    const unsigned iw{r}_{qi} = IRR[((blk * R + {r}) * 32 + lane) * {nimax} + {qi}];")
                 A(f"    const int isrc{r}_{qi} = (int)(iw{r}_{qi} & 31u);")
@@ -491,7 +494,7 @@ class ChainEmitter:
 # run time
 # ---------------------------------------------------------------------------
 
-DEFAULT_OPTS = {"rows": 3, "unroll": 2, "minb": 1, "warps": 4}
+DEFAULT_OPTS = {"rows": 3, "unroll": 4, "minb": 1, "warps": 4, "regs": 128}
 
 
 def options() -> dict:
@@ -549,7 +552,7 @@ def generate(trie, semiring: int, weight_mode: int, sieves, dims: list, opts: di
     if nt > 1024:
         raise NotImplementedError("too many blocks per series")
     warps = -(-(nt // 32) // 4) * 4
-    max_regs = min(255, (65536 // (warps * 32 * opts["minb"])) // 8 * 8)
+    max_regs = min(opts["regs"], 255, (65536 // (warps * 32 * opts["minb"])) // 8 * 8)
     return GeneratedChain(em.source(opts["minb"]), em, max_regs)
 
 
