@@ -36,7 +36,7 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 13            # bump to invalidate cached cubins
+JIT_VERSION = 14            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -171,6 +171,9 @@ class Program:
             combo = getattr(nodes[v], "combo", None)
             if combo is not None:
                 return 1 + sum(1 + t[2] + t[4] for t in combo) + sieves.cost()
+            dp = getattr(nodes[v], "dp", None)
+            if dp is not None:
+                return 2 + len(dp[1])
             c = 2 + (2 if weighted else 0)
             if not self.reals:
                 c += 1 + max(0, sum(1 for e in nodes[v].expo if e != 0) - 1)
@@ -203,14 +206,23 @@ class Program:
     def _chain(self, v):
         """Nodes ``v`` needs, parents first, ``v`` last."""
         combo = getattr(self.trie.nodes[v], "combo", None)
-        if combo is not None:
+        dp = getattr(self.trie.nodes[v], "dp", None)
+        if combo is not None or dp is not None:
+            # several predecessors: the terms of a combination / the states of
+            # the previous level of a separable recurrence (iss/cos.py)
+            memo = self.__dict__.setdefault("_chain_memo", {})
+            if v in memo:
+                return memo[v]
+            preds = [term[1] for term in combo] if combo is not None else \
+                [u for u, _ in dp[1] if u >= 0]
             seen, out = set(), []
-            for term in combo:
-                for a in self._chain(term[1]):
+            for u in preds:
+                for a in self._chain(u):
                     if a not in seen:
                         seen.add(a)
                         out.append(a)
-            return out + [v]
+            memo[v] = out + [v]
+            return memo[v]
         out = []
         while v >= 0:
             out.append(v)
@@ -310,8 +322,9 @@ class Emitter:
             # children of every parent that live in this part
             groups = {}
             for v in part.snodes:
-                if getattr(nodes[v], "combo", None) is None:
+                if getattr(nodes[v], "combo", None) is None and getattr(nodes[v], "dp", None) is None:
                     groups.setdefault(nodes[v].parent, []).append(v)
+            self._step_dp(L, part, sidx)
             # deepest parents first: a node is updated after its children read it
             order = sorted(groups, key=lambda u: -(nodes[u].depth if u >= 0 else 0))
             for u in order:
@@ -371,6 +384,10 @@ class Emitter:
                 L.append(f"double y{v} = 0.0;")
                 for ti, (coeff, node, sp, su, cp, cu) in enumerate(combo):
                     term = f"S[{sidx[node]}]"
+                    if coeff is None:
+                        # separable form: the coefficient is the shared row ``su``
+                        L.append(f"y{v} = fma(x{p.dim_index[su]}, {term}, y{v});")
+                        continue
                     if sp or cp:
                         L.append(f"double z{v}_{ti} = {term};")
                         for _ in range(sp):
@@ -402,6 +419,53 @@ class Emitter:
                 L.append(f"const double w{v} = {expr};")
                 self._update_arctic(L, v, f"w{v}", sidx[v], v in owned, oidx.get(v))
         return L
+
+    def _step_dp(self, L, part, sidx) -> None:
+        """Nodes of a separable recurrence (cosine weighted ISS, iss/cos.py):
+        ``S_v[t] = S_v[t-1] + letter[t] * sum_j row_j[t] * S_{u_j}[t-1]`` -- the
+        states of the previous level weighted with shared rows.  Letter products
+        are formed once per step and distinct letter; deeper levels first, so a
+        node is updated after the nodes that read it."""
+        p, nodes = self.p, self.p.trie.nodes
+        dps = [v for v in part.snodes if getattr(nodes[v], "dp", None) is not None]
+        if not dps:
+            return
+        letters = {}
+        for v in dps:
+            occ = nodes[v].dp[0]
+            if occ and occ not in letters:
+                name = f"lt{len(letters)}"
+                expr = None
+                for d, div in occ:
+                    x = f"x{p.dim_index[d]}"
+                    if expr is None:
+                        expr = x if not div else f"__ddiv_rn(1.0, {x})"
+                    else:
+                        expr = f"{'__ddiv_rn' if div else '__dmul_rn'}({expr}, {x})"
+                L.append(f"const double {name} = {expr};")
+                letters[occ] = name
+        for v in sorted(dps, key=lambda v: -nodes[v].depth):
+            occ, preds = nodes[v].dp
+            z = None
+            for u, row in preds:
+                w = f"x{p.dim_index[row]}"
+                if u < 0:
+                    term = w                                   # first level: the row itself
+                    z = term if z is None else f"__dadd_rn({z}, {term})"
+                elif z is None:
+                    z = f"__dmul_rn({w}, S[{sidx[u]}])"
+                else:
+                    z = f"fma({w}, S[{sidx[u]}], {z})"
+            lt = letters.get(occ)
+            if z is None:
+                val = lt if lt is not None else "1.0"
+            elif lt is None:
+                val = z
+            else:
+                val = f"__dmul_rn({lt}, {z})"
+            L.append(f"const double dv{v} = {val};")
+        for v in dps:
+            L.append(f"S[{sidx[v]}] = __dadd_rn(S[{sidx[v]}], dv{v});")
 
     def _update_reals(self, L, v, val, si, is_owned, oi):
         p = self.p

@@ -31,6 +31,25 @@ __global__ void cos_trig_kernel(double *__restrict__ trig, int n_freq, int t, co
     trig[(size_t)(2 * f + 1) * t + tt] = cos(arg);
 }
 
+// Weight rows of the separable form (fruits_b200/iss/cos.py, _separable_plan):
+// rows[r][t] = coeff_r * sin^a_r cos^b_r of pi t / (freq (T-1)); the powers by
+// repeated multiplication like the reference (fruits/iss/cos.py:40-43).
+__global__ void cos_rows_kernel(double *__restrict__ rows, int n_rows, int t, const float *freqs,
+                                const int *__restrict__ spec)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_rows * t) return;
+    const int r = (int)(i / t), tt = (int)(i - (long long)r * t);
+    const int f = spec[4 * r], coeff = spec[4 * r + 1], a = spec[4 * r + 2], b = spec[4 * r + 3];
+    const double den = (double)freqs[f] * (double)(t - 1);
+    const double arg = 3.141592653589793 * (double)tt / den;
+    const double sv = sin(arg), cv = cos(arg);
+    double v = 1.0;
+    for (int k = 0; k < a; k++) v = __dmul_rn(v, sv);
+    for (int k = 0; k < b; k++) v = __dmul_rn(v, cv);
+    rows[i] = __dmul_rn((double)coeff, v);
+}
+
 struct CosParams {
     const double *X;
     const double *trig;
@@ -236,6 +255,166 @@ static int coswiss_terms_launch(const CosParams &Q, cudaStream_t st)
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Separable form (fruits_b200/iss/cos.py, _separable_plan): the weight of a
+// junction, cos(a-b)^s, is a sum of s+1 products u_k(a) v_k(b), so the sum over
+// all expansion terms factorises level by level into a recurrence with
+// NS = s+1 states per level:
+//   A[0][k]  = cumsum(letter_0 * R0[k])
+//   A[i][k]  = cumsum(letter_i * sum_k' RI[k'][k] * A[i-1][k'][t-1])
+//   y        = sum_k RL[k] * A[P-1][k]                      (total weighting)
+//   A[P-1]   = cumsum(letter * sum_k' RL[k'] * A[P-2][k'][t-1]),  y = A[P-1]   (else)
+// with precomputed weight rows R (fb_cos_rows).  NS * P running sums per
+// (series, frequency) instead of sum_i NS^i; one thread owns one (series,
+// frequency) pair, a tile of COS_TT outputs goes through shared memory and is
+// written as 256-byte row segments.  Same value as the expansion up to the order
+// of the additions (about 1e-14 of the row maximum).
+struct SepParams {
+    const double *X;
+    const double *rows;      // [n_rows][t]
+    const int *word;         // [p][dw] exponents
+    const int *tab;          // [n_freq][NS + NS*NS + NS] row indices: R0, RI[k'][k], RL
+    double *out;             // [n_freq][n][t]
+    long long n, d, t;
+    int p, dw, n_freq, total;
+};
+
+constexpr int SEP_THREADS = 128;
+
+template <int P, int NS>
+__global__ void __launch_bounds__(SEP_THREADS) coswiss_sep_kernel(const SepParams Q)
+{
+    __shared__ double ys[SEP_THREADS][COS_TT + 1];
+    const int T = (int)Q.t, dw = Q.dw, nf = Q.n_freq;
+    const long long task0 = (long long)blockIdx.x * SEP_THREADS;
+    const long long task = task0 + threadIdx.x;
+    const long long ntask = Q.n * nf;
+    const bool live = task < ntask;
+    const long long n = live ? task / nf : 0;
+    const int f = live ? (int)(task - n * nf) : 0;
+    const bool total = Q.total != 0;
+    // letters of the word as packed factor lists (4 bits per occurrence)
+    unsigned long long ops[P];
+    int cnt[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        ops[k] = 0;
+        cnt[k] = 0;
+        for (int d = 0; d < dw; d++) {
+            const int occ = Q.word[k * dw + d];
+            const int m = occ < 0 ? -occ : occ;
+            for (int r = 0; r < m && cnt[k] < 16; r++) {
+                ops[k] |= (unsigned long long)(d | (occ < 0 ? 8 : 0)) << (4 * cnt[k]);
+                cnt[k]++;
+            }
+        }
+    }
+    const int *tb = Q.tab + (size_t)f * (NS + NS * NS + NS);
+    const double *r0[NS], *ri[NS][NS], *rl[NS];
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        r0[k] = Q.rows + (size_t)tb[k] * T;
+        rl[k] = Q.rows + (size_t)tb[NS + NS * NS + k] * T;
+#pragma unroll
+        for (int k2 = 0; k2 < NS; k2++) ri[k][k2] = Q.rows + (size_t)tb[NS + k * NS + k2] * T;
+    }
+    // junction to the right of level i: every level but the last, the last if total
+    double A[P][NS];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int k = 0; k < NS; k++) A[i][k] = 0.0;
+    const double *Xn = Q.X + (size_t)n * Q.d * T;
+    for (int t0 = 0; t0 < T; t0 += COS_TT) {
+        const int tn = min(COS_TT, T - t0);
+        if (live) {
+            for (int tt = 0; tt < tn; tt++) {
+                const int t = t0 + tt;
+                // last level first: level i reads level i-1 at t-1
+#pragma unroll
+                for (int i = P - 1; i >= 0; i--) {
+                    double lt = 1.0;
+                    unsigned long long o = ops[i];
+                    for (int j = 0; j < cnt[i]; j++, o >>= 4) {
+                        const double x = __ldg(Xn + (size_t)(o & 7) * T + t);
+                        lt = (o & 8) ? __ddiv_rn(lt, x) : __dmul_rn(lt, x);
+                    }
+                    const bool junction = (i < P - 1) || total;
+                    if (junction) {
+#pragma unroll
+                        for (int k = 0; k < NS; k++) {
+                            double z;
+                            if (i == 0) {
+                                z = __ldg(r0[k] + t);
+                            } else {
+                                z = __dmul_rn(__ldg(ri[0][k] + t), A[i - 1][0]);
+#pragma unroll
+                                for (int k2 = 1; k2 < NS; k2++)
+                                    z = fma(__ldg(ri[k2][k] + t), A[i - 1][k2], z);
+                            }
+                            A[i][k] = __dadd_rn(A[i][k], __dmul_rn(lt, z));
+                        }
+                    } else {
+                        double z = 1.0;
+                        if (i > 0) {
+                            z = __dmul_rn(__ldg(rl[0] + t), A[i - 1][0]);
+#pragma unroll
+                            for (int k2 = 1; k2 < NS; k2++)
+                                z = fma(__ldg(rl[k2] + t), A[i - 1][k2], z);
+                        }
+                        A[i][0] = __dadd_rn(A[i][0], i > 0 ? __dmul_rn(lt, z) : lt);
+                    }
+                }
+                double y;
+                if (total) {
+                    y = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NS; k++) y = fma(__ldg(rl[k] + t), A[P - 1][k], y);
+                } else {
+                    y = A[P - 1][0];
+                }
+                ys[threadIdx.x][tt] = y;
+            }
+        }
+        __syncthreads();
+        // one warp writes the tile of one (series, frequency) pair per iteration
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int j = warp; j < SEP_THREADS; j += SEP_THREADS / 32) {
+            const long long tk = task0 + j;
+            if (tk < ntask && lane < tn) {
+                const long long nn = tk / nf;
+                const int ff = (int)(tk - nn * nf);
+                Q.out[((size_t)ff * Q.n + nn) * T + t0 + lane] = ys[j][lane];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int P, int NS>
+static int coswiss_sep_launch(const SepParams &Q, cudaStream_t st)
+{
+    const long long tasks = Q.n * Q.n_freq;
+    coswiss_sep_kernel<P, NS><<<(unsigned)((tasks + SEP_THREADS - 1) / SEP_THREADS), SEP_THREADS,
+                                0, st>>>(Q);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NS>
+static int coswiss_sep_dispatch(const SepParams &Q, cudaStream_t st)
+{
+    switch (Q.p) {
+    case 1: return coswiss_sep_launch<1, NS>(Q, st);
+    case 2: return coswiss_sep_launch<2, NS>(Q, st);
+    case 3: return coswiss_sep_launch<3, NS>(Q, st);
+    case 4: return coswiss_sep_launch<4, NS>(Q, st);
+    case 5: return coswiss_sep_launch<5, NS>(Q, st);
+    case 6: return coswiss_sep_launch<6, NS>(Q, st);
+    default: return set_err(FB_ENOSUP, "separable CosWISS kernel: words of up to 6 letters");
+    }
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -250,6 +429,39 @@ int fb_cos_trig(const float *freqs, int n_freq, int64_t t, double *trig, void *s
         trig, n_freq, (int)t, freqs);
     FB_CUDA(cudaGetLastError());
     return 0;
+}
+
+int fb_cos_rows(const float *freqs, int n_freq, int64_t t, const int32_t *spec, int n_rows,
+                double *rows, void *stream)
+{
+    FB_REQUIRE(freqs && spec && rows && n_freq >= 1 && t >= 1 && n_rows >= 1, "bad arguments");
+    const long long total = (long long)n_rows * t;
+    cos_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        rows, n_rows, (int)t, freqs, spec);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_coswiss_sep_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word,
+                        int p, int dw, const double *rows, const int32_t *tab, int n_freq, int ns,
+                        int total, double *out, void *stream)
+{
+    FB_REQUIRE(X && word && rows && tab && out, "null argument");
+    FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && p >= 1 && n_freq >= 1, "bad shape");
+    FB_REQUIRE(dw >= 1 && dw <= d && dw <= 8,
+               "word uses %d dimensions, the input has %lld (at most 8 supported)", dw, (long long)d);
+    if (n == 0) return 0;
+    SepParams Q;
+    Q.X = X; Q.rows = rows; Q.word = word; Q.tab = tab; Q.out = out;
+    Q.n = n; Q.d = d; Q.t = t; Q.p = p; Q.dw = dw; Q.n_freq = n_freq; Q.total = total;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ns) {
+    case 2: return coswiss_sep_dispatch<2>(Q, st);
+    case 3: return coswiss_sep_dispatch<3>(Q, st);
+    case 4: return coswiss_sep_dispatch<4>(Q, st);
+    case 5: return coswiss_sep_dispatch<5>(Q, st);
+    default: return set_err(FB_ENOSUP, "separable CosWISS kernel: exponents 1 to 4");
+    }
 }
 
 int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word, int p,

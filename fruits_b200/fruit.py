@@ -840,7 +840,7 @@ class FruitSlice:
             thr_c = self._thr_compact[1]
         extra, extra_ld = None, 0
         if n_shared:
-            extra = iss._trig(X)              # CosWISS: sin / cos rows, shared by all series
+            extra = iss._rows(X)              # CosWISS: weight rows, shared by all series
         elif wm != be.WEIGHT_NONE:
             rows = 1 if g_ld == 0 else X.shape[0]
             if isinstance(iss.semiring, Reals):

@@ -12,6 +12,7 @@ The randomised variants of the reference (``ffn_size``, ``dropout``) are out
 of scope and raise ``NotImplementedError``.
 """
 import itertools
+import os
 from typing import Generator, Optional, Sequence
 
 import numpy as np
@@ -72,64 +73,184 @@ class CosWISS(ISS):
             costs += [float((self._exponent + 1) ** (p - 1) * len(word))] * len(self._freqs)
         return costs
 
-    def _jit_trie(self, n_dims: int):
-        """-> (trie, number of shared rows) for the kernel generator.
+    # -- separable form ------------------------------------------------------------
+    def _junction(self) -> list:
+        """``[(coefficient, sin exponent, cos exponent)]`` of one junction between
+        two consecutive summation indices, one entry per binomial term:
+        ``cos(a-b)^s = sum_k C(s,k) (cos a cos b)^k (sin a sin b)^(s-k)`` -- the
+        factor of index ``a`` goes to the level of ``a``, the factor of ``b`` to the
+        level of ``b`` (reference :265-287, including its habit of keeping only
+        the first decimal digit of every number)."""
+        e = self._exponent
+        binom = [1]
+        for k in range(e):
+            binom.append(binom[-1] * (e - k) // (k + 1))
+        return [(int(str(binom[k])[0]), int(str(e - k)[0]), int(str(k)[0])) for k in range(e + 1)]
 
-        Every expansion term of every (word, frequency) pair is a word over the
-        input dimensions *augmented with the sin / cos rows of the frequency*:
-        level k multiplies by x^e, then sin^a, then cos^b -- the reference's
-        order, since the trig rows sort after the real dimensions.  The terms
-        form a prefix trie like any word list; the emitted value is the
-        combination ``sum_i coeff_i * S_i [* sin^a cos^b of the total
-        weighting]`` (a virtual node with a ``combo`` list)."""
+    def _separable_plan(self, n_dims: int):
+        """The cosine weighted ISS as a recurrence with ``s+1`` states per level.
+
+        The reference expands every word into ``(s+1)^(p-1)`` terms and computes
+        each as an iterated sum of its own (:16-49).  The weight of a junction is a
+        sum of ``s+1`` products ``u_k(i) v_k(j)``, so the sum over all terms
+        factorises level by level: with ``A[i][k]`` = the sum of all partial terms
+        whose junction ``i`` took binomial term ``k``,
+
+            A[0][k][t] = cumsum( letter_0 * F(s_k, c_k) )
+            A[i][k][t] = cumsum( letter_i * sum_k' d_k' F(s_k'+s_k, c_k'+c_k) * A[i-1][k'][t-1] )
+            y[t]       = sum_k d_k F(s_k, c_k)[t] * A[p-1][k][t]            (total weighting)
+
+        (``F(a, b) = sin^a cos^b`` of the level's own index; the last level of a
+        word without total weighting has no junction to its right and a single
+        state).  ``(s+1) p`` running sums per word and frequency instead of
+        ``sum_i (s+1)^i``; prefixes shared between words are computed once.  Same
+        value as the reference's expansion up to the order of the additions
+        (1e-14 of the row maximum on the goldens).
+
+        -> (nodes, emits, rows): ``nodes`` = ``[(level, letter, [(pred, row)])]``
+        (``pred`` = index into nodes or -1, ``row`` = index into rows or -1),
+        ``emits[w * nf + f]`` = ``[(row, node)]``, ``rows`` = ``[(f, coeff, a, b)]``."""
+        key = ("separable",)
+        if key in self._tables:
+            return self._tables[key]
+        J = self._junction()
+        ns = len(J)
+        rows, row_index = [], {}
+
+        def row(f, coeff, a, b):
+            k = (f, coeff, a, b)
+            if k not in row_index:
+                row_index[k] = len(rows)
+                rows.append(k)
+            return row_index[k]
+
+        nodes, node_index, emits = [], {}, []
+
+        def node(prefix, f, state, level, letter, preds):
+            k = (prefix, f, state)
+            if k not in node_index:
+                node_index[k] = len(nodes)
+                nodes.append((level, letter, preds))
+            return node_index[k]
+
+        for word in self.words:
+            mat = [tuple(int(x) for x in el) for el in word]
+            p = len(mat)
+            nj = p if self._total_weighting else p - 1            # junctions of this word
+            for f in range(len(self._freqs)):
+                prev = None                                         # states of the previous level
+                for i in range(p):
+                    prefix = tuple(mat[:i + 1])
+                    letter = tuple((d, e < 0) for d, e in enumerate(mat[i]) for _ in range(abs(e)))
+                    if i <= nj - 1:                                 # a junction to the right
+                        cur = []
+                        for k in range(ns):
+                            if prev is None:
+                                preds = [(-1, row(f, 1, J[k][1], J[k][2]))]
+                            else:
+                                preds = [(prev[k2], row(f, J[k2][0], J[k2][1] + J[k][1],
+                                                        J[k2][2] + J[k][2])) for k2 in range(ns)]
+                            cur.append(node(prefix, f, k, i, letter, preds))
+                    else:                                           # last level, not total
+                        if prev is None:
+                            preds = []
+                        else:
+                            preds = [(prev[k2], row(f, J[k2][0], J[k2][1], J[k2][2]))
+                                     for k2 in range(ns)]
+                        cur = [node(prefix, f, "last", i, letter, preds)]
+                    prev = cur
+                if nj == p:
+                    emits.append([(row(f, J[k][0], J[k][1], J[k][2]), prev[k]) for k in range(ns)])
+                else:
+                    emits.append([(-1, prev[0])])
+        # emission index = word-major, frequency-minor
+        nf = len(self._freqs)
+        order = [w * nf + f for w in range(len(self.words)) for f in range(nf)]
+        assert order == list(range(len(emits)))
+        self._tables[key] = (nodes, emits, rows)
+        return self._tables[key]
+
+    def _jit_trie(self, n_dims: int):
+        """-> (trie, number of shared rows) for the kernel generator: the
+        separable recurrence (``_separable_plan``) as nodes with several
+        predecessors (``dp``), the weight rows as shared extra "dimensions"
+        ``n_dims + r`` and every emission as a combination of the last level's
+        states."""
         from .._plan import Trie, _Node
         key = ("jit", n_dims)
         if key in self._tables:
             return self._tables[key]
+        nodes, emits, rows = self._separable_plan(n_dims)
+        width = n_dims + len(rows)
+        trie = object.__new__(Trie)
+        trie.nodes, trie.emits = [], []
+
+        def marker(dims):
+            m = [0] * width
+            for d in dims:
+                m[d] = 1
+            return tuple(m)
+
+        for level, letter, preds in nodes:
+            nd = _Node(-1, marker([d for d, _ in letter] + [n_dims + r for _, r in preds]),
+                       0.0, level + 1)
+            nd.dp = (letter, [(u, n_dims + r) for u, r in preds])
+            trie.nodes.append(nd)
+        # emissions in an order that keeps words with a common prefix together
+        # (frequency-major, words sorted by their letters): parts of the generated
+        # kernel then share the states of the prefix
         nf = len(self._freqs)
+        mats = [tuple(tuple(int(x) for x in el) for el in w) for w in self.words]
+        trie.emits = [None] * len(emits)
+        for f in range(nf):
+            for w in sorted(range(len(self.words)), key=lambda w: mats[w]):
+                e = w * nf + f
+                nd = _Node(-1, marker([n_dims + r for r, _ in emits[e] if r >= 0]), 0.0, 1, e)
+                if emits[e][0][0] < 0:
+                    nd.combo = [(1, emits[e][0][1], 0, 0, 0, 0)]
+                else:
+                    nd.combo = [(None, u, 0, n_dims + r, 0, 0) for r, u in emits[e]]
+                trie.emits[e] = len(trie.nodes)
+                trie.nodes.append(nd)
+        trie.max_depth = max(n.depth for n in trie.nodes)
+        self._tables[key] = (trie, len(rows))
+        return self._tables[key]
 
-        class _Term(list):
-            alpha = None
+    def _sep_table(self, dev) -> torch.Tensor:
+        """Row indices of the separable recurrence for ``fb_coswiss_sep_word``:
+        ``[n_freq][ns + ns*ns + ns]`` = first level, inner levels ``[k'][k]``,
+        last level / output (the same for every word)."""
+        key = ("septab", str(dev))
+        if key not in self._tables:
+            _, _, rows = self._separable_plan(0)
+            index = {r: i for i, r in enumerate(rows)}
+            J = self._junction()
+            ns = len(J)
+            tab = []
+            for f in range(len(self._freqs)):
+                # (rows a word set never uses are absent from the plan: any index will do)
+                get = lambda *k: index.get((f,) + k, 0)          # noqa: E731
+                tab += [get(1, J[k][1], J[k][2]) for k in range(ns)]
+                tab += [get(J[k2][0], J[k2][1] + J[k][1], J[k2][2] + J[k][2])
+                        for k2 in range(ns) for k in range(ns)]
+                tab += [get(J[k][0], J[k][1], J[k][2]) for k in range(ns)]
+            self._tables[key] = torch.tensor(np.asarray(tab, dtype=np.int32), device=dev)
+        return self._tables[key]
 
-        terms, owner = [], []
-        for w, word in enumerate(self.words):
-            mat = [list(int(x) for x in el) + [0] * (n_dims - len(el)) for el in word]
-            wts = self._get_weightings(word)
-            p = len(mat)
-            for f in range(nf):
-                for r, row in enumerate(wts):
-                    letters = []
-                    for k in range(p):
-                        trig = [0] * (2 * nf)
-                        trig[2 * f], trig[2 * f + 1] = int(row[2 * k + 1]), int(row[2 * k + 2])
-                        letters.append(mat[k] + trig)
-                    terms.append(_Term(letters))
-                    owner.append((w, f, r))
-        trie = Trie(terms, None, False)
-        term_node = list(trie.emits)
-        for node in trie.nodes:
-            node.emit = -1
-        trie.emits = []
-        i = 0
-        for w, word in enumerate(self.words):
-            wts = self._get_weightings(word)
-            p = len(word)
-            total = wts.shape[1] == 2 * p + 3
-            for f in range(nf):
-                combo = []
-                for row in wts:
-                    sp, cp = (int(row[2 * p + 1]), int(row[2 * p + 2])) if total else (0, 0)
-                    combo.append((int(row[0]), term_node[i], sp, n_dims + 2 * f,
-                                  cp, n_dims + 2 * f + 1))
-                    i += 1
-                # the marker exponents make the trig rows "used" dimensions
-                marker = [0] * (n_dims + 2 * nf)
-                marker[n_dims + 2 * f] = marker[n_dims + 2 * f + 1] = 1
-                node = _Node(-1, tuple(marker), 0.0, 1, len(trie.emits))
-                node.combo = combo
-                trie.nodes.append(node)
-                trie.emits.append(len(trie.nodes) - 1)
-        self._tables[key] = (trie, 2 * nf)
+    def _rows(self, X: torch.Tensor) -> torch.Tensor:
+        """The weight rows of the separable form, ``[n_rows, t]`` on the device:
+        ``coeff * sin^a cos^b`` of ``pi t / (f (t_len - 1))``."""
+        _, _, rows = self._separable_plan(0)
+        key = ("rows", str(X.device), X.shape[2])
+        if key not in self._tables:
+            spec = torch.tensor(np.asarray(rows, dtype=np.int32).reshape(-1, 4), device=X.device)
+            freqs = torch.tensor(np.asarray(self._freqs, dtype=np.float32), device=X.device)
+            out = be.empty((len(rows), X.shape[2]))
+            be.check(be.lib().fb_cos_rows(freqs.data_ptr(), len(self._freqs), X.shape[2],
+                                          spec.data_ptr(), len(rows), out.data_ptr(),
+                                          be.stream_ptr()))
+            self._tables = {k: v for k, v in self._tables.items() if k[0] != "rows"}
+            self._tables[key] = out
         return self._tables[key]
 
     # -- expansion table ---------------------------------------------------------
@@ -196,17 +317,29 @@ class CosWISS(ISS):
         nf = len(self._freqs)
         lo, hi = (0, self.n_iterated_sums()) if emit_range is None else emit_range
         out = be.empty((hi - lo, n, t))
-        trig = self._trig(X)
         L = be.lib()
+        ns = self._exponent + 1
+        # separable recurrence (``_separable_plan``): exponent+1 states per level
+        # instead of (exponent+1)^(p-1) expansion terms
+        sep_ok = 2 <= ns <= 5 and os.environ.get("FRUITS_B200_COS_EXPANSION", "0") != "1"
+        trig = None
         for w in range(lo // nf, -(-hi // nf)):
             mat, wts, mshape, wshape = self._word_tables(w, X.device)
             first, last = w * nf, (w + 1) * nf
             whole = first >= lo and last <= hi
             dst = out[first - lo:last - lo] if whole else be.empty((nf, n, t))
-            be.check(L.fb_coswiss_word(X.data_ptr(), n, d, t, mat.data_ptr(), mshape[0],
-                                       mshape[1], mshape[2], mshape[3], trig.data_ptr(), nf,
-                                       wts.data_ptr(),
-                                       wshape[0], wshape[1], dst.data_ptr(), be.stream_ptr()))
+            if sep_ok and mshape[0] <= 6 and mshape[1] <= 8:
+                be.check(L.fb_coswiss_sep_word(
+                    X.data_ptr(), n, d, t, mat.data_ptr(), mshape[0], mshape[1],
+                    self._rows(X).data_ptr(), self._sep_table(X.device).data_ptr(), nf, ns,
+                    int(bool(self._total_weighting)), dst.data_ptr(), be.stream_ptr()))
+            else:
+                if trig is None:
+                    trig = self._trig(X)
+                be.check(L.fb_coswiss_word(X.data_ptr(), n, d, t, mat.data_ptr(), mshape[0],
+                                           mshape[1], mshape[2], mshape[3], trig.data_ptr(), nf,
+                                           wts.data_ptr(),
+                                           wshape[0], wshape[1], dst.data_ptr(), be.stream_ptr()))
             if not whole:
                 a, b = max(first, lo), min(last, hi)
                 out[a - lo:b - lo] = dst[a - first:b - first]

@@ -257,6 +257,23 @@ FB_API int fb_iss_materialize(const fb_iss_plan *plan, const fb_batch *batch, do
 /* fruits/iss/cos.py:24-25: trig[f][0][t] = sin(pi t / (freq_f (t_len-1))),
  * trig[f][1][t] = cos(...); freqs is a DEVICE array of float32. */
 FB_API int fb_cos_trig(const float *freqs, int n_freq, int64_t t, double *trig, void *stream);
+/* Weight rows of the separable form of the cosine weighted ISS
+ * (fruits/iss/cos.py:16-49 restated as a recurrence with exponent+1 states per
+ * level, see fruits_b200/iss/cos.py): rows[r][t] = coeff * sin^a cos^b of
+ * pi t / (freq_f (t_len-1)), spec = DEVICE int32 [n_rows][4] = (f, coeff, a, b),
+ * freqs = DEVICE float32 [n_freq]. */
+FB_API int fb_cos_rows(const float *freqs, int n_freq, int64_t t, const int32_t *spec,
+                       int n_rows, double *rows, void *stream);
+/* fruits/iss/cos.py:16-49, :289-333 in the separable form: all n_freq iterated
+ * sums of ONE word, out[f][n][t].  word = DEVICE int32 [p][dw] exponents; rows
+ * from fb_cos_rows; tab = DEVICE int32 [n_freq][ns + ns*ns + ns] row indices
+ * (first level, inner levels [k'][k], last level / output), ns = exponent + 1.
+ * FB_ENOSUP for words of more than 6 letters or exponents above 4 (the caller
+ * then uses fb_coswiss_word). */
+FB_API int fb_coswiss_sep_word(const double *X, int64_t n, int64_t d, int64_t t,
+                               const int32_t *word, int p, int dw, const double *rows,
+                               const int32_t *tab, int n_freq, int ns, int total, double *out,
+                               void *stream);
 /* _coswiss (fruits/iss/cos.py:16-49, :171-181) for one word: out[f][n][t].
  * word: device int32 [p][dw] exponent matrix (max_occ = the largest number of
  * occurrences in one letter, sum_d |word[k][d]|), weights: device int32
