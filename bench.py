@@ -14,9 +14,13 @@ One step = one pass of ``Fruit.transform`` over the resident shard (one fused
 CUDA launch).  ``value`` counts series of all ranks per second of the slowest
 rank, inputs resident in HBM.  ``e2e`` is the same pipeline through the public
 API on HOST buffers (pinned), host->device and device->host copies inside the
-timed region.  ``--impl reference`` times the CPU implementation of the path
-(the oracle port of the reference's numba kernels, all host threads) on a
-bounded sample of the same workload.
+timed region, on ALL ranks at the same time (slowest rank counts).  At N > 1
+the assembled feature matrix is verified on every rank (``gather_check``).
+``configs`` (N = 1) carries fit / transform times, routes and parity numbers of
+the other BASELINE.json configurations (C1-C4).  ``--impl reference`` times the
+reference's CPU implementation of the path on the host cores: the unmodified
+numba package (``baseline/_ref``, see baseline/install_ref.sh) when it imports,
+else the oracle port (OpenMP), on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -36,6 +40,7 @@ T_LEN, N_DIMS, N_NODES, N_FEATS = 1024, 3, 445, 2225
 FLOP_PER_SERIES = 2 * N_NODES * T_LEN            # one FMA per node and step
 BYTES_PER_SERIES = 8 * T_LEN * N_DIMS + 8 * N_FEATS
 NOMINAL_FP64_TFLOPS = 37.2                       # 148 SM x 64 DFMA/clk x 1.965 GHz
+METRIC = "time series/sec (features)"
 
 
 def parse_args():
@@ -45,11 +50,15 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--series-per-gpu", type=int, default=524288)
-    ap.add_argument("--e2e-series", type=int, default=0,
-                    help="series per end-to-end step (default: 262144 at N=1 -- 6.4 GB in + 4.7 GB "
-                         "out of pinned host memory -- and 65536 per rank at N>1)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--e2e-series", type=int, default=131072,
+                    help="series per rank and end-to-end step (3.2 GB in + 2.3 GB out of pinned "
+                         "host memory per rank; the same at every N)")
+    ap.add_argument("--ref-seconds", type=float, default=150.0,
+                    help="--impl reference: wall-clock target of all warm-up + timed steps")
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the C1-C4 block (fit / transform / parity of the other configurations)")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-multicast", action="store_true",
                     help="N > 1: copy-engine pushes instead of NVSwitch multicast stores")
@@ -112,56 +121,166 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-# ---------------------------------------------------------------------------
-def cpu_reference(seconds: float, steps: int = 1, warmup: int = 0):
-    """Time the CPU implementation (oracle port, OpenMP over series) of the C5
-    transform on a bounded sample; returns (series/s, cores, sample text)."""
-    import specs
-    from oracle import pipeline as orc
-    from oracle.build import load_oracle
+def host_cores() -> int:
+    return len(os.sched_getaffinity(0))
 
-    orc_lib = load_oracle()
-    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
-    orc_lib.fo_set_num_threads(len(os.sched_getaffinity(0)))
-    cores = int(orc_lib.fo_num_threads())
-    spec = specs.SPECS["C5_sweep"]
-    fitX = specs.make_input("C5_sweep", 64)
-    of = orc.OracleFruit(spec)
-    np.random.seed(0)
-    of.fit(fitX)
-    # calibrate on a small sample, then size the timed sample for ~`seconds`
-    n0 = max(cores, 16)
-    X0 = np.random.default_rng(99).standard_normal((n0, N_DIMS, T_LEN))
-    t0 = time.perf_counter()
-    of.transform(X0)
-    rate0 = n0 / (time.perf_counter() - t0)
-    n = int(max(n0, min(16384, rate0 * seconds / max(steps + warmup, 1))))
-    X = np.random.default_rng(100).standard_normal((n, N_DIMS, T_LEN))
+
+# ---------------------------------------------------------------------------
+# CPU arms: the real reference (numba) and the oracle port (C + OpenMP)
+
+def _c5_inputs(n: int, seed: int = 100):
+    return np.random.default_rng(seed).standard_normal((n, N_DIMS, T_LEN))
+
+
+class PortArm:
+    """oracle/fruits_oracle.c: the reference's kernels restated in C, OpenMP
+    over series (test infrastructure; timed here as the CPU baseline only)."""
+    kind = "port"
+
+    def __init__(self):
+        import specs
+        from oracle import pipeline as orc
+        from oracle.build import load_oracle
+        lib = load_oracle()
+        # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+        lib.fo_set_num_threads(host_cores())
+        self.cores = int(lib.fo_num_threads())
+        self.fruit = orc.OracleFruit(specs.SPECS["C5_sweep"])
+        np.random.seed(0)
+        self.fruit.fit(specs.make_input("C5_sweep", 64))
+        self.what = "oracle port of the reference's numba kernels (C, OpenMP over series)"
+
+    def transform(self, X):
+        return self.fruit.transform(X)
+
+
+class ReferenceArm:
+    """The unmodified reference package (irkri/fruits 1.0.0, numba) from
+    ``$FRUITS_REF`` or ``baseline/_ref`` -- never /root/reference, which does
+    not exist on the GPU box."""
+    kind = "reference"
+
+    def __init__(self):
+        import importlib
+        if not hasattr(np, "NINF"):
+            np.NINF = -np.inf            # fruits/sieving/segment.py:72 needs it on numpy >= 2
+        path = os.environ.get("FRUITS_REF") or os.path.join(ROOT, "baseline", "_ref")
+        if not os.path.isdir(os.path.join(path, "fruits")):
+            raise ImportError(f"no reference package under {path}")
+        os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(ROOT, "baseline", "_numba_cache"))
+        os.environ["NUMBA_NUM_THREADS"] = str(host_cores())
+        # the repository's own `fruits` alias must not shadow the reference
+        saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+                 if k == "fruits" or k.startswith("fruits.")}
+        sys.path.insert(0, path)
+        try:
+            ref = importlib.import_module("fruits")
+            assert os.path.realpath(ref.__file__).startswith(os.path.realpath(path)), ref.__file__
+        finally:
+            sys.path.remove(path)
+        self.modules = {k: sys.modules.pop(k) for k in list(sys.modules)
+                        if k == "fruits" or k.startswith("fruits.")}
+        sys.modules.update(saved)
+        import numba
+        import specs
+        numba.set_num_threads(min(host_cores(), numba.config.NUMBA_NUM_THREADS))
+        self.cores = int(numba.get_num_threads())
+        self.fruit = specs.build_fruit(ref, specs.SPECS["C5_sweep"])
+        np.random.seed(0)
+        self.fruit.fit(specs.make_input("C5_sweep", 64))
+        self.what = (f"unmodified reference package (numba {numba.__version__}, "
+                     f"{numba.config.THREADING_LAYER} threading layer) from {os.path.relpath(path, ROOT)}")
+
+    def transform(self, X):
+        return self.fruit.transform(X)
+
+
+def make_cpu_arm(kind: str):
+    if kind in ("auto", "reference"):
+        try:
+            return ReferenceArm()
+        except Exception as exc:          # noqa: BLE001  (missing package, numba, JIT failure)
+            if kind == "reference":
+                raise
+            print(f"# reference package unavailable ({type(exc).__name__}: {exc}); "
+                  f"timing the oracle port", file=sys.stderr)
+    return PortArm()
+
+
+def time_cpu(arm, n: int, steps: int = 1, warmup: int = 0):
+    X = _c5_inputs(n)
     for _ in range(warmup):
-        of.transform(X)
-    times = []
+        arm.transform(X)
+    t0 = time.perf_counter()
     for _ in range(steps):
-        t0 = time.perf_counter()
-        of.transform(X)
-        times.append(time.perf_counter() - t0)
-    dt = sum(times)
-    return n * steps / dt, cores, (f"{n} series x {N_DIMS} x {T_LEN} per step, {steps} step(s), "
-                                   f"scaled linearly in the number of series"), dt / steps
+        arm.transform(X)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt / steps
+
+
+def calibrate(arm, seconds: float, calls: int, lo: int, hi: int):
+    """Series per call so that ``calls`` calls take about ``seconds``: two
+    calibration calls of different size separate the per-call overhead (numba
+    launches one parallel region per word and sieve) from the per-series cost."""
+    # (sizes large enough that every iterated sum [n, 1024] has left the caches:
+    # the reference streams one such array per word and sieve)
+    n1, n2 = max(128, 4 * arm.cores), max(512, 16 * arm.cores)
+    arm.transform(_c5_inputs(n1, 98))               # JIT / thread pool warm-up
+    _, t1 = time_cpu(arm, n1)
+    _, t2 = time_cpu(arm, n2)
+    per_series = max((t2 - t1) / (n2 - n1), 1e-6)
+    fixed = max(t1 - per_series * n1, 0.0)
+    n = int((seconds / max(calls, 1) - fixed) / per_series)
+    return int(min(max(n, lo), hi)), {"per_call_overhead_s": fixed, "per_series_s": per_series,
+                                      "calibration": [[n1, t1], [n2, t2]]}
+
+
+def cpu_baseline_block():
+    """cpu_baseline of the default run (N = 1, rank 0): the real reference when it
+    imports, the port beside it; each on a bounded sample, two sizes to show that
+    the cost is linear in the number of series."""
+    out = {}
+    for kind in ("reference", "port"):
+        try:
+            arm = ReferenceArm() if kind == "reference" else PortArm()
+        except Exception as exc:          # noqa: BLE001
+            out[kind] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            continue
+        # SURVEY.md 8(d) / BASELINE.md: C5 at N = 2,048 for the reference; the port is
+        # ~3x faster, so it gets a larger sample
+        n = 2048 if kind == "reference" else max(2048, 64 * arm.cores)
+        arm.transform(_c5_inputs(max(64, 2 * arm.cores), 98))      # JIT / thread pool warm-up
+        rate, step_s = time_cpu(arm, n)
+        rate_half, _ = time_cpu(arm, n // 2)
+        out[kind] = {"value": rate, "unit": "series/s", "cores": arm.cores, "kind": kind,
+                     "sample": f"{n} series x {N_DIMS} x {T_LEN}, one transform call "
+                               f"({step_s:.1f} s), scaled linearly in the number of series",
+                     "half_sample_value": rate_half, "what": arm.what}
+    best = out["reference"] if "value" in out.get("reference", {}) else out["port"]
+    block = {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    block["detail"] = out
+    return block
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, cores, sample, step_s = cpu_reference(args.cpu_seconds, args.steps, args.warmup)
+    arm = make_cpu_arm(args.ref_kind)
+    calls = args.steps + args.warmup
+    lo = max(2048, 64 * arm.cores) if arm.kind == "port" else 512
+    n, cal = calibrate(arm, args.ref_seconds, calls, lo, 16384)
+    rate, step_s = time_cpu(arm, n, args.steps, args.warmup)
+    sample = (f"{n} series x {N_DIMS} x {T_LEN} per step, {args.steps} step(s) after "
+              f"{args.warmup} warm-up step(s), scaled linearly in the number of series")
     line = {
-        "impl": "reference", "metric": "time series/sec (features)", "value": rate,
+        "impl": "reference", "metric": METRIC, "value": rate,
         "unit": "series/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, sample_only=True),
-        "cpu_baseline": {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": "series/s", "cores": arm.cores, "kind": arm.kind,
+                         "sample": sample, "what": arm.what, **cal},
         "e2e": {"value": rate, "unit": "series/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -169,8 +288,8 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, sample_only=False):
-    cfg = {
+def workload_config(args):
+    return {
         "workload": ("C5 throughput sweep shard: series x 3 dims x length 1024, words "
                      "of_weight(4, dim=3) EXTENDED (445 iterated sums), sieves NPI(q=(.5,1)) + "
                      "PPV + MAX + MIN + END -> 2225 features"),
@@ -178,9 +297,89 @@ def workload_config(args, sample_only=False):
         "n_features": N_FEATS,
         "l2": "inputs (12.9 GB per GPU) and outputs (9.3 GB) are far larger than the 126 MB L2",
     }
-    if sample_only:
-        cfg["note"] = "CPU arm: bounded sample of the same workload (see cpu_baseline.sample)"
-    return cfg
+
+
+# ---------------------------------------------------------------------------
+# the other BASELINE.json configurations (N = 1): times, routes, parity
+
+# flop per series = c * nodes * T, c = 2 (unweighted Reals, Arctic) or 4
+# (exponentially weighted Reals); slices 0-1 only (the CosWISS slices have no agreed count)
+CONFIG_FLOPS = {"C1_readme": 7200, "C2_full": 428032, "C3_full": 6311936, "C4_twi": 4579328}
+
+
+def config_block(fruits, peak_tflops: float):
+    import torch
+
+    import specs
+    from helpers import parity_report
+
+    gold = os.path.join(ROOT, "tests", "golden")
+    block = {}
+    for name in ("C1_readme", "C2_full", "C3_full", "C4_twi"):
+        Xh = specs.make_input(name)
+        X = torch.from_numpy(Xh).cuda()
+        fruit = specs.build_fruit(fruits, specs.SPECS[name])
+        np.random.seed(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fruit.fit(X)
+        torch.cuda.synchronize()
+        fit_s = time.perf_counter() - t0
+        out = fruit.transform_device(X)                  # module load / JIT on first use
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 5
+        ev[0].record()
+        for _ in range(reps):
+            fruit.transform_device(X, out=out)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        slices, col = [], 0
+        for slc in fruit:
+            k = slc.nfeatures()
+            sub = out[:, col:col + k]
+            ev[0].record()
+            for _ in range(3):
+                slc._transform_device(X, None, None, out, col, sanitize=True)
+            ev[1].record()
+            torch.cuda.synchronize()
+            slices.append({"features": k, "ms": ev[0].elapsed_time(ev[1]) / 3,
+                           "route": getattr(slc, "_last_launch", ("composed",))[0]})
+            col += k
+            del sub
+        entry = {"series": int(X.shape[0]), "dims": int(X.shape[1]), "length": int(X.shape[2]),
+                 "features": int(out.shape[1]), "fit_s": fit_s, "transform_ms": ms,
+                 "series_per_s": X.shape[0] / (ms * 1e-3), "slices": slices}
+        flops = CONFIG_FLOPS[name]
+        ms01 = sum(s["ms"] for s in slices[:2])
+        entry["roofline_slices_0_1"] = {
+            "flop_per_series": flops, "achieved_tflops": flops * X.shape[0] / (ms01 * 1e-3) / 1e12,
+            "frac": flops * X.shape[0] / (ms01 * 1e-3) / 1e12 / peak_tflops, "ms": ms01}
+        # parity against vectors frozen from the real reference (tests/golden)
+        res = out.cpu().numpy()
+        if name == "C1_readme":
+            g = np.load(os.path.join(gold, "pipeline_C1_readme.npz"))
+            entry["parity"] = {"against": "reference golden, all rows",
+                               "bit_identical": bool(np.array_equal(res, g["features"]))}
+        elif name == "C4_twi":
+            # its sieves need no fitting, so the first rows equal the 8-series golden
+            g = np.load(os.path.join(gold, "pipeline_C4_twi.npz"))
+            rep = parity_report(res[:8], g["features"])
+            rep["arctic_slice_bit_identical"] = bool(np.array_equal(res[:8, 1533:],
+                                                                    g["features"][:, 1533:]))
+            entry["parity"] = {"against": "reference golden, first 8 rows", **rep}
+        else:
+            path = os.path.join(gold, f"full_{name}.npz")
+            if os.path.exists(path):
+                g = np.load(path)
+                rep = parity_report(res[g["rows"]], g["features"])
+                entry["parity"] = {"against": f"reference at full size, {len(g['rows'])} rows "
+                                              f"(tests/golden/full_{name}.npz)", **rep}
+        block[name] = entry
+        del X, out
+        torch.cuda.empty_cache()
+    return block
 
 
 # ---------------------------------------------------------------------------
@@ -223,7 +422,6 @@ def run_ours(args):
                                      device=dev, generator=gen)
     gather = world > 1 and not args.no_gather
     n_chunks = 8 if gather else 1
-    rows = S // n_chunks
     from fruits_b200.parallel import transform_sharded
     # N > 1: every rank ends up with the assembled [N*S, F] feature matrix
     # (rank-major rows); the all-gather of row chunk c overlaps the kernel of c+1
@@ -236,10 +434,11 @@ def run_ours(args):
             out = peer.out
             if peer.fused:
                 n_chunks = 1
-                collective = ("fused into the feature kernel: its stores go through the NVSwitch "
-                              "multicast mapping (NVLS) of the symmetric [N*S, F] matrices, so "
-                              "every feature lands in the matrix of every rank as it is written; "
-                              "one device-side barrier per step, no copy or collective kernel")
+                collective = ("fused into the feature kernel: its epilogue stores with multimem.st "
+                              "through the NVSwitch multicast mapping (NVLS) of the symmetric "
+                              "[N*S, F] matrices, so every feature lands in the matrix of every "
+                              "rank as it is written; one device-side barrier per step, no copy "
+                              "or collective kernel")
             else:
                 collective = ("every finished row chunk is pushed into the peers' feature "
                               "matrices (symmetric NVLink peer memory, copy engines, 8 chunks "
@@ -260,15 +459,12 @@ def run_ours(args):
 
     rows = S // n_chunks
 
-    def compute(x, o):
-        fruit.transform_device(x, out=o)
-
     def step():
         if gather:
-            transform_sharded(compute, X, N_FEATS, chunks=n_chunks,
+            transform_sharded(fruit, X, N_FEATS, chunks=n_chunks,
                               out=peer if peer is not None else out)
         else:
-            compute(X, out)
+            fruit.transform_device(X, out=out)
 
     def barrier():
         if world > 1:
@@ -296,8 +492,32 @@ def run_ours(args):
     ms_total = float(t.item())
     value = world * S * args.steps / (ms_total * 1e-3)
 
+    # ---- N > 1: every rank verifies the assembled matrix ----
+    gather_check = None
+    if gather:
+        # a hash (wrapping int64 sum of the bit patterns) of every rank block as this
+        # rank sees it; rank r's own block must also equal a local recompute into
+        # ordinary device memory, element for element
+        blocks = out.view(world, S * N_FEATS).view(torch.int64)
+        mine = blocks.sum(dim=1)                                       # [world]
+        local_ref = torch.empty((S, N_FEATS), dtype=torch.float64, device=dev)
+        fruit.transform_device(X, out=local_ref)
+        own_equal = bool(torch.equal(out[rank * S:(rank + 1) * S], local_ref))
+        own_hash = local_ref.view(torch.int64).sum().reshape(1)
+        del local_ref
+        seen = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(seen, mine)
+        owner = [torch.empty_like(own_hash) for _ in range(world)]
+        dist.all_gather(owner, own_hash)
+        owner = torch.cat(owner)
+        ok = own_equal and all(bool(torch.equal(s, owner)) for s in seen)
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_check = "ok" if int(flag.item()) == 1 else "MISMATCH"
+
     # ---- kernel-only timing of the dominant kernel + fp64 roof (rank 0) ----
-    roofline = e2e = cpu = None
+    roofline = cpu = configs = None
+    peak = None
     if rank == 0:
         kout = out[:S] if not gather else out[rank * S:rank * S + rows]
         kX = X if not gather else X[:rows]
@@ -338,18 +558,21 @@ def run_ours(args):
         hbm = BYTES_PER_SERIES * n_launch / k_s / 1e9
         # DRAM traffic of the kernel from the committed ncu capture, scaled to
         # this launch (traffic is linear in the number of series)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if kern is not None and os.path.exists(tpath):
-            with open(tpath) as f:
-                tr = json.load(f)
-            traffic = ((tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["series_per_launch"]
-                       * n_launch)
+        traffic = tsrc = None
+        for tname in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if kern is not None and os.path.exists(tpath):
+                with open(tpath) as f:
+                    tr = json.load(f)
+                traffic = ((tr["dram_bytes_read"] + tr["dram_bytes_write"])
+                           / tr["series_per_launch"] * n_launch)
+                tsrc = tname
+                break
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic,
             "traffic_note": ("dram__bytes_read+write of one ncu --set full capture "
-                             "(profiles/r01_traffic.json), scaled to series_per_launch; "
+                             f"(profiles/{tsrc}), scaled to series_per_launch; "
                              f"algorithmic bytes per launch = {BYTES_PER_SERIES * n_launch}"),
             "kernel": kdesc, "launches_per_slice": klaunches,
             "kernel_ms": k_s * 1e3, "series_per_launch": n_launch,
@@ -361,33 +584,49 @@ def run_ours(args):
                     "bytes_per_series": BYTES_PER_SERIES},
         }
 
-        # ---- end to end through the public API on pinned host buffers ----
-        E = min(args.e2e_series or (262144 if world == 1 else 65536), S)
-        while True:
-            try:
-                hx = torch.empty((E, N_DIMS, T_LEN), dtype=torch.float64, pin_memory=True)
-                hf = torch.empty((E, N_FEATS), dtype=torch.float64, pin_memory=True)
-                break
-            except RuntimeError:            # not enough pinnable host memory: smaller batch
-                if E <= 8192:
-                    raise
-                hx = hf = None
-                E //= 2
-        hx.copy_(X[:E])
-        hx_np, hf_np = hx.numpy(), hf.numpy()
-        for _ in range(2):
-            fruit.transform(hx_np, out=hf_np)
-        torch.cuda.synchronize()
-        e_steps = max(2, args.steps)
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            fruit.transform(hx_np, out=hf_np)
-        torch.cuda.synchronize()
-        e_s = (time.perf_counter() - t0) / e_steps
-        e2e = {"value": world * E / e_s, "unit": "series/s",
-               "h2d_bytes_per_step": int(hx.numel() * 8), "d2h_bytes_per_step": int(hf.numel() * 8),
-               "series_per_step": E, "ms_per_step": e_s * 1e3,
-               "note": "Fruit.transform(numpy pinned in, numpy pinned out); value scaled by n_gpus"}
+    # ---- end to end through the public API on pinned host buffers, ALL ranks at once ----
+    E = min(args.e2e_series, S)
+    while True:
+        hx = hf = None
+        try:
+            hx = torch.empty((E, N_DIMS, T_LEN), dtype=torch.float64, pin_memory=True)
+            hf = torch.empty((E, N_FEATS), dtype=torch.float64, pin_memory=True)
+            got = 1
+        except RuntimeError:            # not enough pinnable host memory
+            hx = hf = None
+            got = 0
+        flag = torch.tensor([got], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            break
+        if E <= 8192:
+            raise RuntimeError("cannot pin the end-to-end host buffers")
+        E //= 2                         # every rank retries with the same smaller batch
+    hx.copy_(X[:E])
+    hx_np, hf_np = hx.numpy(), hf.numpy()
+    for _ in range(2):
+        fruit.transform(hx_np, out=hf_np)
+    e_steps = max(3, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        fruit.transform(hx_np, out=hf_np)
+    torch.cuda.synchronize()
+    e_s = time.perf_counter() - t0
+    te = torch.tensor([e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_max = float(te.item())
+    barrier()
+    e2e = {"value": world * E * e_steps / e_max, "unit": "series/s",
+           "h2d_bytes_per_step": int(hx.numel() * 8) * world,
+           "d2h_bytes_per_step": int(hf.numel() * 8) * world,
+           "series_per_rank_and_step": E, "steps": e_steps, "ms_per_step": e_max / e_steps * 1e3,
+           "note": ("Fruit.transform(pinned numpy in, pinned numpy out) on every rank at the same "
+                    "time, its own buffers per rank; barrier before, slowest rank counts; byte "
+                    "counts are totals over all ranks")}
+    if rank == 0 and world == 1:
         # the same call with ordinary (pageable) numpy arrays, as a caller of the
         # reference passes them: pinned staging ring + copy threads inside transform
         Ep = min(E, 65536)
@@ -399,18 +638,23 @@ def run_ours(args):
         for _ in range(2):
             fruit.transform(px, out=pf)
         torch.cuda.synchronize()
-        e2e["pageable"] = {"value": world * Ep / ((time.perf_counter() - t0) / 2),
+        e2e["pageable"] = {"value": Ep / ((time.perf_counter() - t0) / 2),
                            "unit": "series/s", "series_per_step": Ep,
                            "note": "plain numpy arrays in and out (host memcpy bound)"}
         del px, pf
-        if not args.no_cpu_baseline and world == 1:
-            rate, cores, sample, _ = cpu_reference(args.cpu_seconds)
-            cpu = {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",
-                   "sample": sample}
+    del hx, hf, hx_np, hf_np
+
+    if rank == 0 and world == 1:
+        if not args.no_configs:
+            del X, out
+            torch.cuda.empty_cache()
+            configs = config_block(fruits, peak)
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_block()
 
     if rank == 0:
         line = {
-            "metric": "time series/sec (features)", "value": value, "unit": "series/s",
+            "metric": METRIC, "value": value, "unit": "series/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -420,6 +664,10 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "fit_seconds": fit_s,
             "collective": collective,
         }
+        if gather_check is not None:
+            line["gather_check"] = gather_check
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -104,6 +104,7 @@ def lib() -> ctypes.CDLL:
         "fb_segment_sieve": ([vp, i64, vp, i32, vp, i32, i32, vp, i64, i64, i64, i64, vp], i32),
         "fb_ppv": ([vp, i64, vp, i32, i32, vp, i64, i64, i64, i64, vp], i32),
         "fb_nan_to_num": ([vp, i64, vp], i32),
+        "fb_multimem_copy": ([vp, i64, vp, i64, i64, i64, vp], i32),
         "fb_order_stats_workspace": ([i64], i64),
         "fb_order_stats": ([vp, i64, i64, i64, i64, vp, vp, vp, vp], i32),
         "fb_order_stats_multi_workspace": ([i64, i32], i64),
@@ -144,7 +145,7 @@ EXPORTED = [
     "fb_slice_rows", "fb_slice_features_ex", "fb_slice_features",
     "fb_iss_materialize", "fb_increments", "fb_row_stats", "fb_standardize",
     "fb_lsum", "fb_nrm_scale", "fb_coquantile", "fb_pretransform",
-    "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_order_stats_workspace",
+    "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_multimem_copy", "fb_order_stats_workspace",
     "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
     "fb_jit_unload", "fb_jit_slice_features", "fb_jit_chain_features", "fb_jit_link", "fb_exp_rows", "fb_cos_trig", "fb_cos_rows", "fb_coswiss_sep_word", "fb_coswiss_word",
     "fb_bayes_word", "fb_order_stats_multi_workspace", "fb_order_stats_multi",

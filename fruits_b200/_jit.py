@@ -36,7 +36,7 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 14            # bump to invalidate cached cubins
+JIT_VERSION = 15            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -644,7 +644,7 @@ class Emitter:
                     val = f"(MN[{oi}] == D_INF ? 0.0 : MN[{oi}])"
                 else:
                     val = endv
-                L.append((e * nf + f, f"fin({val}, a.sanitize)"))
+                L.append((e * nf + f, f"fin({val}, a.sanitize & 1)"))
         return L
 
     def staging_width(self) -> int:
@@ -670,7 +670,7 @@ class Emitter:
         if not sw:
             return (["if (ns_ < a.n) {",
                      "    double *o = a.out + (size_t)ns_ * a.out_ld + a.col0;"]
-                    + [f"    o[{col}] = {expr};" for col, expr in vals] + ["}"])
+                    + [f"    put(o + {col}, {expr}, mc);" for col, expr in vals] + ["}"])
         L = []
         i = 0
         while i < len(vals):
@@ -684,7 +684,7 @@ class Emitter:
             L.append("for (int r = 0; r < 32; r++) {")
             L.append("    if (nrow0 + r >= a.n) break;")
             L.append(f"    double *orow = a.out + (size_t)(nrow0 + r) * a.out_ld + a.col0 + {vals[i][0]};")
-            L.append(f"    for (int e = lane; e < {j - i}; e += 32) orow[e] = stg[r * {sw} + e];")
+            L.append(f"    for (int e = lane; e < {j - i}; e += 32) put(orow + e, stg[r * {sw} + e], mc);")
             L.append("}")
             L.append("__syncwarp();")
             i = j
@@ -771,6 +771,11 @@ class Emitter:
         A("    if (v == D_INF) return __longlong_as_double(0x7fefffffffffffffLL);")
         A("    if (v == D_NINF) return __longlong_as_double(0xffefffffffffffffLL);")
         A("    return v; }")
+        A("// a.sanitize bit 1: a.out is an NVSwitch multicast mapping -- such addresses may")
+        A("// only be accessed with multimem.* instructions (PTX ISA)")
+        A("__device__ __forceinline__ void put(double *p, double v, bool mc) {")
+        A('    if (mc) asm volatile("multimem.st.weak.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");')
+        A("    else *p = v; }")
         A("__device__ __forceinline__ void cp16(double *dst, const double *src) {")
         A('    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
         A("__device__ __forceinline__ void cp8(double *dst, const double *src) {")
@@ -783,6 +788,7 @@ class Emitter:
         A("    const int sg = warp / PPC;")
         A(f"    const long long nbase = (long long)(blockIdx.x / {len(p.parts) // self.ppc}u) * (GPC * 32);")
         A("    const int T = (int)a.t;")
+        A("    const bool mc = (a.sanitize & 2) != 0; (void)mc;")
         A("    // tile buffers: [2][GPC*32 series][ROW] then the weighting rows")
         A("    double *xbuf = smem;")
         A("    double *ebuf = smem + 2 * GPC * 32 * ROW;")
@@ -982,6 +988,7 @@ class Emitter:
             A("    } break;")
         A("    default: break;")
         A("    }")
+        A("    if (mc) __threadfence_system();")
         A("}")
         del du
         return "\n".join(src) + "\n"
@@ -1230,14 +1237,19 @@ class JitSlice:
     def n_launches(self, n_series: int = 0, length: int = 0) -> int:
         return 1
 
-    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize) -> None:
+    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize, multicast=None) -> None:
         """X[n, d, t] cuda float64; extra: weighting rows or None;
-        thr_compact: [n_emit * len(cols)] cuda float64."""
+        thr_compact: [n_emit * len(cols)] cuda float64.  ``multicast`` =
+        (address, row stride) of the same rows in an NVSwitch multicast
+        mapping: the kernel then stores there (with ``multimem.st``) instead of
+        into ``out``."""
         batch = be.FbBatch()
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape
         n_thr = 0 if thr_compact is None else thr_compact.numel()
         be.check(be.lib().fb_jit_slice_features(
             self.handle, ctypes.byref(self.geo), ctypes.byref(batch), be.ptr(extra),
-            int(extra_ld), be.ptr(thr_compact), n_thr, out.data_ptr(), out.stride(0), int(col0),
-            int(sanitize), be.stream_ptr()))
+            int(extra_ld), be.ptr(thr_compact), n_thr,
+            out.data_ptr() if multicast is None else int(multicast[0]),
+            out.stride(0) if multicast is None else int(multicast[1]), int(col0),
+            int(bool(sanitize)) | (2 if multicast is not None else 0), be.stream_ptr()))

@@ -40,7 +40,7 @@ from dataclasses import dataclass
 from . import _backend as be
 from . import _jit
 
-CHAIN_VERSION = 2
+CHAIN_VERSION = 3
 MIN_SERIES = 512           # from this batch size on a chain kernel is compiled (cached on disk)
 MIN_SERIES_CACHED = 16     # ... and from this size on an already compiled one is used
 
@@ -354,7 +354,7 @@ class ChainEmitter:
                 val = f"(mn{r} == D_INF ? 0.0 : mn{r})"
             else:
                 val = f"S{r}"
-            L.append(f"    o[{f}] = fin({val}, a.sanitize);")
+            L.append(f"    put(o + {f}, fin({val}, a.sanitize & 1), mc);")
         L.append("}")
         return L
 
@@ -390,6 +390,10 @@ class ChainEmitter:
             flat_irr += iw + [0] * (nimax - len(iw))
         A(f"__device__ const unsigned short IRR[{NB * R * 32 * nimax}] = {{"
           + ",".join(map(str, flat_irr)) + "};")
+        A("// a.sanitize bit 1: a.out is an NVSwitch multicast mapping (multimem.* only)")
+        A("__device__ __forceinline__ void put(double *p, double v, bool mc) {")
+        A('    if (mc) asm volatile("multimem.st.weak.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");')
+        A("    else *p = v; }")
         A("__device__ __forceinline__ double fin(double v, int sanitize) {")
         A("    if (!sanitize) return v;")
         A("    if (v != v) return 0.0;")
@@ -480,9 +484,11 @@ class ChainEmitter:
         src.extend(masked)
         A("    }")
         # ---- epilogue ----
+        A("    const bool mc = (a.sanitize & 2) != 0;")
         for r in range(R):
             for ln in self.epilogue(r):
                 A("    " + ln)
+        A("    if (mc) __threadfence_system();")
         A("}")
         return "\n".join(src) + "\n"
 
@@ -601,14 +607,16 @@ class JitChain:
     def n_launches(self, n_series: int = 0, length: int = 0) -> int:
         return 1
 
-    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize) -> None:
+    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize, multicast=None) -> None:
         batch = be.FbBatch()
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape
         n_thr = 0 if thr_compact is None else thr_compact.numel()
         be.check(be.lib().fb_jit_chain_features(
             self.handle, ctypes.byref(self.geo), ctypes.byref(batch), be.ptr(thr_compact), n_thr,
-            out.data_ptr(), out.stride(0), int(col0), int(sanitize), be.stream_ptr()))
+            out.data_ptr() if multicast is None else int(multicast[0]),
+            out.stride(0) if multicast is None else int(multicast[1]), int(col0),
+            int(bool(sanitize)) | (2 if multicast is not None else 0), be.stream_ptr()))
 
 
 def _device_index() -> int:

@@ -185,6 +185,25 @@ static inline unsigned grid_for(long long total, int block)
     return (unsigned)g;
 }
 
+// rows x cols block of doubles -> the same block of an NVSwitch multicast mapping:
+// every store is replicated by the switch into the buffer of every GPU of the
+// multicast group.  Multicast addresses may only be accessed with multimem.*
+// instructions (PTX ISA), hence this kernel instead of a memcpy.
+__global__ void multimem_copy_kernel(const double *__restrict__ src, long long src_ld,
+                                     double *mc_dst, long long dst_ld, long long rows,
+                                     long long cols)
+{
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols, c = i - r * cols;
+        const double v = src[r * src_ld + c];
+        asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(mc_dst + r * dst_ld + c), "d"(v)
+                     : "memory");
+    }
+    __threadfence_system();
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -235,6 +254,19 @@ int fb_nan_to_num(double *a, int64_t total, void *stream)
     FB_REQUIRE(a || total == 0, "bad arguments");
     if (total <= 0) return 0;
     nan_to_num_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, total);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fb_multimem_copy(const double *src, int64_t src_ld, double *mc_dst, int64_t dst_ld,
+                     int64_t rows, int64_t cols, void *stream)
+{
+    FB_REQUIRE(rows >= 0 && cols >= 0 && (rows * cols == 0 || (src && mc_dst)), "bad arguments");
+    if (rows * cols == 0) return 0;
+    const long long total = rows * cols;
+    const long long blocks = (total + 255) / 256;
+    multimem_copy_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0,
+                           (cudaStream_t)stream>>>(src, src_ld, mc_dst, dst_ld, rows, cols);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -225,9 +225,15 @@ class Fruit:
         return X
 
     def transform_device(self, Xd: torch.Tensor, callbacks=None, cache=None,
-                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         out: Optional[torch.Tensor] = None, multicast=None) -> torch.Tensor:
         """``transform`` on device tensors; ``out`` may be a preallocated
-        ``[n, >= nfeatures]`` row-major tensor (or a view of rows of one)."""
+        ``[n, >= nfeatures]`` row-major tensor (or a view of rows of one).
+
+        ``multicast`` = ``(address, row stride)`` of the same rows inside an
+        NVSwitch multicast mapping (``parallel.PeerGather``): the features are
+        then stored THERE -- into the matrix of every rank of the multicast group,
+        this rank's ``out`` included -- by the generated kernels themselves, or
+        copied there with ``fb_multimem_copy`` by the slices on other routes."""
         callbacks = callbacks or []
         cache_ = SharedSeedCache(Xd) if cache is None else cache
         n = Xd.shape[0]
@@ -237,7 +243,8 @@ class Fruit:
             for callback in callbacks:
                 callback.on_next_slice()
             k = slc.nfeatures()
-            slc._transform_device(Xd, callbacks, cache_, result, index, sanitize=True)
+            slc._transform_device(Xd, callbacks, cache_, result, index, sanitize=True,
+                                  multicast=multicast)
             index += k
         return result
 
@@ -694,8 +701,23 @@ class FruitSlice:
         return dev
 
     def _transform_device(self, X: torch.Tensor, callbacks, cache, out: torch.Tensor,
-                          col0: int, sanitize: bool) -> None:
-        """Write the features of this slice into ``out[:, col0:col0+nfeatures]``."""
+                          col0: int, sanitize: bool, multicast=None) -> None:
+        """Write the features of this slice into ``out[:, col0:col0+nfeatures]``
+        (``multicast``: see ``Fruit.transform_device``)."""
+        self._multicast = multicast
+        try:
+            self._transform_device_(X, callbacks, cache, out, col0, sanitize)
+        finally:
+            self._multicast = None
+        if multicast is not None and X.shape[0] and \
+                getattr(self, "_last_launch", ("",))[0] not in ("fb_jit_slice", "fb_jit_chain"):
+            # this slice wrote ordinary memory: replicate its columns
+            be.check(be.lib().fb_multimem_copy(
+                out.data_ptr() + 8 * col0, out.stride(0), int(multicast[0]) + 8 * col0,
+                int(multicast[1]), X.shape[0], self.nfeatures(), be.stream_ptr()))
+
+    def _transform_device_(self, X: torch.Tensor, callbacks, cache, out: torch.Tensor,
+                           col0: int, sanitize: bool) -> None:
         if not self._fitted:
             raise RuntimeError("Missing call of self.fit")
         if X.dim() != 3:
@@ -852,7 +874,8 @@ class FruitSlice:
             else:
                 extra = g
                 extra_ld = g_ld
-        kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize)
+        kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize,
+                    multicast=getattr(self, "_multicast", None))
         self._last_launch = ("fb_jit_chain" if chain else "fb_jit_slice",
                              kern.n_launches(X.shape[0], X.shape[2]), kern)
 
@@ -930,6 +953,7 @@ class FruitSlice:
         if sanitize:
             be.check(be.lib().fb_nan_to_num(buf.data_ptr(), buf.numel(), be.stream_ptr()))
         out[:, col0:col0 + nf_total] = buf
+        self._last_launch = ("composed", 0, None)
 
     def fit_transform(self, X):
         self.fit(X)

@@ -23,20 +23,6 @@ import torch
 import torch.distributed as dist
 
 
-class _DevicePointer:
-    """``__cuda_array_interface__`` of a raw device address (float64, C order)."""
-
-    def __init__(self, ptr: int, shape: tuple) -> None:
-        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape),
-                                         "typestr": "<f8", "version": 2, "strides": None}
-
-
-def _wrap_device_pointer(ptr: int, shape: tuple, device) -> torch.Tensor:
-    """Zero-copy tensor over ``ptr`` (used for the multicast mapping, which
-    torch does not hand out as a tensor)."""
-    return torch.as_tensor(_DevicePointer(ptr, shape), device=device)
-
-
 def shard_rows(n: int, world: int, rank: int):
     """Contiguous row block ``[lo, hi)`` of rank ``rank`` (first ranks get the
     remainder rows)."""
@@ -86,8 +72,12 @@ def gather_fit_sample(X_local: torch.Tensor, n_total: int, fit_sample_size, grou
     sample = torch.zeros((idx_t.numel(),) + tuple(X_local.shape[1:]), dtype=X_local.dtype,
                          device=X_local.device)
     sample[mine] = X_local.index_select(0, idx_t[mine] - lo)
-    # every sampled row is owned by exactly one rank: the sum assembles them
-    dist.all_reduce(sample, op=dist.ReduceOp.SUM, group=group)
+    # every sampled row is owned by exactly one rank and the others hold the bit
+    # pattern 0: an INTEGER sum of the bit patterns assembles the rows exactly
+    # (a floating point sum would turn -0.0 into +0.0 and drop NaN payloads, and
+    # 1 / -0.0 = -inf in a letter with a negative exponent)
+    assert sample.dtype == torch.float64
+    dist.all_reduce(sample.view(torch.int64), op=dist.ReduceOp.SUM, group=group)
     return sample
 
 
@@ -184,12 +174,13 @@ class PeerGather:
         """True if the kernels can store straight into all ranks' matrices."""
         return self.mc_ptr != 0
 
-    def multicast_rows(self, lo: int, hi: int) -> torch.Tensor:
-        """Write-only view of this rank's rows ``[lo, hi)`` in the multicast
-        address space: every store lands in the same rows of the matrix of
-        every rank (own included).  Must never be read."""
-        offset = ((self.rank * self.S + lo) * self.F) * 8
-        return _wrap_device_pointer(self.mc_ptr + offset, (hi - lo, self.F), self.out.device)
+    def multicast_rows(self, lo: int, hi: int):
+        """``(address, row stride in elements)`` of this rank's rows ``[lo, hi)``
+        in the multicast address space: every ``multimem.st`` to it lands in the
+        same rows of the matrix of every rank (own included).  A raw address on
+        purpose: multicast mappings may only be touched by ``multimem.*``
+        instructions, so it is never wrapped into a tensor or handed to torch."""
+        return self.mc_ptr + ((self.rank * self.S + lo) * self.F) * 8, self.F
 
     def rows(self, lo: int, hi: int) -> torch.Tensor:
         """This rank's rows ``[lo, hi)`` inside its own matrix (compute target)."""
@@ -216,27 +207,44 @@ class PeerGather:
         return self.out
 
 
-def transform_sharded(compute: Callable[[torch.Tensor, torch.Tensor], None],
-                      X_local: torch.Tensor, n_feats: int, chunks: int = 8, group=None,
+def _check_equal_shards(S: int, dev, group) -> None:
+    """All ranks must hold the same number of rows: the assembled matrix is
+    ``[world * S, F]`` with rank-major rows and every collective below uses
+    equal sizes (uneven shards would hang or land rows at wrong offsets)."""
+    t = torch.tensor([S, -S], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    if int(t[0]) != -int(t[1]):
+        raise ValueError(f"transform_sharded needs equally sized shards (this rank holds {S} "
+                         f"rows, the ranks hold between {-int(t[1])} and {int(t[0])}); pad the "
+                         f"batch or use shard sizes that divide it")
+
+
+def transform_sharded(fruit, X_local: torch.Tensor, n_feats: int, chunks: int = 8, group=None,
                       out=None) -> torch.Tensor:
     """All ranks hold ``S`` rows; returns the assembled ``[world*S, n_feats]``
     feature matrix (rank-major row order, identical on every rank).
 
-    ``compute(X_rows, out_rows)`` writes the features of a row block (e.g.
-    ``lambda x, o: fruit.transform_device(x, out=o)``).  The rows are processed
-    in ``chunks`` pieces.  With ``out`` a :class:`PeerGather` every finished
-    piece is pushed to the peers by the copy engines while the next piece is
-    computed; otherwise the pieces are all-gathered with NCCL on a side
-    stream."""
+    ``fruit`` is a fitted :class:`~fruits_b200.Fruit` (or, for tests, a callable
+    ``compute(X_rows, out_rows)`` that writes the features of a row block).
+    With ``out`` a :class:`PeerGather` whose multicast mapping is available the
+    feature kernels store straight into the matrices of all ranks
+    (``multimem.st``); else every finished row piece is pushed to the peers by
+    the copy engines while the next piece is computed; without a
+    ``PeerGather`` the pieces are all-gathered with NCCL on a side stream."""
     world = dist.get_world_size(group)
     S = X_local.shape[0]
     dev = X_local.device
+    is_fruit = hasattr(fruit, "transform_device")
+    compute = (lambda x, o: fruit.transform_device(x, out=o)) if is_fruit else fruit
+    if world > 1:
+        _check_equal_shards(S, dev, group)
     if isinstance(out, PeerGather):
-        if out.fused:
+        if out.fused and is_fruit:
             # the kernels store through the NVSwitch multicast mapping: compute and
             # all-gather are one launch, nothing is left to overlap
             if S:
-                compute(X_local, out.multicast_rows(0, S))
+                fruit.transform_device(X_local, out=out.rows(0, S),
+                                       multicast=out.multicast_rows(0, S))
             return out.finish()
         chunks = max(1, min(chunks, S)) if S else 1
         for lo, hi in (shard_rows(S, chunks, c) for c in range(chunks)):

@@ -219,6 +219,8 @@ FB_API int fb_jit_slice_features(fb_jit_kernel *k, const fb_jit_geometry *geo,
                                  const fb_batch *batch, const double *extra, int64_t extra_ld,
                                  const double *thr, int64_t n_thr, double *out, int64_t out_ld,
                                  int64_t col0, int sanitize, void *stream);
+/* (`sanitize`: bit 0 = np.nan_to_num of the features (fruits/fruit.py:172), bit 1 =
+ * `out` is an NVSwitch multicast mapping, stored to with multimem.st) */
 
 /* Lane-per-node form for deep Arctic tries (generator: fruits_b200/_jit_chain.py):
  * the 24-48-letter alternating-sign chains of experiments/fruit_reduced.py:42-49
@@ -342,6 +344,14 @@ FB_API int fb_ppv(const double *V, int64_t ld, const double *q, int nq, int segm
                   int64_t out_ld, int64_t col0, int64_t rows, int64_t t, void *stream);
 /* np.nan_to_num(a, nan=0.0) in place (fruits/fruit.py:172). */
 FB_API int fb_nan_to_num(double *a, int64_t total, void *stream);
+
+/* Multi-GPU assembly of the feature matrix (north_star (3)): copy
+ * a rows x cols block of features into the same block of an NVSwitch multicast
+ * mapping (NVLS) with multimem.st, i.e. into the matrix of every rank at once.
+ * Used for the slices that are not written by a generated kernel (those store
+ * through the mapping themselves, flag bit 1 of `sanitize` in fb_jit_*_features). */
+FB_API int fb_multimem_copy(const double *src, int64_t src_ld, double *mc_dst, int64_t dst_ld,
+                            int64_t rows, int64_t cols, void *stream);
 
 /* -- fit: exact order statistics for np.quantile (segment.py:66-75) -- */
 FB_API int64_t fb_order_stats_workspace(int64_t P);

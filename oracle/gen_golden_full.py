@@ -17,8 +17,8 @@ What is frozen (tests/golden/full_<name>.npz):
   fruits/preparation/transform.py:92-158).
 * C2 only (the full transform finishes in seconds): ``counts`` = the
   integer-valued NPI columns of ALL rows as uint16, ``count_cols`` their
-  column indices, and ``row_sha`` = sha256 per row of the bit-exact arctic
-  slice.
+  column indices, and ``row_sha_slice<i>`` = sha256 per row of the bit-exact
+  columns (``exact_cols_slice<i>``: NPI counts and END) of the arctic slice.
 * ``source`` says which program produced each slice ("reference" = the numba
   package at /root/reference; "oracle" only if the reference did not finish).
 
@@ -99,8 +99,12 @@ def main(name, n_rows):
         for si, slc in enumerate(spec["slices"]):
             k = fruit.get_slice(si).nfeatures()
             if slc["iss"][0].get("semiring") == "arctic":
+                # (MPI means are sums whose order numba's fastmath leaves open: not hashed;
+                # + 0.0 turns -0.0 into +0.0, the sign of zero is unspecified under fastmath)
+                exact = np.array([c for c in range(col, col + k) if "| MPI" not in labels[c]])
+                out[f"exact_cols_slice{si}"] = exact
                 out[f"row_sha_slice{si}"] = np.array(
-                    [hashlib.sha256(np.ascontiguousarray(r[j, col:col + k]).tobytes()).hexdigest()[:16]
+                    [hashlib.sha256(np.ascontiguousarray(r[j, exact] + 0.0).tobytes()).hexdigest()[:16]
                      for j in range(r.shape[0])])
             col += k
     path = os.path.join(GOLD, f"full_{name}.npz")

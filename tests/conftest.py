@@ -26,3 +26,14 @@ def pytest_sessionstart(session):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Parity reports of the weighted configurations (rtol violations, count
+    flips) next to the other run artefacts."""
+    import json
+    import helpers
+    out = os.path.join(ROOT, "gpurun_out")
+    if helpers.REPORTS and os.path.isdir(out):
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(helpers.REPORTS, f, indent=1, sort_keys=True)

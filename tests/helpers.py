@@ -56,3 +56,32 @@ def oracle_thresholds(of):
                 q = sv.fitted_q if sv.name in ("PPV", "CPV") else sv.quantiles
                 rows.append(np.asarray(q, dtype=np.float64).ravel())
     return np.concatenate(rows) if rows else np.zeros(0)
+
+
+def parity_report(got, ref, rtol=1e-9):
+    """Numbers SURVEY.md section 8(d) asks to report beside a tolerance check of
+    weighted (floating point) features: how many elements violate the
+    elementwise rtol, how many of those are integer counts that moved by exactly
+    one (a value within rounding of its threshold), and the worst relative error
+    of the rest."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    scale = np.maximum(np.abs(ref), 1.0)
+    diff = np.abs(got - ref)
+    diff = np.where((got == ref) | (np.isnan(got) & np.isnan(ref)), 0.0, diff)
+    bad = diff > rtol * scale
+    integer = (ref == np.round(ref)) & (got == np.round(got))
+    flips = bad & integer & (diff == 1.0)
+    other = bad & ~flips
+    return {"elements": int(ref.size), "rtol": rtol, "rtol_violations": int(bad.sum()),
+            "count_flips": int(flips.sum()), "other_violations": int(other.sum()),
+            "max_rel_err_non_flip": float(np.max(np.where(flips, 0.0, diff / scale), initial=0.0))}
+
+
+REPORTS = {}
+
+
+def record_report(name, report):
+    """Keep a parity report for the session summary (tests/conftest.py writes
+    them to gpurun_out/parity_report.json when that directory exists)."""
+    REPORTS[name] = report
+    print(f"[parity] {name}: {report}")

@@ -37,6 +37,10 @@ def _worker(rank, world, port, n_total, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         X = torch.arange(n_total * 2 * 5, dtype=torch.float64).reshape(n_total, 2, 5)
+        # bit patterns a floating point sum over zero-filled rows would lose:
+        # -0.0 (1 / -0.0 = -inf in a letter with a negative exponent) and a NaN payload
+        X[:, 1, 0] = -0.0
+        X[:, 1, 1] = torch.tensor([0x7ff8000000000abc], dtype=torch.int64).view(torch.float64)
         lo, hi = shard_rows(n_total, world, rank)
         Xl = X[lo:hi].clone()
         # fit sample: all ranks end up with the rows rank 0's RNG state selects
@@ -49,8 +53,10 @@ def _worker(rank, world, port, n_total, q):
         i1 = np.random.randint(0, n_total)
         i2 = np.random.choice(n_total, size=n_total // 2, replace=False)
         expect_after = np.random.random()
-        ok = (torch.equal(one, X[i1:i1 + 1]) and torch.equal(frac, X[i2])
+        bits = lambda a: a.contiguous().view(torch.int64)        # noqa: E731
+        ok = (torch.equal(bits(one), bits(X[i1:i1 + 1])) and torch.equal(bits(frac), bits(X[i2]))
               and after == expect_after)
+        ok = ok and bool(torch.signbit(frac[:, 1, 0]).all())
 
         # chunked all-gather of features: S rows per rank, rank-major result
         S = hi - lo
@@ -63,6 +69,12 @@ def _worker(rank, world, port, n_total, q):
         ok = ok and torch.equal(feats, X[:, 0, :3] * 10 + 1)
         feats1 = transform_sharded(compute, Xl, 3, chunks=1)
         ok = ok and torch.equal(feats1, feats)
+        # uneven shards are refused on every rank instead of hanging or mis-placing rows
+        try:
+            transform_sharded(compute, Xl[:S - rank], 3, chunks=1)
+            ok = False
+        except ValueError as exc:
+            ok = ok and "equally sized" in str(exc)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

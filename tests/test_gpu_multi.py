@@ -45,12 +45,27 @@ def _worker(rank, world, port, mode, q):
             dist.destroy_process_group()
             return
     for _ in range(2):                      # the second pass reuses the peer buffers
-        res = transform_sharded(lambda x, o: fruit.transform_device(x, out=o), Xl, nf,
-                                chunks=3, out=out)
+        res = transform_sharded(fruit, Xl, nf, chunks=3, out=out)
     torch.cuda.synchronize()
     # single-GPU result of the whole batch with the same thresholds
     ref = fruit.transform_device(torch.from_numpy(X).to(dev))
-    q.put((rank, bool(torch.equal(res, ref)), res.shape))
+    same = bool(torch.equal(res, ref))
+    if mode == "multicast":
+        # a fruit whose slices take different routes: generated kernel (multimem.st in
+        # its epilogue), generic kernel and composed route (fb_multimem_copy)
+        mixed = specs.build_fruit(fruits, {"slices": specs.SPECS["C1_readme"]["slices"]
+                                           + [specs.SPECS["R_mixed"]["slices"][1]]})
+        Xm = np.random.default_rng(6).random((world * 4200, 3, 60)) + 0.1
+        Xml = torch.from_numpy(Xm[rank * 4200:(rank + 1) * 4200]).to(dev)
+        np.random.seed(4)
+        fit_sharded(mixed, Xml, world * 4200)
+        pg = PeerGather(4200, mixed.nfeatures(), multicast=True)
+        resm = transform_sharded(mixed, Xml, mixed.nfeatures(), out=pg)
+        torch.cuda.synchronize()
+        refm = mixed.transform_device(torch.from_numpy(Xm).to(dev))
+        routes = {getattr(slc, "_last_launch", ("?",))[0] for slc in mixed}
+        same = same and bool(torch.equal(resm, refm)) and len(routes) >= 2
+    q.put((rank, same, res.shape))
     dist.barrier()
     dist.destroy_process_group()
 

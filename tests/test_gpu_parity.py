@@ -21,6 +21,7 @@ import specs
 from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, KAT_X, SIEVE_KATS, make_iss_input,
                    make_prep_input, make_sieve_input)
 from helpers import (assert_close, assert_exact, fitted_thresholds, oracle_thresholds,
+                     parity_report, record_report,
                      rowmax_rel_err)
 
 pytestmark = pytest.mark.gpu
@@ -110,7 +111,10 @@ def test_pipeline_golden(name, golden_dir):
 
 def _assert_features_close(res, ref, what):
     """Weighted slices: values within 1e-9; an integer count may move by one
-    when an increment sits within rounding of its threshold."""
+    when an increment sits within rounding of its threshold.  The numbers of
+    rtol violations and count flips are reported (helpers.parity_report)."""
+    rep = parity_report(res, ref)
+    record_report(what, rep)
     scale = np.maximum(np.abs(ref), 1.0)
     bad = np.abs(res - ref) > 1e-9 * scale
     assert bad.mean() <= 2e-4, f"{what}: {bad.sum()} of {bad.size} features beyond 1e-9"
@@ -1025,3 +1029,51 @@ def test_extra_pipeline_golden(name, golden_dir):
                       sorted(set(np.linspace(0, res.shape[1] - 1, 23).astype(int))))
     assert labels == str(g["labels"])
     assert fruit.summary() == str(g["summary"])
+
+
+# ---------------------------------------------------------------------------
+# (k) BASELINE sizes against golden vectors frozen from the REAL reference
+# (oracle/gen_golden_full.py: the reference's own fit on the full input, its
+# transform of all / of sampled rows)
+
+def _slice_feature_bounds(fruit):
+    b = [0]
+    for slc in fruit:
+        b.append(b[-1] + slc.nfeatures())
+    return b
+
+
+def test_c2_full_size_against_the_reference(golden_dir):
+    """experiments/fruit_reduced.py, all four slices, at BASELINE size
+    (1,000 x 1 x 512): every threshold of the full fit, the features of 64 rows,
+    the NPI counts of ALL rows and the arctic slice of all rows bit for bit."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "full_C2_full.npz"))
+    X = specs.make_input("C2_full")
+    assert X.shape[0] == int(g["n"]) == 1000
+    fruit = specs.build_fruit(fruits, specs.SPECS["C2_full"])
+    np.random.seed(0)
+    fruit.fit(X)
+    thr = fitted_thresholds(fruit)
+    tb = g["thr_slices"]
+    assert thr.shape == g["thresholds"].shape
+    # slice 1 (arctic, unweighted): bit-identical thresholds; the others: device exp / sin / cos
+    assert_exact(thr[tb[1]:tb[2]], g["thresholds"][tb[1]:tb[2]], "C2 full arctic thresholds")
+    assert_close(thr, g["thresholds"], 1e-9, "C2 full thresholds")
+    res = fruit.transform(X)
+    assert res.shape == (1000, int(g["nfeatures"])) == (1000, 4431)
+    fb = _slice_feature_bounds(fruit)
+    rows = g["rows"]
+    exact = g["exact_cols_slice1"]         # arctic slice without the MPI means (summation order)
+    assert fb[1] <= exact.min() and exact.max() < fb[2] and exact.size == 4 * 188
+    assert_exact(res[rows][:, exact], g["features"][:, exact], "C2 full arctic rows")
+    assert_close(res[rows][:, fb[1]:fb[2]], g["features"][:, fb[1]:fb[2]], 1e-12, "C2 arctic MPI")
+    _assert_features_close(res[rows], g["features"], "C2_full 64 rows vs reference")
+    # all 1,000 rows: integer counts, and one hash per row of the bit-exact slice
+    cnt = res[:, g["count_cols"]]
+    rep = parity_report(cnt, g["counts"].astype(np.float64))
+    record_report("C2_full NPI counts of all rows vs reference", rep)
+    assert rep["rtol_violations"] == rep["count_flips"] <= 2e-4 * cnt.size, rep
+    sha = [hashlib.sha256(np.ascontiguousarray(res[j, exact] + 0.0).tobytes()).hexdigest()[:16]
+           for j in range(res.shape[0])]
+    assert sha == [str(x) for x in g["row_sha_slice1"]]

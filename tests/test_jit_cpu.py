@@ -187,5 +187,5 @@ def test_staged_epilogue_writes_every_feature_column_once(name, si, ppc, tt, ndi
     em0 = _jit.Emitter(prog, dims, ppc, 8, True, tt, stage=0)
     assert em0.staging_width() == 0
     direct = [ln for part in prog.parts if part.owned for ln in em0.epilogue_code(part)
-              if ln.strip().startswith("o[")]
+              if ln.strip().startswith("put(o + ")]
     assert len(direct) == len(trie.emits) * nf

@@ -223,3 +223,25 @@ def test_two_letter_word_against_brute_force(semiring):
                     want[s, T] = max(X[s, 0, i] + X[s, 1, j] + a0 * (g[i] - g[j])
                                      for j in range(T + 1) for i in range(j + 1))
         np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+def test_full_size_goldens_describe_the_baseline_inputs(golden_dir):
+    """tests/golden/full_*.npz (oracle/gen_golden_full.py): frozen from the real
+    reference at BASELINE size; the GPU tests compare against them.  Here: the
+    files belong to the seeded inputs of tests/specs.py and are self-consistent
+    (the generator checked the oracle against them when it wrote them)."""
+    import hashlib
+    import glob
+    paths = sorted(glob.glob(os.path.join(golden_dir, "full_*.npz")))
+    assert any(p.endswith("full_C2_full.npz") for p in paths)
+    for path in paths:
+        g = np.load(path)
+        name = os.path.basename(path)[len("full_"):-len(".npz")]
+        X = specs.make_input(name)
+        sha = hashlib.sha256(np.ascontiguousarray(X).tobytes()).hexdigest()[:16]
+        assert sha == str(g["xsha"]) and X.shape[0] == int(g["n"])
+        assert str(g["source"]) == "reference"
+        nslices = len(specs.SPECS[name]["slices"])
+        assert g["thr_slices"].shape == (nslices + 1,) and g["thr_slices"][-1] == g["thresholds"].size
+        assert g["features"].shape == (g["rows"].size, int(g["nfeatures"]))
+        assert np.isfinite(g["features"]).all()
