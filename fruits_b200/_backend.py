@@ -110,6 +110,12 @@ def lib() -> ctypes.CDLL:
         "fb_order_stats_multi_workspace": ([i64, i32], i64),
         "fb_order_stats_multi": ([vp, i64, i64, i64, i64, i32, ctypes.POINTER(ctypes.c_int32),
                                   ctypes.POINTER(ctypes.c_int64), vp, vp, vp, vp, vp], i32),
+        "fb_order_stats_dist_layout": ([i64, i32, ctypes.POINTER(ctypes.c_int64)], i32),
+        "fb_order_stats_dist": ([i32, vp, i64, i64, i64, i64, i64, i32,
+                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64),
+                                 vp, vp, vp, vp, vp], i32),
+        "fb_order_stats_dist8_layout": ([i64, ctypes.POINTER(ctypes.c_int64)], i32),
+        "fb_order_stats_dist8": ([i32, vp, i64, i64, i64, i64, i64, vp, vp, vp, vp], i32),
         "fb_fp64_peak": ([vp, i32, i32, vp], i32),
         "fb_jit_compile": ([ctypes.c_char_p, ctypes.c_char_p, i32, i32, ctypes.POINTER(vp),
                             ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t], i32),
@@ -149,6 +155,8 @@ EXPORTED = [
     "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
     "fb_jit_unload", "fb_jit_slice_features", "fb_jit_chain_features", "fb_jit_link", "fb_exp_rows", "fb_cos_trig", "fb_cos_rows", "fb_coswiss_sep_word", "fb_coswiss_word",
     "fb_bayes_word", "fb_order_stats_multi_workspace", "fb_order_stats_multi",
+    "fb_order_stats_dist_layout", "fb_order_stats_dist", "fb_order_stats_dist8_layout",
+    "fb_order_stats_dist8",
 ]
 
 

@@ -36,7 +36,7 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 15            # bump to invalidate cached cubins
+JIT_VERSION = 16            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -772,7 +772,9 @@ class Emitter:
         A("    if (v == D_NINF) return __longlong_as_double(0xffefffffffffffffLL);")
         A("    return v; }")
         A("// a.sanitize bit 1: a.out is an NVSwitch multicast mapping -- such addresses may")
-        A("// only be accessed with multimem.* instructions (PTX ISA)")
+        A("// only be accessed with multimem.* instructions (PTX ISA).  No fence here: the")
+        A("// stores are complete at system scope when the grid ends, and the ranks meet in")
+        A("// the device-side barrier launched behind this kernel (parallel.PeerGather.finish)")
         A("__device__ __forceinline__ void put(double *p, double v, bool mc) {")
         A('    if (mc) asm volatile("multimem.st.weak.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");')
         A("    else *p = v; }")
@@ -988,7 +990,6 @@ class Emitter:
             A("    } break;")
         A("    default: break;")
         A("    }")
-        A("    if (mc) __threadfence_system();")
         A("}")
         del du
         return "\n".join(src) + "\n"

@@ -40,7 +40,7 @@ from dataclasses import dataclass
 from . import _backend as be
 from . import _jit
 
-CHAIN_VERSION = 3
+CHAIN_VERSION = 4
 MIN_SERIES = 512           # from this batch size on a chain kernel is compiled (cached on disk)
 MIN_SERIES_CACHED = 16     # ... and from this size on an already compiled one is used
 
@@ -488,7 +488,6 @@ class ChainEmitter:
         for r in range(R):
             for ln in self.epilogue(r):
                 A("    " + ln)
-        A("    if (mc) __threadfence_system();")
         A("}")
         return "\n".join(src) + "\n"
 

@@ -473,6 +473,177 @@ __global__ void __launch_bounds__(256) sel2_finish_kernel(Sel2State *st, const u
     }
 }
 
+// ---------------------------------------------------------------------------
+// Row-sharded form of the multi-selection (fb_order_stats_dist): every rank
+// holds a share of the rows of each problem, the thresholds are quantiles over
+// ALL rows (fruits/sieving/segment.py:66-75).  Same three reads of the local
+// data as above, but the histograms are summed over the ranks between the
+// passes (the host all-reduces the regions fb_order_stats_dist_layout names),
+// so every rank walks the same buckets; the remaining 40 bits are resolved on
+// the LOCAL candidate lists with five more 8-bit histograms, summed the same way.
+struct DistAux {
+    unsigned long long rank24;      // rank inside the 24-bit bucket (before the candidate passes)
+};
+
+__global__ void seld_export_kernel(const Sel2State *st, long long *sums, long long *mins, int ns)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ns) return;
+    sums[2 * q] = (long long)st[q].n_nan;
+    sums[2 * q + 1] = 0;
+    // unsigned keys -> signed order for an integer MIN all-reduce
+    mins[2 * q] = (long long)(st[q].min_above ^ 0x8000000000000000ULL);
+    mins[2 * q + 1] = (long long)(~0ULL ^ 0x8000000000000000ULL);
+}
+
+__global__ void seld_import_kernel(Sel2State *st, DistAux *aux, const long long *sums,
+                                   const long long *mins, int ns)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ns) return;
+    st[q].n_nan = (unsigned long long)sums[2 * q];
+    st[q].min_above = (unsigned long long)mins[2 * q] ^ 0x8000000000000000ULL;
+    aux[q].rank24 = st[q].rank;
+}
+
+// pick the bin of the previous candidate pass (summed histogram), then count the
+// local candidates of the next pass; one CTA per (problem, selection)
+__global__ void __launch_bounds__(256) seld_cand_kernel(Sel2State *st, const unsigned long long *cand,
+                                                      unsigned *h256, int pick_shift, int hist_shift)
+{
+    __shared__ unsigned h[256];
+    __shared__ unsigned long long s_prefix;
+    const int q = blockIdx.x;
+    Sel2State &S = st[q];
+    if (S.bucket > (unsigned long long)SEL2_CAP) return;      // reported as not done
+    unsigned *hg = h256 + (size_t)q * 256;
+    if (threadIdx.x == 0) {
+        unsigned long long prefix = S.prefix, rank = S.rank;
+        if (pick_shift >= 0) {
+            unsigned long long acc = 0;
+            int b = 0;
+            for (; b < 256; b++) {
+                if (rank < acc + hg[b]) break;
+                acc += hg[b];
+            }
+            prefix |= (unsigned long long)b << pick_shift;
+            rank -= acc;
+            S.prefix = prefix;
+            S.rank = rank;
+        }
+        s_prefix = prefix;
+    }
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    if (hist_shift >= 0) {
+        const unsigned n = min(S.n_cand, (unsigned)SEL2_CAP);
+        const unsigned long long *c = cand + (size_t)q * SEL2_CAP;
+        const unsigned long long himask = ~0ULL << (hist_shift + 8);
+        const unsigned long long prefix = s_prefix;
+        for (unsigned i = threadIdx.x; i < n; i += 256) {
+            const unsigned long long key = c[i];
+            if ((key & himask) == prefix) atomicAdd(&h[(key >> hist_shift) & 255], 1u);
+        }
+        __syncthreads();
+    }
+    hg[threadIdx.x] = h[threadIdx.x];
+}
+
+// after the last pick: local count of candidates <= x_(k) and the smallest one above
+__global__ void __launch_bounds__(256) seld_succ_kernel(const Sel2State *st, const unsigned long long *cand,
+                                                      long long *sums, long long *mins)
+{
+    __shared__ unsigned long long red_min[8], red_cnt[8];
+    const int q = blockIdx.x;
+    const Sel2State &S = st[q];
+    if (S.bucket > (unsigned long long)SEL2_CAP) return;
+    const unsigned n = min(S.n_cand, (unsigned)SEL2_CAP);
+    const unsigned long long *c = cand + (size_t)q * SEL2_CAP;
+    const unsigned long long keyk = S.prefix;
+    unsigned long long cle = 0, mgt = ~0ULL;
+    for (unsigned i = threadIdx.x; i < n; i += 256) {
+        const unsigned long long key = c[i];
+        if (key <= keyk) cle++;
+        else if (key < mgt) mgt = key;
+    }
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) {
+        cle += __shfl_xor_sync(0xffffffffu, cle, sft);
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, mgt, sft);
+        mgt = o < mgt ? o : mgt;
+    }
+    if ((threadIdx.x & 31) == 0) { red_cnt[threadIdx.x >> 5] = cle; red_min[threadIdx.x >> 5] = mgt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cle = 0; mgt = ~0ULL;
+        for (int w = 0; w < 8; w++) { cle += red_cnt[w]; mgt = red_min[w] < mgt ? red_min[w] : mgt; }
+        sums[2 * q + 1] = (long long)cle;
+        mins[2 * q + 1] = (long long)(mgt ^ 0x8000000000000000ULL);
+    }
+}
+
+__global__ void seld_out_kernel(const Sel2State *st, const DistAux *aux, const long long *sums,
+                                const long long *mins, Sel2Args a, long long m_global, int ns,
+                                double *lo, double *hi, int *done)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ns) return;
+    const Sel2State &S = st[q];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (S.bucket > (unsigned long long)SEL2_CAP) { done[q] = 0; lo[q] = nan; hi[q] = nan; return; }
+    const unsigned long long cle = (unsigned long long)sums[2 * q + 1];
+    const unsigned long long mgt = (unsigned long long)mins[2 * q + 1] ^ 0x8000000000000000ULL;
+    double a_ = key_value(S.prefix), b_ = a_;
+    if (a.k[q % a.n_sel] + 1 < (unsigned long long)m_global) {
+        if (aux[q].rank24 + 1 < cle) b_ = a_;
+        else if (mgt != ~0ULL) b_ = key_value(mgt);
+        else b_ = key_value(S.min_above);
+    }
+    if (S.n_nan) { a_ = nan; b_ = nan; }
+    lo[q] = a_;
+    hi[q] = b_;
+    done[q] = 1;
+}
+
+// the eight-pass select (fb_order_stats) in the same row-sharded form
+__global__ void sel8_export_kernel(const SelState *st, long long *sums, long long *mins, int P)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    sums[2 * p] = (long long)st[p].count_le;
+    sums[2 * p + 1] = (long long)st[p].n_nan;
+    mins[p] = (long long)(st[p].min_gt ^ 0x8000000000000000ULL);
+}
+
+__global__ void sel8_import_kernel(SelState *st, const long long *sums, const long long *mins, int P)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    st[p].count_le = (unsigned long long)sums[2 * p];
+    st[p].n_nan = (unsigned long long)sums[2 * p + 1];
+    st[p].min_gt = (unsigned long long)mins[p] ^ 0x8000000000000000ULL;
+}
+
+struct DistLayout {
+    size_t state, hist, cand, h256, sums, mins, aux, total;
+};
+
+static DistLayout dist_layout(long long P, int n_sel)
+{
+    const size_t ns = (size_t)P * n_sel;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    DistLayout L;
+    L.state = 0;
+    L.hist = up(ns * sizeof(Sel2State));
+    L.cand = L.hist + up(ns * SEL2_BINS * sizeof(unsigned));
+    L.h256 = L.cand + up(ns * (size_t)SEL2_CAP * sizeof(unsigned long long));
+    L.sums = L.h256 + up(ns * 256 * sizeof(unsigned));
+    L.mins = L.sums + up(ns * 2 * sizeof(long long));
+    L.aux = L.mins + up(ns * 2 * sizeof(long long));
+    L.total = L.aux + up(ns * sizeof(DistAux)) + 256;
+    return L;
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -567,6 +738,165 @@ int fb_order_stats_multi(const double *V, int64_t ldp, int64_t P, int64_t M, int
     sel2_scan_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(state, hist, ns, 40);
     sel2_compact_kernel<<<grid, SEL_THREADS, 0, st>>>(a, state, cand);
     sel2_finish_kernel<<<ns, 256, 0, st>>>(state, cand, a, lo, hi, done);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* Row-sharded form of fb_order_stats (eight 8-bit passes over materialised
+ * values): layout = byte offsets of hist (uint32 [P*256], summed after phases
+ * 0..7), sums (int64 [P*2], summed after phase 8), mins (int64 [P], MIN after
+ * phase 8), then the workspace size. */
+int fb_order_stats_dist8_layout(int64_t P, int64_t *layout)
+{
+    FB_REQUIRE(layout && P >= 0, "bad arguments");
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t hist = up((size_t)P * sizeof(SelState));
+    const size_t sums = hist + up((size_t)P * 256 * sizeof(unsigned));
+    const size_t mins = sums + up((size_t)P * 2 * sizeof(long long));
+    layout[0] = (int64_t)hist;
+    layout[1] = (int64_t)sums;
+    layout[2] = (int64_t)mins;
+    layout[3] = (int64_t)(mins + up((size_t)P * sizeof(long long)) + 256);
+    return 0;
+}
+
+int fb_order_stats_dist8(int phase, const double *V, int64_t ldp, int64_t P, int64_t m_local,
+                         int64_t m_global, int64_t k, double *lo, double *hi, void *work,
+                         void *stream)
+{
+    FB_REQUIRE(lo && hi && work && (m_local == 0 || V), "null argument");
+    FB_REQUIRE(P >= 0 && m_local >= 0 && m_global >= 1 && k >= 0 && k < m_global,
+               "bad sizes P=%lld m_local=%lld m_global=%lld k=%lld", (long long)P,
+               (long long)m_local, (long long)m_global, (long long)k);
+    FB_REQUIRE(m_global < (1LL << 31), "more than 2^31 values per problem");
+    FB_REQUIRE(P <= 65535, "too many problems in one call (%lld)", (long long)P);
+    FB_REQUIRE(phase >= 0 && phase <= 9, "phase %d", phase);
+    if (P == 0) return 0;
+    int64_t lay[4];
+    fb_order_stats_dist8_layout(P, lay);
+    char *w = (char *)work;
+    SelState *state = (SelState *)w;
+    unsigned *hist = (unsigned *)(w + lay[0]);
+    long long *sums = (long long *)(w + lay[1]);
+    long long *mins = (long long *)(w + lay[2]);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Pi = (int)P;
+    const long long per_cta = (long long)SEL_THREADS * SEL_ITEMS;
+    dim3 grid((unsigned)((m_local + per_cta - 1) / per_cta), (unsigned)Pi);
+    if (phase == 0)
+        sel_init_kernel<<<(Pi * 256 + 255) / 256, 256, 0, st>>>(state, hist, Pi, (unsigned long long)k);
+    else if (phase <= 8)
+        sel_scan_kernel<<<(Pi * 32 + 127) / 128, 128, 0, st>>>(state, hist, Pi, 56 - 8 * (phase - 1));
+    if (phase <= 7) {
+        if (grid.x) sel_hist_kernel<<<grid, SEL_THREADS, 0, st>>>(V, ldp, m_local, state, hist, 56 - 8 * phase);
+    } else if (phase == 8) {
+        if (grid.x) sel_final_kernel<<<grid, SEL_THREADS, 0, st>>>(V, ldp, m_local, state);
+        sel8_export_kernel<<<(Pi + 127) / 128, 128, 0, st>>>(state, sums, mins, Pi);
+    } else {
+        sel8_import_kernel<<<(Pi + 127) / 128, 128, 0, st>>>(state, sums, mins, Pi);
+        sel_out_kernel<<<(Pi + 127) / 128, 128, 0, st>>>(state, Pi, (unsigned long long)k, m_global, lo, hi);
+    }
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* Row-sharded multi-selection.  layout[0..3] = byte offsets inside the workspace
+ * of: hist (uint32 [P*n_sel*4096], summed after phases 0 and 1), h256 (uint32
+ * [P*n_sel*256], summed after phases 3..7), sums (int64 [P*n_sel*2], summed
+ * after phases 2 and 8), mins (int64 [P*n_sel*2], MIN after phases 2 and 8);
+ * layout[4] = workspace size in bytes. */
+int fb_order_stats_dist_layout(int64_t P, int n_sel, int64_t *layout)
+{
+    FB_REQUIRE(layout && P >= 0 && n_sel >= 1 && n_sel <= SEL2_MAXSEL, "bad arguments");
+    const DistLayout L = dist_layout(P, n_sel);
+    layout[0] = (int64_t)L.hist;
+    layout[1] = (int64_t)L.h256;
+    layout[2] = (int64_t)L.sums;
+    layout[3] = (int64_t)L.mins;
+    layout[4] = (int64_t)L.total;
+    return 0;
+}
+
+/* One phase (0..9) of the row-sharded selection: V holds this rank's m_local
+ * doubles (whole rows of length t) of every one of the P problems, k[s] is the
+ * rank inside the m_global values of all ranks.  Between the phases the host
+ * all-reduces the regions named above; after phase 9 lo / hi / done are as in
+ * fb_order_stats_multi, identical on every rank. */
+int fb_order_stats_dist(int phase, const double *V, int64_t ldp, int64_t P, int64_t m_local,
+                        int64_t m_global, int64_t t, int n_sel, const int32_t *inc,
+                        const int64_t *k, double *lo, double *hi, int32_t *done, void *work,
+                        void *stream)
+{
+    FB_REQUIRE(inc && k && lo && hi && done && work, "null argument");
+    FB_REQUIRE(P >= 0 && m_local >= 0 && t >= 1 && m_local % t == 0 && m_global >= 1,
+               "bad sizes P=%lld m_local=%lld t=%lld", (long long)P, (long long)m_local, (long long)t);
+    FB_REQUIRE(m_local == 0 || V, "null data");
+    FB_REQUIRE(m_global < (1LL << 31), "more than 2^31 values per problem");
+    FB_REQUIRE(n_sel >= 1 && n_sel <= SEL2_MAXSEL, "1..%d selections per call", SEL2_MAXSEL);
+    FB_REQUIRE(P <= 65535 && t < (1LL << 31), "too many problems in one call (%lld)", (long long)P);
+    FB_REQUIRE(phase >= 0 && phase <= 9, "phase %d", phase);
+    if (P == 0) return 0;
+    Sel2Args a;
+    a.V = V; a.ldp = ldp; a.M = m_local; a.t = (int)t; a.n_sel = n_sel;
+    for (int s = 0; s < SEL2_MAXSEL; s++) { a.inc[s] = 0; a.k[s] = 0; }
+    for (int s = 0; s < n_sel; s++) {
+        FB_REQUIRE(inc[s] >= 0 && inc[s] <= 2, "increment depth %d (0..2 here)", inc[s]);
+        FB_REQUIRE(k[s] >= 0 && k[s] < m_global, "bad rank %lld", (long long)k[s]);
+        a.inc[s] = inc[s];
+        a.k[s] = (unsigned long long)k[s];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ns = (int)P * n_sel;
+    const DistLayout L = dist_layout(P, n_sel);
+    char *w = (char *)work;
+    Sel2State *state = (Sel2State *)(w + L.state);
+    unsigned *hist = (unsigned *)(w + L.hist);
+    unsigned long long *cand = (unsigned long long *)(w + L.cand);
+    unsigned *h256 = (unsigned *)(w + L.h256);
+    long long *sums = (long long *)(w + L.sums);
+    long long *mins = (long long *)(w + L.mins);
+    DistAux *aux = (DistAux *)(w + L.aux);
+    const long long per_cta = (long long)SEL_THREADS * SEL_ITEMS;
+    dim3 grid((unsigned)((m_local + per_cta - 1) / per_cta), (unsigned)P);
+    const size_t smem = (size_t)n_sel * SEL2_BINS * sizeof(unsigned);
+    if (phase <= 1) {
+        FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
+        FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
+    }
+    const int tb = (ns + 127) / 128;
+    switch (phase) {
+    case 0:
+        sel2_init_kernel<<<(ns * 64 + 255) / 256, 256, 0, st>>>(state, hist, ns, a);
+        if (grid.x) sel2_hist_kernel<0><<<grid, SEL_THREADS, smem, st>>>(a, state, hist);
+        break;
+    case 1:
+        sel2_scan_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(state, hist, ns, 52);
+        if (grid.x) sel2_hist_kernel<1><<<grid, SEL_THREADS, smem, st>>>(a, state, hist);
+        break;
+    case 2:
+        sel2_scan_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(state, hist, ns, 40);
+        if (grid.x) sel2_compact_kernel<<<grid, SEL_THREADS, 0, st>>>(a, state, cand);
+        seld_export_kernel<<<tb, 128, 0, st>>>(state, sums, mins, ns);
+        break;
+    case 3:
+        seld_import_kernel<<<tb, 128, 0, st>>>(state, aux, sums, mins, ns);
+        seld_cand_kernel<<<ns, 256, 0, st>>>(state, cand, h256, -1, 32);
+        break;
+    case 4: case 5: case 6: case 7: {
+        const int pick = 32 - 8 * (phase - 4);
+        seld_cand_kernel<<<ns, 256, 0, st>>>(state, cand, h256, pick, pick - 8);
+        break;
+    }
+    case 8:
+        seld_cand_kernel<<<ns, 256, 0, st>>>(state, cand, h256, 0, -1);
+        seld_succ_kernel<<<ns, 256, 0, st>>>(state, cand, sums, mins);
+        break;
+    default:
+        seld_out_kernel<<<tb, 128, 0, st>>>(state, aux, sums, mins, a, m_global, ns, lo, hi, done);
+        break;
+    }
     FB_CUDA(cudaGetLastError());
     return 0;
 }

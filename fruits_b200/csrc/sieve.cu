@@ -201,7 +201,6 @@ __global__ void multimem_copy_kernel(const double *__restrict__ src, long long s
         asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(mc_dst + r * dst_ld + c), "d"(v)
                      : "memory");
     }
-    __threadfence_system();
 }
 
 }  // namespace fb

@@ -563,10 +563,16 @@ class FruitSlice:
         iss = self._iss[0]
         n, _, t = prepared.shape
         n_emit = iss.n_iterated_sums()
-        # multi-GPU fit (parallel.fit_sharded): every rank holds the whole fit
-        # sample and fits its contiguous share of the iterated sums; the fitted
-        # sieve copies (a few numbers each) are exchanged afterwards
+        # multi-GPU fit (parallel.fit_sharded), either
+        #  * ``_row_shard``: ``prepared`` holds only this rank's rows of the sample;
+        #    every rank walks all iterated sums and the selections sum their
+        #    histograms over the ranks (thresholds identical everywhere), or
+        #  * ``_fit_shard``: every rank holds the whole sample and fits its
+        #    contiguous share of the iterated sums; the fitted sieve copies (a few
+        #    numbers each) are exchanged afterwards
+        rs = getattr(self, "_row_shard", None)
         shard = getattr(self, "_fit_shard", None)
+        n_all = n if rs is None else rs.n_sample            # rows of the whole fit sample
         first, last = (0, n_emit) if shard is None else shard[0](
             n_emit, getattr(iss, "_emit_costs", lambda: None)())
         has_ppv = any(isinstance(sv, PPV) for sv in self._sieves)
@@ -578,16 +584,26 @@ class FruitSlice:
                 for _ in range(lo, hi):
                     for sv in self._sieves:
                         if isinstance(sv, PPV):
-                            sv._draw(n)
+                            sv._draw(n_all)
+
+        def qmulti(V, pairs):
+            return quantile_multi(V, t, pairs) if rs is None else rs.quantile_multi(V, t, pairs)
+
+        def qrows(V, q, rows_global):
+            return quantile_rows(V, q) if rs is None else rs.quantile_rows(V, q, rows_global * t)
 
         skip_draws(0, first)
         local = []
+        # (row-sharded: the chunk size follows the largest shard, so that all ranks
+        # run the same number of chunks -- and of collectives)
+        n_chunk = n if rs is None else rs.n_local_max(prepared.device)
         for _, chunk in iss.iter_chunks(prepared, max_bytes=_FIT_CHUNK_BYTES,
-                                        emit_range=None if shard is None else (first, last)):
+                                        emit_range=None if shard is None else (first, last),
+                                        rows_for_size=n_chunk):
             G = chunk.shape[0]
             copies = [[sieve.copy() for sieve in self._sieves] for _ in range(G)]
             # replay the reference's RNG consumption: node-major, sieve order
-            draws = [[sv._draw(n) if isinstance(sv, PPV) else None for sv in row]
+            draws = [[sv._draw(n_all) if isinstance(sv, PPV) else None for sv in row]
                      for row in copies]
             pre_cache, q_cache = {}, {}
 
@@ -604,14 +620,14 @@ class FruitSlice:
             pairs = []
             for sv in self._sieves:
                 if isinstance(sv, PPV):
-                    if max(int(sv._sample_size * n), 1) == n:
+                    if max(int(sv._sample_size * n_all), 1) == n_all:
                         pairs += [(0, q) for q, const in sv._q_c_input if not const]
                 elif isinstance(sv, SegmentSieve) and 0 <= sv._inc <= 2:
                     pairs += [(sv._inc, q) for q in sv._q if q not in (1.0, -1.0, 0)]
             pairs = sorted(set(pairs))
             if pairs:
                 q_cache.update({pair: vals for pair, vals in
-                                quantile_multi(chunk.reshape(G, n * t), t, pairs).items()
+                                qmulti(chunk.reshape(G, n * t), pairs).items()
                                 if vals is not None})
 
             def quant(sv, q):
@@ -619,7 +635,7 @@ class FruitSlice:
                 if (key, q) not in q_cache:
                     # other depths (cumulative sums, > 2) and buckets of equal values
                     # too large for the candidate list: select on the materialised rows
-                    q_cache[(key, q)] = quantile_rows(pretransformed(sv)[1], q)
+                    q_cache[(key, q)] = qrows(pretransformed(sv)[1], q, n_all)
                 return q_cache[(key, q)]
 
             for si, sieve in enumerate(self._sieves):
@@ -631,18 +647,23 @@ class FruitSlice:
                             if const:
                                 continue
                             sel = draws[e][si][qi]
-                            if len(sel) == n:
+                            if len(sel) == n_all:
                                 sv._q[qi] = quant(sv, q)[e]
                             else:
-                                idx = torch.as_tensor(sel, device=chunk.device, dtype=torch.long)
+                                # a subsample of the sample rows (positions in the sample)
+                                mine = sel if rs is None else rs.local_rows_of(np.sort(sel))
+                                idx = torch.as_tensor(mine, device=chunk.device, dtype=torch.long)
                                 rows = chunk[e].index_select(0, idx).reshape(1, -1)
-                                sv._q[qi] = quantile_rows(rows, q)[0]
+                                sv._q[qi] = qrows(rows, q, len(sel))[0]
                 elif isinstance(sieve, SegmentSieve):
                     need = [q for q in sieve._q if q not in (1.0, -1.0, 0)]
                     vals = {q: quant(sieve, q) for q in need}
                     for e in range(G):
                         copies[e][si]._set_quantiles({q: vals[q][e] for q in need})
                 else:
+                    if rs is not None:
+                        raise NotImplementedError(
+                            f"{type(sieve).__name__} cannot be fitted on a row-sharded sample")
                     for e in range(G):
                         copies[e][si]._fit_device(chunk[e])
             local.extend(copies)

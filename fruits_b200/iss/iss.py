@@ -252,13 +252,16 @@ class ISS(Seed):
             first = last
         return out
 
-    def iter_chunks(self, X: torch.Tensor, max_bytes: int = 1 << 30, emit_range=None):
+    def iter_chunks(self, X: torch.Tensor, max_bytes: int = 1 << 30, emit_range=None,
+                    rows_for_size: int = None):
         """Yield ``(emit_lo, tensor[g, n, t])`` over all emissions (or those in
-        ``emit_range``), at most ``max_bytes`` per chunk."""
+        ``emit_range``), at most ``max_bytes`` per chunk (sized as if ``X`` had
+        ``rows_for_size`` rows: ranks with different shards then cut the same
+        chunks) and at most 65,535 emissions (one select launch)."""
         n_emit = self.n_iterated_sums()
         first, last = (0, n_emit) if emit_range is None else emit_range
-        per = X.shape[0] * X.shape[2] * 8
-        step = max(1, min(n_emit, max_bytes // max(per, 1)))
+        per = (X.shape[0] if rows_for_size is None else rows_for_size) * X.shape[2] * 8
+        step = max(1, min(n_emit, max_bytes // max(per, 1), 65535))
         lookup = self._lookup(X.contiguous())
         for lo in range(first, last, step):
             hi = min(last, lo + step)

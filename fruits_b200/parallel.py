@@ -81,15 +81,184 @@ def gather_fit_sample(X_local: torch.Tensor, n_total: int, fit_sample_size, grou
     return sample
 
 
+def exchange_rows(T_local: torch.Tensor, n_total: int, need, group=None) -> torch.Tensor:
+    """Rows ``need`` (global row numbers, any order, repeats allowed) of a
+    row-sharded tensor: rank r holds the rows ``shard_rows(n_total, world, r)``
+    in ``T_local``.  One all-to-all of the requests, one of the rows."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = T_local.device
+    need = torch.as_tensor(np.asarray(need, dtype=np.int64), device=dev)
+    bounds = [shard_rows(n_total, world, r) for r in range(world)]
+    starts = torch.tensor([b[0] for b in bounds] + [n_total], dtype=torch.int64, device=dev)
+    owner = torch.searchsorted(starts, need, right=True) - 1
+    order = torch.argsort(owner, stable=True)
+    req = need[order].contiguous()
+    send_counts = torch.bincount(owner, minlength=world).to(torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    asked = torch.empty((sum(rc),), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(asked, req, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    lo = bounds[rank][0]
+    rows = T_local.index_select(0, asked - lo).contiguous()
+    got = torch.empty((sum(sc),) + tuple(T_local.shape[1:]), dtype=T_local.dtype, device=dev)
+    dist.all_to_all_single(got, rows, output_split_sizes=sc, input_split_sizes=rc, group=group)
+    out = torch.empty_like(got)
+    out[order] = got
+    return out
+
+
+class RowShard:
+    """Fit on a row-sharded sample: every rank keeps only the
+    sample rows it owns; a threshold -- a quantile over the WHOLE sample of one
+    iterated sum (fruits/sieving/segment.py:66-75) -- comes from a radix select
+    whose histograms are summed over the ranks between the passes
+    (``fb_order_stats_dist``).  All ranks end with the same thresholds; nothing
+    but histograms (a few kB per iterated sum) crosses NVLink."""
+
+    def __init__(self, positions: np.ndarray, n_sample: int, group=None) -> None:
+        self.positions = np.asarray(positions, dtype=np.int64)     # sample positions held here
+        self.n_sample = int(n_sample)                              # rows of the whole sample
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self._n_max = None
+
+    def n_local_max(self, dev) -> int:
+        """Largest local row count over the ranks: chunk sizes are derived from
+        it, so every rank runs the same number of chunks (and collectives)."""
+        if self._n_max is None:
+            t = torch.tensor([len(self.positions)], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._n_max = max(int(t.item()), 1)
+        return self._n_max
+
+    def local_rows_of(self, sel: np.ndarray) -> np.ndarray:
+        """Local row numbers of the sample positions ``sel`` held by this rank."""
+        idx = np.searchsorted(self.positions, sel)
+        idx = np.clip(idx, 0, max(len(self.positions) - 1, 0))
+        hit = (len(self.positions) > 0) & (self.positions[idx] == sel) if len(self.positions) else \
+            np.zeros(len(sel), dtype=bool)
+        return idx[hit]
+
+    # -- distributed order statistics -------------------------------------------
+    def _reduce(self, work: torch.Tensor, off: int, count: int, dtype, op) -> None:
+        width = 4 if dtype == torch.int32 else 8
+        region = work[off:off + count * width].view(dtype)
+        dist.all_reduce(region, op=op, group=self.group)
+
+    def quantile_multi(self, V: torch.Tensor, t: int, pairs: list, n_rows: int = None) -> dict:
+        """``sieving.abstract.quantile_multi`` over the rows of all ranks:
+        ``V[P, n_local * t]`` holds this rank's rows of every problem."""
+        import ctypes
+
+        from . import _backend as be
+        from .sieving.abstract import _lerp, _virtual_index
+        V = V.contiguous()
+        P, m_local = V.shape
+        M = (self.n_sample if n_rows is None else n_rows) * t
+        out = {}
+        L = be.lib()
+        for g in range(0, len(pairs), 4):
+            grp = pairs[g:g + 4]
+            S = len(grp)
+            kg = [_virtual_index(M, q) for _, q in grp]
+            incs = (ctypes.c_int32 * S)(*[int(i) for i, _ in grp])
+            ks = (ctypes.c_int64 * S)(*[int(k) for k, _ in kg])
+            lay = (ctypes.c_int64 * 5)()
+            be.check(L.fb_order_stats_dist_layout(P, S, lay))
+            work = torch.zeros((lay[4],), dtype=torch.uint8, device=V.device)
+            lo, hi = be.empty((P, S)), be.empty((P, S))
+            done = be.empty((P, S), dtype=torch.int32)
+            ns = P * S
+            for phase in range(10):
+                be.check(L.fb_order_stats_dist(phase, V.data_ptr(), m_local, P, m_local, M, int(t),
+                                               S, incs, ks, lo.data_ptr(), hi.data_ptr(),
+                                               done.data_ptr(), work.data_ptr(), be.stream_ptr()))
+                if phase in (0, 1):
+                    self._reduce(work, lay[0], ns * 4096, torch.int32, dist.ReduceOp.SUM)
+                elif phase in (2, 8):
+                    self._reduce(work, lay[2], ns * 2, torch.int64, dist.ReduceOp.SUM)
+                    self._reduce(work, lay[3], ns * 2, torch.int64, dist.ReduceOp.MIN)
+                elif 3 <= phase <= 7:
+                    self._reduce(work, lay[1], ns * 256, torch.int32, dist.ReduceOp.SUM)
+            packed = torch.cat([lo, hi, done.to(torch.float64)], dim=1).cpu().numpy()
+            for s, (pair, (k, gamma)) in enumerate(zip(grp, kg)):
+                if not packed[:, 2 * S + s].all():
+                    out[pair] = None
+                    continue
+                a = packed[:, s]
+                b = packed[:, S + s] if k < M - 1 else a
+                out[pair] = _lerp(a, b, gamma)
+        return out
+
+    def quantile_rows(self, V: torch.Tensor, q: float, m_global: int) -> np.ndarray:
+        """``sieving.abstract.quantile_rows`` over the values of all ranks:
+        ``V[P, m_local]`` = this rank's values of every problem."""
+        import ctypes
+
+        from . import _backend as be
+        from .sieving.abstract import _lerp, _virtual_index
+        V = V.contiguous()
+        P, m_local = V.shape
+        k, gamma = _virtual_index(m_global, q)
+        L = be.lib()
+        lay = (ctypes.c_int64 * 4)()
+        be.check(L.fb_order_stats_dist8_layout(P, lay))
+        work = torch.zeros((lay[3],), dtype=torch.uint8, device=V.device)
+        lo, hi = be.empty((P,)), be.empty((P,))
+        for phase in range(10):
+            be.check(L.fb_order_stats_dist8(phase, V.data_ptr(), m_local, P, m_local, m_global,
+                                            int(k), lo.data_ptr(), hi.data_ptr(), work.data_ptr(),
+                                            be.stream_ptr()))
+            if phase <= 7:
+                self._reduce(work, lay[0], P * 256, torch.int32, dist.ReduceOp.SUM)
+            elif phase == 8:
+                self._reduce(work, lay[1], P * 2, torch.int64, dist.ReduceOp.SUM)
+                self._reduce(work, lay[2], P, torch.int64, dist.ReduceOp.MIN)
+        a = lo.cpu().numpy()
+        b = hi.cpu().numpy() if k < m_global - 1 else a
+        return _lerp(a, b, gamma)
+
+
+def _draw_sample_positions(n_total: int, fit_sample_size) -> np.ndarray:
+    """The draw of ``FruitSlice._select_fit_sample`` (fruits/fruit.py:430-438)."""
+    if isinstance(fit_sample_size, int) and fit_sample_size == 1:
+        return np.array([np.random.randint(0, n_total)], dtype=np.int64)
+    s = max(int(fit_sample_size * n_total), 1)
+    return np.random.choice(n_total, size=s, replace=False).astype(np.int64)
+
+
+def _rows_ok(slc) -> bool:
+    """Can this slice be fitted on a row-sharded sample?  Needs: preparateurs
+    whose fit looks at one series at a time, one ISS, sieves whose fit is a
+    quantile (SegmentSieve family, PPV) or nothing."""
+    from .sieving.implicit import PPV
+    from .sieving.segment import SegmentSieve
+    if len(slc.get_iss()) != 1:
+        return False
+    if not all(p._row_independent_fit() for p in slc.get_preparateurs()):
+        return False
+    for sv in slc.get_sieves():
+        if sv.requires_fitting and not isinstance(sv, (SegmentSieve, PPV)):
+            return False
+    return True
+
+
 def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, group=None,
-                shard_nodes: bool = True) -> None:
-    """``Fruit.fit`` on a row-sharded batch.  The fit sample is gathered on
-    every rank (quantiles are global over the sample, fruits/sieving/segment.py:66-75);
-    with ``shard_nodes`` the iterated sums of a slice are split over the ranks
-    -- each rank selects the thresholds of its share through the whole sample
-    and the fitted sieves are exchanged -- otherwise every rank fits everything.
-    Either way the thresholds are bit-identical on all ranks and equal to a
-    single-GPU fit."""
+                shard_nodes: bool = True, shard: str = "auto") -> None:
+    """``Fruit.fit`` on a row-sharded batch; thresholds are bit-identical on
+    all ranks and equal to a single-GPU fit of the whole batch.
+
+    ``shard="rows"`` (the default wherever a slice allows it, ``_rows_ok``): the
+    fit sample STAYS sharded -- every rank keeps the sampled rows it owns,
+    materialises their iterated sums and the quantiles come from a radix select
+    whose histograms are all-reduced (:class:`RowShard`).  No rank ever holds
+    more than its share of the sample, slices whose sieves need no fitting touch
+    no sample at all, and L1 / L2 weightings get the rows of the raw-input cache
+    they need from their owners (reference quirk: fruits/cache.py:97-112).
+
+    ``shard="nodes"``: the sample is gathered on every rank and the iterated
+    sums are split over the ranks (``shard_nodes``), fitted sieves exchanged."""
     from . import _backend as be
     from .cache import SharedSeedCache
     if n_total is None:
@@ -97,16 +266,26 @@ def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, gro
         dist.all_reduce(sizes, group=group)
         n_total = int(sizes.item())
     sync_numpy_rng(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_rows(n_total, world, rank)
+    if hi - lo != X_local.shape[0]:
+        raise ValueError(f"rank {rank} must hold the rows [{lo}, {hi}) of the batch "
+                         f"(shard_rows), got {X_local.shape[0]} rows")
     for slc in fruit:
+        rows_mode = shard in ("auto", "rows") and X_local.is_cuda and _rows_ok(slc)
+        if shard == "rows" and not rows_mode:
+            raise NotImplementedError("this slice cannot be fitted on a row-sharded sample")
+        if rows_mode:
+            _fit_slice_rows(slc, X_local, n_total, lo, hi, group)
+            continue
         for iss in slc.get_iss():
             w = iss.weighting
             if w is not None and not getattr(w, "_on_prepared", True) and any(
                     s.requires_fitting for s in slc.get_sieves()):
                 raise NotImplementedError(
-                    "sharded fit of sieves on L1/L2-weighted sums needs the raw-input cache "
+                    "node-sharded fit of sieves on L1/L2-weighted sums needs the raw-input cache "
                     "of the whole batch (reference quirk: fruits/cache.py:97-112)")
         sample = gather_fit_sample(X_local, n_total, slc.fit_sample_size, group)
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
 
         def exchange(copies):
             parts = [None] * world
@@ -126,6 +305,52 @@ def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, gro
             del slc._select_fit_sample
             slc.__dict__.pop("_fit_shard", None)
     fruit._fitted = True
+
+
+class _ShardedCache:
+    """``SharedSeedCache`` of a row-sharded batch, seen from the fit sample: the
+    reference builds the cache on the WHOLE batch and reads row ``j`` of it for
+    sample position ``j`` (fruits/cache.py:97-112), whoever owns that row."""
+
+    def __init__(self, X_local, n_total, positions, group) -> None:
+        from .cache import SharedSeedCache
+        self._local = SharedSeedCache(X_local)
+        self._n_total, self._positions, self._group = n_total, positions, group
+        self._memo = {}
+
+    def get_device(self, cache_id, key, X=None):
+        k = (cache_id, key)
+        if k not in self._memo:
+            mine = self._local.get_device(cache_id, key)            # rows of this rank
+            self._memo[k] = exchange_rows(mine, self._n_total, self._positions, self._group)
+        return self._memo[k]
+
+    def get(self, cache_id, key, X=None):
+        return self.get_device(cache_id, key, X).cpu().numpy()
+
+
+def _fit_slice_rows(slc, X_local, n_total, lo, hi, group) -> None:
+    """One slice on a row-sharded sample (see ``fit_sharded``)."""
+    idx = _draw_sample_positions(n_total, slc.fit_sample_size)      # same draw on every rank
+    mine = np.nonzero((idx >= lo) & (idx < hi))[0]                  # sample positions held here
+    needs_rows = (any(sv.requires_fitting for sv in slc.get_sieves())
+                  or any(p.requires_fitting for p in slc.get_preparateurs()))
+    if needs_rows:
+        rows = torch.as_tensor(idx[mine] - lo, device=X_local.device, dtype=torch.long)
+        sample = X_local.index_select(0, rows)
+    else:
+        # nothing to fit (e.g. experiments/fruit_twi.py): the draw above keeps the RNG in
+        # step with the reference, the sample itself is never looked at
+        sample, mine = X_local[:1], mine[:1]
+    rs = RowShard(mine, len(idx), group)
+    cache = _ShardedCache(X_local, n_total, mine, group)
+    try:
+        slc._select_fit_sample = lambda X: X
+        slc._row_shard = rs
+        slc._fit_device(sample, cache)
+    finally:
+        del slc._select_fit_sample
+        slc.__dict__.pop("_row_shard", None)
 
 
 class PeerGather:

@@ -18,3 +18,8 @@ class Preparateur(Seed, ABC):
         """Per-dimension description ``[(source_dim, inc, std), ...]`` if the
         ISS kernel can apply this preparateur while loading X, else None."""
         return None
+
+    def _row_independent_fit(self) -> bool:
+        """True if ``fit`` looks at one series at a time (or at nothing), so a
+        row-sharded fit sample needs no exchange (``parallel.fit_sharded``)."""
+        return True

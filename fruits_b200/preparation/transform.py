@@ -128,6 +128,9 @@ class STD(Preparateur):
     def _fusable(self):
         return "std" if self._separately else None
 
+    def _row_independent_fit(self) -> bool:
+        return bool(self._separately)      # else: one mean / std over the whole sample
+
     def _copy(self) -> "STD":
         # like the reference (transform.py:146-147) the copy drops std_eps
         return STD(self._separately, self._div_std)

@@ -28,6 +28,9 @@ class _Carrier(Preparateur):
             self._preparateur._cache = self._cache
         return self._preparateur
 
+    def _row_independent_fit(self) -> bool:
+        return self._preparateur is None or self._preparateur._row_independent_fit()
+
 
 class DIM(_Carrier):
     """The untouched dimensions first, then ``preparateur`` applied to the

@@ -371,6 +371,31 @@ FB_API int fb_order_stats_multi(const double *V, int64_t ldp, int64_t P, int64_t
                                 int n_sel, const int32_t *inc, const int64_t *k, double *lo,
                                 double *hi, int32_t *done, void *work, void *stream);
 
+/* -- row-sharded fit: the thresholds are quantiles over the whole
+ * fit sample (fruits/sieving/segment.py:66-75) while every rank holds a share of
+ * its rows.  The selections run in phases over the LOCAL rows; between the phases
+ * the host sums (MINs) small regions of the workspace over the ranks, so all
+ * ranks walk the same radix buckets and end with the same order statistics:
+ *   fb_order_stats_dist   three reads of the local data (12 + 12 bits) and five
+ *                         8-bit passes over the local candidate lists, phases 0..9;
+ *                         layout = byte offsets of {hist u32[P*n_sel*4096] (SUM after
+ *                         phases 0, 1), h256 u32[P*n_sel*256] (SUM after 3..7), sums
+ *                         i64[P*n_sel*2] (SUM after 2, 8), mins i64[P*n_sel*2] (MIN after
+ *                         2, 8)}, workspace bytes
+ *   fb_order_stats_dist8  eight 8-bit passes over materialised local values, phases
+ *                         0..9; layout = {hist u32[P*256] (SUM after 0..7), sums
+ *                         i64[P*2] (SUM after 8), mins i64[P] (MIN after 8)}, bytes.
+ * k is the rank among the m_global values of all ranks (< 2^31). */
+FB_API int fb_order_stats_dist_layout(int64_t P, int n_sel, int64_t *layout);
+FB_API int fb_order_stats_dist(int phase, const double *V, int64_t ldp, int64_t P,
+                               int64_t m_local, int64_t m_global, int64_t t, int n_sel,
+                               const int32_t *inc, const int64_t *k, double *lo, double *hi,
+                               int32_t *done, void *work, void *stream);
+FB_API int fb_order_stats_dist8_layout(int64_t P, int64_t *layout);
+FB_API int fb_order_stats_dist8(int phase, const double *V, int64_t ldp, int64_t P,
+                                int64_t m_local, int64_t m_global, int64_t k, double *lo,
+                                double *hi, void *work, void *stream);
+
 /* -- measurement -- */
 /* fp64 FMA microbenchmark (grid x 256 threads x iters*64 DFMA each; out holds
  * grid*256 doubles): the measured fp64 roof bench.py reports against. */

@@ -69,6 +69,11 @@ def _worker(rank, world, port, n_total, q):
         ok = ok and torch.equal(feats, X[:, 0, :3] * 10 + 1)
         feats1 = transform_sharded(compute, Xl, 3, chunks=1)
         ok = ok and torch.equal(feats1, feats)
+        # rows of a row-sharded tensor, requested by global row number (any order, repeats)
+        from fruits_b200.parallel import exchange_rows
+        need = [n_total - 1, 0, 3, 3, lo] if rank == 0 else [1, hi - 1]
+        got = exchange_rows(Xl, n_total, need)
+        ok = ok and torch.equal(bits(got), bits(X[need]))
         # uneven shards are refused on every rank instead of hanging or mis-placing rows
         try:
             transform_sharded(compute, Xl[:S - rank], 3, chunks=1)

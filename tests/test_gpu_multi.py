@@ -21,7 +21,34 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, mode, q):
+def _run_guarded(fn, rank, *args):
+    """Report an exception of one rank through the queue instead of leaving the
+    other rank waiting in a collective until the test times out."""
+    import traceback
+    q = args[-1]
+    try:
+        fn(rank, *args)
+    except BaseException:          # noqa: BLE001
+        q.put((rank, "error", traceback.format_exc()))
+        os._exit(1)
+
+
+def _collect(procs, q, n):
+    results = []
+    for _ in range(n):
+        r = q.get(timeout=300)
+        if len(r) > 1 and isinstance(r[1], str) and r[1] == "error":
+            for p in procs:
+                p.kill()
+            pytest.fail(f"rank {r[0]} raised:\n{r[2]}")
+        results.append(r)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return results
+
+
+def _worker_(rank, world, port, mode, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -70,6 +97,10 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
+def _worker(rank, world, port, mode, q):
+    _run_guarded(_worker_, rank, world, port, mode, q)
+
+
 @pytest.mark.parametrize("mode", ["multicast", "peer", "nccl"])
 def test_two_gpu_sharded_transform(mode):
     if torch.cuda.device_count() < 2:
@@ -80,10 +111,7 @@ def test_two_gpu_sharded_transform(mode):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    results = _collect(procs, q, len(procs))
     if any(same is None for _, same, _ in results):
         pytest.skip("no NVSwitch multicast support on this box")
     for rank, same, shape in results:
@@ -91,7 +119,7 @@ def test_two_gpu_sharded_transform(mode):
         assert same, f"rank {rank}: assembled matrix differs from the single-GPU transform"
 
 
-def _fit_worker(rank, world, port, q):
+def _fit_worker_(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -109,31 +137,65 @@ def _fit_worker(rank, world, port, q):
                                  "semiring": "arctic"}],
                         "sieves": [["MAX", {"q": [-1.0, 0.5]}], ["NPI", {"q": [0.5, 1.0]}]],
                         "fit_sample_size": 1.0}]}
+    # the reference's cache quirk (fruits/cache.py:97-112): L1 weighting on the raw
+    # input + fitted sieves + a subsample; an arctic chain whose increments are mostly
+    # 0 (the eight-pass fallback of the select); a one-series sample (one rank empty)
+    spec["slices"] += [
+        {"preps": [["INC", {}]],
+         "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended", "weighting": ["L1", {}]}],
+         "sieves": [["NPI", {"q": [0.4, 1.0]}], ["MPI", {"q": [0.1, 0.9], "inc": 0}], ["END", {}]],
+         "fit_sample_size": 0.5},
+        {"iss": [{"words": {"alternate_sign": [6 * "[1]", 3 * "[1][2]"]}, "mode": "extended",
+                  "semiring": "arctic"}],
+         "sieves": [["NPI", {"q": [0.5, 1.0], "inc": i}] for i in range(3)] + [["END", {}]],
+         "fit_sample_size": 1.0},
+        {"iss": [{"words": ["[1]", "[12]"], "mode": "extended"}],
+         "sieves": [["NPI", {"q": [0.5, 1.0]}], ["PPV", {}]], "fit_sample_size": 1},
+        {"iss": [{"words": ["[1][1]"]}], "sieves": [["NPI", {}], ["END", {}]],
+         "fit_sample_size": 1.0}]
     n = 301
     X = np.random.default_rng(8).standard_normal((n, 2, 120)).cumsum(axis=2)
     lo, hi = shard_rows(n, world, rank)
     Xl = torch.from_numpy(X[lo:hi]).to(dev)
-    np.random.seed(40 + rank)                # different states: rank 0's is broadcast
-    if rank == 0:
-        np.random.seed(40)
-    fruit = specs.build_fruit(fruits, spec)
-    fit_sharded(fruit, Xl, n)
-    after = np.random.random()
     single = specs.build_fruit(fruits, spec)
     np.random.seed(40)
     single.fit(torch.from_numpy(X).to(dev))
     after_single = np.random.random()
-    same = bool(np.array_equal(fitted_thresholds(fruit), fitted_thresholds(single)))
-    feats = bool(torch.equal(fruit.transform_device(Xl), single.transform_device(Xl)))
-    q.put((rank, same, feats, after == after_single, len(fitted_thresholds(fruit))))
+    ok_thr = ok_feats = ok_rng = True
+    n_thr = 0
+    for mode in ("rows", "nodes"):
+        np.random.seed(40 + rank)                # different states: rank 0's is broadcast
+        if rank == 0:
+            np.random.seed(40)
+        sp = spec if mode == "rows" else {"slices": spec["slices"][:2] + spec["slices"][3:]}
+        fruit = specs.build_fruit(fruits, sp)
+        fit_sharded(fruit, Xl, n, shard="auto" if mode == "rows" else "nodes")
+        after = np.random.random()
+        if mode == "rows":
+            ref, ref_after = single, after_single
+        else:                                    # (node mode refuses the L1 quirk slice)
+            ref = specs.build_fruit(fruits, sp)
+            np.random.seed(40)
+            ref.fit(torch.from_numpy(X).to(dev))
+            ref_after = np.random.random()
+        ok_thr &= bool(np.array_equal(fitted_thresholds(fruit), fitted_thresholds(ref)))
+        ok_feats &= bool(torch.equal(fruit.transform_device(Xl), ref.transform_device(Xl)))
+        ok_rng &= after == ref_after
+        n_thr += len(fitted_thresholds(fruit))
+    q.put((rank, ok_thr, ok_feats, ok_rng, n_thr))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_gpu_fit_splits_iterated_sums():
-    """fit_sharded: each rank fits its share of the iterated sums on the whole
-    gathered sample; thresholds, features and the consumption of the global
-    numpy RNG equal a single-GPU fit of the whole batch."""
+def _fit_worker(rank, world, port, q):
+    _run_guarded(_fit_worker_, rank, world, port, q)
+
+
+def test_two_gpu_fit_sharded():
+    """fit_sharded, row mode (the sample stays sharded, the selections sum their
+    histograms over the ranks) and node mode (the sample is gathered, each rank
+    fits its share of the iterated sums): thresholds, features and the
+    consumption of the global numpy RNG equal a single-GPU fit of the whole batch."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     ctx = mp.get_context("spawn")
@@ -142,10 +204,7 @@ def test_two_gpu_fit_splits_iterated_sums():
     procs = [ctx.Process(target=_fit_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    results = _collect(procs, q, len(procs))
     for rank, same, feats, rng_ok, n_thr in results:
         assert n_thr > 0
         assert same, f"rank {rank}: thresholds differ from the single-GPU fit"

@@ -1077,3 +1077,135 @@ def test_c2_full_size_against_the_reference(golden_dir):
     sha = [hashlib.sha256(np.ascontiguousarray(res[j, exact] + 0.0).tobytes()).hexdigest()[:16]
            for j in range(res.shape[0])]
     assert sha == [str(x) for x in g["row_sha_slice1"]]
+
+
+# ---------------------------------------------------------------------------
+# (l) row-sharded fit on one GPU: the phases of the distributed selection with
+# the ranks emulated one after the other (their workspaces reduced by hand), and
+# parallel.fit_sharded in a process group of one
+
+def _emulated_reduce(works, off, count, dtype, op):
+    width = 4 if dtype == torch.int32 else 8
+    regions = [w[off:off + count * width].view(dtype) for w in works]
+    total = torch.stack(regions).sum(0) if op == "sum" else torch.stack(regions).min(0).values
+    for r in regions:
+        r.copy_(total)
+
+
+@pytest.mark.parametrize("counts", [(700, 300, 0), (1, 0, 0), (512, 512, 513)])
+def test_row_sharded_selection_phases(counts):
+    """fb_order_stats_dist / fb_order_stats_dist8 with emulated ranks (one of them
+    without rows) equal np.quantile over the concatenated rows; ties and a
+    bucket of equal values larger than the candidate list included."""
+    import ctypes
+    from fruits_b200 import _backend as be
+    from fruits_b200.sieving.abstract import _lerp, _virtual_index
+    L = be.lib()
+    t, P = 64, 5
+    rng = np.random.default_rng(sum(counts))
+    n = sum(counts)
+    Y = rng.standard_normal((P, n, t)).cumsum(axis=2)
+    Y[1] = np.round(Y[1])                        # many ties
+    Y[2, :, 10:] = Y[2, :, 9:10]                 # increments mostly exactly 0
+    bounds = np.cumsum((0,) + counts)
+    shards = [torch.from_numpy(np.ascontiguousarray(Y[:, bounds[r]:bounds[r + 1]])).cuda()
+              .reshape(P, -1) for r in range(len(counts))]
+    M = n * t
+    pairs = [(0, 0.5), (1, 0.3), (2, 0.9), (1, 0.5)]
+    S = len(pairs)
+    kg = [_virtual_index(M, q) for _, q in pairs]
+    incs = (ctypes.c_int32 * S)(*[i for i, _ in pairs])
+    ks = (ctypes.c_int64 * S)(*[k for k, _ in kg])
+    lay = (ctypes.c_int64 * 5)()
+    be.check(L.fb_order_stats_dist_layout(P, S, lay))
+    works = [torch.zeros((lay[4],), dtype=torch.uint8, device="cuda") for _ in counts]
+    outs = [(be.empty((P, S)), be.empty((P, S)), be.empty((P, S), dtype=torch.int32)) for _ in counts]
+    ns = P * S
+    for phase in range(10):
+        for V, w, (lo, hi, done) in zip(shards, works, outs):
+            be.check(L.fb_order_stats_dist(phase, V.data_ptr() if V.numel() else 0, V.shape[1], P,
+                                           V.shape[1], M, t, S, incs, ks, lo.data_ptr(),
+                                           hi.data_ptr(), done.data_ptr(), w.data_ptr(),
+                                           be.stream_ptr()))
+        if phase in (0, 1):
+            _emulated_reduce(works, lay[0], ns * 4096, torch.int32, "sum")
+        elif phase in (2, 8):
+            _emulated_reduce(works, lay[2], ns * 2, torch.int64, "sum")
+            _emulated_reduce(works, lay[3], ns * 2, torch.int64, "min")
+        elif 3 <= phase <= 7:
+            _emulated_reduce(works, lay[1], ns * 256, torch.int32, "sum")
+
+    def increments(a, depth):
+        for _ in range(depth):
+            a = np.concatenate([np.zeros_like(a[..., :1]), np.diff(a, axis=-1)], axis=-1)
+        return a
+
+    lo0, hi0, done0 = (x.cpu().numpy() for x in outs[0])
+    for r in range(1, len(counts)):              # every rank ends with the same answer
+        for a, b in zip(outs[0], outs[r]):
+            assert_exact(a.cpu().numpy(), b.cpu().numpy(), "ranks disagree")
+    for s, ((inc, q), (k, gamma)) in enumerate(zip(pairs, kg)):
+        want = np.array([np.quantile(increments(Y[p], inc).ravel(), q) for p in range(P)])
+        got = _lerp(lo0[:, s], hi0[:, s] if k < M - 1 else lo0[:, s], gamma)
+        ok = done0[:, s].astype(bool)
+        assert_exact(got[ok], want[ok], f"dist select inc={inc} q={q}")
+        assert ok[0] and ok[3] and ok[4]         # (rows 1-2 may exceed the candidate list)
+    # the eight-pass form on materialised values
+    for inc, q in ((1, 0.5), (0, 0.25)):
+        vals = [torch.from_numpy(np.ascontiguousarray(
+            increments(Y[:, bounds[r]:bounds[r + 1]], inc))).cuda().reshape(P, -1)
+            for r in range(len(counts))]
+        k, gamma = _virtual_index(M, q)
+        lay8 = (ctypes.c_int64 * 4)()
+        be.check(L.fb_order_stats_dist8_layout(P, lay8))
+        works8 = [torch.zeros((lay8[3],), dtype=torch.uint8, device="cuda") for _ in counts]
+        outs8 = [(be.empty((P,)), be.empty((P,))) for _ in counts]
+        for phase in range(10):
+            for V, w, (lo, hi) in zip(vals, works8, outs8):
+                be.check(L.fb_order_stats_dist8(phase, V.data_ptr() if V.numel() else 0,
+                                                V.shape[1], P, V.shape[1], M, k, lo.data_ptr(),
+                                                hi.data_ptr(), w.data_ptr(), be.stream_ptr()))
+            if phase <= 7:
+                _emulated_reduce(works8, lay8[0], P * 256, torch.int32, "sum")
+            elif phase == 8:
+                _emulated_reduce(works8, lay8[1], P * 2, torch.int64, "sum")
+                _emulated_reduce(works8, lay8[2], P, torch.int64, "min")
+        a, b = outs8[0][0].cpu().numpy(), outs8[0][1].cpu().numpy()
+        want = np.array([np.quantile(increments(Y[p], inc).ravel(), q) for p in range(P)])
+        assert_exact(_lerp(a, b if k < M - 1 else a, gamma), want, f"dist8 inc={inc} q={q}")
+
+
+def test_fit_sharded_rows_in_a_group_of_one():
+    """parallel.fit_sharded(shard="rows") with world size 1: the whole row-sharded
+    path (sample positions, sharded raw-input cache, phased selections) on one
+    GPU equals ``Fruit.fit``."""
+    import torch.distributed as dist
+    from fruits_b200.parallel import fit_sharded
+    spec = {"slices": [
+        {"preps": [["INC", {}]],
+         "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended", "weighting": ["L1", {}]}],
+         "sieves": [["NPI", {"q": [0.4, 1.0]}], ["MPI", {"q": [0.1, 0.9], "inc": 0}],
+                    ["PPV", {"sample_size": 0.5}], ["END", {}]], "fit_sample_size": 0.5},
+        {"iss": [{"words": {"alternate_sign": [6 * "[1]", 3 * "[1][2]"]}, "mode": "extended",
+                  "semiring": "arctic"}],
+         "sieves": [["NPI", {"q": [0.5, 1.0], "inc": i}] for i in range(3)] + [["END", {}]],
+         "fit_sample_size": 1.0},
+        {"iss": [{"words": ["[1]", "[12]"], "mode": "extended"}],
+         "sieves": [["NPI", {"q": [0.5, 1.0]}], ["PPV", {}]], "fit_sample_size": 1}]}
+    X = torch.from_numpy(np.random.default_rng(8).standard_normal((301, 2, 120)).cumsum(axis=2)).cuda()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        fruit = specs.build_fruit(fruits, spec)
+        np.random.seed(40)
+        fit_sharded(fruit, X, shard="rows")
+        after = np.random.random()
+    finally:
+        dist.destroy_process_group()
+    single = specs.build_fruit(fruits, spec)
+    np.random.seed(40)
+    single.fit(X)
+    assert after == np.random.random()
+    assert_exact(fitted_thresholds(fruit), fitted_thresholds(single), "row-sharded fit thresholds")
+    assert torch.equal(fruit.transform_device(X), single.transform_device(X))
