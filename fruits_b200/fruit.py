@@ -587,10 +587,15 @@ class FruitSlice:
                             sv._draw(n_all)
 
         def qmulti(V, pairs):
-            return quantile_multi(V, t, pairs) if rs is None else rs.quantile_multi(V, t, pairs)
+            if rs is None:
+                return quantile_multi(V, t, pairs)
+            # (a rank without sample rows carries one placeholder row: zero values here)
+            return rs.quantile_multi(V if rs.n_local else V[:, :0], t, pairs)
 
         def qrows(V, q, rows_global):
-            return quantile_rows(V, q) if rs is None else rs.quantile_rows(V, q, rows_global * t)
+            if rs is None:
+                return quantile_rows(V, q)
+            return rs.quantile_rows(V if rs.n_local else V[:, :0], q, rows_global * t)
 
         skip_draws(0, first)
         local = []

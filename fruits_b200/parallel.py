@@ -121,6 +121,7 @@ class RowShard:
         self.n_sample = int(n_sample)                              # rows of the whole sample
         self.group = group
         self.world = dist.get_world_size(group)
+        self.n_local = len(self.positions)                         # (0: placeholder row only)
         self._n_max = None
 
     def n_local_max(self, dev) -> int:
@@ -335,15 +336,27 @@ def _fit_slice_rows(slc, X_local, n_total, lo, hi, group) -> None:
     mine = np.nonzero((idx >= lo) & (idx < hi))[0]                  # sample positions held here
     needs_rows = (any(sv.requires_fitting for sv in slc.get_sieves())
                   or any(p.requires_fitting for p in slc.get_preparateurs()))
-    if needs_rows:
-        rows = torch.as_tensor(idx[mine] - lo, device=X_local.device, dtype=torch.long)
-        sample = X_local.index_select(0, rows)
-    else:
+    cache_rows = mine
+    if not needs_rows:
         # nothing to fit (e.g. experiments/fruit_twi.py): the draw above keeps the RNG in
         # step with the reference, the sample itself is never looked at
         sample, mine = X_local[:1], mine[:1]
+        cache_rows = mine
+    elif len(mine):
+        rows = torch.as_tensor(idx[mine] - lo, device=X_local.device, dtype=torch.long)
+        sample = X_local.index_select(0, rows)
+    else:
+        # none of the sampled rows lives here (small samples): this rank still takes part
+        # in every collective, with a placeholder row that no selection looks at
+        sample = torch.ones((1,) + tuple(X_local.shape[1:]), dtype=X_local.dtype,
+                            device=X_local.device)
+        cache_rows = np.zeros(1, dtype=np.int64)
+    if sample.shape[0] == 0:
+        sample = torch.ones((1,) + tuple(X_local.shape[1:]), dtype=X_local.dtype,
+                            device=X_local.device)
+        cache_rows = np.zeros(1, dtype=np.int64)
     rs = RowShard(mine, len(idx), group)
-    cache = _ShardedCache(X_local, n_total, mine, group)
+    cache = _ShardedCache(X_local, n_total, cache_rows, group)
     try:
         slc._select_fit_sample = lambda X: X
         slc._row_shard = rs

@@ -30,6 +30,8 @@ def _run_guarded(fn, rank, *args):
         fn(rank, *args)
     except BaseException:          # noqa: BLE001
         q.put((rank, "error", traceback.format_exc()))
+        q.close()
+        q.join_thread()                # the feeder thread must flush before the process dies
         os._exit(1)
 
 
