@@ -1079,6 +1079,41 @@ def test_c2_full_size_against_the_reference(golden_dir):
     assert sha == [str(x) for x in g["row_sha_slice1"]]
 
 
+def test_c3_full_size_against_the_reference(golden_dir):
+    """experiments/fruit_general.py, all four slices, at BASELINE size
+    (10,000 x 6 x 1,024): all 40,334 thresholds of the reference's own full fit
+    (102 minutes of numba on 8 cores; 1,731 + 1,150 iterated sums, 10.2 M values
+    per quantile, the arctic slice with its buckets of equal increments through
+    the eight-pass fallback of the select) and the features of 16 sampled rows."""
+    g = np.load(os.path.join(golden_dir, "full_C3_full.npz"))
+    X = specs.make_input("C3_full")
+    assert X.shape == (10000, 6, 1024) and int(g["n"]) == 10000
+    fruit = specs.build_fruit(fruits, specs.SPECS["C3_full"])
+    np.random.seed(0)
+    fruit.fit(torch.from_numpy(X).cuda())
+    thr = fitted_thresholds(fruit)
+    tb = g["thr_slices"]
+    assert thr.shape == g["thresholds"].shape == (40334,)
+    assert_exact(thr[tb[1]:tb[2]], g["thresholds"][tb[1]:tb[2]], "C3 full arctic thresholds")
+    for si in range(4):
+        a, b = thr[tb[si]:tb[si + 1]], g["thresholds"][tb[si]:tb[si + 1]]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        rel = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)
+        record_report(f"C3_full thresholds slice {si}",
+                      {"thresholds": int(fin.sum()), "bit_identical": int((a[fin] == b[fin]).sum()),
+                       "max_rel_err": float(rel.max(initial=0.0))})
+    assert_close(thr, g["thresholds"], 1e-9, "C3 full thresholds")
+    rows = g["rows"]
+    res = fruit.transform(np.ascontiguousarray(X[rows]))
+    assert res.shape == g["features"].shape == (16, 20167)
+    fb = _slice_feature_bounds(fruit)
+    exact = np.array([c for c in range(fb[1], fb[2]) if (c - fb[1]) % 7 not in (3, 4, 5)])
+    assert_exact(res[:, exact], g["features"][:, exact], "C3 full arctic rows (counts, END)")
+    assert_close(res[:, fb[1]:fb[2]], g["features"][:, fb[1]:fb[2]], 1e-12, "C3 arctic MPI")
+    _assert_features_close(res, g["features"], "C3_full 16 rows vs reference")
+
+
 # ---------------------------------------------------------------------------
 # (l) row-sharded fit on one GPU: the phases of the distributed selection with
 # the ranks emulated one after the other (their workspaces reduced by hand), and
