@@ -253,62 +253,61 @@ class Fruit:
         return self.transform(X, callbacks=callbacks)
 
     def summary(self) -> str:
-        """Reference: fruit.py:186-213."""
-        summary = 80*"=" + "\n"
-        ident_string = "Fruit"
-        if self.name != "":
-            ident_string += f" {self.name!r}"
-        ident_string += f" -> Features: {self.nfeatures()}"
-        summary += "<" + f"{ident_string: ^78}" + ">\n"
-        summary += 80*"=" + "\n"
-        n = len(self._slices)
-        if n % 2 != 0:
-            n -= 1
-        for islc in range(0, n, 2):
-            summary += "|" + 38*"-" + "||" + 38*"-" + "|\n"
-            left = self._slices[islc].summary().split("\n")
-            right = self._slices[islc+1].summary().split("\n")
-            left += [38*" " for _ in range(len(right)-len(left))]
-            right += [38*" " for _ in range(len(left)-len(right))]
-            summary += "\n".join(f"|{l}||{r}|" for l, r in zip(left, right))
-            summary += "\n|" + 38*"-" + "||" + 38*"-" + "|\n"
-        if len(self._slices) % 2 != 0:
-            summary += "|" + 38*"-" + "|\n|"
-            summary += self._slices[-1].summary().replace("\n", "|\n|")
-            summary += "|\n|" + 38*"-" + "|\n"
-        summary += f"{'':=^80}"
-        return summary
+        """Text overview, two slices side by side (same layout as the
+        reference's ``Fruit.summary``, fruit.py:186-213: the golden vectors hold
+        its output for the BASELINE pipelines)."""
+        bar, gap = "=" * 80, "-" * 38
+        title = "Fruit" + (f" {self.name!r}" if self.name else "")
+        title += f" -> Features: {self.nfeatures()}"
+        lines = [bar, "<" + title.center(78) + ">", bar]
+        blocks = [slc.summary().split("\n") for slc in self._slices]
+        for left, right in zip(blocks[0::2], blocks[1::2]):
+            height = max(len(left), len(right))
+            left = left + [" " * 38] * (height - len(left))
+            right = right + [" " * 38] * (height - len(right))
+            lines.append(f"|{gap}||{gap}|")
+            lines += [f"|{a}||{b}|" for a, b in zip(left, right)]
+            lines.append(f"|{gap}||{gap}|")
+        if len(blocks) % 2:
+            lines.append(f"|{gap}|")
+            lines += [f"|{row}|" for row in blocks[-1]]
+            lines.append(f"|{gap}|")
+        lines.append(bar)
+        return "\n".join(lines)
+
+    def _clone(self, suffix: str, how: str) -> "Fruit":
+        twin = Fruit(self.name + suffix)
+        for slc in self._slices:
+            twin.cut(getattr(slc, how)())
+        return twin
 
     def copy(self) -> "Fruit":
-        copy_ = Fruit(self.name + " (Copy)")
-        for slc in self._slices:
-            copy_.cut(slc.copy())
-        return copy_
+        """New fruit over the same seed objects, unfitted (fruit.py:215-220)."""
+        return self._clone(" (Copy)", "copy")
 
     def deepcopy(self) -> "Fruit":
-        copy_ = Fruit(self.name + " (Deepcopy)")
-        for slc in self._slices:
-            copy_.cut(slc.deepcopy())
-        return copy_
+        """New fruit over copies of all seeds, unfitted (fruit.py:222-227)."""
+        return self._clone(" (Deepcopy)", "deepcopy")
 
     def label(self, index: int,
               level: Literal["prepared", "iterated sums", "features"] = "features",
               verbose: Literal[1, 2] = 1) -> str:
-        """Label of one feature / iterated sum / preparateur chain
-        (reference: fruit.py:229-261)."""
-        i = 0
-        while index >= 0:
+        """Label of one feature / iterated sum / preparateur chain, counted over
+        all slices (fruit.py:229-261)."""
+        def size(slc):
             if level == "prepared":
-                total = len(self.get_slice(i).get_preparateurs())
-            elif level == "iterated sums":
-                total = self.get_slice(i).niteratedsums()
-            elif level == "features":
-                total = self.get_slice(i).nfeatures()
-            if index < total:
-                return self.get_slice(i).label(index, level, verbose)
-            index -= total
-            i += 1
-        raise RuntimeError("Label index out of range")
+                return len(slc.get_preparateurs())
+            if level == "iterated sums":
+                return slc.niteratedsums()
+            return slc.nfeatures()
+
+        if index < 0:
+            raise RuntimeError("Label index out of range")
+        for slc in self._slices:
+            if index < size(slc):
+                return slc.label(index, level, verbose)
+            index -= size(slc)
+        raise IndexError("Label index out of range")
 
     def __len__(self) -> int:
         return len(self._slices)
@@ -987,96 +986,75 @@ class FruitSlice:
 
     # -- text ------------------------------------------------------------------------
     def summary(self) -> str:
-        """Reference: fruit.py:561-597."""
-        summary = f"{f'FruitSlice -> {self.nfeatures()}': ^38}"
-        summary += "\n" + 38*"-" + "\n"
-        summary += f"{f'Preparateurs ({len(self._preparateurs)}):': <38}"
-        summary += "\n"
-        summary += "\n".join(f"{f'    + {x}': <38}" for x in self._preparateurs)
-        if len(self._preparateurs) == 0:
-            summary += 38*" "
-        summary += "\n"
-        summary += f"{f'ISS Calculators ({len(self._iss)}):': <38}"
-        if len(self._iss) == 0:
-            summary += 38*" "
+        """Text block of 38 columns (layout of the reference, fruit.py:561-597)."""
+        def row(text=""):
+            return f"{text:<38}"
+
+        lines = [f"{f'FruitSlice -> {self.nfeatures()}':^38}", "-" * 38,
+                 row(f"Preparateurs ({len(self._preparateurs)}):")]
+        lines += [row(f"    + {prep}") for prep in self._preparateurs] or [row()]
+        lines.append(row(f"ISS Calculators ({len(self._iss)}):") + ("" if self._iss else row()))
         for iss in self._iss:
-            summary += f"\n{f'    + {iss} -> {iss.n_iterated_sums()}': <38}"
-            summary += f"\n{f'       | words: {len(iss.words)}': <38}"
-            semiring = iss.semiring.__class__.__name__
-            summary += f"\n{f'       | semiring: {semiring}': <38}"
-            weighting = "None" if iss.weighting is None else iss.weighting.__class__.__name__
-            summary += f"\n{f'       | weighting: {weighting}': <38}"
-        if len(self._iss) == 0:
-            summary += "\n"
-        summary += f"\n{f'Sieves ({len(self._sieves)}):': <38}"
-        if len(self._sieves) == 0:
-            summary += "\n" + 38*" "
-        for sv in self._sieves:
-            name = sv.__class__.__name__
-            summary += f"\n{f'    + {name} -> {sv.nfeatures()}': <38}"
-        return summary
+            weighting = "None" if iss.weighting is None else type(iss.weighting).__name__
+            lines += [row(f"    + {iss} -> {iss.n_iterated_sums()}"),
+                      row(f"       | words: {len(iss.words)}"),
+                      row(f"       | semiring: {type(iss.semiring).__name__}"),
+                      row(f"       | weighting: {weighting}")]
+        if not self._iss:
+            lines.append("")
+        lines.append(row(f"Sieves ({len(self._sieves)}):"))
+        lines += [row(f"    + {type(sv).__name__} -> {sv.nfeatures()}")
+                  for sv in self._sieves] or [row()]
+        return "\n".join(lines)
+
+    def _seeds(self) -> list:
+        return self._preparateurs + self._iss + self._sieves
 
     def copy(self) -> "FruitSlice":
-        """Shallow copy: same seed objects, no fitted state."""
-        copy_ = FruitSlice()
-        for preparateur in self._preparateurs:
-            copy_.add(preparateur)
-        for iss in self._iss:
-            copy_.add(iss)
-        for sieve in self._sieves:
-            copy_.add(sieve)
-        return copy_
+        """Same seed objects in a new, unfitted slice (fruit.py:599-609: the
+        reference's shallow copy does not carry ``fit_sample_size`` over)."""
+        twin = FruitSlice()
+        twin.add(*self._seeds())
+        return twin
 
     def deepcopy(self) -> "FruitSlice":
-        """Deep copy: copied seeds, no fitted state."""
-        copy_ = FruitSlice()
-        for preparateur in self._preparateurs:
-            copy_.add(preparateur.copy())
-        for iss in self._iss:
-            copy_.add(iss.copy())
-        for sieve in self._sieves:
-            copy_.add(sieve.copy())
-        copy_.fit_sample_size = self.fit_sample_size
-        return copy_
+        """Copies of all seeds in a new, unfitted slice (fruit.py:611-623)."""
+        twin = FruitSlice()
+        twin.add(*[seed.copy() for seed in self._seeds()])
+        twin.fit_sample_size = self.fit_sample_size
+        return twin
 
     def label(self, index: int,
               level: Literal["prepared", "iterated sums", "features"] = "features",
               verbose: Literal[1, 2] = 1) -> str:
-        """Reference: fruit.py:625-686."""
-        string = ""
+        """``preparateurs | words | sieve`` of one feature (fruit.py:625-686);
+        ``verbose=1`` drops the arguments of the preparateurs and the semiring /
+        weighting suffix of the words."""
+        def short(text, sep):
+            return text.split(sep)[0] if verbose == 1 else text
+
+        preps = [short(p.label(), "(") for p in self._preparateurs]
         if level == "prepared":
-            for i in range(index+1):
-                label = self._preparateurs[i].label()
-                if verbose == 1:
-                    label = label.split("(")[0]
-                string += f"{label} -> "
-            return "input" if string == "" else string[:-4]
-        for prep in self._preparateurs:
-            label = prep.label()
-            if verbose == 1:
-                label = label.split("(")[0]
-            string += f"{label} -> "
-        if string != "":
-            string = string[:-4] + " | "
-        findex = 0
-        if level == "features":
-            index, findex = map(int, divmod(
-                index, int(np.sum([s.nfeatures() for s in self._sieves]))))
-        n_i = self.niteratedsums()
-        for i in range(len(self.get_iss())):
-            word_index = int((index % n_i) // (n_i / self.get_iss()[i].n_iterated_sums()))
-            label = self.get_iss()[i].label(word_index)
-            if verbose == 1:
-                label = label.split(" : ")[0]
-            string += label + " -> "
-            n_i /= self.get_iss()[i].n_iterated_sums()
+            return " -> ".join(preps[:index + 1]) or "input"
+        parts = [" -> ".join(preps)] if preps else []
+        per_node = int(np.sum([sv.nfeatures() for sv in self._sieves]))
+        node, feat = divmod(index, per_node) if level == "features" else (index, 0)
+        # mixed radix over the ISS of the slice, first ISS most significant
+        # (fruits/fruit.py:440-454 iterates them nested in that order)
+        words, span = [], self.niteratedsums()
+        for iss in self._iss:
+            span //= iss.n_iterated_sums()
+            words.append(short(iss.label((node // span) % iss.n_iterated_sums()), " : "))
+        if words:
+            parts.append(" -> ".join(words))
         if level == "iterated sums":
-            return "input" if string == "" else string[:-4]
-        if string != "":
-            string = string[:-4] + " | "
-        for i in range(len(self._sieves)):
-            if findex < self._sieves[i].nfeatures():
-                string += self._sieves[i].label(findex)
-                return string
-            findex -= self._sieves[i].nfeatures()
-        raise RuntimeError("Feature index out of range")
+            if preps and not words:
+                # (no ISS in the slice: the reference cuts four characters off
+                # "<preparateurs> | ", fruit.py:671-672 -- kept for fidelity)
+                return (parts[0] + " | ")[:-4]
+            return " | ".join(parts) or "input"
+        for sv in self._sieves:
+            if feat < sv.nfeatures():
+                return " | ".join(parts + [sv.label(feat)])
+            feat -= sv.nfeatures()
+        raise IndexError("Feature index out of range")
