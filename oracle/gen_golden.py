@@ -265,6 +265,61 @@ def gen_pipelines(cases=None):
             summary=np.array(fruit.summary()))
 
 
+def gen_corbeille():
+    """Caller side of the path: two small datasets
+    in the UCR .txt layout (committed under tests/golden/ucr/), what the
+    REFERENCE's ``corbeille.data.load`` makes of them, and the features /
+    accuracy of the steps of ``corbeille.fruitify``
+    (experiments/corbeille/corbeille/fruitifier.py:50-72) run with the reference's
+    Fruit.  (fruitifier.py itself imports matplotlib through fruitalyser, which
+    this image lacks; data.py imports on its own.)"""
+    import importlib.util
+    print("[corbeille]")
+    spec_ = importlib.util.spec_from_file_location(
+        "ref_corbeille_data", os.path.join(REF, "experiments", "corbeille", "corbeille", "data.py"))
+    rdata = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(rdata)
+    root = os.path.join(GOLD, "ucr")
+    rng = np.random.default_rng(21)
+    for name, comma, nan in (("Delta", False, False), ("Eps", True, True)):
+        os.makedirs(os.path.join(root, name), exist_ok=True)
+        for split, n in (("TRAIN", 36), ("TEST", 24)):
+            y = rng.integers(1, 3, size=n)
+            X = (0.4 * rng.standard_normal((n, 48)).cumsum(axis=1)
+                 + (y[:, None] == 2) * 2.5 * np.sin(np.linspace(0, 3 * np.pi, 48)))
+            if nan:
+                X[0, 0] = np.nan
+                X[1, 5:8] = np.nan
+                X[2, -1] = np.nan
+            raw = np.concatenate([y[:, None].astype(float), np.round(X, 6)], axis=1)
+            np.savetxt(os.path.join(root, name, f"{name}_{split}.txt"), raw, fmt="%.6f",
+                       delimiter="," if comma else "  ")
+    out = {}
+    for name in ("Delta", "Eps"):
+        Xtr, ytr, Xte, yte = rdata.load(os.path.join(root, name))
+        out.update({f"{name}_X_train": Xtr, f"{name}_y_train": ytr, f"{name}_X_test": Xte,
+                    f"{name}_y_test": yte})
+        kept = rdata.load(os.path.join(root, name), keep_nan=True)[0]
+        out[f"{name}_X_train_keep_nan"] = kept
+        # the steps of fruitify with the reference's Fruit and default classifier
+        from sklearn.linear_model import RidgeClassifierCV
+        from sklearn.pipeline import Pipeline
+        from sklearn.preprocessing import FunctionTransformer, StandardScaler
+        fruit = specs.build_fruit(ref, specs.SPECS["C2_reduced"])
+        A, B = np.nan_to_num(Xtr), np.nan_to_num(Xte)
+        np.random.seed(0)
+        fruit.fit(A)
+        ftr, fte = fruit.transform(A), fruit.transform(B)
+        clf = Pipeline(steps=[("scaler", StandardScaler()),
+                              ("nantonum", FunctionTransformer(np.nan_to_num)),
+                              ("ridge", RidgeClassifierCV(alphas=np.logspace(-3, 3, 10)))])
+        clf.fit(ftr, ytr)
+        out[f"{name}_features_train"], out[f"{name}_features_test"] = ftr, fte
+        out[f"{name}_accuracy"] = np.array(clf.score(fte, yte))
+        print(f"  {name}: train {Xtr.shape}, test {Xte.shape}, accuracy {float(out[name + '_accuracy']):.3f}")
+    np.savez_compressed(os.path.join(GOLD, "corbeille.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["words", "iss", "sieves", "preps", "pipelines"]
     for w in which:

@@ -719,6 +719,40 @@ def test_corbeille_fruitify_on_ucr_layout(tmp_path):
     assert (tmp_path / "res.csv").exists()
 
 
+def test_corbeille_fruitify_equals_the_reference(golden_dir):
+    """``corbeille.fruitify`` on the committed UCR-layout datasets: the features it
+    classifies are ``Fruit.transform`` of the loaded arrays, they agree with the
+    features of the reference's Fruit on the same files (corbeille.npz), and the
+    default classifier reaches the reference's accuracy."""
+    import corbeille
+    g = np.load(os.path.join(golden_dir, "corbeille.npz"))
+    for name in ("Delta", "Eps"):
+        data = corbeille.data.load(os.path.join(golden_dir, "ucr", name))
+        seen = []
+
+        class Spy:                                     # a classifier that keeps what it is given
+            def __init__(self):
+                self.inner = corbeille.fruitifier._default_classifier()
+
+            def fit(self, F, y):
+                seen.append(F.copy())
+                self.inner.fit(F, y)
+
+            def score(self, F, y):
+                seen.append(F.copy())
+                return self.inner.score(F, y)
+
+        fruit = specs.build_fruit(fruits, specs.SPECS["C2_reduced"])
+        np.random.seed(0)
+        seconds, acc = corbeille.fruitify(data, fruit, classifier=Spy())
+        assert seconds > 0
+        assert_exact(seen[0], fruit.transform(np.nan_to_num(data[0])), "fruitify train features")
+        assert_exact(seen[1], fruit.transform(np.nan_to_num(data[2])), "fruitify test features")
+        _assert_features_close(seen[0], g[f"{name}_features_train"], f"corbeille {name} train")
+        _assert_features_close(seen[1], g[f"{name}_features_test"], f"corbeille {name} test")
+        assert abs(acc - float(g[f"{name}_accuracy"])) <= 1.0 / len(data[3]) + 1e-12
+
+
 @pytest.mark.parametrize("n", [40, 4100])          # generic kernel / generated kernel
 def test_degenerate_values_match_the_oracle(n):
     """Division by zero under negative exponents (inf, nan), overflow to +-inf,

@@ -313,3 +313,23 @@ def test_reference_experiment_scripts_build_unchanged(script, n_slices, n_featur
     spec.loader.exec_module(mod)
     assert isinstance(mod.fruit, fruits.Fruit)
     assert len(mod.fruit) == n_slices and mod.fruit.nfeatures() == n_features
+
+
+def test_corbeille_loader_equals_the_reference(golden_dir):
+    """tests/golden/ucr/* read by ``corbeille.data.load`` equals, bit for bit, what
+    the reference's loader returns for the same files (frozen in corbeille.npz by
+    oracle/gen_golden.py: labels, NaN forward fill, comma and blank separated)."""
+    import corbeille
+    g = np.load(os.path.join(golden_dir, "corbeille.npz"))
+    root = os.path.join(golden_dir, "ucr")
+    names = []
+    for name, Xtr, ytr, Xte, yte in corbeille.data.load_all(root):
+        names.append(name)
+        for got, key in ((Xtr, "X_train"), (ytr, "y_train"), (Xte, "X_test"), (yte, "y_test")):
+            want = g[f"{name}_{key}"]
+            assert got.shape == want.shape and got.dtype == want.dtype, (name, key)
+            assert np.array_equal(got, want), (name, key)
+        kept = corbeille.data.load(os.path.join(root, name), keep_nan=True)[0]
+        assert np.array_equal(kept, g[f"{name}_X_train_keep_nan"], equal_nan=True)
+    assert names == ["Delta", "Eps"]
+    assert np.isnan(g["Eps_X_train_keep_nan"]).sum() == 5
