@@ -36,7 +36,7 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 16            # bump to invalidate cached cubins
+JIT_VERSION = 17            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -705,8 +705,11 @@ class Emitter:
         nthr = max(1, len(p.trie.emits) * self.ntc)
         src = [self._common(), f"__constant__ double TH[{nthr}];"]
         for name in sorted({self.part_name(pi) for pi in range(len(p.parts))}):
-            src.append(f'extern "C" __device__ void {name}(const Args a);')
-        src.append(f'extern "C" __global__ void __launch_bounds__(NT, {minb}) fb_jit_slice(const Args a)')
+            src.append(f'extern "C" __device__ __attribute__((noreturn)) void {name}(const Args &a);')
+        src.append("// (the parts never return -- no callee-saved registers go to local memory -- and")
+        src.append("// read the kernel parameters in place: __grid_constant__ makes &a a device address)")
+        src.append(f'extern "C" __global__ void __launch_bounds__(NT, {minb}) '
+                   'fb_jit_slice(const __grid_constant__ Args a)')
         src.append("{")
         src.append("    // consecutive CTAs work on the same series with different parts: the")
         src.append("    // input tile is read from HBM once and hits L2 for the other parts")
@@ -782,7 +785,8 @@ class Emitter:
         A('    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
         A("__device__ __forceinline__ void cp8(double *dst, const double *src) {")
         A('    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
-        A(f'extern "C" __device__ __noinline__ void {self.part_name(pi)}(const Args a)')
+        A(f'extern "C" __device__ __noinline__ __attribute__((noreturn)) void '
+          f'{self.part_name(pi)}(const Args &a)')
         A("{")
         A("    extern __shared__ __align__(16) double smem[];")
         A("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
@@ -990,6 +994,11 @@ class Emitter:
             A("    } break;")
         A("    default: break;")
         A("    }")
+        A("    // the kernel has nothing left to do after its part: end the thread here, so")
+        A("    // that the compiler need not save / restore the caller's registers (measured:")
+        A("    // 208 B of local-memory stores and loads per thread, 0.6x the feature bytes)")
+        A('    asm volatile("exit;");')
+        A("    __builtin_unreachable();")
         A("}")
         del du
         return "\n".join(src) + "\n"
