@@ -1211,7 +1211,7 @@ def build_cubin(gen: Generated) -> bytes:
 class JitSlice:
     """The loaded plan-specialised kernel of one slice."""
 
-    _loaded: dict = {}     # source digest -> JitSlice
+    _loaded: dict = {}     # (source digest, device) -> JitSlice (a cudaLibrary belongs to a context)
 
     def __init__(self, gen: Generated) -> None:
         self.em = gen.em
@@ -1235,11 +1235,13 @@ class JitSlice:
     def load(cls, gen: Generated, cached_only: bool = False) -> "JitSlice":
         """The loaded kernel of ``gen``; with ``cached_only`` only if it is
         already in memory or compiled on disk (else ``NotCompiled``)."""
-        key = gen.digest()
+        import torch
+        digest = gen.digest()
+        key = (digest, torch.cuda.current_device() if torch.cuda.is_available() else -1)
         obj = cls._loaded.get(key)
         if obj is None:
-            if cached_only and not os.path.exists(os.path.join(CACHE_DIR, key + ".cubin")):
-                raise NotCompiled(key)
+            if cached_only and not os.path.exists(os.path.join(CACHE_DIR, digest + ".cubin")):
+                raise NotCompiled(digest)
             obj = cls(gen)
             cls._loaded[key] = obj
         return obj

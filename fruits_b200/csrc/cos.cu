@@ -244,11 +244,8 @@ static int coswiss_terms_launch(const CosParams &Q, cudaStream_t st)
     const size_t smem = sizeof(double) * ((size_t)Q.dw * COS_TT + (size_t)fpc * 2 * COS_TT +
                                           (size_t)fpc * Q.n_terms * (COS_TT + 1) + Q.n_terms);
     auto kern = coswiss_terms_kernel<P, EMAX>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    if (smem > 48 * 1024)        // per launch: the attribute belongs to the current device
         FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     dim3 grid((unsigned)Q.n, (unsigned)((Q.n_freq + fpc - 1) / fpc));
     kern<<<grid, threads, smem, st>>>(Q, fpc);
     FB_CUDA(cudaGetLastError());

@@ -626,11 +626,10 @@ int lns_launch(const LnsParams &p, cudaStream_t stream)
     size_t smem = (size_t)LNS_WARPS *
                   lns_warp_doubles(RMAX, p.du, p.na, WM != FB_WEIGHT_NONE,
                                    POL::MAT && RMAX <= 4 && p.mat_stage) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
+    // (per launch, not cached: the attribute belongs to the current device, and a
+    // process may drive several)
+    if (smem > 48 * 1024)
         FB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const long long tasks = p.n * p.n_blocks;
     if (tasks == 0) return 0;
     const long long grid = (tasks + LNS_WARPS - 1) / LNS_WARPS;

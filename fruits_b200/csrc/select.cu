@@ -724,14 +724,11 @@ int fb_order_stats_multi(const double *V, int64_t ldp, int64_t P, int64_t M, int
     const long long per_cta = (long long)SEL_THREADS * SEL_ITEMS;
     dim3 grid((unsigned)((M + per_cta - 1) / per_cta), (unsigned)P);
     const size_t smem = (size_t)n_sel * SEL2_BINS * sizeof(unsigned);
-    static bool configured = false;
-    if (!configured) {
-        FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
-        FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
-        configured = true;
-    }
+    // (per call: the attribute belongs to the current device)
+    FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
+    FB_CUDA(cudaFuncSetAttribute(sel2_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SEL2_MAXSEL * SEL2_BINS * (int)sizeof(unsigned)));
     sel2_hist_kernel<0><<<grid, SEL_THREADS, smem, st>>>(a, state, hist);
     sel2_scan_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(state, hist, ns, 52);
     sel2_hist_kernel<1><<<grid, SEL_THREADS, smem, st>>>(a, state, hist);

@@ -826,7 +826,8 @@ class FruitSlice:
         if mode != "0" and not n_shared and _jit_chain.suitable(trie, iss.semiring._code, wm):
             first = mode == "force" or _jit_chain.chain_like(trie)
             kinds = ["chain", "slice"] if first else ["slice", "chain"]
-        base_key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0)
+        base_key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0,
+                    X.device.index)        # (a loaded module belongs to one device)
         memo = getattr(iss, "_jit_memo", None)
         if memo is None or memo[0] is not trie:
             memo = (trie, {})

@@ -1,8 +1,9 @@
-"""Fruit.fit on N GPUs (iterated sums split over the ranks, parallel.fit_sharded)
-against the single-GPU fit of the same batch.
+"""Fruit.fit on N GPUs (parallel.fit_sharded: row mode -- the sample stays
+sharded, histograms are all-reduced -- and node mode -- the sample is gathered,
+the iterated sums are split) against the single-GPU fit of the same batch.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        scripts/fit_sharded_time.py C3_general
+        scripts/fit_sharded_time.py C3_full [rows|nodes]
 """
 import os
 import sys
@@ -23,6 +24,7 @@ from helpers import fitted_thresholds  # noqa: E402
 
 if __name__ == "__main__":
     name = sys.argv[1] if len(sys.argv) > 1 else "C3_general"
+    mode = sys.argv[2] if len(sys.argv) > 2 else "auto"
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -39,7 +41,8 @@ if __name__ == "__main__":
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fit_sharded(fruit, Xl, n)
+        torch.cuda.reset_peak_memory_stats()
+        fit_sharded(fruit, Xl, n, shard=mode)
         torch.cuda.synchronize()
         dist.barrier()
         times.append(time.perf_counter() - t0)
@@ -54,7 +57,8 @@ if __name__ == "__main__":
         torch.cuda.synchronize()
         t1 = time.perf_counter() - t0
         same = bool(np.array_equal(thr, fitted_thresholds(single), equal_nan=True))
-        print(f"{name}: fit on {world} GPUs {times[-1]:.3f} s (first call {times[0]:.3f} s), "
+        print(f"{name} [{mode}]: fit on {world} GPUs {times[-1]:.3f} s (first call {times[0]:.3f} s), "
+              f"peak device memory {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB, "
               f"single GPU {t1:.3f} s, {len(thr)} thresholds identical={same}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
