@@ -585,6 +585,18 @@ def run_ours(args):
         }
 
     # ---- end to end through the public API on pinned host buffers, ALL ranks at once ----
+    # (the pinned buffers are first touched by a thread bound to the CPUs next to
+    # this rank's GPU, so that the DMA does not cross the socket interconnect)
+    affinity = os.sched_getaffinity(0)
+    numa = "unbound"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        near = os.sched_getaffinity(0)
+        numa = f"{len(near)} of {len(affinity)} CPUs"
+    except Exception as exc:              # noqa: BLE001  (no NVML / not permitted: unbound)
+        numa = f"unbound ({type(exc).__name__})"
     E = min(args.e2e_series, S)
     while True:
         hx = hf = None
@@ -643,6 +655,8 @@ def run_ours(args):
                            "note": "plain numpy arrays in and out (host memcpy bound)"}
         del px, pf
     del hx, hf, hx_np, hf_np
+    e2e["host_affinity"] = numa
+    os.sched_setaffinity(0, affinity)
 
     if rank == 0 and world == 1:
         if not args.no_configs:
