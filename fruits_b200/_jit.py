@@ -36,7 +36,7 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 17            # bump to invalidate cached cubins
+JIT_VERSION = 19            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -271,7 +271,7 @@ class Emitter:
     """CUDA source of one slice program."""
 
     def __init__(self, prog: Program, dims: list, ppc: int, gpc: int, shared_extra: bool,
-                 tt: int = 8, n_shared_rows: int = 0, stage: int = 1) -> None:
+                 tt: int = 8, n_shared_rows: int = 0, stage: int = 1, abi: int = 3) -> None:
         """dims[u] = (raw_dim, inc) of used dimension u; ppc/gpc = parts and
         series groups per CTA; shared_extra: the weighting rows are the same
         for every series (Indices)."""
@@ -279,6 +279,7 @@ class Emitter:
         self.ppc, self.gpc = ppc, gpc
         self.tt = tt                 # time steps per shared-memory tile (even)
         self.stage = stage
+        self.abi = abi
         self.shared_extra = shared_extra
         self.sv = prog.sieves
         self.cols = self.sv.thr_cols()
@@ -690,6 +691,12 @@ class Emitter:
             i = j
         return L
 
+    def _noret(self) -> str:
+        return "__attribute__((noreturn)) " if self.abi >= 1 else ""
+
+    def _param(self) -> str:
+        return {0: "const Args a", 1: "const Args a", 2: "const Args &a", 3: "const Args &a_"}[self.abi]
+
     # -- whole kernel ------------------------------------------------------------
     def part_name(self, pi: int) -> str:
         # padding parts (the part count is rounded up to whole groups) share one
@@ -705,11 +712,11 @@ class Emitter:
         nthr = max(1, len(p.trie.emits) * self.ntc)
         src = [self._common(), f"__constant__ double TH[{nthr}];"]
         for name in sorted({self.part_name(pi) for pi in range(len(p.parts))}):
-            src.append(f'extern "C" __device__ __attribute__((noreturn)) void {name}(const Args &a);')
+            src.append(f'extern "C" __device__ {self._noret()}void {name}({self._param()});')
         src.append("// (the parts never return -- no callee-saved registers go to local memory -- and")
         src.append("// read the kernel parameters in place: __grid_constant__ makes &a a device address)")
         src.append(f'extern "C" __global__ void __launch_bounds__(NT, {minb}) '
-                   'fb_jit_slice(const __grid_constant__ Args a)')
+                   f'fb_jit_slice(const {"__grid_constant__ " if self.abi >= 2 else ""}Args a)')
         src.append("{")
         src.append("    // consecutive CTAs work on the same series with different parts: the")
         src.append("    // input tile is read from HBM once and hits L2 for the other parts")
@@ -785,9 +792,11 @@ class Emitter:
         A('    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
         A("__device__ __forceinline__ void cp8(double *dst, const double *src) {")
         A('    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }')
-        A(f'extern "C" __device__ __noinline__ __attribute__((noreturn)) void '
-          f'{self.part_name(pi)}(const Args &a)')
+        A(f'extern "C" __device__ __noinline__ {self._noret()}void '
+          f'{self.part_name(pi)}({self._param()})')
         A("{")
+        if self.abi == 3:
+            A("    const Args a = a_;      // into registers once: no reloads behind the cp.async fences")
         A("    extern __shared__ __align__(16) double smem[];")
         A("    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;")
         A("    const int part = 0;")
@@ -997,8 +1006,9 @@ class Emitter:
         A("    // the kernel has nothing left to do after its part: end the thread here, so")
         A("    // that the compiler need not save / restore the caller's registers (measured:")
         A("    // 208 B of local-memory stores and loads per thread, 0.6x the feature bytes)")
-        A('    asm volatile("exit;");')
-        A("    __builtin_unreachable();")
+        if self.abi >= 1:
+            A('    asm volatile("exit;");')
+            A("    __builtin_unreachable();")
         A("}")
         del du
         return "\n".join(src) + "\n"
@@ -1051,7 +1061,9 @@ class FbJitGeometry(ctypes.Structure):
 
 
 DEFAULT_OPTS = {"budget": 70, "ppc": 2, "gpc": 8, "minb": 1, "unroll": 2, "tt": 16,
-                "stage": 1}        # epilogue: features through shared memory, coalesced rows
+                "stage": 1,        # epilogue: features through shared memory, coalesced rows
+                "abi": 3}          # part functions: 0 by value + return, 1 by value + exit,
+                                   # 2 by reference + exit, 3 = 2 with a local copy of the struct
 
 
 def options() -> dict:
@@ -1103,7 +1115,9 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
             and "FRUITS_B200_JIT_OPTS" not in os.environ):
         # deep or sieve-heavy tries: fewer, larger parts (one CTA per SM, 255 registers);
         # measured on C4 slice 0 (depth 9, overhead 1.21 -> 1.08): 92 -> 71 ms
-        opts = dict(opts, budget=150, ppc=1, gpc=8, minb=1, unroll=1)      # 256 threads x 255 registers
+        # (256 threads x 255 registers; with every register in use the parts take their
+        # parameters by value: measured on C4 slice 0, abi 1 / 2 / 3 = 70.4 / 75.5 / 90.2 ms)
+        opts = dict(opts, budget=150, ppc=1, gpc=8, minb=1, unroll=1, abi=1)
         prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                        parts_multiple=opts["ppc"])
     # (plans without another fused route -- CosWISS -- may spill a few sums to local memory)
@@ -1116,7 +1130,7 @@ def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list
     for gpc, tt in ((opts["gpc"], opts["tt"]), (opts["gpc"], 8), (max(1, opts["gpc"] // 2), 8),
                     (max(1, opts["gpc"] // 4), 8), (1, 4), (1, 2)):
         cand = Emitter(prog, dims, opts["ppc"], gpc, shared_extra, tt, n_shared_rows,
-                       opts.get("stage", 1))
+                       opts.get("stage", 1), opts.get("abi", 3))
         if cand.smem_bytes() <= 200 * 1024:
             em = cand
             break
