@@ -19,11 +19,12 @@ FB_MAX_USED_DIMS = 7
 FB_RING = 256
 FB_MAX_ALPHAS = 4
 FB_MAX_FEATS = 16
-FB_NTHR = 12
+FB_NTHR = 16
 
 SEMIRING_REALS, SEMIRING_ARCTIC, SEMIRING_BAYESIAN = 0, 1, 2
 WEIGHT_NONE, WEIGHT_TOTAL, WEIGHT_NONTOTAL = 0, 1, 2
 FEAT_CNT, FEAT_AVG, FEAT_PPV, FEAT_MAX, FEAT_MIN, FEAT_END = range(6)
+FEAT_XPI, FEAT_LPI, FEAT_CUR, FEAT_CPV = range(6, 10)
 SIEVE_NPI, SIEVE_MPI, SIEVE_MAX, SIEVE_MIN, SIEVE_XPI, SIEVE_LPI, SIEVE_END, SIEVE_CUR = range(8)
 POLICY_MAT = 0
 

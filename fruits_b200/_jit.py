@@ -36,12 +36,13 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 19            # bump to invalidate cached cubins
+JIT_VERSION = 20            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
 _COL_U = {0: (0, 1), 1: (2, 3), 2: (4, 5)}
 _COL_PPV, _COL_MAX, _COL_MIN = 6, (8, 9), (10, 11)
+_COL_CPV, _COL_CUR = 7, (12, 13)
 
 
 # ---------------------------------------------------------------------------
@@ -59,24 +60,41 @@ class SieveSet:
     mn: bool = False
     hi: bool = False                # finite upper bounds possible
     mmb: bool = False               # MAX/MIN restricted to (lo, hi]
+    xpi: tuple = (False, False, False)     # mean index of the selected increments of a unit
+    lpi: tuple = (False, False, False)     # longest run of selected increments of a unit
+    cur: bool = False               # sum of the squared second increments in (lo, hi]
+    cpv: bool = False               # rising edges of (y >= threshold)
 
     @staticmethod
     def make(feats, bounded_hi, bounded_mm) -> "SieveSet":
-        cnt, avg = [False] * 3, [False] * 3
-        ppv = mx = mn = False
+        cnt, avg, xpi, lpi = [False] * 3, [False] * 3, [False] * 3, [False] * 3
+        ppv = mx = mn = cur = cpv = False
         for kind, arg in feats:
-            if kind in (be.FEAT_CNT, be.FEAT_AVG):
-                cnt[arg] = True
+            if kind in (be.FEAT_CNT, be.FEAT_AVG, be.FEAT_XPI, be.FEAT_LPI):
+                cnt[arg] = True                  # the unit (its predicate and count) is on
                 if kind == be.FEAT_AVG:
                     avg[arg] = True
+                elif kind == be.FEAT_XPI:
+                    xpi[arg] = True
+                elif kind == be.FEAT_LPI:
+                    lpi[arg] = True
             elif kind == be.FEAT_PPV:
                 ppv = True
             elif kind == be.FEAT_MAX:
                 mx = True
             elif kind == be.FEAT_MIN:
                 mn = True
+            elif kind == be.FEAT_CUR:
+                cur = True
+            elif kind == be.FEAT_CPV:
+                cpv = True
         return SieveSet(list(feats), tuple(cnt), tuple(avg), ppv, mx, mn,
-                        bool(bounded_hi), bool(bounded_mm))
+                        bool(bounded_hi), bool(bounded_mm), tuple(xpi), tuple(lpi), cur, cpv)
+
+    @property
+    def rank2(self) -> bool:
+        """Accumulators only the thread-per-series kernel knows."""
+        return any(self.xpi) or any(self.lpi) or self.cur or self.cpv
 
     def thr_cols(self) -> list:
         cols = []
@@ -91,6 +109,10 @@ class SieveSet:
             cols += list(_COL_MAX)
         if self.mn and self.mmb:
             cols += list(_COL_MIN)
+        if self.cpv:
+            cols.append(_COL_CPV)
+        if self.cur:
+            cols += list(_COL_CUR)
         return cols
 
     # registers (32-bit) of sieve state per emitted node
@@ -99,9 +121,10 @@ class SieveSet:
         ncnt = sum(self.cnt) + (1 if self.ppv else 0)
         r += (ncnt + 1) // 2
         r += 2 * sum(self.avg)
-        if self.cnt[2]:
+        if self.cnt[2] or self.cur:
             r += 2          # previous first increment
         r += 2 * (int(self.mx) + int(self.mn))
+        r += sum(self.xpi) + 2 * sum(self.lpi) + (2 if self.cur else 0) + (2 if self.cpv else 0)
         return r
 
     # rough issue slots per emitted node and step
@@ -119,6 +142,7 @@ class SieveSet:
         c += 3 * (int(self.mx) + int(self.mn))
         if self.mmb:
             c += 2 * (int(self.mx) + int(self.mn))
+        c += sum(self.xpi) + 3 * sum(self.lpi) + (6 if self.cur else 0) + (5 if self.cpv else 0)
         return c
 
 
@@ -535,34 +559,63 @@ class Emitter:
         cregs = self._cnt_layout()
 
         def unit(k, val):
+            """Accumulators of the increment unit ``k`` fed with ``val``: one
+            predicate ``lo < val [<= hi]``, then count (NPI), sum (MPI), sum of
+            the time indices (XPI), current / longest run (LPI)."""
             reg, hi16 = cregs[("U", k)]
             inc = "0x10000" if hi16 else "1"
-            outs = [f'"+r"(CN[{oi}][{reg}])']
-            if sv.avg[k]:
-                outs.append(f'"+d"(SM{k}[{oi}])')
-            iv = len(outs)                      # operand index of the value
-            ins = [f'"d"({val})', f'"d"({self.th(e, _COL_U[k][0])})']
-            asm = ["{ .reg .pred p;", f"setp.gt.f64 p, %{iv}, %{iv + 1};"]
+            outs = {"cn": f'"+r"(CN[{oi}][{reg}])'}
+            ins = {"v": f'"d"({val})', "lo": f'"d"({self.th(e, _COL_U[k][0])})'}
+            asm = ["{ .reg .pred p;", "setp.gt.f64 p, %v, %lo;"]
             if sv.hi:
-                ins.append(f'"d"({self.th(e, _COL_U[k][1])})')
-                asm.append(f"setp.le.and.f64 p, %{iv}, %{iv + 2}, p;")
-            asm.append(f"@p add.u32 %0, %0, {inc};")
+                ins["hi"] = f'"d"({self.th(e, _COL_U[k][1])})'
+                asm.append("setp.le.and.f64 p, %v, %hi, p;")
+            asm.append(f"@p add.u32 %cn, %cn, {inc};")
             if sv.avg[k]:
-                asm.append(f"@p add.rn.f64 %1, %1, %{iv};")
+                outs["sm"] = f'"+d"(SM{k}[{oi}])'
+                asm.append("@p add.rn.f64 %sm, %sm, %v;")
+            if sv.xpi[k]:
+                outs["xs"] = f'"+r"(XS{k}[{oi}])'
+                ins["tix"] = '"r"(tix)'
+                asm.append("@p add.u32 %xs, %xs, %tix;")
+            if sv.lpi[k]:
+                outs["lc"] = f'"+r"(LC{k}[{oi}])'
+                outs["ll"] = f'"+r"(LL{k}[{oi}])'
+                asm += ["@p add.u32 %lc, %lc, 1;", "@!p mov.u32 %lc, 0;", "max.u32 %ll, %ll, %lc;"]
             asm.append("}")
-            L.append('asm("' + " ".join(asm) + '" : ' + ", ".join(outs) + " : " + ", ".join(ins) + ");")
+            text = " ".join(asm)
+            # operands are numbered outputs first, then inputs (longest names first, so
+            # that %lo is not mistaken for a prefix of another placeholder)
+            names = list(outs) + list(ins)
+            for name in sorted(names, key=len, reverse=True):
+                text = text.replace("%" + name, "%" + str(names.index(name)))
+            L.append('asm("' + text + '" : ' + ", ".join(outs.values()) + " : "
+                     + ", ".join(ins.values()) + ");")
 
         if sv.cnt[0]:
             unit(0, out)
-        if sv.cnt[1] or sv.cnt[2]:
+        if sv.cnt[1] or sv.cnt[2] or sv.cur:
             # (the very first step sees prev = 0 / -inf instead of the zero
             # padding of the reference; fixup() repairs these units after it)
             L.append(f"const double d{v} = __dadd_rn({out}, -{prev});")
             if sv.cnt[1]:
                 unit(1, f"d{v}")
-            if sv.cnt[2]:
+            if sv.cnt[2] or sv.cur:
                 L.append(f"const double dd{v} = __dadd_rn(d{v}, -D1[{oi}]); D1[{oi}] = d{v};")
+            if sv.cnt[2]:
                 unit(2, f"dd{v}")
+            if sv.cur:
+                # CUR: sum of dd^2 over lo < dd <= hi (fruits/sieving/segment.py:246-258)
+                L.append('asm("{ .reg .pred p; .reg .f64 s; setp.gt.f64 p, %1, %2; '
+                         'setp.le.and.f64 p, %1, %3, p; fma.rn.f64 s, %1, %1, %0; '
+                         f'selp.f64 %0, s, %0, p; }}" : "+d"(SQ[{oi}]) : "d"(dd{v}), '
+                         f'"d"({self.th(e, _COL_CUR[0])}), "d"({self.th(e, _COL_CUR[1])}));')
+        if sv.cpv:
+            # CPV: rising edges of (y >= threshold); CPP = the indicator of the previous
+            # step, 1 before the first (the increments of the indicator are zero padded)
+            L.append('asm("{ .reg .pred p; .reg .u32 c, e; setp.ge.f64 p, %2, %3; selp.u32 c, 1, 0, p; '
+                     'not.b32 e, %1; and.b32 e, e, c; add.u32 %0, %0, e; mov.u32 %1, c; }" : '
+                     f'"+r"(CPC[{oi}]), "+r"(CPP[{oi}]) : "d"({out}), "d"({self.th(e, _COL_CPV)}));')
         if sv.ppv:
             reg, hi16 = cregs[("P", 0)]
             inc = "0x10000" if hi16 else "1"
@@ -601,8 +654,14 @@ class Emitter:
                 L.append(f"CN[{oi}][{reg}] = (CN[{oi}][{reg}] & {keep}) | (({cond}) ? {one} : 0u);")
                 if sv.avg[k]:
                     L.append(f"SM{k}[{oi}] = 0.0;")
-            if sv.cnt[2]:
+                if sv.xpi[k]:
+                    L.append(f"XS{k}[{oi}] = 0u;")           # index 0 adds nothing
+                if sv.lpi[k]:
+                    L.append(f"LC{k}[{oi}] = LL{k}[{oi}] = ({cond}) ? 1u : 0u;")
+            if sv.cnt[2] or sv.cur:
                 L.append(f"D1[{oi}] = 0.0;")
+            if sv.cur:
+                L.append(f"SQ[{oi}] = 0.0;")                  # the first second increment is 0
         return L
 
     def _cnt_layout(self):
@@ -643,6 +702,16 @@ class Emitter:
                     val = f"(MX[{oi}] == D_NINF ? 0.0 : MX[{oi}])"
                 elif kind == be.FEAT_MIN:
                     val = f"(MN[{oi}] == D_INF ? 0.0 : MN[{oi}])"
+                elif kind == be.FEAT_XPI:
+                    c = count(oi, ("U", arg))
+                    val = f"({c} ? __ddiv_rn((double)XS{arg}[{oi}], (double){c}) : 0.0)"
+                elif kind == be.FEAT_LPI:
+                    val = f"(double)LL{arg}[{oi}]"
+                elif kind == be.FEAT_CUR:
+                    val = f"SQ[{oi}]"
+                elif kind == be.FEAT_CPV:
+                    # 2 * edges / length rounded up to even (fruits/sieving/implicit.py:173-176)
+                    val = f"__ddiv_rn((double)(2u * CPC[{oi}]), (double)(T + (T & 1)))"
                 else:
                     val = endv
                 L.append((e * nf + f, f"fin({val}, a.sanitize & 1)"))
@@ -761,7 +830,7 @@ class Emitter:
         wm = p.weight_mode
         ns = max(1, max(len(pt.snodes) for pt in parts))
         no = max(1, max(len(pt.owned) for pt in parts))
-        need_first = sv.cnt[1] or sv.cnt[2]
+        need_first = sv.cnt[1] or sv.cnt[2] or sv.cur
         ncr = max(1, self.n_cnt_regs())
         nthr = max(1, len(p.trie.emits) * self.ntc)
         du = len(p.used)
@@ -816,12 +885,21 @@ class Emitter:
         for k in range(3):
             if sv.avg[k]:
                 A(f"    double SM{k}[{no}];")
-        if sv.cnt[2]:
+        if sv.cnt[2] or sv.cur:
             A(f"    double D1[{no}];")
         if sv.mx:
             A(f"    double MX[{no}];")
         if sv.mn:
             A(f"    double MN[{no}];")
+        for k in range(3):
+            if sv.xpi[k]:
+                A(f"    unsigned XS{k}[{no}];")
+            if sv.lpi[k]:
+                A(f"    unsigned LC{k}[{no}], LL{k}[{no}];")
+        if sv.cur:
+            A(f"    double SQ[{no}];")
+        if sv.cpv:
+            A(f"    unsigned CPC[{no}], CPP[{no}];")
         init = "0.0" if p.reals else "D_NINF"
         A("#pragma unroll")
         A(f"    for (int i = 0; i < {ns}; i++) {{ S[i] = {init};"
@@ -834,12 +912,21 @@ class Emitter:
         for k in range(3):
             if sv.avg[k]:
                 A(f"        SM{k}[i] = 0.0;")
-        if sv.cnt[2]:
+        if sv.cnt[2] or sv.cur:
             A("        D1[i] = 0.0;")
         if sv.mx:
             A("        MX[i] = D_NINF;")
         if sv.mn:
             A("        MN[i] = D_INF;")
+        for k in range(3):
+            if sv.xpi[k]:
+                A(f"        XS{k}[i] = 0u;")
+            if sv.lpi[k]:
+                A(f"        LC{k}[i] = 0u; LL{k}[i] = 0u;")
+        if sv.cur:
+            A("        SQ[i] = 0.0;")
+        if sv.cpv:
+            A("        CPC[i] = 0u; CPP[i] = 1u;")
         A("    }")
         # previous raw values of the dimensions that are read as increments
         inc_rows = sorted({self.row_of[d[0]] for d in self.dims if d is not None and d[1]})
@@ -957,6 +1044,7 @@ class Emitter:
             A("#pragma unroll 1")
             A("            for (; tt < stop; tt++) {")
             A("                const bool is0 = (t0 + tt) == 0;")
+            A("                const unsigned tix = (unsigned)(t0 + tt); (void)tix;")
             for ln in self._loads() + self.step(part) + self._after():
                 A("                " + ln)
             A("            }")

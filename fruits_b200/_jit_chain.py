@@ -543,6 +543,8 @@ def generate(trie, semiring: int, weight_mode: int, sieves, dims: list, opts: di
     if not suitable(trie, semiring, weight_mode):
         raise NotImplementedError("the chain kernel covers unweighted Arctic plans")
     opts = options() if opts is None else opts
+    if sieves.rank2:
+        raise NotImplementedError("XPI / LPI / CUR / CPV accumulators: thread-per-series kernel")
     if len(dims) > 200 or any(abs(e) > 127 for n in trie.nodes for e in n.expo):
         raise NotImplementedError("letter outside the chain kernel's tables")
     if trie.max_depth > 250:

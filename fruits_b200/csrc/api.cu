@@ -126,6 +126,7 @@ int fb_slice_policy(const fb_sieve_plan *sv, int bounded_hi, int bounded_mm)
         } else if (k == FB_FEAT_PPV) ppv = true;
         else if (k == FB_FEAT_MAX) mx = true;
         else if (k == FB_FEAT_MIN) mn = true;
+        else if (k >= FB_FEAT_XPI && k <= FB_FEAT_CPV) return FB_ENOSUP;   // generated kernels only
         else if (k != FB_FEAT_END) return FB_EINVAL;
     }
     if (bounded_hi || bounded_mm) return POL_G;

@@ -33,7 +33,8 @@ from .sieving.implicit import PPV
 from .sieving.segment import SegmentSieve
 
 _FEAT_CODE = {"CNT": be.FEAT_CNT, "AVG": be.FEAT_AVG, "PPV": be.FEAT_PPV,
-              "MAX": be.FEAT_MAX, "MIN": be.FEAT_MIN, "END": be.FEAT_END}
+              "MAX": be.FEAT_MAX, "MIN": be.FEAT_MIN, "END": be.FEAT_END,
+              "XPI": be.FEAT_XPI, "LPI": be.FEAT_LPI, "CUR": be.FEAT_CUR, "CPV": be.FEAT_CPV}
 
 
 class Fruit:
@@ -468,12 +469,14 @@ class FruitSlice:
             if f is None:
                 return None
             kind, arg = f
-            if kind in ("CNT", "AVG"):
-                key = ("U", arg)
+            if kind in ("CNT", "AVG", "XPI", "LPI"):
+                key = ("U", arg)             # one (lo, hi] interval per increment depth
                 bounded_hi |= (sv._q[1] != 1.0) or (sv._q[0] > sv._q[1])
             elif kind in ("MAX", "MIN"):
                 key = (kind, 0)
                 bounded_mm |= tuple(sv._q) != (-1.0, 1.0)
+            elif kind == "CUR":
+                key = ("CUR", 0)             # (several CUR / AVG / STD sieves share one interval)
             else:
                 key = None
             if key is not None:
@@ -482,8 +485,9 @@ class FruitSlice:
             feats.append((_FEAT_CODE[kind], arg))
         if len(feats) > be.FB_MAX_FEATS:
             return None
-        if sum(1 for s in self._sieves if isinstance(s, PPV)) > 1:
-            return None
+        for code in (be.FEAT_PPV, be.FEAT_CPV):          # one fitted threshold column each
+            if sum(1 for k, _ in feats if k == code) > 1:
+                return None
         return feats, bounded_hi, bounded_mm
 
     def _is_fusable(self, n_dims: int, callbacks, length: int = 0) -> bool:
@@ -704,22 +708,25 @@ class FruitSlice:
             return self._thr_memo[1]
         tab = np.zeros((n_emit, be.FB_NTHR))
         tab[:, 1::2] = np.inf
+        tab[:, 7] = 0.0
         tab[:, 8] = -np.inf
         tab[:, 10] = -np.inf
+        tab[:, 12] = -np.inf
         for e in range(n_emit):
             for sv in self._sieves_for(e):
                 kind, arg = sv._fused()
-                if kind == "PPV":
+                if kind in ("PPV", "CPV"):
                     if not hasattr(sv, "_q"):
-                        raise RuntimeError("Missing call of PPV.fit()")
-                    tab[e, 6] = sv._q[0]
+                        raise RuntimeError(f"Missing call of {kind}.fit()")
+                    tab[e, 6 if kind == "PPV" else 7] = sv._q[0]
                     continue
                 if kind == "END":
                     continue
                 if not sv.requires_fitting:
                     sv._get_unfitted_quantiles()
                 q = sv._quantiles
-                col = {"CNT": 2 * arg, "AVG": 2 * arg, "MAX": 8, "MIN": 10}[kind]
+                col = {"CNT": 2 * arg, "AVG": 2 * arg, "XPI": 2 * arg, "LPI": 2 * arg,
+                       "MAX": 8, "MIN": 10, "CUR": 12}[kind]
                 tab[e, col], tab[e, col + 1] = q[0], q[1]
         dev = be.to_device(np.ascontiguousarray(tab))
         self._thr_memo = (n_emit, dev)

@@ -136,6 +136,8 @@ class CPV(PPV):
         return super()._transform_device(X)
 
     def _fused(self):
+        if not self._segments and len(self._q_c_input) == 1:
+            return ("CPV", 0)
         return None
 
     def _copy(self) -> "CPV":

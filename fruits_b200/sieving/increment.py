@@ -69,7 +69,15 @@ class XPI(IncrementSieve):
     """Mean index of the increments in ``(q_k, q_{k+1}]``."""
     _kind = be.SIEVE_XPI
 
+    def _fused(self):
+        ok = self._fusable_shape() and 0 <= self._inc <= 2
+        return ("XPI", self._inc) if ok else None
+
 
 class LPI(IncrementSieve):
     """Longest run of consecutive increments in ``(q_k, q_{k+1}]``."""
     _kind = be.SIEVE_LPI
+
+    def _fused(self):
+        ok = self._fusable_shape() and 0 <= self._inc <= 2
+        return ("LPI", self._inc) if ok else None

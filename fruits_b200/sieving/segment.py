@@ -213,6 +213,9 @@ class CUR(SegmentSieve):
                                           arr.shape[1], 2, be.stream_ptr()))
         super()._apply(inc2, out, col0)
 
+    def _fused(self):
+        return ("CUR", 0) if self._fusable_shape() else None
+
 
 class AVG(CUR):
     """Reference :277-317.  Its ``_transform`` (:303-307) calls

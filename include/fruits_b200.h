@@ -124,13 +124,22 @@ typedef struct fb_batch {
 #define FB_FEAT_MAX 3
 #define FB_FEAT_MIN 4
 #define FB_FEAT_END 5
+/* generated kernels only (the generic kernel answers FB_ENOSUP):
+ *   XPI: fruits/sieving/increment.py:166-199   LPI: :202-239   (arg = increment depth)
+ *   CUR: fruits/sieving/segment.py:228-260 (also AVG / STD, which call its backend)
+ *   CPV: fruits/sieving/implicit.py:156-190 */
+#define FB_FEAT_XPI 6
+#define FB_FEAT_LPI 7
+#define FB_FEAT_CUR 8
+#define FB_FEAT_CPV 9
 #define FB_MAX_FEATS 16
 
 /* Threshold table layout per emitted iterated sum (row of FB_NTHR doubles):
  *   [0..1] (lo, hi] of increment depth 0   [2..3] depth 1   [4..5] depth 2
- *   [6]    PPV threshold                   [7] unused
- *   [8..9] (lo, hi] of MAX                 [10..11] (lo, hi] of MIN */
-#define FB_NTHR 12
+ *   [6]    PPV threshold                   [7] CPV threshold
+ *   [8..9] (lo, hi] of MAX                 [10..11] (lo, hi] of MIN
+ *   [12..13] (lo, hi] of CUR               [14..15] unused */
+#define FB_NTHR 16
 
 typedef struct fb_sieve_plan {
     int32_t n_feats;                 /* features per emitted iterated sum */

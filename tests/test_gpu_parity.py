@@ -1065,6 +1065,47 @@ def test_extra_pipeline_golden(name, golden_dir):
     assert fruit.summary() == str(g["summary"])
 
 
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
+@pytest.mark.parametrize("shape", [(37, 2, 1), (70, 2, 2), (64, 2, 33), (300, 2, 129)])
+def test_rank2_sieves_fused_equal_composed_and_oracle(semiring, shape, monkeypatch):
+    """XPI / LPI / CUR / CPV as accumulators of the generated kernel (the ISS tensor
+    stays in registers) against the composed route (materialise + stand-alone sieve
+    kernels, the only route they had before) and against the oracle."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [3, 2]}, "mode": "extended",
+                                 "semiring": semiring}],
+                        "sieves": [["NPI", {"q": [0.4, 1.0]}], ["XPI", {"q": [0.4, 1.0]}],
+                                   ["LPI", {"inc": 2, "q": [0.3, 1.0]}], ["XPI", {"inc": 0, "q": [0.2, 1.0]}],
+                                   ["LPI", {"inc": 0, "q": [0.2, 1.0]}], ["CUR", {"q": [-1.0, 0.7]}],
+                                   ["CPV", {}], ["PPV", {}], ["MPI", {"inc": 2, "q": [0.3, 1.0]}],
+                                   ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(shape[0] + shape[2]).standard_normal(shape).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(5)
+    fruit.fit(X)
+    monkeypatch.setenv("FRUITS_B200_JIT", "force")
+    monkeypatch.setenv("FRUITS_B200_CHAIN", "0")
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    monkeypatch.setenv("FRUITS_B200_JIT", "0")
+    comp = fruit.transform(X)
+    assert _routes(fruit) == ["composed"]
+    of = orc.OracleFruit(spec)
+    np.random.seed(5)
+    of.fit(X)
+    ref = of.transform(X)
+    nf = 10
+    summed = np.zeros(ref.shape[1], dtype=bool)
+    for f in (5, 8):                           # CUR, MPI: sums (order of the additions)
+        summed[f::nf] = True
+    assert_exact(res[:, ~summed], comp[:, ~summed], "fused vs composed route")
+    assert_exact(res[:, ~summed], ref[:, ~summed], "fused vs oracle")
+    assert_close(res[:, summed], comp[:, summed], 1e-12, "CUR / MPI vs composed")
+    assert_close(res[:, summed], ref[:, summed], 1e-12, "CUR / MPI vs oracle")
+
+
 # ---------------------------------------------------------------------------
 # (k) BASELINE sizes against golden vectors frozen from the REAL reference
 # (oracle/gen_golden_full.py: the reference's own fit on the full input, its

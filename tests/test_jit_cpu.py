@@ -189,3 +189,37 @@ def test_staged_epilogue_writes_every_feature_column_once(name, si, ppc, tt, ndi
     direct = [ln for part in prog.parts if part.owned for ln in em0.epilogue_code(part)
               if ln.strip().startswith("put(o + ")]
     assert len(direct) == len(trie.emits) * nf
+
+
+def test_rank2_sieves_compile_into_the_thread_per_series_kernel(tmp_path, monkeypatch):
+    """XPI / LPI / CUR / CPV as accumulators of the
+    generated kernel: source -> NVRTC -> nvJitLink without a GPU; the chain kernel
+    and the generic kernel decline them."""
+    import ctypes
+    monkeypatch.setattr(_jit, "CACHE_DIR", str(tmp_path))
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended"}],
+                        "sieves": [["NPI", {"q": [0.4, 1.0]}], ["XPI", {"q": [0.4, 1.0]}],
+                                   ["LPI", {"inc": 2}], ["XPI", {"inc": 0, "q": [0.2, 0.9]}],
+                                   ["CUR", {"q": [-1.0, 0.7]}], ["CPV", {}], ["PPV", {}], ["END", {}]]}]}
+    fruit = specs.build_fruit(fruits, spec)
+    slc = fruit._slices[0]
+    feats, bhi, bmm = slc._fused_sieves()
+    assert [k for k, _ in feats] == [be.FEAT_CNT, be.FEAT_XPI, be.FEAT_LPI, be.FEAT_XPI, be.FEAT_CUR,
+                                     be.FEAT_CPV, be.FEAT_PPV, be.FEAT_END]
+    sieves = _jit.SieveSet.make(feats, bhi, bmm)
+    assert sieves.rank2 and sieves.xpi == (True, True, False) and sieves.lpi == (False, False, True)
+    assert set(sieves.thr_cols()) >= {0, 1, 2, 3, 4, 5, 6, 7, 12, 13}
+    trie = slc._iss[0].trie()
+    gen = _jit.generate(trie, be.SEMIRING_REALS, be.WEIGHT_NONE, sieves,
+                        [(d, 1) for d in trie.used_dims()], True, _jit.options())
+    src = "\n".join(gen.parts)
+    assert "XS1[" in src and "LL2[" in src and "SQ[" in src and "CPC[" in src
+    assert _jit.build_cubin(gen)[:4] == b"\x7fELF"
+    with pytest.raises(NotImplementedError):
+        _jit_chain.generate(trie, be.SEMIRING_ARCTIC, be.WEIGHT_NONE, sieves, [(0, 0), (1, 0)])
+    sp = be.FbSievePlan()
+    sp.n_feats = len(feats)
+    for f, (kind, arg) in enumerate(feats):
+        sp.kind[f], sp.arg[f] = kind, arg
+    assert be.lib().fb_slice_policy(ctypes.byref(sp), 0, 0) < 0
