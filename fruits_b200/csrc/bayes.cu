@@ -1,12 +1,17 @@
-// bayes.cu -- iterated sums over the Bayesian (max, times) semiring
-// (reference: fruits/iss/semiring.py:461-601), SURVEY.md section 8(f) rank 2.
+// bayes.cu -- iterated sums whose "sum" is a maximum, as a block scan over T:
+// the Bayesian (max, times) semiring (reference: fruits/iss/semiring.py:461-601,
+// SURVEY.md section 8(f) rank 2) and the Arctic (max, plus) semiring
+// (fruits/iss/semiring.py:282-338) for batches too small to fill the GPU with
+// one lane per trie node.
 //
 //   B_k[t] = max_{s <= t} ( B_{k-1}[s] * prod_d x_d[s]^{e_k[d]} ),   B_{-1} = 1
+//   A_k[t] = max_{s <= t} ( A_{k-1}[s] + sum_d  e_k[d] * x_d[s]  ),  A_{-1} = 0
 //
 // Unlike the real semiring the "sum" is a maximum, which is exactly
 // associative, and level k reads level k-1 at the SAME time step (no shift).
-// So this is the one place on the path where a parallel scan reproduces the
-// reference bit for bit: one CTA owns one series of one word, its threads own
+// So a parallel scan reproduces the reference bit for bit (the real semiring's
+// sequential floating point sum does not allow that): one CTA owns one series
+// of one word, its threads own
 // consecutive time steps of a tile, every level is an element-wise product
 // (the reference's order: one multiplication / division per letter occurrence,
 // dimensions ascending, then the weighting factor) followed by a block-wide
@@ -63,6 +68,9 @@ __device__ __forceinline__ double block_cummax(double v, double carry, double *w
     return bmax(pre, v);
 }
 
+// ARCTIC: letters add e * x (one FMA per dimension, ascending, like numba's
+// contraction of `tmp + el * Z[dim]`), weightings add / subtract g * alpha.
+template <bool ARCTIC>
 __global__ void __launch_bounds__(BAYES_THREADS) bayes_word_kernel(const BayesParams P)
 {
     __shared__ double warp_tot[BAYES_THREADS / 32];
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(BAYES_THREADS) bayes_word_kernel(const BayesPa
         const int t = t0 + threadIdx.x;
         const bool live = t < T;
         const double gv = (gn && live) ? gn[t] : 0.0;
-        double v = 1.0;
+        double v = ARCTIC ? 0.0 : 1.0;
         for (int k = 0; k < p; k++) {
             const int *e = P.word + k * md;
             if (live) {
@@ -90,8 +98,12 @@ __global__ void __launch_bounds__(BAYES_THREADS) bayes_word_kernel(const BayesPa
                     const int occ = e[d];
                     if (occ) {
                         const double x = Xn[(size_t)d * T + t];
-                        for (int r = 0; r < occ; r++) v = __dmul_rn(v, x);
-                        for (int r = 0; r < -occ; r++) v = __ddiv_rn(v, x);
+                        if (ARCTIC) {
+                            v = fma((double)occ, x, v);
+                        } else {
+                            for (int r = 0; r < occ; r++) v = __dmul_rn(v, x);
+                            for (int r = 0; r < -occ; r++) v = __ddiv_rn(v, x);
+                        }
                     }
                 }
             } else {
@@ -102,24 +114,28 @@ __global__ void __launch_bounds__(BAYES_THREADS) bayes_word_kernel(const BayesPa
             double c;
             if (nontotal) {
                 // semiring.py:466-495
-                if (k > 0 && live) v = __dmul_rn(v, exp(-gv * (double)P.alpha[k - 1]));
+                if (k > 0 && live)
+                    v = ARCTIC ? fma(-gv, (double)P.alpha[k - 1], v)
+                               : __dmul_rn(v, exp(-gv * (double)P.alpha[k - 1]));
                 if (o) {
                     const double r = block_cummax(v, carry_emit[k], warp_tot, &c);
                     if (live) o[t] = r;
                     if (threadIdx.x == 0) carry_emit[k] = c;
                 }
                 if (k < p - 1) {
-                    if (live) v = __dmul_rn(v, exp(gv * (double)P.alpha[k]));
+                    if (live)
+                        v = ARCTIC ? fma(gv, (double)P.alpha[k], v)
+                                   : __dmul_rn(v, exp(gv * (double)P.alpha[k]));
                     v = block_cummax(v, carry_chain[k], warp_tot, &c);
                     if (threadIdx.x == 0) carry_chain[k] = c;
                 }
             } else {
                 // semiring.py:503-527 (also the unweighted case: alpha = 0, g = 0)
                 const double a = total ? (double)P.alpha[k] : 0.0;
-                if (total && live) v = __dmul_rn(v, exp(gv * a));
+                if (total && live) v = ARCTIC ? fma(gv, a, v) : __dmul_rn(v, exp(gv * a));
                 v = block_cummax(v, carry_chain[k], warp_tot, &c);
                 if (threadIdx.x == 0) carry_chain[k] = c;
-                if (total && live) v = __dmul_rn(v, exp(-gv * a));
+                if (total && live) v = ARCTIC ? fma(-gv, a, v) : __dmul_rn(v, exp(-gv * a));
                 if (o && live) o[t] = v;
             }
         }
@@ -133,9 +149,9 @@ using namespace fb;
 
 extern "C" {
 
-int fb_bayes_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word, int p,
-                  int md, const float *alpha, const double *g, int64_t g_ld, int weight_mode,
-                  int extended, double *out, void *stream)
+static int scan_word(bool arctic, const double *X, int64_t n, int64_t d, int64_t t,
+                     const int32_t *word, int p, int md, const float *alpha, const double *g,
+                     int64_t g_ld, int weight_mode, int extended, double *out, void *stream)
 {
     FB_REQUIRE(X && word && alpha && out, "null argument");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && p >= 1 && md >= 1 && md <= d, "bad shape");
@@ -149,9 +165,28 @@ int fb_bayes_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_
     P.X = X; P.word = word; P.alpha = alpha; P.g = g; P.out = out;
     P.n = n; P.d = d; P.t = t; P.g_ld = g_ld;
     P.p = p; P.md = md; P.extended = extended; P.wm = weight_mode;
-    bayes_word_kernel<<<(unsigned)n, BAYES_THREADS, 0, (cudaStream_t)stream>>>(P);
+    if (arctic)
+        bayes_word_kernel<true><<<(unsigned)n, BAYES_THREADS, 0, (cudaStream_t)stream>>>(P);
+    else
+        bayes_word_kernel<false><<<(unsigned)n, BAYES_THREADS, 0, (cudaStream_t)stream>>>(P);
     FB_CUDA(cudaGetLastError());
     return 0;
+}
+
+int fb_bayes_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word, int p,
+                  int md, const float *alpha, const double *g, int64_t g_ld, int weight_mode,
+                  int extended, double *out, void *stream)
+{
+    return scan_word(false, X, n, d, t, word, p, md, alpha, g, g_ld, weight_mode, extended, out,
+                     stream);
+}
+
+int fb_arctic_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word, int p,
+                   int md, const float *alpha, const double *g, int64_t g_ld, int weight_mode,
+                   int extended, double *out, void *stream)
+{
+    return scan_word(true, X, n, d, t, word, p, md, alpha, g, g_ld, weight_mode, extended, out,
+                     stream);
 }
 
 }  // extern "C"

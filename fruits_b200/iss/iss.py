@@ -199,7 +199,9 @@ class ISS(Seed):
             self._check_input(X)
         X = X.contiguous()
         if isinstance(self.semiring, Bayesian):
-            return self._materialize_bayesian(X, emit_range, lookup)
+            return self._materialize_scan(X, emit_range, lookup)
+        if isinstance(self.semiring, Arctic) and self._arctic_scan(X.shape[0], emit_range):
+            return self._materialize_scan(X, emit_range, lookup, arctic=True)
         rows = be.lib().fb_slice_rows(be.POLICY_MAT)
         pieces = self._dim_pieces(emit_range, trusted)
         if len(pieces) > 1:
@@ -217,10 +219,33 @@ class ISS(Seed):
                                              be.stream_ptr()))
         return out
 
-    def _materialize_bayesian(self, X: torch.Tensor, emit_range, lookup) -> torch.Tensor:
-        """Word by word through ``fb_bayes_word`` (reference: iss.py:42-63 with
-        ``Bayesian.iterated_sum_fast``, semiring.py:530-566): word ``i`` emits
-        its last ``extended_i`` prefixes (all but those an earlier word emitted)."""
+    def _arctic_scan(self, n_series: int, emit_range) -> bool:
+        """Arctic sums through the block scan over T (``fb_arctic_word``, one CTA
+        per series and word) instead of the lane-per-node interpreter?
+        ``FRUITS_B200_ARCTIC_SCAN``: "1" always, "0" never.  Default, from
+        ``scripts/arctic_scan_vs_serial.py`` on the 48-letter chains of
+        ``fruit_general.py`` (same bits either way): the scan wins whenever a whole
+        ISS of chain-like words is materialised in one call (1.0 vs 1.1 ms for one
+        series, 8.9 vs 20.1 ms for 2,048 x 1,024); it recomputes every word from its
+        first letter, so bushy tries and the emission-range chunks of ``fit`` keep
+        the trie kernel."""
+        import os
+        mode = os.environ.get("FRUITS_B200_ARCTIC_SCAN", "auto")
+        if mode in ("0", "1"):
+            return mode == "1"
+        if n_series <= 4:
+            return True
+        from .._jit_chain import chain_like
+        return emit_range is None and n_series <= 4096 and chain_like(self.trie())
+
+    def _materialize_scan(self, X: torch.Tensor, emit_range, lookup,
+                          arctic: bool = False) -> torch.Tensor:
+        """Word by word through the block scan over T -- ``fb_bayes_word``
+        (reference: iss.py:42-63 with ``Bayesian.iterated_sum_fast``,
+        semiring.py:530-566) or ``fb_arctic_word`` (``Arctic._iterated_sum_fast``,
+        :354-404): word ``i`` emits its last ``extended_i`` prefixes (all but
+        those an earlier word emitted)."""
+        kernel = be.lib().fb_arctic_word if arctic else be.lib().fb_bayes_word
         n, d, t = X.shape
         g, g_ld = self._lookup(X) if lookup is None else lookup
         lo, hi = (0, self.n_iterated_sums()) if emit_range is None else emit_range
@@ -243,7 +268,7 @@ class ISS(Seed):
                 mat, alpha, (p, md) = tabs[key]
                 whole = first >= lo and last <= hi
                 dst = out[first - lo:last - lo] if whole else be.empty((ext, n, t))
-                be.check(be.lib().fb_bayes_word(
+                be.check(kernel(
                     X.data_ptr(), n, d, t, mat.data_ptr(), p, md, alpha.data_ptr(), be.ptr(g),
                     g_ld, self._weight_mode(), ext, dst.data_ptr(), be.stream_ptr()))
                 if not whole:

@@ -304,6 +304,14 @@ FB_API int fb_coswiss_word(const double *X, int64_t n, int64_t d, int64_t t, con
 FB_API int fb_bayes_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word,
                          int p, int md, const float *alpha, const double *g, int64_t g_ld,
                          int weight_mode, int extended, double *out, void *stream);
+/* The same block scan over T for one word of the Arctic (max, plus) semiring
+ * (fruits/iss/semiring.py:282-338; the running maximum is exactly associative,
+ * so the result is bit-identical to the time-serial kernels): used by
+ * ISS.transform / fit for batches too small to fill the GPU with one lane per
+ * trie node. */
+FB_API int fb_arctic_word(const double *X, int64_t n, int64_t d, int64_t t, const int32_t *word,
+                          int p, int md, const float *alpha, const double *g, int64_t g_ld,
+                          int weight_mode, int extended, double *out, void *stream);
 
 /* -- preparateurs, lookups, raw-input cache -- */
 

@@ -59,6 +59,32 @@ def test_iss_golden(name, golden_dir):
         assert_close(res, g[name], 1e-9, name)
 
 
+@pytest.mark.parametrize("name", sorted(n for n in ISS_CASES if n.startswith("arctic")))
+@pytest.mark.parametrize("length", [None, 300, 1000])
+def test_arctic_block_scan_over_time(name, length, golden_dir, monkeypatch):
+    """The Arctic semiring through the block scan over T (``fb_arctic_word``: warp
+    shuffles + warp totals in shared memory + carry between tiles; a running
+    maximum is exactly associative): bit-identical to the time-serial
+    lane-per-node kernel on every arctic case -- unweighted, Indices and L1
+    weighted, total and not -- for lengths below, at and across the 256-step
+    tile, and to the goldens frozen from the reference."""
+    g = np.load(os.path.join(golden_dir, "iss.npz"))
+    desc, shape, kind = ISS_CASES[name]
+    if length is not None:
+        shape = (shape[0], shape[1], length)
+    X = make_iss_input(shape, kind)
+    monkeypatch.setenv("FRUITS_B200_ARCTIC_SCAN", "0")
+    serial = specs.build_iss(fruits, desc).transform(X)
+    monkeypatch.setenv("FRUITS_B200_ARCTIC_SCAN", "1")
+    scan = specs.build_iss(fruits, desc).transform(X)
+    assert_exact(scan, serial, name + " block scan vs time-serial kernel")
+    if length is None:
+        if _exact_iss(desc):
+            assert_exact(scan, g[name], name)
+        else:
+            assert_close(scan, g[name], 1e-9, name)
+
+
 @pytest.mark.parametrize("name", sorted(SIEVE_CASES))
 def test_sieve_golden(name, golden_dir):
     g = np.load(os.path.join(golden_dir, "sieves.npz"))
