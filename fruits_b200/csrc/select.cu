@@ -187,6 +187,10 @@ struct Sel2State {
     unsigned long long bucket;      // keys in the chosen bucket
     unsigned long long min_above;   // smallest key above the 24-bit bucket
     unsigned long long n_nan;
+    // a bucket too large for the candidate list is usually ONE value many times (the
+    // increments of an arctic running maximum are mostly exactly 0): smallest and
+    // largest key of such a bucket -- equal => the order statistic is that value
+    unsigned long long eq_min, eq_max;
     unsigned int n_cand;
     int done;
 };
@@ -233,6 +237,8 @@ __global__ void sel2_init_kernel(Sel2State *st, unsigned *hist, int n_states, Se
         st[i].bucket = 0;
         st[i].min_above = ~0ULL;
         st[i].n_nan = 0;
+        st[i].eq_min = ~0ULL;
+        st[i].eq_max = 0ULL;
         st[i].n_cand = 0;
         st[i].done = 0;
     }
@@ -334,11 +340,14 @@ __global__ void __launch_bounds__(SEL_THREADS) sel2_compact_kernel(Sel2Args a, S
     const double *v = a.V + p * a.ldp;
     int max_inc = 0;
     unsigned long long pre[SEL2_MAXSEL], mab[SEL2_MAXSEL], nn[SEL2_MAXSEL];
+    unsigned long long emin[SEL2_MAXSEL], emax[SEL2_MAXSEL];
     bool fits[SEL2_MAXSEL];
 #pragma unroll
     for (int s = 0; s < SEL2_MAXSEL; s++) {
         mab[s] = ~0ULL;
         nn[s] = 0;
+        emin[s] = ~0ULL;
+        emax[s] = 0ULL;
         fits[s] = false;
         pre[s] = 0;
         if (s < S) {
@@ -372,6 +381,9 @@ __global__ void __launch_bounds__(SEL_THREADS) sel2_compact_kernel(Sel2Args a, S
                             const unsigned idx = atomicAdd(&st[p * S + s].n_cand, 1u);
                             if (idx < (unsigned)SEL2_CAP)
                                 cand[((size_t)(p * S + s)) * SEL2_CAP + idx] = key;
+                        } else {
+                            emin[s] = key < emin[s] ? key : emin[s];
+                            emax[s] = key > emax[s] ? key : emax[s];
                         }
                     } else if (top > pre[s] && key < mab[s]) {
                         mab[s] = key;
@@ -393,7 +405,33 @@ __global__ void __launch_bounds__(SEL_THREADS) sel2_compact_kernel(Sel2Args a, S
                 if (m != ~0ULL) atomicMin(&st[p * S + s].min_above, m);
                 if (c) atomicAdd(&st[p * S + s].n_nan, c);
             }
+            if (!fits[s]) {
+                unsigned long long lo_ = emin[s], hi_ = emax[s];
+#pragma unroll
+                for (int sft = 16; sft; sft >>= 1) {
+                    const unsigned long long a_ = __shfl_xor_sync(0xffffffffu, lo_, sft);
+                    const unsigned long long b_ = __shfl_xor_sync(0xffffffffu, hi_, sft);
+                    lo_ = a_ < lo_ ? a_ : lo_;
+                    hi_ = b_ > hi_ ? b_ : hi_;
+                }
+                if ((threadIdx.x & 31) == 0 && lo_ != ~0ULL) {
+                    atomicMin(&st[p * S + s].eq_min, lo_);
+                    atomicMax(&st[p * S + s].eq_max, hi_);
+                }
+            }
         }
+}
+
+// order statistics of a bucket that holds one value only: x_(k) is that value, and
+// so is x_(k+1) unless x_(k) is the last element of the bucket
+__device__ __forceinline__ bool sel2_single_value(const Sel2State &S, unsigned long long k,
+                                                  unsigned long long m, double *a_, double *b_)
+{
+    if (S.eq_min != S.eq_max) return false;
+    *a_ = key_value(S.eq_min);
+    *b_ = *a_;
+    if (k + 1 < m && S.rank + 1 >= S.bucket) *b_ = key_value(S.min_above);
+    return true;
 }
 
 // one CTA per (problem, selection): the remaining 40 bits on the candidate list
@@ -408,7 +446,14 @@ __global__ void __launch_bounds__(256) sel2_finish_kernel(Sel2State *st, const u
     Sel2State &S = st[q];
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     if (S.bucket > (unsigned long long)SEL2_CAP) {
-        if (threadIdx.x == 0) { done[q] = 0; lo[q] = nan; hi[q] = nan; }
+        if (threadIdx.x == 0) {
+            double a_ = nan, b_ = nan;
+            const bool ok = sel2_single_value(S, a.k[s], (unsigned long long)a.M, &a_, &b_);
+            if (ok && S.n_nan) { a_ = nan; b_ = nan; }
+            done[q] = ok ? 1 : 0;
+            lo[q] = a_;
+            hi[q] = b_;
+        }
         return;
     }
     const unsigned n = S.n_cand;
@@ -492,8 +537,10 @@ __global__ void seld_export_kernel(const Sel2State *st, long long *sums, long lo
     sums[2 * q] = (long long)st[q].n_nan;
     sums[2 * q + 1] = 0;
     // unsigned keys -> signed order for an integer MIN all-reduce
-    mins[2 * q] = (long long)(st[q].min_above ^ 0x8000000000000000ULL);
-    mins[2 * q + 1] = (long long)(~0ULL ^ 0x8000000000000000ULL);
+    mins[4 * q] = (long long)(st[q].min_above ^ 0x8000000000000000ULL);
+    mins[4 * q + 1] = (long long)(~0ULL ^ 0x8000000000000000ULL);
+    mins[4 * q + 2] = (long long)(st[q].eq_min ^ 0x8000000000000000ULL);
+    mins[4 * q + 3] = (long long)(~st[q].eq_max ^ 0x8000000000000000ULL);    // MIN of ~x = ~MAX of x
 }
 
 __global__ void seld_import_kernel(Sel2State *st, DistAux *aux, const long long *sums,
@@ -502,7 +549,9 @@ __global__ void seld_import_kernel(Sel2State *st, DistAux *aux, const long long 
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= ns) return;
     st[q].n_nan = (unsigned long long)sums[2 * q];
-    st[q].min_above = (unsigned long long)mins[2 * q] ^ 0x8000000000000000ULL;
+    st[q].min_above = (unsigned long long)mins[4 * q] ^ 0x8000000000000000ULL;
+    st[q].eq_min = (unsigned long long)mins[4 * q + 2] ^ 0x8000000000000000ULL;
+    st[q].eq_max = ~((unsigned long long)mins[4 * q + 3] ^ 0x8000000000000000ULL);
     aux[q].rank24 = st[q].rank;
 }
 
@@ -578,7 +627,7 @@ __global__ void __launch_bounds__(256) seld_succ_kernel(const Sel2State *st, con
         cle = 0; mgt = ~0ULL;
         for (int w = 0; w < 8; w++) { cle += red_cnt[w]; mgt = red_min[w] < mgt ? red_min[w] : mgt; }
         sums[2 * q + 1] = (long long)cle;
-        mins[2 * q + 1] = (long long)(mgt ^ 0x8000000000000000ULL);
+        mins[4 * q + 1] = (long long)(mgt ^ 0x8000000000000000ULL);
     }
 }
 
@@ -590,9 +639,19 @@ __global__ void seld_out_kernel(const Sel2State *st, const DistAux *aux, const l
     if (q >= ns) return;
     const Sel2State &S = st[q];
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    if (S.bucket > (unsigned long long)SEL2_CAP) { done[q] = 0; lo[q] = nan; hi[q] = nan; return; }
+    if (S.bucket > (unsigned long long)SEL2_CAP) {
+        double a_ = nan, b_ = nan;
+        Sel2State T_ = S;
+        T_.rank = aux[q].rank24;
+        const bool ok = sel2_single_value(T_, a.k[q % a.n_sel], (unsigned long long)m_global, &a_, &b_);
+        if (ok && S.n_nan) { a_ = nan; b_ = nan; }
+        done[q] = ok ? 1 : 0;
+        lo[q] = a_;
+        hi[q] = b_;
+        return;
+    }
     const unsigned long long cle = (unsigned long long)sums[2 * q + 1];
-    const unsigned long long mgt = (unsigned long long)mins[2 * q + 1] ^ 0x8000000000000000ULL;
+    const unsigned long long mgt = (unsigned long long)mins[4 * q + 1] ^ 0x8000000000000000ULL;
     double a_ = key_value(S.prefix), b_ = a_;
     if (a.k[q % a.n_sel] + 1 < (unsigned long long)m_global) {
         if (aux[q].rank24 + 1 < cle) b_ = a_;
@@ -639,7 +698,7 @@ static DistLayout dist_layout(long long P, int n_sel)
     L.h256 = L.cand + up(ns * (size_t)SEL2_CAP * sizeof(unsigned long long));
     L.sums = L.h256 + up(ns * 256 * sizeof(unsigned));
     L.mins = L.sums + up(ns * 2 * sizeof(long long));
-    L.aux = L.mins + up(ns * 2 * sizeof(long long));
+    L.aux = L.mins + up(ns * 4 * sizeof(long long));
     L.total = L.aux + up(ns * sizeof(DistAux)) + 256;
     return L;
 }
@@ -800,7 +859,7 @@ int fb_order_stats_dist8(int phase, const double *V, int64_t ldp, int64_t P, int
 /* Row-sharded multi-selection.  layout[0..3] = byte offsets inside the workspace
  * of: hist (uint32 [P*n_sel*4096], summed after phases 0 and 1), h256 (uint32
  * [P*n_sel*256], summed after phases 3..7), sums (int64 [P*n_sel*2], summed
- * after phases 2 and 8), mins (int64 [P*n_sel*2], MIN after phases 2 and 8);
+ * after phases 2 and 8), mins (int64 [P*n_sel*4], MIN after phases 2 and 8);
  * layout[4] = workspace size in bytes. */
 int fb_order_stats_dist_layout(int64_t P, int n_sel, int64_t *layout)
 {

@@ -179,7 +179,7 @@ class RowShard:
                     self._reduce(work, lay[0], ns * 4096, torch.int32, dist.ReduceOp.SUM)
                 elif phase in (2, 8):
                     self._reduce(work, lay[2], ns * 2, torch.int64, dist.ReduceOp.SUM)
-                    self._reduce(work, lay[3], ns * 2, torch.int64, dist.ReduceOp.MIN)
+                    self._reduce(work, lay[3], ns * 4, torch.int64, dist.ReduceOp.MIN)
                 elif 3 <= phase <= 7:
                     self._reduce(work, lay[1], ns * 256, torch.int32, dist.ReduceOp.SUM)
             packed = torch.cat([lo, hi, done.to(torch.float64)], dim=1).cpu().numpy()

@@ -397,7 +397,7 @@ FB_API int fb_order_stats_multi(const double *V, int64_t ldp, int64_t P, int64_t
  *                         8-bit passes over the local candidate lists, phases 0..9;
  *                         layout = byte offsets of {hist u32[P*n_sel*4096] (SUM after
  *                         phases 0, 1), h256 u32[P*n_sel*256] (SUM after 3..7), sums
- *                         i64[P*n_sel*2] (SUM after 2, 8), mins i64[P*n_sel*2] (MIN after
+ *                         i64[P*n_sel*2] (SUM after 2, 8), mins i64[P*n_sel*4] (MIN after
  *                         2, 8)}, workspace bytes
  *   fb_order_stats_dist8  eight 8-bit passes over materialised local values, phases
  *                         0..9; layout = {hist u32[P*256] (SUM after 0..7), sums

@@ -1267,7 +1267,7 @@ def test_row_sharded_selection_phases(counts):
             _emulated_reduce(works, lay[0], ns * 4096, torch.int32, "sum")
         elif phase in (2, 8):
             _emulated_reduce(works, lay[2], ns * 2, torch.int64, "sum")
-            _emulated_reduce(works, lay[3], ns * 2, torch.int64, "min")
+            _emulated_reduce(works, lay[3], ns * 4, torch.int64, "min")
         elif 3 <= phase <= 7:
             _emulated_reduce(works, lay[1], ns * 256, torch.int32, "sum")
 
@@ -1285,7 +1285,8 @@ def test_row_sharded_selection_phases(counts):
         got = _lerp(lo0[:, s], hi0[:, s] if k < M - 1 else lo0[:, s], gamma)
         ok = done0[:, s].astype(bool)
         assert_exact(got[ok], want[ok], f"dist select inc={inc} q={q}")
-        assert ok[0] and ok[3] and ok[4]         # (rows 1-2 may exceed the candidate list)
+        assert ok[0] and ok[3] and ok[4]         # (rows 1-2 may exceed the candidate list;
+        #                                          one value many times is resolved anyway)
     # the eight-pass form on materialised values
     for inc, q in ((1, 0.5), (0, 0.25)):
         vals = [torch.from_numpy(np.ascontiguousarray(
