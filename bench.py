@@ -273,9 +273,14 @@ def run_reference(args):
     # per-series cost of the numba reference grows with the batch (every iterated sum
     # [n, 1024] is streamed through memory once per word and sieve), so its sample is
     # capped near the size BASELINE.md quotes (2,048); the port gets >= 64 series per core
-    lo, hi = (max(2048, 64 * arm.cores), 16384) if arm.kind == "port" else (512, 4096)
+    lo, hi = (max(2048, 64 * arm.cores), 16384) if arm.kind == "port" else (256, 1024)
     budget = max(args.ref_seconds - (time.perf_counter() - t_start), 30.0)
     n, cal = calibrate(arm, budget, calls, lo, hi)
+    if arm.kind == "reference":
+        # a fixed ladder of sample sizes (1,024 unless the budget forces less): the
+        # reference's rate depends on the batch size (337 / 204 / 152 series/s at 1,024 /
+        # 2,048 / 4,096 series on 16 cores), so runs on different boxes stay comparable
+        n = max(s_ for s_ in (256, 512, 1024) if s_ <= max(n, 256))
     rate, step_s = time_cpu(arm, n, args.steps, args.warmup)
     sample = (f"{n} series x {N_DIMS} x {T_LEN} per step, {args.steps} step(s) after "
               f"{args.warmup} warm-up step(s), scaled linearly in the number of series")
