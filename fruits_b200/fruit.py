@@ -139,7 +139,8 @@ class Fruit:
             raise ValueError("out must be a C-contiguous float64 array [n_series, nfeatures]")
         oh = torch.from_numpy(out)
         row_bytes = Xh[0].numel() * 8 + nf * 8 if n else 1
-        rows = max(1, min(n, (256 << 20) // max(row_bytes, 1)))
+        chunk_mb = int(os.environ.get("FRUITS_B200_HOST_CHUNK_MB", "256"))
+        rows = max(1, min(n, (chunk_mb << 20) // max(row_bytes, 1)))
         # every step of transform is independent per series, so row chunks can
         # be processed on their own (a user-supplied cache refers to all rows)
         single = bool(callbacks) or cache is not None or n <= rows

@@ -4,19 +4,24 @@ The hot path is embarrassingly parallel over series (every numba kernel of
 the reference is a ``prange`` over axis 0, e.g. fruits/iss/semiring.py:184),
 so the multi-GPU layout is: one process per GPU (``torch.distributed``, NCCL),
 rank ``r`` owns the contiguous rows ``[r*S, (r+1)*S)`` of the batch, the plan
-and the fitted thresholds (a few kB) are replicated, and the only exchange is
-one all-gather of the ``[S, F]`` feature blocks so that every rank ends up
-with the full feature matrix.  The gather runs per row chunk on a side stream
-and overlaps the kernels of the next chunk.
+and the fitted thresholds (a few kB) are replicated, and the only exchange of
+``transform`` is the assembly of the ``[world*S, F]`` feature matrix on every
+rank.  ``PeerGather`` fuses it into the feature kernels: their epilogue stores
+with ``multimem.st`` through the NVSwitch multicast mapping of a symmetric
+allocation; the fallbacks push row chunks with the copy engines or all-gather
+them with NCCL on a side stream.
 
-Fit: the fit sample is drawn on rank 0 with the global numpy RNG (same draws
-as the reference, fruits/fruit.py:430-438), the owning ranks contribute the
-sampled rows, and the iterated sums are split over the ranks: a threshold is a
-quantile over the WHOLE sample of one iterated sum, so rank r materialises and
-selects its share of the iterated sums and the fitted sieves (a few numbers
-each) are all-gathered -- thresholds are identical on all ranks.
+Fit (``fit_sharded``): every rank draws the same sample positions with the
+global numpy RNG (same draws as the reference, fruits/fruit.py:430-438) and
+keeps only the sampled rows it owns.  A threshold is a quantile over the WHOLE
+sample of one iterated sum (fruits/sieving/segment.py:66-75): the radix
+selections run in phases over the local rows and all-reduce their histograms
+(``RowShard``), so all ranks end with the same thresholds and nothing but
+histograms crosses NVLink.  ``shard="nodes"`` is the alternative for slices
+that cannot be fitted row by row: the sample is gathered (bit-exactly) and the
+iterated sums are split over the ranks instead.
 """
-from typing import Callable, Optional
+from typing import Optional
 
 import numpy as np
 import torch

@@ -21,8 +21,7 @@ import specs
 from cases import (ISS_CASES, PIPE_CASES, PREP_CASES, SIEVE_CASES, SUMMING_SIEVES, IMPLICIT_SIEVES, sieve_kind, unwrap, KAT_X, SIEVE_KATS, make_iss_input,
                    make_prep_input, make_sieve_input)
 from helpers import (assert_close, assert_exact, fitted_thresholds, oracle_thresholds,
-                     parity_report, record_report,
-                     rowmax_rel_err)
+                     parity_report, record_report)
 
 pytestmark = pytest.mark.gpu
 
