@@ -128,6 +128,8 @@ def lib() -> ctypes.CDLL:
         "fb_jit_unload": ([vp], i32),
         "fb_jit_slice_features": ([vp, vp, ctypes.POINTER(FbBatch), vp, i64, vp, i64, vp, i64, i64,
                                    i32, vp], i32),
+        "fb_jit_slice_features_cut": ([vp, vp, ctypes.POINTER(FbBatch), vp, i64, vp, i64, vp, vp,
+                                       i64, i64, i32, vp], i32),
         "fb_jit_chain_features": ([vp, vp, ctypes.POINTER(FbBatch), vp, i64, vp, i64, i64, i32,
                                    vp], i32),
         "fb_cos_trig": ([vp, i32, i64, vp, vp], i32),
@@ -155,7 +157,7 @@ EXPORTED = [
     "fb_lsum", "fb_nrm_scale", "fb_coquantile", "fb_pretransform",
     "fb_segment_sieve", "fb_ppv", "fb_nan_to_num", "fb_multimem_copy", "fb_order_stats_workspace",
     "fb_order_stats", "fb_fp64_peak", "fb_jit_compile", "fb_jit_free", "fb_jit_load",
-    "fb_jit_unload", "fb_jit_slice_features", "fb_jit_chain_features", "fb_jit_link", "fb_exp_rows", "fb_cos_trig", "fb_cos_rows", "fb_coswiss_sep_word", "fb_coswiss_word",
+    "fb_jit_unload", "fb_jit_slice_features", "fb_jit_slice_features_cut", "fb_jit_chain_features", "fb_jit_link", "fb_exp_rows", "fb_cos_trig", "fb_cos_rows", "fb_coswiss_sep_word", "fb_coswiss_word",
     "fb_bayes_word", "fb_arctic_word", "fb_order_stats_multi_workspace", "fb_order_stats_multi",
     "fb_order_stats_dist_layout", "fb_order_stats_dist", "fb_order_stats_dist8_layout",
     "fb_order_stats_dist8",

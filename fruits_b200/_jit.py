@@ -36,7 +36,7 @@ from dataclasses import dataclass, field
 
 from . import _backend as be
 
-JIT_VERSION = 20            # bump to invalidate cached cubins
+JIT_VERSION = 21            # bump to invalidate cached cubins
 CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "jit")
 
 # threshold table columns (include/fruits_b200.h, FB_NTHR)
@@ -64,9 +64,10 @@ class SieveSet:
     lpi: tuple = (False, False, False)     # longest run of selected increments of a unit
     cur: bool = False               # sum of the squared second increments in (lo, hi]
     cpv: bool = False               # rising edges of (y >= threshold)
+    cut: bool = False               # segment sieves look at [0, cut[series]) only
 
     @staticmethod
-    def make(feats, bounded_hi, bounded_mm) -> "SieveSet":
+    def make(feats, bounded_hi, bounded_mm, cut: bool = False) -> "SieveSet":
         cnt, avg, xpi, lpi = [False] * 3, [False] * 3, [False] * 3, [False] * 3
         ppv = mx = mn = cur = cpv = False
         for kind, arg in feats:
@@ -89,12 +90,17 @@ class SieveSet:
             elif kind == be.FEAT_CPV:
                 cpv = True
         return SieveSet(list(feats), tuple(cnt), tuple(avg), ppv, mx, mn,
-                        bool(bounded_hi), bool(bounded_mm), tuple(xpi), tuple(lpi), cur, cpv)
+                        bool(bounded_hi), bool(bounded_mm), tuple(xpi), tuple(lpi), cur, cpv,
+                        bool(cut))
 
     @property
     def rank2(self) -> bool:
         """Accumulators only the thread-per-series kernel knows."""
-        return any(self.xpi) or any(self.lpi) or self.cur or self.cpv
+        return any(self.xpi) or any(self.lpi) or self.cur or self.cpv or self.cut
+
+    @property
+    def end(self) -> bool:
+        return any(kind == be.FEAT_END for kind, _ in self.feats)
 
     def thr_cols(self) -> list:
         cols = []
@@ -125,6 +131,8 @@ class SieveSet:
             r += 2          # previous first increment
         r += 2 * (int(self.mx) + int(self.mn))
         r += sum(self.xpi) + 2 * sum(self.lpi) + (2 if self.cur else 0) + (2 if self.cpv else 0)
+        if self.cut and self.end:
+            r += 2          # the value at the end of the segment
         return r
 
     # rough issue slots per emitted node and step
@@ -143,6 +151,8 @@ class SieveSet:
         if self.mmb:
             c += 2 * (int(self.mx) + int(self.mn))
         c += sum(self.xpi) + 3 * sum(self.lpi) + (6 if self.cur else 0) + (5 if self.cpv else 0)
+        if self.cut and self.end:
+            c += 2
         return c
 
 
@@ -566,7 +576,11 @@ class Emitter:
             inc = "0x10000" if hi16 else "1"
             outs = {"cn": f'"+r"(CN[{oi}][{reg}])'}
             ins = {"v": f'"d"({val})', "lo": f'"d"({self.th(e, _COL_U[k][0])})'}
-            asm = ["{ .reg .pred p;", "setp.gt.f64 p, %v, %lo;"]
+            if sv.cut:
+                ins["live"] = '"r"(live)'
+                asm = ["{ .reg .pred p, q;", "setp.ne.b32 q, %live, 0;", "setp.gt.and.f64 p, %v, %lo, q;"]
+            else:
+                asm = ["{ .reg .pred p;", "setp.gt.f64 p, %v, %lo;"]
             if sv.hi:
                 ins["hi"] = f'"d"({self.th(e, _COL_U[k][1])})'
                 asm.append("setp.le.and.f64 p, %v, %hi, p;")
@@ -606,10 +620,13 @@ class Emitter:
                 unit(2, f"dd{v}")
             if sv.cur:
                 # CUR: sum of dd^2 over lo < dd <= hi (fruits/sieving/segment.py:246-258)
-                L.append('asm("{ .reg .pred p; .reg .f64 s; setp.gt.f64 p, %1, %2; '
+                live = ("setp.ne.b32 q, %4, 0; setp.gt.and.f64 p, %1, %2, q; " if sv.cut
+                        else "setp.gt.f64 p, %1, %2; ")
+                L.append('asm("{ .reg .pred p, q; .reg .f64 s; ' + live +
                          'setp.le.and.f64 p, %1, %3, p; fma.rn.f64 s, %1, %1, %0; '
                          f'selp.f64 %0, s, %0, p; }}" : "+d"(SQ[{oi}]) : "d"(dd{v}), '
-                         f'"d"({self.th(e, _COL_CUR[0])}), "d"({self.th(e, _COL_CUR[1])}));')
+                         f'"d"({self.th(e, _COL_CUR[0])}), "d"({self.th(e, _COL_CUR[1])})'
+                         + (', "r"(live)' if sv.cut else "") + ");")
         if sv.cpv:
             # CPV: rising edges of (y >= threshold); CPP = the indicator of the previous
             # step, 1 before the first (the increments of the indicator are zero padded)
@@ -624,14 +641,20 @@ class Emitter:
         for on, arr, cmp_, cols in ((sv.mx, "MX", "gt", _COL_MAX), (sv.mn, "MN", "lt", _COL_MIN)):
             if not on:
                 continue
-            asm = ["{ .reg .pred p;", f"setp.{cmp_}.f64 p, %1, %0;"]
+            asm = ["{ .reg .pred p, q;", f"setp.{cmp_}.f64 p, %1, %0;"]
             ins = [f'"d"({out})']
             if sv.mmb:
                 asm.append("setp.gt.and.f64 p, %1, %2, p;")
                 asm.append("setp.le.and.f64 p, %1, %3, p;")
                 ins += [f'"d"({self.th(e, cols[0])})', f'"d"({self.th(e, cols[1])})']
+            if sv.cut:
+                ins.append('"r"(live)')
+                asm.append(f"setp.ne.and.b32 p, %{len(ins)}, 0, p;")
             asm.append("selp.f64 %0, %1, %0, p; }")
             L.append('asm("' + " ".join(asm) + f'" : "+d"({arr}[{oi}]) : ' + ", ".join(ins) + ");")
+        if sv.cut and sv.end:
+            # END of the segment: the value at step cut - 1
+            L.append(f"EN[{oi}] = last ? {out} : EN[{oi}];")
 
     def fixup(self, part: Part) -> list:
         """After the step t = 0: the increments of the reference are zero
@@ -650,6 +673,8 @@ class Emitter:
                 cond = f"(0.0 > {self.th(e, _COL_U[k][0])})"
                 if sv.hi:
                     cond += f" && (0.0 <= {self.th(e, _COL_U[k][1])})"
+                if sv.cut:
+                    cond += " && (cend > 0)"
                 keep, one = ("0x0000ffffu", "0x10000u") if hi16 else ("0xffff0000u", "1u")
                 L.append(f"CN[{oi}][{reg}] = (CN[{oi}][{reg}] & {keep}) | (({cond}) ? {one} : 0u);")
                 if sv.avg[k]:
@@ -690,6 +715,8 @@ class Emitter:
         for oi, v in enumerate(part.owned):
             e = nodes[v].emit
             endv = f"OP[{sidx[v]}]" if p.weight_mode == be.WEIGHT_TOTAL else f"S[{sidx[v]}]"
+            if sv.cut:
+                endv = f"EN[{oi}]"
             for f, (kind, arg) in enumerate(sv.feats):
                 if kind == be.FEAT_CNT:
                     val = f"(double){count(oi, ('U', arg))}"
@@ -819,7 +846,7 @@ class Emitter:
         A(f"#define EROW {erow}")
         A("#define D_INF __longlong_as_double(0x7ff0000000000000LL)")
         A("#define D_NINF __longlong_as_double(0xfff0000000000000LL)")
-        A("struct Args { const double *X; const double *E; double *out; long long n, d, t, e_ld, out_ld, col0; int sanitize; };")
+        A("struct Args { const double *X; const double *E; double *out; long long n, d, t, e_ld, out_ld, col0; int sanitize; const int *cut; };")
         return "\n".join(src)
 
     def source(self, pi: int) -> str:
@@ -900,6 +927,8 @@ class Emitter:
             A(f"    double SQ[{no}];")
         if sv.cpv:
             A(f"    unsigned CPC[{no}], CPP[{no}];")
+        if sv.cut and sv.end:
+            A(f"    double EN[{no}];")
         init = "0.0" if p.reals else "D_NINF"
         A("#pragma unroll")
         A(f"    for (int i = 0; i < {ns}; i++) {{ S[i] = {init};"
@@ -927,7 +956,16 @@ class Emitter:
             A("        SQ[i] = 0.0;")
         if sv.cpv:
             A("        CPC[i] = 0u; CPP[i] = 1u;")
+        if sv.cut and sv.end:
+            A("        EN[i] = 0.0;")
         A("    }")
+        if sv.cut:
+            # segment [0, cend) of this lane's series (fruits/sieving/segment.py:51-64);
+            # END reads position cend - 1, wrapping like the reference's negative index
+            A("    const long long nser_ = nbase + sg * 32 + lane;")
+            A("    const int craw = a.cut ? a.cut[nser_ < a.n ? nser_ : a.n - 1] : T;")
+            A("    const int cend = craw < 0 ? 0 : (craw > T ? T : craw);")
+            A("    const int eidx = craw >= 1 ? craw - 1 : craw - 1 + T;  (void)eidx;")
         # previous raw values of the dimensions that are read as increments
         inc_rows = sorted({self.row_of[d[0]] for d in self.dims if d is not None and d[1]})
         for r in inc_rows:
@@ -1045,6 +1083,9 @@ class Emitter:
             A("            for (; tt < stop; tt++) {")
             A("                const bool is0 = (t0 + tt) == 0;")
             A("                const unsigned tix = (unsigned)(t0 + tt); (void)tix;")
+            if sv.cut:
+                A("                const int live = (int)tix < cend; const bool last = (int)tix == eidx;")
+                A("                (void)live; (void)last;")
             for ln in self._loads() + self.step(part) + self._after():
                 A("                " + ln)
             A("            }")
@@ -1351,8 +1392,10 @@ class JitSlice:
     def n_launches(self, n_series: int = 0, length: int = 0) -> int:
         return 1
 
-    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize, multicast=None) -> None:
-        """X[n, d, t] cuda float64; extra: weighting rows or None;
+    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize, multicast=None,
+               cuts=None) -> None:
+        """X[n, d, t] cuda float64; extra: weighting rows or None; cuts: int32 [n]
+        end of the sieved segment per series (kernels generated with a cut);
         thr_compact: [n_emit * len(cols)] cuda float64.  ``multicast`` =
         (address, row stride) of the same rows in an NVSwitch multicast
         mapping: the kernel then stores there (with ``multimem.st``) instead of
@@ -1361,9 +1404,11 @@ class JitSlice:
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape
         n_thr = 0 if thr_compact is None else thr_compact.numel()
-        be.check(be.lib().fb_jit_slice_features(
+        if self.em.sv.cut and cuts is None:
+            raise ValueError("this kernel was generated for a cut: pass the cut table")
+        be.check(be.lib().fb_jit_slice_features_cut(
             self.handle, ctypes.byref(self.geo), ctypes.byref(batch), be.ptr(extra),
-            int(extra_ld), be.ptr(thr_compact), n_thr,
+            int(extra_ld), be.ptr(thr_compact), n_thr, be.ptr(cuts),
             out.data_ptr() if multicast is None else int(multicast[0]),
             out.stride(0) if multicast is None else int(multicast[1]), int(col0),
             int(bool(sanitize)) | (2 if multicast is not None else 0), be.stream_ptr()))

@@ -40,7 +40,7 @@ from dataclasses import dataclass
 from . import _backend as be
 from . import _jit
 
-CHAIN_VERSION = 4
+CHAIN_VERSION = 5
 MIN_SERIES = 512           # from this batch size on a chain kernel is compiled (cached on disk)
 MIN_SERIES_CACHED = 16     # ... and from this size on an already compiled one is used
 
@@ -375,7 +375,7 @@ class ChainEmitter:
         A(f"#define PAD {self.pad}")
         A("#define D_INF __longlong_as_double(0x7ff0000000000000LL)")
         A("#define D_NINF __longlong_as_double(0xfff0000000000000LL)")
-        A("struct Args { const double *X; const double *E; double *out; long long n, d, t, e_ld, out_ld, col0; int sanitize; };")
+        A("struct Args { const double *X; const double *E; double *out; long long n, d, t, e_ld, out_ld, col0; int sanitize; const int *cut; };")
         A(f"__constant__ double TH[{nthr}];")
         A(f"__device__ const unsigned NODE[{NB * R * 32}] = {{" + ",".join(map(str, node_w)) + "};")
         npmax = max(1, max(p.npairs))
@@ -608,7 +608,8 @@ class JitChain:
     def n_launches(self, n_series: int = 0, length: int = 0) -> int:
         return 1
 
-    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize, multicast=None) -> None:
+    def launch(self, X, extra, extra_ld, thr_compact, out, col0, sanitize, multicast=None,
+               cuts=None) -> None:
         batch = be.FbBatch()
         batch.X = X.data_ptr()
         batch.n, batch.d, batch.t = X.shape

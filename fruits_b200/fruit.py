@@ -465,6 +465,11 @@ class FruitSlice:
         kernel, else None.  ``features`` holds one ``(kind, arg)`` per sieve."""
         feats, unit_q = [], {}
         bounded_hi = bounded_mm = False
+        cuts = {sv._cut_key() for sv in self._sieves if isinstance(sv, SegmentSieve)}
+        if len(cuts) > 1:
+            return None           # segment sieves with different cuts: one table per kernel
+        self._fused_cut = next((sv for sv in self._sieves if isinstance(sv, SegmentSieve)
+                                and sv._cut_key() is not None), None)
         for sv in self._sieves:
             f = sv._fused()
             if f is None:
@@ -776,8 +781,10 @@ class FruitSlice:
         if out.stride(1) != 1:
             raise ValueError("feature matrix must be row-major")
         feats, bounded_hi, bounded_mm = self._fused_sieves()
-        jit_only = getattr(iss, "_jit_only", False)
-        compile_ok = _jit.enabled(n) or (jit_only and _jit.enabled())
+        # rank-2 accumulators and cuts exist in the thread-per-series kernel only
+        jit_only = getattr(iss, "_jit_only", False) or self._fused_cut is not None or any(
+            k in (be.FEAT_XPI, be.FEAT_LPI, be.FEAT_CUR, be.FEAT_CPV) for k, _ in feats)
+        compile_ok = _jit.enabled(n) or (getattr(iss, "_jit_only", False) and _jit.enabled())
         # mid-size batches: the generated kernel only if it has been compiled already
         cached_ok = not compile_ok and n >= _jit.MIN_SERIES_CACHED and _jit.enabled()
         if not compile_ok and _jit.enabled() and self._chain_first(iss, len(dims)):
@@ -824,7 +831,8 @@ class FruitSlice:
         materialise = any(dims[u][2] for u in real)
         jdims = [((u, 0) if materialise else (dims[u][0], dims[u][1])) if u < len(dims)
                  else ("row", u - len(dims)) for u in used]
-        sieves = _jit.SieveSet.make(feats, bounded_hi, bounded_mm)
+        cut_sv = getattr(self, "_fused_cut", None)
+        sieves = _jit.SieveSet.make(feats, bounded_hi, bounded_mm, cut=cut_sv is not None)
         g, g_ld = iss._lookup(X)
         wm = iss._weight_mode()
         # unweighted Arctic plans: the lane-per-node chain kernel (``_jit_chain.py``) first
@@ -835,7 +843,8 @@ class FruitSlice:
             first = mode == "force" or _jit_chain.chain_like(trie)
             kinds = ["chain", "slice"] if first else ["slice", "chain"]
         base_key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0,
-                    X.device.index)        # (a loaded module belongs to one device)
+                    X.device.index,        # (a loaded module belongs to one device)
+                    cut_sv is not None)
         memo = getattr(iss, "_jit_memo", None)
         if memo is None or memo[0] is not trie:
             memo = (trie, {})
@@ -908,14 +917,22 @@ class FruitSlice:
             else:
                 extra = g
                 extra_ld = g_ld
+        cuts = None
+        if cut_sv is not None:
+            # end of the sieved segment per series: the second column of the sorted cut
+            # table [0, cut] (fruits/sieving/segment.py:51-64), float cuts from the cache
+            cut_sv._cache = cache
+            cuts = cut_sv._cuts_device(X.shape[0], X.shape[2])[:, 1].to(torch.int32).contiguous()
         kern.launch(X.contiguous(), extra, extra_ld, thr_c, out, col0, sanitize,
-                    multicast=getattr(self, "_multicast", None))
+                    multicast=getattr(self, "_multicast", None), cuts=cuts)
         self._last_launch = ("fb_jit_chain" if chain else "fb_jit_slice",
                              kern.n_launches(X.shape[0], X.shape[2]), kern)
 
     def _transform_generic(self, X, out, col0, sanitize, dims, feats, bounded_hi,
                            bounded_mm) -> None:
         """Generic trie-interpreting kernel (``csrc/lns.cuh``)."""
+        if getattr(self, "_fused_cut", None) is not None:
+            raise NotImplementedError("cuts are not built into the generic kernel")
         iss = self._iss[0]
         L = be.lib()
         n, d, t = X.shape

@@ -151,7 +151,16 @@ class SegmentSieve(FeatureSieve, ABC):
         return string
 
     def _fusable_shape(self) -> bool:
-        return self._default_cut() and len(self._q) == 2
+        # one segment [0, cut) -- the whole series by default -- and one (lo, hi] interval
+        return len(self._cut) == 1 and len(self._q) == 2
+
+    def _cut_key(self):
+        """None for the default cut, else what identifies the segment: sieves of a
+        slice can share the generated kernel's per-series cut table only if equal."""
+        if self._default_cut():
+            return None
+        c = self._cut[0]
+        return (float(c), self._coquantile_norm) if isinstance(c, float) else (int(c), None)
 
 
 class MAX(SegmentSieve):
@@ -195,7 +204,7 @@ class END(SegmentSieve):
             self._kind, out.data_ptr(), out.stride(0), col0, n, t, be.stream_ptr()))
 
     def _fused(self):
-        return ("END", 0) if self._default_cut() and len(self._q) == 2 else None
+        return ("END", 0) if self._fusable_shape() else None
 
 
 class CUR(SegmentSieve):

@@ -230,6 +230,17 @@ FB_API int fb_jit_slice_features(fb_jit_kernel *k, const fb_jit_geometry *geo,
                                  int64_t col0, int sanitize, void *stream);
 /* (`sanitize`: bit 0 = np.nan_to_num of the features (fruits/fruit.py:172), bit 1 =
  * `out` is an NVSwitch multicast mapping, stored to with multimem.st) */
+/* The same with a cut: the segment sieves (NPI, MPI, XPI, LPI, MAX, MIN, CUR, END)
+ * look at the time steps [0, cuts[series]) only -- one int or float ("coquantile")
+ * `cut` argument of the reference's SegmentSieve (fruits/sieving/segment.py:51-64,
+ * fruits/cache.py:16-22, :98-107); END is the value at cuts[series] - 1.  cuts =
+ * DEVICE int32 [n] or NULL (whole series).  The kernel must have been generated
+ * for a cut (fruits_b200/_jit.py, SieveSet.cut). */
+FB_API int fb_jit_slice_features_cut(fb_jit_kernel *k, const fb_jit_geometry *geo,
+                                     const fb_batch *batch, const double *extra,
+                                     int64_t extra_ld, const double *thr, int64_t n_thr,
+                                     const int32_t *cuts, double *out, int64_t out_ld,
+                                     int64_t col0, int sanitize, void *stream);
 
 /* Lane-per-node form for deep Arctic tries (generator: fruits_b200/_jit_chain.py):
  * the 24-48-letter alternating-sign chains of experiments/fruit_reduced.py:42-49

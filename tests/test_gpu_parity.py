@@ -1131,6 +1131,50 @@ def test_rank2_sieves_fused_equal_composed_and_oracle(semiring, shape, monkeypat
     assert_close(res[:, summed], ref[:, summed], 1e-12, "CUR / MPI vs oracle")
 
 
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
+@pytest.mark.parametrize("cut", [0.4, 0.999, 0.001, 30, 1, -3])
+def test_single_cut_fused_equals_composed_and_oracle(cut, semiring, monkeypatch):
+    """One int or float ("coquantile") cut shared by the segment sieves of a slice
+    (fruits/sieving/segment.py:51-64, fruits/cache.py:16-22): the generated kernel
+    gets the end of the segment per series as a table and sieves [0, cut) only --
+    no materialised ISS tensor -- with the numbers of the composed route and of
+    the oracle, END included (the value at cut - 1)."""
+    from oracle import pipeline as orc
+    sieves = [["NPI", {"cut": cut, "q": [0.4, 1.0]}], ["MPI", {"cut": cut, "q": [0.4, 1.0]}],
+              ["XPI", {"cut": cut, "inc": 2, "q": [0.5, 1.0]}], ["LPI", {"cut": cut, "inc": 0, "q": [0.3, 1.0]}],
+              ["MAX", {"cut": cut}], ["MIN", {"cut": cut, "q": [0.2, 0.9]}], ["CUR", {"cut": cut}],
+              ["PPV", {}], ["CPV", {}], ["END", {"cut": cut}]]
+    spec = {"slices": [{"preps": [["INC", {}]],
+                        "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended",
+                                 "semiring": semiring}],
+                        "sieves": sieves, "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(17).standard_normal((150, 2, 97)).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(5)
+    fruit.fit(X)
+    monkeypatch.setenv("FRUITS_B200_JIT", "force")
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    monkeypatch.setenv("FRUITS_B200_JIT", "0")
+    comp = fruit.transform(X)
+    assert _routes(fruit) == ["composed"]
+    of = orc.OracleFruit(spec)
+    np.random.seed(5)
+    of.fit(X)
+    ref = of.transform(X)
+    nf = len(sieves)
+    summed = np.zeros(ref.shape[1], dtype=bool)
+    for f in (1, 6):                           # MPI, CUR: sums (order of the additions)
+        summed[f::nf] = True
+    assert_exact(res[:, ~summed], comp[:, ~summed], "fused vs composed route")
+    assert_exact(res[:, ~summed], ref[:, ~summed], "fused vs oracle")
+    assert_close(res[:, summed], comp[:, summed], 1e-12, "MPI / CUR vs composed")
+    assert_close(res[:, summed], ref[:, summed], 1e-12, "MPI / CUR vs oracle")
+    # sieves with different cuts do not share a kernel: composed route
+    mixed = specs.build_fruit(fruits, {"slices": [dict(spec["slices"][0], sieves=sieves[:1] + [["END", {}]])]})
+    assert mixed.get_slice(0)._fused_sieves() is None
+
+
 # ---------------------------------------------------------------------------
 # (k) BASELINE sizes against golden vectors frozen from the REAL reference
 # (oracle/gen_golden_full.py: the reference's own fit on the full input, its
