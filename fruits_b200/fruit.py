@@ -850,9 +850,12 @@ class FruitSlice:
             memo = (trie, {})
             iss._jit_memo = memo
 
-        def kernel_of(kind):
+        def kernel_of(kind, chain_warps=None):
             chain = kind == "chain"
-            key = base_key + ((kind, tuple(sorted(_jit_chain.options().items()))) if chain
+            copts = _jit_chain.options()
+            if chain_warps is not None:
+                copts["warps"] = chain_warps
+            key = base_key + ((kind, tuple(sorted(copts.items()))) if chain
                               else (kind, _jit.options_key()))
             kern = memo[1].get(key)
             if kern == "not compiled":
@@ -862,7 +865,7 @@ class FruitSlice:
             if kern is None:
                 try:
                     if chain:
-                        gen = _jit_chain.generate(trie, iss.semiring._code, wm, sieves, jdims)
+                        gen = _jit_chain.generate(trie, iss.semiring._code, wm, sieves, jdims, copts)
                     else:
                         # a plan without another fused route may keep part of its sums
                         # in local memory
@@ -881,6 +884,9 @@ class FruitSlice:
             if isinstance(kern, NotImplementedError):
                 raise kern
             if chain and not kern.fits(X.shape[2]):
+                # the whole series of a CTA sits in shared memory: fewer series per CTA
+                if kern.em.spc > 1:
+                    return kernel_of(kind, max(1, kern.em.nb * (kern.em.spc // 2)))
                 raise NotImplementedError("series too long for the chain kernel's staging")
             return kern
 

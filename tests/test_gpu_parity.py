@@ -1175,6 +1175,25 @@ def test_single_cut_fused_equals_composed_and_oracle(cut, semiring, monkeypatch)
     assert mixed.get_slice(0)._fused_sieves() is None
 
 
+def test_chain_kernel_long_series_fewer_series_per_cta(monkeypatch):
+    """The chain kernel stages whole series in shared memory; for long series it is
+    regenerated with fewer series per CTA before the generic kernel has to take
+    over: same numbers as the generic kernel."""
+    spec = {"slices": [dict(specs.SPECS["C4_twi"]["slices"][1], fit_sample_size=1)]}
+    X = np.random.default_rng(4).standard_normal((40, 1, 9000)).cumsum(axis=2)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(0)
+    fruit.fit(X)
+    monkeypatch.setenv("FRUITS_B200_JIT", "force")
+    res = fruit.transform(X)
+    route, _, kern = fruit.get_slice(0)._last_launch
+    assert route == "fb_jit_chain" and kern.em.spc < 4 and kern.fits(9000)
+    monkeypatch.setenv("FRUITS_B200_JIT", "0")
+    gen = fruit.transform(X)
+    assert _routes(fruit) == ["fb::lns_kernel"]
+    assert_exact(res, gen, "chain kernel (fewer series per CTA) vs generic kernel")
+
+
 # ---------------------------------------------------------------------------
 # (k) BASELINE sizes against golden vectors frozen from the REAL reference
 # (oracle/gen_golden_full.py: the reference's own fit on the full input, its
