@@ -333,3 +333,58 @@ def test_corbeille_loader_equals_the_reference(golden_dir):
         assert np.array_equal(kept, g[f"{name}_X_train_keep_nan"], equal_nan=True)
     assert names == ["Delta", "Eps"]
     assert np.isnan(g["Eps_X_train_keep_nan"]).sum() == 5
+
+
+def test_coswiss_separable_plan_reproduces_the_reference_on_the_host(golden_dir):
+    """``CosWISS._separable_plan`` -- the cosine weighted ISS as a recurrence with
+    exponent+1 states per level instead of (exponent+1)^(p-1) expansion terms --
+    evaluated with numpy (no GPU): equal to the reference's outputs (cos.npz, frozen
+    from fruits/iss/cos.py) to 1e-12 of the row maximum on all five cases."""
+    from cases import COS_CASES, make_iss_input
+    from helpers import rowmax_rel_err
+    g = np.load(os.path.join(golden_dir, "cos.npz"))
+    for name, (desc, shape, kind) in COS_CASES.items():
+        X = make_iss_input(shape, kind)
+        iss = specs.build_iss(fruits, desc)
+        nodes, emits, rows = iss._separable_plan(shape[1])
+        n, d, T = shape
+        W = []
+        for f, coeff, a, b in rows:
+            arg = np.pi * np.arange(T) / (float(np.float32(iss._freqs[f])) * (T - 1))
+            w = np.ones(T)
+            for _ in range(a):
+                w = w * np.sin(arg)
+            for _ in range(b):
+                w = w * np.cos(arg)
+            W.append(coeff * w)
+        S = [None] * len(nodes)
+        for i, (level, letter, preds) in enumerate(nodes):      # predecessors come first
+            lt = np.ones((n, T))
+            for dim, div in letter:
+                lt = lt / X[:, dim, :] if div else lt * X[:, dim, :]
+            if not preds:
+                val = lt
+            else:
+                z = np.zeros((n, T))
+                for u, r in preds:
+                    if u < 0:
+                        z = z + W[r]
+                    else:
+                        assert u < i
+                        prev = np.concatenate([np.zeros((n, 1)), S[u][:, :-1]], axis=1)
+                        z = z + W[r] * prev
+                val = lt * z
+            S[i] = np.cumsum(val, axis=1)
+        out = []
+        for terms in emits:
+            y = np.zeros((n, T))
+            for r, u in terms:
+                y = y + (S[u] if r < 0 else W[r] * S[u])
+            out.append(y)
+        out = np.stack(out)
+        assert out.shape == g[name].shape
+        assert rowmax_rel_err(out, g[name]).max() < 1e-12, name
+    # the C3 slice: 1,830 running sums instead of the 15,050 of the expansion
+    big = specs.build_iss(fruits, specs.SPECS["C3_cos"]["slices"][1]["iss"][0])
+    nodes, emits, rows = big._separable_plan(12)
+    assert (len(nodes), len(emits), len(rows)) == (1830, 575, 60)
