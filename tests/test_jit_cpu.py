@@ -223,3 +223,44 @@ def test_rank2_sieves_compile_into_the_thread_per_series_kernel(tmp_path, monkey
     for f, (kind, arg) in enumerate(feats):
         sp.kind[f], sp.arg[f] = kind, arg
     assert be.lib().fb_slice_policy(ctypes.byref(sp), 0, 0) < 0
+
+
+def test_chain_schedule_simulated_on_the_host_equals_the_oracle():
+    """The tables of the chain kernel (position -> lane / row, parent wiring, skew)
+    driven by a numpy simulation of its schedule -- every node works on
+    t = step - (depth - 1) and reads its parent's value from before the step --
+    reproduce the oracle's Arctic iterated sums bit for bit (C2 slice 1: letters
+    +-x, so the FMA of the kernel is an exact addition here)."""
+    from oracle import pipeline as orc
+    desc = specs.SPECS["C2_reduced"]["slices"][1]["iss"][0]
+    trie, iss, sieves, _ = _program("C2_reduced", 1)
+    prog = _jit_chain.ChainProgram(trie, sieves, 3)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((3, 2, 40)).cumsum(axis=2)
+    n, _, T = X.shape
+    want = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))        # [emit, n, T]
+    got = np.full_like(want, np.nan)
+    node_w, pair_w, irr_w = prog.tables()
+    R = prog.rows
+    for b, block in enumerate(prog.blocks):
+        S = np.full((len(block), n), -np.inf)
+        for s in range(T + prog.max_skew):
+            old = S.copy()
+            for i, sl in enumerate(block):
+                r, lane = i % R, i // R
+                w_ = node_w[(b * R + r) * 32 + lane]
+                skew, root = (w_ >> 16) & 0xff, (w_ >> 24) & 1
+                assert skew == trie.nodes[sl.node].depth - 1 and root == (sl.parent < 0)
+                tl = s - skew
+                if not 0 <= tl < T:
+                    continue
+                val = np.zeros(n) if root else old[sl.parent]
+                for pw in pair_w[(b * R + r) * 32 + lane]:
+                    e = ((pw >> 8) & 0xff) - (256 if (pw >> 8) & 0x80 else 0)
+                    if e:
+                        val = val + e * X[:, prog.used[pw & 0xff], tl]
+                S[i] = np.maximum(S[i], val)
+                emit = w_ & 0xffff
+                if emit != 0xffff:
+                    got[emit, :, tl] = S[i]
+    assert np.array_equal(got, want)
