@@ -40,7 +40,7 @@ from dataclasses import dataclass
 from . import _backend as be
 from . import _jit
 
-CHAIN_VERSION = 5
+CHAIN_VERSION = 6
 MIN_SERIES = 512           # from this batch size on a chain kernel is compiled (cached on disk)
 MIN_SERIES_CACHED = 16     # ... and from this size on an already compiled one is used
 
@@ -68,10 +68,13 @@ def partition(trie, rows: int) -> list:
     cap = 32 * rows
     if trie.max_depth > cap:
         raise NotImplementedError("word longer than one block of the chain kernel")
+    dup_ok = chain_like(trie)        # (bushy tries would duplicate a node per sibling)
     order = trie.dfs()
     n_blocks = max(1, -(-len(order) // cap))
     while True:
         target = -(-len(order) // n_blocks)
+        # lanes left over by the owned nodes of a block may carry duplicates
+        spare = 0
         blocks, cur, pos, owned = [], [], {}, 0
         for v in order:
             chain, a = [], v
@@ -83,8 +86,21 @@ def partition(trie, rows: int) -> list:
                 blocks.append(cur)
                 cur, pos, owned = [], {}, 0
                 need = list(reversed(chain))
+            par = trie.nodes[v].parent
+            if (dup_ok and need == [v] and par >= 0 and pos[par] != len(cur) - 1
+                    and trie.nodes[par].depth <= 2
+                    and len(cur) + trie.nodes[par].depth + 1 <= cap - spare):
+                # a branch off a shallow node that sits far back in the block (the second
+                # word of an alternating-sign pair shares only its first letter): a
+                # duplicate of that node right here keeps the parent in the previous slot
+                # -- no indexed shuffle in every step -- for the price of a free lane
+                need = list(reversed(chain))
             for a in need:
                 par = trie.nodes[a].parent
+                if a in pos and a != v:
+                    cur.append(Slot(a, False, len(cur) - 1 if par >= 0 else -1))
+                    pos[a] = len(cur) - 1          # later nodes hang off the duplicate
+                    continue
                 pos[a] = len(cur)
                 cur.append(Slot(a, a == v, pos[par] if par >= 0 else -1))
             owned += 1

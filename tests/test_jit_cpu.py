@@ -52,7 +52,7 @@ def test_deep_arctic_chain_is_not_for_the_thread_per_series_kernel():
                       [(d, 0) for d in trie.used_dims()], True, _jit.options())
 
 
-@pytest.mark.parametrize("name,si,blocks,slots", [("C2_reduced", 1, 2, 188), ("C3_general", 1, 4, 380),
+@pytest.mark.parametrize("name,si,blocks,slots", [("C2_reduced", 1, 2, 192), ("C3_general", 1, 4, 384),
                                                   ("C4_twi", 1, 1, 96)])
 def test_chain_layout_of_the_arctic_slices(name, si, blocks, slots):
     """Lane-per-node layout (fruits_b200/_jit_chain.py): every emission owned
@@ -73,7 +73,9 @@ def test_chain_layout_of_the_arctic_slices(name, si, blocks, slots):
             assert (par < 0 and sl.parent == -1) or pos[par] == sl.parent
             pos[sl.node] = i
             irregular += sl.parent >= 0 and sl.parent != i - 1
-    assert irregular <= len(prog.blocks) * 2
+    # (the second word of an alternating-sign pair branches off the first letter of the
+    # first: that letter is duplicated in a free lane, so no parent needs an indexed shuffle)
+    assert irregular == 0 and not any(prog.irregular)
     assert prog.max_skew == trie.max_depth - 1
     node_w, pair_w, irr_w = prog.tables()
     assert len(node_w) == len(pair_w) == len(irr_w) == blocks * 3 * 32
