@@ -183,6 +183,11 @@ class Program:
         self.weight_mode = weight_mode
         self.sieves = sieves
         self.reals = semiring == be.SEMIRING_REALS
+        # (max, times): the Arctic schedule with products instead of sums
+        # (fruits/iss/semiring.py:461-494); its exponential weightings stay on the scan kernel
+        self.bayes = semiring == be.SEMIRING_BAYESIAN
+        if self.bayes and weight_mode != be.WEIGHT_NONE:
+            raise NotImplementedError("weighted Bayesian sums are not generated")
         self.used = trie.used_dims()
         self.dim_index = {d: u for u, d in enumerate(self.used)}
         nodes = trie.nodes
@@ -209,7 +214,9 @@ class Program:
             if dp is not None:
                 return 2 + len(dp[1])
             c = 2 + (2 if weighted else 0)
-            if not self.reals:
+            if self.bayes:
+                c += 1 + max(0, sum(abs(e) for e in nodes[v].expo) - 1)
+            elif not self.reals:
                 c += 1 + max(0, sum(1 for e in nodes[v].expo if e != 0) - 1)
             return c + (sieves.cost() if owned else 0)
 
@@ -448,9 +455,22 @@ class Emitter:
                 else:
                     base = f"A2[{sidx[u]}]"
                 expr = base
-                for d, e in enumerate(nodes[v].expo):
-                    if e != 0:
-                        expr = f"fma({float(e)!r}, x{p.dim_index[d]}, {expr})"
+                if p.bayes:
+                    # one multiplication / division per letter occurrence, dimensions
+                    # ascending (semiring.py:476-482); 1.0 * x is x
+                    expr = f"S[{sidx[u]}]" if u >= 0 else None
+                    for d, e in enumerate(nodes[v].expo):
+                        x = f"x{p.dim_index[d]}"
+                        for _ in range(abs(e)):
+                            if expr is None:
+                                expr = x if e > 0 else f"__ddiv_rn(1.0, {x})"
+                            else:
+                                expr = f"{'__dmul_rn' if e > 0 else '__ddiv_rn'}({expr}, {x})"
+                    expr = "1.0" if expr is None else expr
+                else:
+                    for d, e in enumerate(nodes[v].expo):
+                        if e != 0:
+                            expr = f"fma({float(e)!r}, x{p.dim_index[d]}, {expr})"
                 L.append(f"const double w{v} = {expr};")
                 self._update_arctic(L, v, f"w{v}", sidx[v], v in owned, oidx.get(v))
         return L
@@ -1225,8 +1245,9 @@ def enabled(n_series: int = None) -> bool:
 
 
 MIN_SERIES = 4096          # from this batch size on a slice is compiled (seconds, cached on disk)
-MIN_SERIES_CACHED = 1024   # ... and from this size on an already compiled kernel is used:
-                           # it beats the generic kernel from ~1,000 series (scripts/crossover.py)
+MIN_SERIES_CACHED = 1000   # ... and from this size on an already compiled kernel is used:
+                           # it beats the generic kernel from ~1,000 series (scripts/crossover.py;
+                           # C2 slice 0, 1,000 x 512: 0.60 against 0.73 ms)
 
 
 class NotCompiled(NotImplementedError):

@@ -782,8 +782,10 @@ class FruitSlice:
             raise ValueError("feature matrix must be row-major")
         feats, bounded_hi, bounded_mm = self._fused_sieves()
         # rank-2 accumulators and cuts exist in the thread-per-series kernel only
+        # ... and so do the Bayesian sums
         jit_only = getattr(iss, "_jit_only", False) or self._fused_cut is not None or any(
-            k in (be.FEAT_XPI, be.FEAT_LPI, be.FEAT_CUR, be.FEAT_CPV) for k, _ in feats)
+            k in (be.FEAT_XPI, be.FEAT_LPI, be.FEAT_CUR, be.FEAT_CPV) for k, _ in feats) or \
+            iss.semiring._code == be.SEMIRING_BAYESIAN
         compile_ok = _jit.enabled(n) or (getattr(iss, "_jit_only", False) and _jit.enabled())
         # mid-size batches: the generated kernel only if it has been compiled already
         cached_ok = not compile_ok and n >= _jit.MIN_SERIES_CACHED and _jit.enabled()

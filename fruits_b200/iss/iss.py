@@ -63,8 +63,9 @@ class ISS(Seed):
 
     @property
     def _fusable_iss(self) -> bool:
-        # the Bayesian semiring has no trie kernel: sieved on materialised sums
-        return not isinstance(self.semiring, Bayesian)
+        # the Bayesian semiring has no generic trie kernel: unweighted it is compiled
+        # into the generated kernel (_jit.py), weighted it is sieved on materialised sums
+        return not isinstance(self.semiring, Bayesian) or self.weighting is None
 
     # -- plan ------------------------------------------------------------------
     def _weight_mode(self) -> int:

@@ -36,7 +36,7 @@ extern "C" {
 /* fruits/iss/semiring.py: Reals (:161), Arctic (:341) */
 #define FB_SEMIRING_REALS   0
 #define FB_SEMIRING_ARCTIC  1
-#define FB_SEMIRING_BAYESIAN 2  /* fb_bayes_word only: not a trie-kernel semiring */
+#define FB_SEMIRING_BAYESIAN 2  /* fb_bayes_word and generated kernels; not the generic trie kernel */
 /* fruits/iss/semiring.py:27-35: no weighting, Weighting.total True/False */
 #define FB_WEIGHT_NONE      0
 #define FB_WEIGHT_TOTAL     1

@@ -1131,6 +1131,36 @@ def test_rank2_sieves_fused_equal_composed_and_oracle(semiring, shape, monkeypat
     assert_close(res[:, summed], ref[:, summed], 1e-12, "CUR / MPI vs oracle")
 
 
+@pytest.mark.parametrize("shape", [(70, 2, 96), (33, 3, 41), (1, 2, 2)])
+def test_bayesian_fused_equals_composed_and_oracle(shape, monkeypatch):
+    """Unweighted Bayesian (max, times) sums compiled into the generated kernel (the
+    ISS tensor stays in registers: fruits/iss/semiring.py:461-494, one multiplication /
+    division per letter occurrence, then the running maximum) against the composed
+    route (fb_bayes_word block scan + stand-alone sieves) and the oracle."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"iss": [{"words": ["[1][-2][2]", "[11][2]", "[2][22][1][12]", "[2][1]"],
+                                 "mode": "extended", "semiring": "bayesian"}],
+                        "sieves": [["NPI", {"q": [0.4, 1.0]}], ["PPV", {}], ["MAX", {}], ["MIN", {}],
+                                   ["LPI", {"inc": 0, "q": [0.2, 1.0]}], ["CPV", {}], ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = 0.25 + 1.5 * np.random.default_rng(shape[0]).random(shape)
+    fruit = specs.build_fruit(fruits, spec)
+    np.random.seed(5)
+    fruit.fit(X)
+    monkeypatch.setenv("FRUITS_B200_JIT", "force")
+    res = fruit.transform(X)
+    assert _routes(fruit) == ["fb_jit_slice"]
+    monkeypatch.setenv("FRUITS_B200_JIT", "0")
+    comp = fruit.transform(X)
+    assert _routes(fruit) == ["composed"]
+    of = orc.OracleFruit(spec)
+    np.random.seed(5)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    assert_exact(res, comp, "fused vs composed route")
+    assert_exact(res, of.transform(X), "fused vs oracle")
+
+
 @pytest.mark.parametrize("semiring", ["reals", "arctic"])
 @pytest.mark.parametrize("cut", [0.4, 0.999, 0.001, 30, 1, -3])
 def test_single_cut_fused_equals_composed_and_oracle(cut, semiring, monkeypatch):

@@ -227,6 +227,33 @@ def test_rank2_sieves_compile_into_the_thread_per_series_kernel(tmp_path, monkey
     assert be.lib().fb_slice_policy(ctypes.byref(sp), 0, 0) < 0
 
 
+def test_bayesian_sums_compile_into_the_thread_per_series_kernel(tmp_path, monkeypatch):
+    """Unweighted Bayesian (max, times) sums (fruits/iss/semiring.py:461-494) as a
+    third semiring of the generated kernel: one multiplication / division per letter
+    occurrence, then the running maximum; weighted ones are declined (scan kernel)."""
+    monkeypatch.setattr(_jit, "CACHE_DIR", str(tmp_path))
+    spec = {"slices": [{"iss": [{"words": ["[1][-2]", "[11][2]", "[2][22][1]"], "mode": "extended",
+                                 "semiring": "bayesian"}],
+                        "sieves": [["NPI", {"q": [0.4, 1.0]}], ["MAX", {}], ["END", {}]]}]}
+    fruit = specs.build_fruit(fruits, spec)
+    slc = fruit._slices[0]
+    assert slc._is_fusable(2, None, 64)
+    feats, bhi, bmm = slc._fused_sieves()
+    sieves = _jit.SieveSet.make(feats, bhi, bmm)
+    trie = slc._iss[0].trie()
+    gen = _jit.generate(trie, be.SEMIRING_BAYESIAN, be.WEIGHT_NONE, sieves,
+                        [(d, 0) for d in trie.used_dims()], True, _jit.options())
+    src = "\n".join(gen.parts)
+    assert "__ddiv_rn(" in src and "__dmul_rn(__dmul_rn(" in src and "fma(" not in src.split("epilogue")[0]
+    assert _jit.build_cubin(gen)[:4] == b"\x7fELF"
+    with pytest.raises(NotImplementedError):
+        _jit.generate(trie, be.SEMIRING_BAYESIAN, be.WEIGHT_TOTAL, sieves,
+                      [(d, 0) for d in trie.used_dims()], True, _jit.options())
+    weighted = {"slices": [dict(spec["slices"][0], iss=[dict(spec["slices"][0]["iss"][0],
+                                                             weighting=["Indices", {}])])]}
+    assert not specs.build_fruit(fruits, weighted)._slices[0]._is_fusable(2, None, 64)
+
+
 def test_chain_schedule_simulated_on_the_host_equals_the_oracle():
     """The tables of the chain kernel (position -> lane / row, parent wiring, skew)
     driven by a numpy simulation of its schedule -- every node works on
