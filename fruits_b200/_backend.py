@@ -181,7 +181,13 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """``cudaStream_t`` of torch's current stream on the current device."""
+    if _raw_stream is not None:         # (no Stream object per call: this sits on every launch)
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -1255,13 +1255,21 @@ class NotCompiled(NotImplementedError):
 
 
 def generate(trie, semiring: int, weight_mode: int, sieves: SieveSet, dims: list,
-             shared_extra: bool, opts: dict, n_shared_rows: int = 0, max_state_regs: int = 0):
+             shared_extra: bool, opts: dict, n_shared_rows: int = 0, max_state_regs: int = 0,
+             small_batch: bool = False):
     """-> Generated: one translation unit per trie part plus the kernel that
     dispatches to them.  Raises NotImplementedError for plans the generated
-    kernel cannot hold (the caller then uses the generic kernel)."""
+    kernel cannot hold (the caller then uses the generic kernel).
+
+    ``small_batch``: fewer than ``MIN_SERIES`` series -- too few CTAs for the layout
+    with fewer, larger parts, so the plan keeps the many-parts layout if it fits
+    (C2, 1,000 series: slice 0 0.33 -> 0.27 ms, CosWISS slices 0.34 -> 0.31 and
+    0.45 -> 0.38 ms)."""
     prog = Program(trie, semiring, weight_mode, sieves, reg_budget=opts["budget"],
                    parts_multiple=opts["ppc"])
+    narrow_fits = prog.overhead <= 1.6 and prog.max_regs <= (max_state_regs or 190)
     if ((prog.overhead > 1.15 or prog.max_regs > opts["budget"] + 20 or sieves.regs() > 6)
+            and not (small_batch and narrow_fits)
             and "FRUITS_B200_JIT_OPTS" not in os.environ):
         # deep or sieve-heavy tries: fewer, larger parts (one CTA per SM, 255 registers);
         # measured on C4 slice 0 (depth 9, overhead 1.21 -> 1.08): 92 -> 71 ms

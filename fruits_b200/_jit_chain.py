@@ -539,8 +539,11 @@ def chain_like(trie) -> bool:
     """Long words with few branches (on average at least 8 nodes per leaf): the
     lane-per-node layout wires almost every parent for free.  Bushy tries are
     better served by the thread-per-series kernel when it can hold them."""
-    leaves = sum(1 for n in trie.nodes if not n.children)
-    return len(trie.nodes) >= 8 * max(leaves, 1)
+    like = trie.__dict__.get("_chain_like")
+    if like is None:
+        leaves = sum(1 for n in trie.nodes if not n.children)
+        like = trie._chain_like = len(trie.nodes) >= 8 * max(leaves, 1)
+    return like
 
 
 @dataclass

@@ -72,10 +72,14 @@ class Trie:
         return nid
 
     def used_dims(self) -> list:
-        dims = set()
-        for n in self.nodes:
-            dims.update(d for d, e in enumerate(n.expo) if e != 0)
-        return sorted(dims)
+        # (a trie is not modified once built; every transform call asks)
+        used = self.__dict__.get("_used")
+        if used is None:
+            dims = set()
+            for n in self.nodes:
+                dims.update(d for d, e in enumerate(n.expo) if e != 0)
+            used = self._used = sorted(dims)
+        return list(used)
 
     def dfs(self) -> list:
         order = []

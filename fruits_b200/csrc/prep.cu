@@ -80,6 +80,114 @@ __global__ void row_stats_kernel(const double *__restrict__ X, double *__restric
     stats[2 * r + 1] = sd + eps;
 }
 
+// The same sums with one WARP per row: the recursion above always ends in blocks of
+// <= 128 values ("leaves": eight interleaved running sums, combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then a tail of < 8 values), and the blocks are
+// combined in post-order.  Eight lanes own the eight running sums of a leaf (four leaves per
+// warp at a time, 64-byte segments per load), an xor butterfly over 1, 2, 4 is numpy's
+// combination (addition is commutative, so both partners hold the same bits), and lane 0
+// replays the post-order merges on a small stack -- every addition has the operands and the
+// order of the one-thread version, so the bits are the same, without the strided reads.
+constexpr int RS_WARPS = 4;
+constexpr int RS_MAXL = 1024;       // leaves of a row of at most 65,536 values
+constexpr int RS_MAXT = 65536;
+
+template <class F>
+__device__ double warp_pairwise_sum(const double *a, const int *loff, const int *llen,
+                                    const int *lmrg, int nleaves, double *stack, F f)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, k = lane & 7;
+    int sp = 0;
+    for (int b = 0; b < nleaves; b += 4) {
+        const int li = b + grp;
+        const bool valid = li < nleaves;
+        const int off = valid ? loff[li] : 0, n = valid ? llen[li] : 0;
+        const double *x = a + off;
+        double res = 0.0;
+        if (n >= 8) {
+            res = f(x[k]);
+            const int body = n - (n & 7);
+#pragma unroll 5
+            for (int i = 8; i < 128; i += 8)
+                if (i < body) res = __dadd_rn(res, f(x[i + k]));
+        }
+        res = __dadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 1));
+        res = __dadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 2));
+        res = __dadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 4));
+        if (n >= 8) {
+            for (int i = n - (n & 7); i < n; i++) res = __dadd_rn(res, f(x[i]));
+        } else {
+            res = 0.0;
+            for (int i = 0; i < n; i++) res = __dadd_rn(res, f(x[i]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double s = __shfl_sync(0xffffffffu, res, j * 8);
+            if (lane == 0 && b + j < nleaves) {
+                stack[sp++] = s;
+                for (int m = lmrg[b + j]; m > 0; m--) {
+                    const double hi = stack[--sp], lo = stack[--sp];
+                    stack[sp++] = __dadd_rn(lo, hi);
+                }
+            }
+        }
+    }
+    double total = lane == 0 ? stack[0] : 0.0;
+    return __shfl_sync(0xffffffffu, total, 0);
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+row_stats_warp_kernel(const double *__restrict__ X, double *__restrict__ stats, long long rows,
+                      int t, int div_std, double eps)
+{
+    __shared__ int loff[RS_MAXL], llen[RS_MAXL], lmrg[RS_MAXL];
+    __shared__ int nleaves_s;
+    __shared__ double stacks[RS_WARPS][24];
+    if (threadIdx.x == 0) {
+        // post-order walk of pairwise_sum's recursion (the same for every row)
+        int so[24], sn[24], sph[24], sp = 0, nl = 0;
+        so[0] = 0; sn[0] = t; sph[0] = 0; sp = 1;
+        while (sp > 0) {
+            --sp;
+            const int off = so[sp], n = sn[sp], ph = sph[sp];
+            if (n <= 128) {
+                loff[nl] = off; llen[nl] = n; lmrg[nl] = 0; nl++;
+            } else if (ph == 0) {
+                int n2 = n / 2;
+                n2 -= n2 % 8;
+                so[sp] = off; sn[sp] = n; sph[sp] = 1; sp++;
+                so[sp] = off + n2; sn[sp] = n - n2; sph[sp] = 0; sp++;
+                so[sp] = off; sn[sp] = n2; sph[sp] = 0; sp++;
+            } else {
+                lmrg[nl - 1]++;
+            }
+        }
+        nleaves_s = nl;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * RS_WARPS + warp;
+    if (r >= rows) return;
+    const double *x = X + r * t;
+    const int nl = nleaves_s;
+    const double mean = warp_pairwise_sum(x, loff, llen, lmrg, nl, stacks[warp],
+                                          [](double v) { return v; }) / (double)t;
+    double sd = 1.0;
+    if (div_std) {
+        __syncwarp();
+        const double var = warp_pairwise_sum(x, loff, llen, lmrg, nl, stacks[warp],
+                                             [mean](double v) {
+                                                 const double c = __dadd_rn(v, -mean);
+                                                 return __dmul_rn(c, c);
+                                             }) / (double)t;
+        sd = sqrt(var);
+    }
+    if (lane == 0) {
+        stats[2 * r] = mean;
+        stats[2 * r + 1] = sd + eps;
+    }
+}
+
 __global__ void standardize_kernel(const double *__restrict__ X, const double *__restrict__ stats,
                                    double *__restrict__ out, long long rows, int t)
 {
@@ -208,8 +316,12 @@ int fb_row_stats(const double *X, double *stats, int64_t rows, int64_t t, int di
 {
     FB_REQUIRE(X && stats && rows >= 0 && t >= 1, "bad arguments");
     if (rows == 0) return 0;
-    row_stats_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
-        X, stats, rows, (int)t, div_std, eps);
+    if (t <= RS_MAXT)
+        row_stats_warp_kernel<<<(unsigned)((rows + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, 0,
+                                (cudaStream_t)stream>>>(X, stats, rows, (int)t, div_std, eps);
+    else
+        row_stats_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+            X, stats, rows, (int)t, div_std, eps);
     FB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -507,7 +507,10 @@ class FruitSlice:
         w = self._iss[0].weighting
         if w is not None and getattr(w, "_on_prepared", False):
             return False
-        return self._fused_dims(n_dims) is not None and self._fused_sieves() is not None
+        if self._fused_dims(n_dims) is None:
+            return False
+        self._fs_memo = self._fused_sieves()      # (_transform_fused takes it from here)
+        return self._fs_memo is not None
 
     # -- fit -------------------------------------------------------------------------
     def fit(self, X, cache: Optional[SharedSeedCache] = None) -> None:
@@ -780,7 +783,7 @@ class FruitSlice:
                 f"words use dimension {iss.max_dim()} but the prepared input has {len(dims)}")
         if out.stride(1) != 1:
             raise ValueError("feature matrix must be row-major")
-        feats, bounded_hi, bounded_mm = self._fused_sieves()
+        feats, bounded_hi, bounded_mm = self.__dict__.pop("_fs_memo", None) or self._fused_sieves()
         # rank-2 accumulators and cuts exist in the thread-per-series kernel only
         # ... and so do the Bayesian sums
         jit_only = getattr(iss, "_jit_only", False) or self._fused_cut is not None or any(
@@ -844,9 +847,10 @@ class FruitSlice:
         if mode != "0" and not n_shared and _jit_chain.suitable(trie, iss.semiring._code, wm):
             first = mode == "force" or _jit_chain.chain_like(trie)
             kinds = ["chain", "slice"] if first else ["slice", "chain"]
+        small = X.shape[0] < _jit.MIN_SERIES          # (layout choice of _jit.generate)
         base_key = (tuple(jdims), tuple(feats), bounded_hi, bounded_mm, g_ld == 0,
                     X.device.index,        # (a loaded module belongs to one device)
-                    cut_sv is not None)
+                    cut_sv is not None, small)
         memo = getattr(iss, "_jit_memo", None)
         if memo is None or memo[0] is not trie:
             memo = (trie, {})
@@ -873,7 +877,7 @@ class FruitSlice:
                         # in local memory
                         spill = 450 if getattr(iss, "_jit_only", False) else 0
                         gen = _jit.generate(trie, iss.semiring._code, wm, sieves, jdims,
-                                            g_ld == 0, _jit.options(), n_shared, spill)
+                                            g_ld == 0, _jit.options(), n_shared, spill, small)
                 except NotImplementedError as exc:
                     memo[1][key] = exc          # remembered: planning is host work
                     raise

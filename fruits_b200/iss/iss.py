@@ -74,8 +74,9 @@ class ISS(Seed):
         return be.WEIGHT_TOTAL if self.weighting.total else be.WEIGHT_NONTOTAL
 
     def _signature(self):
+        # (evaluated on every transform call: no array is built for the default alphas)
         return (tuple(str(w) for w in self.words),
-                tuple(tuple(float(a) for a in w.alpha) for w in self.words)
+                tuple(None if w._alpha is None else w._alpha.tobytes() for w in self.words)
                 if self.weighting is not None else None,
                 self.mode, self.semiring._code, self._weight_mode())
 

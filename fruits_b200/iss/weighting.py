@@ -41,6 +41,18 @@ class Weighting(ABC):
     def get_lookup_device(self, X: torch.Tensor):
         """-> (g tensor, shared flag)"""
 
+    def _memoized_row(self, X: torch.Tensor, build):
+        """The shared row of a lookup that depends on the length only: built (and copied
+        to the device) once per (length, device, parameters), not on every transform."""
+        if getattr(self, "_transform", None) is not None:
+            return build(X)                      # a Python transform may carry state
+        key = (X.shape[2], X.device, tuple(sorted(
+            (k, v) for k, v in self.__dict__.items() if k not in ("_row_memo", "_cache"))))
+        memo = self.__dict__.get("_row_memo")
+        if memo is None or memo[0] != key:
+            self._row_memo = memo = (key, build(X))
+        return memo[1]
+
     def get_lookup(self, X) -> np.ndarray:
         """``g[n, length]`` as a host array (reference API)."""
         Xd = be.to_device(X)
@@ -76,6 +88,9 @@ class Indices(Weighting):
         self._scale = scale
 
     def get_lookup_device(self, X: torch.Tensor):
+        return self._memoized_row(X, self._shared_row)
+
+    def _shared_row(self, X: torch.Tensor):
         length = X.shape[2]
         r = np.arange(1, length + 1)
         if self._relative:
@@ -137,6 +152,9 @@ class Plateaus(Weighting):
         self._scale = scale
 
     def get_lookup_device(self, X: torch.Tensor):
+        return self._memoized_row(X, self._shared_row)
+
+    def _shared_row(self, X: torch.Tensor):
         length = X.shape[2]
         r = np.ones(length)
         step = int(length / self._nplateaus)

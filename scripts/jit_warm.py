@@ -50,18 +50,25 @@ def warm(name: str) -> None:
                   f"{len(genc.em.p.blocks)} blocks x {genc.em.p.rows} rows, "
                   f"{genc.em.spc} series/CTA, {time.time() - t0:.1f} s", flush=True)
             continue
-        try:
-            gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
-                                _jit.SieveSet.make(feats, bhi, bmm), jdims, shared, _jit.options(),
-                                n_shared, 450 if getattr(iss, "_jit_only", False) else 0)
-        except NotImplementedError as exc:
-            print(f"{name} slice {si}: generic kernel ({exc})", flush=True)
-            continue
-        cubin = _jit.build_cubin(gen)
-        em = gen.em
-        print(f"{name} slice {si}: {len(trie.nodes)} nodes, {len(gen.parts)} parts, "
-              f"{32 * em.ppc * em.gpc} threads/CTA, <= {gen.max_regs} registers, "
-              f"{len(cubin) // 1024} KB cubin, {time.time() - t0:.1f} s", flush=True)
+        seen = set()
+        for small in (False, True):           # the layout for < _jit.MIN_SERIES series too
+            try:
+                gen = _jit.generate(trie, iss.semiring._code, iss._weight_mode(),
+                                    _jit.SieveSet.make(feats, bhi, bmm), jdims, shared,
+                                    _jit.options(), n_shared,
+                                    450 if getattr(iss, "_jit_only", False) else 0, small)
+            except NotImplementedError as exc:
+                print(f"{name} slice {si}: generic kernel ({exc})", flush=True)
+                break
+            if gen.digest() in seen:
+                continue
+            seen.add(gen.digest())
+            t0 = time.time()
+            cubin = _jit.build_cubin(gen)
+            em = gen.em
+            print(f"{name} slice {si}{' (small batches)' if small else ''}: {len(trie.nodes)} nodes, "
+                  f"{len(gen.parts)} parts, {32 * em.ppc * em.gpc} threads/CTA, <= {gen.max_regs} "
+                  f"registers, {len(cubin) // 1024} KB cubin, {time.time() - t0:.1f} s", flush=True)
 
 
 if __name__ == "__main__":

@@ -30,10 +30,25 @@ if __name__ == "__main__":
             print(f"{opts}: {type(exc).__name__}: {exc}", flush=True)
             continue
         torch.cuda.synchronize()
+        # device time without the host in the way: replay one captured call
+        reps, run = 5, (lambda: fruit.transform_device(X, out=out))
+        if os.environ.get("SWEEP_GRAPH", "1") == "1":
+            try:
+                g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+                st.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(st):
+                    run()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g, stream=st):
+                        run()
+                torch.cuda.synchronize()
+                reps, run = 20, g.replay
+            except Exception as exc:      # noqa: BLE001
+                print(f"(no graph: {type(exc).__name__})", flush=True)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev[0].record()
-        for _ in range(5):
-            fruit.transform_device(X, out=out)
+        for _ in range(reps):
+            run()
         ev[1].record()
         torch.cuda.synchronize()
         route, _, kern = fruit.get_slice(0)._last_launch
@@ -42,5 +57,5 @@ if __name__ == "__main__":
         same = "" if ref is None else f" equal_to_first={bool(torch.equal(out, ref))}"
         if ref is None:
             ref = out.clone()
-        print(f"{name} slice {si} [{opts}]: {ev[0].elapsed_time(ev[1]) / 5:8.2f} ms route={route} {shape}{same}",
+        print(f"{name} slice {si} [{opts}]: {ev[0].elapsed_time(ev[1]) / reps:8.3f} ms route={route} {shape}{same}",
               flush=True)
