@@ -1322,11 +1322,14 @@ class Generated:
     em: Emitter
 
     def digest(self) -> str:
-        h = hashlib.sha256(f"v{JIT_VERSION} r{self.max_regs}\n".encode())
-        for src in self.parts + [self.entry]:
-            h.update(src.encode())
-            h.update(b"\0")
-        return h.hexdigest()[:24]
+        d = self.__dict__.get("_digest")
+        if d is None:
+            h = hashlib.sha256(f"v{JIT_VERSION} r{self.max_regs}\n".encode())
+            for src in self.parts + [self.entry]:
+                h.update(src.encode())
+                h.update(b"\0")
+            d = self._digest = h.hexdigest()[:24]
+        return d
 
 
 def _nvrtc(src: str, name: str, relocatable: bool, max_regs: int) -> bytes:

@@ -864,11 +864,11 @@ class FruitSlice:
             key = base_key + ((kind, tuple(sorted(copts.items()))) if chain
                               else (kind, _jit.options_key()))
             kern = memo[1].get(key)
-            if kern == "not compiled":
-                if cached_only:
-                    raise _jit.NotCompiled("not compiled")
-                kern = None                     # a large batch pays for the compilation
-            if kern is None:
+            gen = None
+            if isinstance(kern, tuple):         # ("not compiled", planned source)
+                gen, kern = kern[1], None       # a large batch pays for the compilation, a
+                                                # mid-size one looks for the cubin again
+            if kern is None and gen is None:
                 try:
                     if chain:
                         gen = _jit_chain.generate(trie, iss.semiring._code, wm, sieves, jdims, copts)
@@ -881,10 +881,11 @@ class FruitSlice:
                 except NotImplementedError as exc:
                     memo[1][key] = exc          # remembered: planning is host work
                     raise
+            if kern is None:
                 try:
                     kern = (_jit_chain.JitChain if chain else _jit.JitSlice).load(gen, cached_only)
                 except _jit.NotCompiled:
-                    memo[1][key] = "not compiled"      # do not plan again on every call
+                    memo[1][key] = ("not compiled", gen)      # do not plan again on every call
                     raise
                 memo[1][key] = kern
             if isinstance(kern, NotImplementedError):

@@ -1019,7 +1019,7 @@ def test_words_over_many_dimensions():
 
 
 def test_mid_size_batches_use_a_compiled_kernel_only_if_it_exists(monkeypatch):
-    """1,024 <= n < 4,096: the generated kernel is used when its cubin is in
+    """1,000 <= n < 4,096: the generated kernel is used when its cubin is in
     memory or on disk, never compiled for such a batch; identical numbers on
     either route."""
     from fruits_b200 import _jit
