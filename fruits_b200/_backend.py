@@ -139,6 +139,20 @@ def lib() -> ctypes.CDLL:
         "fb_bayes_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, i32, i32, vp, vp], i32),
         "fb_arctic_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, i32, i32, vp, vp], i32),
         "fb_exp_rows": ([vp, vp, i64, i64, ctypes.POINTER(ctypes.c_float), i32, vp], i32),
+        # csrc/prep_more.cu: the preparateurs beside INC / STD / NRM
+        "fb_time_mask": ([vp, vp, i64, i64, i64, vp, vp, vp, i64, vp], i32),
+        "fb_time_shift": ([vp, vp, i64, i64, i64, vp], i32),
+        "fb_lead_lag": ([vp, vp, i64, i64, vp], i32),
+        "fb_moving_average": ([vp, vp, i64, i64, i64, vp], i32),
+        "fb_random_increments": ([vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp], i32),
+        "fb_dim_project": ([vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp], i32),
+        "fb_ffn": ([vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp], i32),
+        "fb_dim_pow": ([vp, vp, vp, i64, i64, i64, vp], i32),
+        "fb_abs_mean_max": ([vp, vp, i64, i64, i64, vp], i32),
+        "fb_rotate2": ([vp, vp, i64, i64, dbl, vp], i32),
+        "fb_spe_range": ([vp, vp, i64, i64, dbl, dbl, i32, i32, vp], i32),
+        "fb_wave_embed": ([vp, vp, vp, i64, i64, i64, i64, i32, vp], i32),
+        "fb_clip_where": ([vp, vp, i64, dbl, dbl, i32, vp], i32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -161,6 +175,9 @@ EXPORTED = [
     "fb_bayes_word", "fb_arctic_word", "fb_order_stats_multi_workspace", "fb_order_stats_multi",
     "fb_order_stats_dist_layout", "fb_order_stats_dist", "fb_order_stats_dist8_layout",
     "fb_order_stats_dist8",
+    "fb_time_mask", "fb_time_shift", "fb_lead_lag", "fb_moving_average",
+    "fb_random_increments", "fb_dim_project", "fb_ffn", "fb_dim_pow", "fb_abs_mean_max",
+    "fb_rotate2", "fb_spe_range", "fb_wave_embed", "fb_clip_where",
 ]
 
 

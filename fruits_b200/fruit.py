@@ -143,7 +143,9 @@ class Fruit:
         rows = max(1, min(n, (chunk_mb << 20) // max(row_bytes, 1)))
         # every step of transform is independent per series, so row chunks can
         # be processed on their own (a user-supplied cache refers to all rows)
-        single = bool(callbacks) or cache is not None or n <= rows
+        single = bool(callbacks) or cache is not None or n <= rows or not all(
+            p._row_independent_transform() for slc in self._slices
+            for p in slc.get_preparateurs())       # (FUN: user code that sees the whole batch)
         if single:
             res = self.transform_device(be.to_device(Xh), callbacks, cache)
             oh.copy_(res)
@@ -771,8 +773,40 @@ class FruitSlice:
             return
         if self._is_fusable(X.shape[1], callbacks, X.shape[2]):
             self._transform_fused(X.contiguous(), cache, out, col0, sanitize)
-        else:
+        elif not self._transform_prepared_fused(X, callbacks, cache, out, col0, sanitize):
             self._transform_composed(X, callbacks or [], cache, out, col0, sanitize)
+
+    def _transform_prepared_fused(self, X, callbacks, cache, out, col0, sanitize) -> bool:
+        """Leading preparateurs the kernels cannot apply while they load the
+        input (everything but ``INC`` / ``STD`` / ``NEW``) write a prepared copy
+        with their own streaming kernel; the rest of the slice then takes the
+        fused route on that copy, so the iterated sums still never reach HBM.
+        False if the slice cannot be fused behind any prefix."""
+        preps = self._preparateurs
+        if callbacks or not preps:
+            return False
+        saved = preps
+        try:
+            for k in range(1, len(saved) + 1):
+                self._preparateurs = saved[k:]
+                if self._fused_dims(1) is not None:
+                    break
+            else:
+                return False
+            if not self._is_fusable(X.shape[1], callbacks, X.shape[2]):
+                return False          # ISS or sieves keep the slice off the fused route anyway
+            prepared = X
+            for prep in saved[:k]:
+                prep._cache = cache
+                prepared = prep._transform_device(prepared)
+            if prepared.dim() != 3:
+                raise ValueError("preparateurs must return (n_series, n_dimensions, length)")
+            if not self._is_fusable(prepared.shape[1], callbacks, prepared.shape[2]):
+                return False
+            self._transform_fused(prepared.contiguous(), cache, out, col0, sanitize)
+            return True
+        finally:
+            self._preparateurs = saved
 
     def _transform_fused(self, X, cache, out, col0, sanitize) -> None:
         iss = self._iss[0]

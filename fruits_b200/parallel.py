@@ -242,7 +242,8 @@ def _rows_ok(slc) -> bool:
     from .sieving.segment import SegmentSieve
     if len(slc.get_iss()) != 1:
         return False
-    if not all(p._row_independent_fit() for p in slc.get_preparateurs()):
+    if not all(p._row_independent_fit() and not p._needs_raw_cache()
+               for p in slc.get_preparateurs()):
         return False
     for sv in slc.get_sieves():
         if sv.requires_fitting and not isinstance(sv, (SegmentSieve, PPV)):
@@ -291,6 +292,10 @@ def fit_sharded(fruit, X_local: torch.Tensor, n_total: Optional[int] = None, gro
                 raise NotImplementedError(
                     "node-sharded fit of sieves on L1/L2-weighted sums needs the raw-input cache "
                     "of the whole batch (reference quirk: fruits/cache.py:97-112)")
+        if any(p._needs_raw_cache() for p in slc.get_preparateurs()):
+            raise NotImplementedError(
+                "preparateurs that read the raw-input cache (WIN, SPE(step_transform=...)) "
+                "cannot be fitted on a sharded batch")
         sample = gather_fit_sample(X_local, n_total, slc.fit_sample_size, group)
 
         def exchange(copies):

@@ -23,3 +23,14 @@ class Preparateur(Seed, ABC):
         """True if ``fit`` looks at one series at a time (or at nothing), so a
         row-sharded fit sample needs no exchange (``parallel.fit_sharded``)."""
         return True
+
+    def _row_independent_transform(self) -> bool:
+        """True if ``transform`` treats every series on its own, so a host batch
+        may be streamed through the GPU in row chunks (``Fruit._transform_host``);
+        false for user code that sees the whole batch (``FUN``)."""
+        return True
+
+    def _needs_raw_cache(self) -> bool:
+        """True if ``transform`` reads the cache of the raw batch (``WIN``,
+        ``SPE(step_transform=...)``): a fit on a gathered sample cannot serve it."""
+        return False

@@ -31,6 +31,12 @@ class _Carrier(Preparateur):
     def _row_independent_fit(self) -> bool:
         return self._preparateur is None or self._preparateur._row_independent_fit()
 
+    def _row_independent_transform(self) -> bool:
+        return self._preparateur is None or self._preparateur._row_independent_transform()
+
+    def _needs_raw_cache(self) -> bool:
+        return self._preparateur is not None and self._preparateur._needs_raw_cache()
+
 
 class DIM(_Carrier):
     """The untouched dimensions first, then ``preparateur`` applied to the

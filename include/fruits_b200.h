@@ -346,6 +346,61 @@ FB_API int fb_nrm_scale(const double *in, double *out, int64_t rows, int64_t t, 
 FB_API int fb_coquantile(const double *S, int64_t *out, int64_t n, int64_t t, double q,
                          void *stream);
 
+/* -- the remaining preparateurs (csrc/prep_more.cu): each writes a prepared
+ *    copy [n][d'][t'] that the ISS kernels read like raw input -- */
+
+/* DIL (fruits/preparation/filter.py:55-61), DOT (:185-190), PDD (:253-259),
+ * CTS(pseudo_shift=True) (transform.py:940-941), WIN (filter.py:97-113):
+ * out = X where keep[t] != 0 (keep == NULL: everywhere) and t lies in the
+ * Python slice lo[i]+lo_off : hi[i] of its series (lo == hi == NULL:
+ * everywhere), 0.0 elsewhere.  keep: uint8[t], lo / hi: int64[n] on the device. */
+FB_API int fb_time_mask(const double *X, double *out, int64_t n, int64_t d, int64_t t,
+                        const uint8_t *keep, const int64_t *lo, const int64_t *hi,
+                        int64_t lo_off, void *stream);
+/* CTS (transform.py:943-944): out[k] = x[min(k + shift, t - 1)] per row. */
+FB_API int fb_time_shift(const double *X, double *out, int64_t rows, int64_t t, int64_t shift,
+                         void *stream);
+/* LAG (transform.py:291-298): rows x t -> (2 rows) x (2t - 1), lead row then lag row. */
+FB_API int fb_lead_lag(const double *X, double *out, int64_t rows, int64_t t, void *stream);
+/* MAV._backend (transform.py:233-239): out[k-1] = sum(x[k-width:k]) / width, 0 in front. */
+FB_API int fb_moving_average(const double *X, double *out, int64_t rows, int64_t t,
+                             int64_t width, void *stream);
+/* RIN._backend (transform.py:447-468); kernel f64[d][width], ndim i32[n_out], dims i32[d] on
+ * the device; pad = width reproduces adaptive_width (:537-543), else 0.  out[n][n_out][t]. */
+FB_API int fb_random_increments(const double *X, const double *kernel, const int32_t *ndim,
+                                const int32_t *dims, double *out, int64_t n, int64_t d,
+                                int64_t t, int n_out, int width, int pad, void *stream);
+/* JLD._backend (transform.py:651-670); kernel f64[sum(ndim)], bias f64[n_out]. */
+FB_API int fb_dim_project(const double *X, const double *kernel, const double *bias,
+                          const int32_t *ndim, const int32_t *dims, double *out, int64_t n,
+                          int64_t d, int64_t t, int n_out, void *stream);
+/* FFN._transform (transform.py:362-376); mean = fb_row_stats output (center) or NULL;
+ * W1 f64[d_hidden][d], b1 f64[d_hidden], W2 f64[d_out][d_hidden].  out[n][d_out][t]. */
+FB_API int fb_ffn(const double *X, const double *mean, const double *W1, const double *b1,
+                  const double *W2, double *out, int64_t n, int64_t d, int64_t t, int d_hidden,
+                  int d_out, int relu_out, void *stream);
+/* RDW._transform (transform.py:601-602): x ** w[dim]. */
+FB_API int fb_dim_pow(const double *X, const double *w, double *out, int64_t n, int64_t d,
+                      int64_t t, void *stream);
+/* RDW._fit (transform.py:592): out[j] = max_t(mean_i |x[i][j][t]|). */
+FB_API int fb_abs_mean_max(const double *X, double *out, int64_t n, int64_t d, int64_t t,
+                           void *stream);
+/* RPE._backend (transform.py:859-875): X[n][2][t] rotated by k / den, den = T ** freq. */
+FB_API int fb_rotate2(const double *X, double *out, int64_t n, int64_t t, double den,
+                      void *stream);
+/* SPE._transform (transform.py:790-802): the argument of the wave (src == NULL: k / den in
+ * one row; else src / den, or src / src[r][t-1] ** freq if per_row_last), through np.sin
+ * if apply_sin.  den = T ** freq from the host. */
+FB_API int fb_spe_range(const double *src, double *out, int64_t rows, int64_t t, double den,
+                        double freq, int per_row_last, int apply_sin, void *stream);
+/* SPE._transform (transform.py:803-810): X[x_rows][d][t] * (or +) wave[wave_rows][1][t] with
+ * numpy's broadcasting (equal row counts, or one of them 1); out has the larger row count. */
+FB_API int fb_wave_embed(const double *X, const double *wave, double *out, int64_t x_rows,
+                         int64_t wave_rows, int64_t d, int64_t t, int additive, void *stream);
+/* QTC._transform (transform.py:990-1001): np.where(X > q, bound, X) (lower: X < q). */
+FB_API int fb_clip_where(const double *X, double *out, int64_t total, double q, double bound,
+                         int lower, void *stream);
+
 /* -- sieves on materialised arrays (stand-alone seeds, general cuts, fit) -- */
 
 /* fruits/sieving/increment.py:63-71 _pre_transform: inc > 0 increments,

@@ -170,6 +170,35 @@ def gen_preps():
     np.savez_compressed(os.path.join(GOLD, "preps.npz"), **out)
 
 
+def gen_preps2():
+    """The preparateurs beside INC / STD / NRM: fit under a seed on X, transform
+    X and a second batch, the RNG state behind fit."""
+    from oracle import preps as more
+    from cases import PREP2_CASES, PREP2_EXACT, make_prep2_inputs
+    print("[preparateurs 2]")
+    out = {}
+    for name, desc in PREP2_CASES.items():
+        X, X2 = make_prep2_inputs(name)
+        p = specs._prep(ref, desc)
+        np.random.seed(7)
+        p.fit(X)
+        state_r = np.random.random()              # where the generator stands after fit
+        r, r2 = p.transform(X), p.transform(X2)
+        np.random.seed(7)
+        st = more.fit_prep(desc, X)
+        state_o = np.random.random()
+        assert state_r == state_o, f"{name}: fit consumed the RNG differently"
+        o = more.transform_prep(desc, st, X, orc.RawCache(X))
+        o2 = more.transform_prep(desc, st, X2, orc.RawCache(X2))
+        for a, b, what in ((o, r, name), (o2, r2, name + " (second batch)")):
+            if desc[0] in PREP2_EXACT:
+                check_equal(a, b, f"prep {what}")
+            else:
+                check_close(a, b, f"prep {what}", rtol=1e-12)
+        out[name], out[name + "_2"], out[name + "_rng"] = r, r2, np.array(state_r)
+    np.savez_compressed(os.path.join(GOLD, "preps2.npz"), **out)
+
+
 # ---------------------------------------------------------------------------
 def ref_thresholds(fruit):
     rows = []

@@ -195,8 +195,28 @@ def nrm(X, scale_dim=False):
     return out
 
 
-def apply_prep(prep, X, state=None):
-    """Transform with one preparateur description ``[name, args]``."""
+_STATELESS_PREPS = ("INC", "STD", "NRM")
+
+
+def fit_prep_state(prep, X):
+    """What ``fit`` leaves on a preparateur (None for INC / STD / NRM; the state
+    of the wrapped preparateur for NEW / DIM; ``oracle/preps.py`` otherwise)."""
+    name, args = prep
+    if name in _STATELESS_PREPS:
+        return None
+    if name == "NEW":
+        return None if args is None else fit_prep_state(args, X)
+    if name == "DIM":
+        dims = args["dim"] if isinstance(args["dim"], (list, tuple)) else [args["dim"]]
+        return fit_prep_state(args["preparateur"], np.ascontiguousarray(X[:, list(dims), :]))
+    from . import preps as more
+    return more.fit_prep(prep, X)
+
+
+def apply_prep(prep, X, state=None, cache=None):
+    """Transform with one preparateur description ``[name, args]``; ``state``
+    from ``fit_prep_state`` (fitted on X itself if omitted), ``cache`` the
+    ``RawCache`` of the raw batch."""
     name, args = prep
     if name == "INC":
         # fruits/preparation/transform.py:62-76
@@ -225,14 +245,18 @@ def apply_prep(prep, X, state=None):
         # fruits/preparation/wrapper.py:78-96
         if args is None:
             return np.concatenate((X, X), axis=1)
-        return np.concatenate((X, apply_prep(args, X)), axis=1)
+        return np.concatenate((X, apply_prep(args, X, state, cache)), axis=1)
     if name == "DIM":
         # fruits/preparation/wrapper.py:37-43: the chosen dimensions (in the given
         # order) transformed and appended behind the untouched ones
         dims = args["dim"] if isinstance(args["dim"], (list, tuple)) else [args["dim"]]
-        inner = apply_prep(args["preparateur"], np.ascontiguousarray(X[:, list(dims), :]))
+        inner = apply_prep(args["preparateur"], np.ascontiguousarray(X[:, list(dims), :]),
+                           state, cache)
         return np.concatenate((np.delete(X, list(dims), axis=1), inner), axis=1)
-    raise NotImplementedError(name)
+    from . import preps as more          # MAV, LAG, FFN, RIN, ... DIL, WIN, DOT, PDD
+    if state is None:
+        state = more.fit_prep(prep, X)
+    return more.transform_prep(prep, state, X, cache)
 
 
 # ---------------------------------------------------------------------------
@@ -638,8 +662,10 @@ class OracleSlice:
     def fit(self, X, cache):
         # fruits/fruit.py:456-496
         prepared = self._sample(X)
+        self.prep_states = []
         for prep in self.spec.get("preps", []):
-            prepared = apply_prep(prep, prepared)
+            self.prep_states.append(fit_prep_state(prep, prepared))
+            prepared = apply_prep(prep, prepared, self.prep_states[-1], cache)
         if not any(s.requires_fitting() for s in self.sieves):
             self.sieves_extended = []
             return
@@ -653,8 +679,8 @@ class OracleSlice:
     def transform(self, X, cache):
         # fruits/fruit.py:498-553
         prepared = X
-        for prep in self.spec.get("preps", []):
-            prepared = apply_prep(prep, prepared)
+        for prep, state in zip(self.spec.get("preps", []), self.prep_states):
+            prepared = apply_prep(prep, prepared, state, cache)
         out = np.zeros((prepared.shape[0], self.nfeatures()))
         k = 0
         for i, itsum in enumerate(iterate_iss(prepared, self.spec["iss"], cache)):

@@ -171,6 +171,69 @@ PREP_CASES = {
 
 
 
+# the preparateurs beside INC / STD / NRM (fruits/preparation/transform.py:212-1048,
+# filter.py); "@name" = a callable of oracle/preps.py::CALLABLES.  Frozen from the
+# reference by ``oracle/gen_golden.py preps2`` (fit under np.random.seed(7) on the first
+# input, transform of both inputs, state of the RNG behind fit).
+PREP2_CASES = {
+    "nrm_scale_dim": ["NRM", {"scale_dim": True}],
+    "mav": ["MAV", {}],
+    "mav_float": ["MAV", {"width": 0.25}],
+    "mav_wide": ["MAV", {"width": 64}],
+    "lag": ["LAG", {}],
+    "ffn": ["FFN", {}],
+    "ffn_out3_relu": ["FFN", {"d_out": 3, "d_hidden": 5, "center": False, "relu_out": True}],
+    "rin": ["RIN", {}],
+    "rin_w4_adaptive": ["RIN", {"width": 4, "adaptive_width": True}],
+    "rin_outdim2_sum1": ["RIN", {"width": 3, "out_dim": 2, "force_sum_one": True}],
+    "rin_kernel": ["RIN", {"kernel": [[1.0, -0.5], [0.25, 0.5], [2.0, 0.0]]}],
+    "rin_callable": ["RIN", {"width": "@half"}],
+    "rdw": ["RDW", {}],
+    "rdw_uniform": ["RDW", {"dist": "uniform"}],
+    "jld": ["JLD", {"dim": 2}],
+    "jld_distribute_bias": ["JLD", {"dim": 2, "distribute": True, "bias": True}],
+    "jld_float": ["JLD", {"dim": 0.99, "bias": True}],
+    "spe": ["SPE", {"freq": 0.5}],
+    "spe_additive_maxlen": ["SPE", {"freq": 0.3, "operation": "additive", "max_length": 100}],
+    "spe_L1": ["SPE", {"freq": 0.5, "step_transform": "L1"}],
+    "spe_L2_cos_maxlen": ["SPE", {"freq": 0.7, "step_transform": "L2", "function": "@cos",
+                                  "max_length": 30}],
+    "rpe": ["RPE", {"freq": 0.5}],
+    "rpe_maxlen": ["RPE", {"freq": 0.25, "max_length": 100}],
+    "cts": ["CTS", {"s": 3}],
+    "cts_float": ["CTS", {"s": 0.25}],
+    "cts_pseudo": ["CTS", {"s": 5, "pseudo_shift": True}],
+    "cts_long": ["CTS", {"s": 100}],
+    "qtc": ["QTC", {"q": 0.7}],
+    "qtc_lower_bound": ["QTC", {"q": 0.2, "lower": True, "bound": -1.5}],
+    "fun": ["FUN", {"f": "@sq"}],
+    "dil": ["DIL", {}],
+    "dil_clusters": ["DIL", {"clusters": 0.2}],
+    "win": ["WIN", {"start": 0.1, "end": 0.8}],
+    "win_negative_start": ["WIN", {"start": -0.1, "end": 0.5}],
+    "dot": ["DOT", {}],
+    "dot_float": ["DOT", {"n": 0.1, "first": 0.3}],
+    "dot_first": ["DOT", {"n": 3, "first": 1}],
+    "pdd": ["PDD", {}],
+    "pdd_dense": ["PDD", {"density": 0.5, "proportion": 0.3}],
+}
+# plain numpy in the reference (copies, masks, np.where): compared bit for bit; the others
+# are numba fastmath loops, BLAS or libm calls: 1e-12 of the row maximum
+PREP2_EXACT = ("NRM", "LAG", "CTS", "QTC", "FUN", "DIL", "WIN", "DOT", "PDD")
+
+
+def make_prep2_inputs(name: str):
+    """(fit / first transform input, second transform input) of a PREP2 case."""
+    X = make_prep_input()
+    X2 = np.random.default_rng(6).standard_normal((4, 3, 40)).cumsum(axis=2)
+    if PREP2_CASES[name][0] == "RPE":          # two-dimensional series only
+        X, X2 = np.ascontiguousarray(X[:, :2]), np.ascontiguousarray(X2[:, :2])
+    if PREP2_CASES[name][0] == "RDW":          # x ** w: positive values (plus one negative row)
+        X, X2 = np.abs(X) + 0.5, np.abs(X2) + 0.5
+        X2[1, 2] *= -1.0
+    return X, X2
+
+
 def make_prep_input():
     X = np.random.default_rng(5).standard_normal((6, 3, 40)).cumsum(axis=2)
     X[2, 1] = 4.0
@@ -189,7 +252,8 @@ PIPE_CASES = {
 COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
 # pipelines of the rank 2-3 components, frozen from the reference
-EXTRA_PIPE_CASES = {"R_mixed": ("R_mixed", 40), "R_rng": ("R_rng", 30)}
+EXTRA_PIPE_CASES = {"R_mixed": ("R_mixed", 40), "R_rng": ("R_rng", 30),
+                    "R_preps": ("R_preps", 36)}
 
 
 

@@ -123,6 +123,26 @@ SPECS["R_rng"] = {"slices": [
      "sieves": [["PPV", {"sample_size": 0.25}], ["MAX", {"q": [-1.0, 0.5]}]],
      "fit_sample_size": 1}]}
 
+# the preparateurs beside INC / STD in front of every kind of slice: a prepared copy, then
+# the fused kernels (slices 0-2, FruitSlice._transform_prepared_fused) or the composed
+# route (slice 3: two cuts); fit draws from the RNG in the preparateurs, too
+SPECS["R_preps"] = {"slices": [
+    {"preps": [["LAG", {}], ["INC", {}]],
+     "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended"}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["END", {}]], "fit_sample_size": 1.0},
+    {"preps": [["DOT", {"n": 3}], ["NEW", ["INC", {}]], ["STD", {}]],
+     "iss": [{"words": {"of_weight": [2, 2]}, "mode": "extended",
+              "weighting": ["Indices", {}]}],
+     "sieves": _seven_sieves(), "fit_sample_size": 1.0},
+    {"preps": [["INC", {}], ["RIN", {"width": 3}], ["MAV", {"width": 4}]],
+     "iss": [{"words": ["[1][2]", "[2][-1][1]"], "mode": "extended", "semiring": "arctic"}],
+     "sieves": [["MAX", {}], ["MIN", {}], ["PPV", {}]], "fit_sample_size": 0.5},
+    {"preps": [["WIN", {"start": 0.1, "end": 0.9}], ["JLD", {"dim": 2, "bias": True}],
+               ["QTC", {"q": 0.9}]],
+     "iss": [{"words": ["[1]", "[1][2]"], "mode": "extended"}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["END", {"cut": [7, -1]}]],
+     "fit_sample_size": 1}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -131,7 +151,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
-              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -142,6 +162,8 @@ def make_input(name: str, n: int = None) -> np.ndarray:
         return np.random.default_rng(1234).standard_normal((n, D, T))
     if name == "R_mixed":
         return np.random.default_rng(42).random((n, D, T)) + 0.1
+    if name == "R_preps":
+        return np.random.default_rng(44).standard_normal((n, D, T)).cumsum(axis=2)
     if name == "R_rng":
         return np.random.default_rng(43).standard_normal((n, D, T)).cumsum(axis=2)
     return np.random.default_rng(0).standard_normal((n, D, T)).cumsum(axis=2)
@@ -167,6 +189,9 @@ def _prep(mod, desc):
         return mod.preparation.NEW(None if args is None else _prep(mod, args))
     if name == "DIM":
         return mod.preparation.DIM(_prep(mod, args["preparateur"]), args["dim"])
+    if any(isinstance(v, str) and v.startswith("@") for v in args.values()) or "kernel" in args:
+        from oracle.preps import resolve          # named callables, kernel arrays (tests only)
+        args = resolve(args)
     return getattr(mod.preparation, name)(**args)
 
 

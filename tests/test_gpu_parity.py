@@ -1066,7 +1066,114 @@ def test_reference_kat_sieve_table(kat):
     np.testing.assert_allclose(got, np.array(want, dtype=float), rtol=1e-12, atol=1e-15)
 
 
-@pytest.mark.parametrize("name", ["R_mixed", "R_rng"])
+@pytest.mark.parametrize("name", sorted(__import__("cases").PREP2_CASES))
+def test_prep2_golden(name, golden_dir):
+    """MAV, LAG, FFN, RIN, RDW, JLD, SPE, RPE, CTS, QTC, FUN, DIL, WIN, DOT, PDD and
+    NRM(scale_dim=True) (csrc/prep_more.cu) against outputs frozen from the
+    reference: fit under a seed, transform of the fit batch and of a second
+    batch, numpy arrays and device tensors, the RNG left where the reference
+    leaves it.  Copies / masks / np.where are bit-identical; the reference's
+    numba fastmath loops, BLAS and libm calls within 1e-12 of the row maximum."""
+    from cases import PREP2_CASES, PREP2_EXACT, make_prep2_inputs
+    g = np.load(os.path.join(golden_dir, "preps2.npz"))
+    desc = PREP2_CASES[name]
+    X, X2 = make_prep2_inputs(name)
+    prep = specs._prep(fruits, desc)
+    np.random.seed(7)
+    prep.fit(X)
+    assert np.random.random() == float(g[name + "_rng"]), "fit consumed the RNG differently"
+    res, res2 = prep.transform(X), prep.transform(X2)
+    on_device = prep.transform(torch.from_numpy(X2).cuda())
+    assert isinstance(on_device, torch.Tensor) and on_device.is_cuda
+    for got, key in ((res, name), (res2, name + "_2"), (on_device.cpu().numpy(), name + "_2")):
+        assert got.dtype == np.float64 and got.flags.c_contiguous
+        if desc[0] in PREP2_EXACT:
+            assert_exact(got, g[key], key)
+        else:
+            assert_close(got, g[key], 1e-12, key)
+    again = prep.copy()
+    assert not hasattr(again, "_kernel") and not hasattr(again, "_weights")    # copies are unfitted
+
+
+def test_preparateur_edge_shapes():
+    """Shapes at the edges: one time step, windows longer than the series, empty
+    batches, the cache-row quirk of WIN / SPE on a one-series fit sample."""
+    P = fruits.preparation
+    one = np.array([[[2.0], [3.0]]])
+    np.testing.assert_array_equal(P.LAG().transform(one), [[[2.0], [2.0], [3.0], [3.0]]])
+    np.testing.assert_array_equal(P.CTS(1).fit_transform(one), one)
+    np.testing.assert_array_equal(P.MAV(5).fit_transform(one), np.zeros_like(one))
+    np.testing.assert_array_equal(P.MAV(1).fit_transform(one), one)
+    X = np.random.default_rng(3).standard_normal((5, 2, 17)).cumsum(axis=2)
+    empty = X[:0]
+    for prep in (P.LAG(), P.CTS(2), P.DOT(), P.MAV(3), P.RPE(0.5), P.JLD(3), P.FFN()):
+        prep.fit(X)
+        assert prep.transform(empty).shape[0] == 0
+    # numpy broadcasting of one series against the cached sums of a batch (what a
+    # fit_sample_size=1 fit does, fruits/cache.py:97-112): the batch size comes back
+    cache = fruits.cache.SharedSeedCache(X)
+    spe = P.SPE(0.5, step_transform="L1")
+    spe._cache = cache
+    try:
+        got = spe._transform_device(torch.from_numpy(X[2:3]).cuda()).cpu().numpy()
+    finally:
+        del spe._cache
+    l1 = np.cumsum(np.abs(np.diff(X[:, 0, :], prepend=X[:, :1, 0])), axis=1)
+    want = X[2:3] * np.sin(l1 / l1[:, -1:] ** 0.5)[:, np.newaxis, :]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    win = P.WIN(0.2, 0.7)
+    win._cache = cache
+    try:
+        got = win._transform_device(torch.from_numpy(X[3:5]).cuda()).cpu().numpy()
+    finally:
+        del win._cache
+    l2 = np.cumsum(np.diff(X[:, 0, :], prepend=X[:, :1, 0]) ** 2, axis=1)
+    want = np.zeros((2, 2, 17))
+    for i in range(2):          # rows 0 and 1 of the cache serve rows 3 and 4 of X
+        a, b = np.sum(l2[i] <= 0.2 * l2[i, -1]) - 1, np.sum(l2[i] <= 0.7 * l2[i, -1])
+        want[i, :, a:b] = X[3 + i, :, a:b]
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError):
+        P.RPE(0.5).transform(np.zeros((1, 3, 4)))
+    with pytest.raises(RuntimeError):
+        P.MAV(-1).fit_transform(X)           # (like the reference: fit sets no width)
+    with pytest.raises(RuntimeError):
+        P.DIL().transform(X)
+
+
+def test_prepared_copy_then_fused_kernels(golden_dir, monkeypatch):
+    """A slice whose preparateurs the kernels cannot apply while loading
+    (LAG, DOT, RIN, MAV ...) writes a prepared copy and still takes a fused
+    kernel -- the iterated sums are not materialised -- with the features of the
+    composed route."""
+    X = specs.make_input("R_preps")
+    fruit = specs.build_fruit(fruits, specs.SPECS["R_preps"])
+    np.random.seed(0)
+    fruit.fit(X)
+    routes = []
+    FS = fruits.fruit.FruitSlice
+    fused, composed = FS._transform_fused, FS._transform_composed
+    monkeypatch.setattr(FS, "_transform_fused",
+                        lambda self, *a, **k: (routes.append("fused"), fused(self, *a, **k))[1])
+    monkeypatch.setattr(FS, "_transform_composed",
+                        lambda self, *a, **k: (routes.append("composed"), composed(self, *a, **k))[1])
+    res = fruit.transform(X)
+    assert routes == ["fused", "fused", "fused", "composed"]
+    monkeypatch.setattr(FS, "_transform_prepared_fused", lambda self, *a, **k: False)
+    routes.clear()
+    ref = fruit.transform(X)
+    assert routes == ["composed"] * 4
+    _assert_features_close(res, ref, "prepared copy + fused kernel vs composed route")
+    # more series than the thread-per-series kernels ask for: same pipeline, generated kernels
+    big = np.random.default_rng(9).standard_normal((4200, 2, 48)).cumsum(axis=2)
+    monkeypatch.undo()
+    a = fruit.transform(big)
+    monkeypatch.setattr(FS, "_transform_prepared_fused", lambda self, *a, **k: False)
+    b = fruit.transform(big)
+    _assert_features_close(a, b, "generated kernels on the prepared copy vs composed route")
+
+
+@pytest.mark.parametrize("name", ["R_mixed", "R_rng", "R_preps"])
 def test_extra_pipeline_golden(name, golden_dir):
     """Frozen outputs of the real reference: ``R_mixed`` -- a Bayesian slice
     (rank-2 sieves, sieve wrappers) and a slice of two chained ISS; ``R_rng``
@@ -1079,11 +1186,16 @@ def test_extra_pipeline_golden(name, golden_dir):
     np.random.seed(0)
     fruit.fit(X)
     res = fruit.transform(X)
-    assert_exact(fitted_thresholds(fruit), g["thresholds"], "thresholds")
-    if name == "R_rng":
-        assert_exact(res, g["features"], "features")
+    if name == "R_preps":
+        # preparateurs in front (fastmath loops of the reference: 1e-12) and a weighted slice
+        assert_close(fitted_thresholds(fruit), g["thresholds"], 1e-9, "thresholds")
+        _assert_features_close(res, g["features"], name)
     else:
-        assert_close(res, g["features"], 1e-12, "features")      # CUR: summation order
+        assert_exact(fitted_thresholds(fruit), g["thresholds"], "thresholds")
+        if name == "R_rng":
+            assert_exact(res, g["features"], "features")
+        else:
+            assert_close(res, g["features"], 1e-12, "features")      # CUR: summation order
     labels = "|".join(fruit.label(i) for i in
                       sorted(set(np.linspace(0, res.shape[1] - 1, 23).astype(int))))
     assert labels == str(g["labels"])

@@ -159,8 +159,14 @@ def test_error_behaviour():
         fruits.semiring.Arctic(argmax=True)
     with pytest.raises(NotImplementedError):
         fruits.ISS([fruits.words.Word()])
-    with pytest.raises(NotImplementedError):
-        fruits.preparation.MAV()
+    with pytest.raises(ValueError):
+        fruits.preparation.MAV(width=1.5)
+    with pytest.raises(ValueError):
+        fruits.preparation.JLD(dim=1.5)
+    with pytest.raises(ValueError):
+        fruits.preparation.PDD(density=2.0)
+    with pytest.raises(TypeError):
+        fruits.preparation.DOT(n="3")
     with pytest.raises(ValueError):
         fruits.preparation.INC(depth=0)
     with pytest.raises(ValueError):
@@ -388,3 +394,65 @@ def test_coswiss_separable_plan_reproduces_the_reference_on_the_host(golden_dir)
     big = specs.build_iss(fruits, specs.SPECS["C3_cos"]["slices"][1]["iss"][0])
     nodes, emits, rows = big._separable_plan(12)
     assert (len(nodes), len(emits), len(rows)) == (1830, 575, 60)
+
+
+def test_all_reference_preparateurs_exist_with_reference_strings():
+    """Every preparateur name of the reference constructs, copies and prints
+    like the reference (fruits/preparation/transform.py, filter.py: ``__str__``
+    is what ``Fruit.summary`` and ``label`` show)."""
+    P = fruits.preparation
+    f = abs
+    want = {
+        P.INC(): "INC(1, 1, True)", P.STD(): "STD(True, True)", P.NRM(True): "NRM(True)",
+        P.MAV(0.1): "MAV(0.1)", P.LAG(): "LAG()", P.FFN(2, 3, False, True): "FFN(2, 3, False, True)",
+        P.RIN(2, True, 1, True): "RIN(2, True, 1, True, None)", P.RDW("uniform"): "RDW('uniform')",
+        P.JLD(4, True, True): "JLD(4, True, True)",
+        P.SPE(0.5, "additive", None, "L1", 9): "SPE(0.5, additive, None, L1, 9)",
+        P.RPE(0.3, 7): "RPE(0.3, 7)", P.CTS(0.2, True): "CTS(0.2, True)",
+        P.QTC(0.4, True, 1.0): "QTC(0.4, True, 1.0)", P.FUN(f): f"FUN({f})",
+        P.DIL(0.3): "DIL(clusters=0.3)", P.WIN(0.1, 0.9): "WIN(start=0.1, end=0.9)",
+        P.DOT(3, 1): "DOT(n=3, first=1)", P.PDD(0.2, 0.4): "PDD(density=0.2, proportion=0.4)",
+    }
+    for prep, text in want.items():
+        assert str(prep) == text and str(prep.copy()) == text
+        assert type(prep.copy()) is type(prep) and prep.copy() is not prep
+    assert P.MAV(3) == P.MAV(3) and P.MAV(3) != P.MAV(4)
+    assert P.CTS(2) == P.CTS(2) and P.LAG() == P.LAG() and P.QTC(0.5) != P.QTC(0.6)
+    assert P.FUN(f) != P.FUN(f) and P.FFN() != P.FFN()      # (no __eq__ in the reference)
+    with pytest.raises(TypeError):
+        P.WIN(0.1, 0.9) == 3
+    assert not P.LAG().requires_fitting and not P.WIN(0, 1).requires_fitting
+    assert P.MAV().requires_fitting and P.CTS(1).requires_fitting      # (Seed default)
+    # what a row-sharded fit and the chunked host path need to know
+    assert not P.QTC(0.5)._row_independent_fit() and P.RIN()._row_independent_fit()
+    assert not P.FUN(f)._row_independent_transform() and not P.NEW(P.FUN(f))._row_independent_transform()
+    assert P.WIN(0, 1)._needs_raw_cache() and P.SPE(0.5, step_transform="L2")._needs_raw_cache()
+    assert not P.SPE(0.5)._needs_raw_cache()
+
+
+def test_preparateur_fits_draw_like_the_oracle():
+    """``fit`` of the random preparateurs only looks at the shape of its input
+    and draws from the global numpy RNG: same weights and same generator state
+    as the oracle restatement (which gen_golden.py pinned to the reference)."""
+    import torch
+    from cases import PREP2_CASES, make_prep2_inputs
+    from oracle import preps as more
+    for name in ("ffn", "ffn_out3_relu", "rin", "rin_w4_adaptive", "rin_outdim2_sum1",
+                 "rin_callable", "rdw_uniform", "jld", "jld_distribute_bias", "jld_float",
+                 "dil", "dil_clusters", "dot_float", "pdd", "pdd_dense", "mav_float"):
+        desc = PREP2_CASES[name]
+        X, _ = make_prep2_inputs(name)
+        np.random.seed(7)
+        st = more.fit_prep(desc, X)
+        after = np.random.random()
+        prep = specs._prep(fruits, desc)
+        np.random.seed(7)
+        prep._fit_device(torch.from_numpy(X))       # (shape only: no GPU needed)
+        assert np.random.random() == after, name
+        got = {"w1": "_weights1", "b": "_biases", "w2": "_weights2", "kernel": "_kernel",
+               "ndim": "_ndim_per_kernel", "dims": "_dims_per_kernel", "weights": "_weights",
+               "bias": "_bias_weights", "indices": "_indices", "lengths": "_lengths",
+               "n": "_n", "first": "_first", "width": "_width", "w": "_w"}
+        for key, val in st.items():
+            np.testing.assert_array_equal(np.asarray(getattr(prep, got[key])), np.asarray(val),
+                                          err_msg=f"{name}.{key}")

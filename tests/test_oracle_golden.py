@@ -125,7 +125,30 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng"])
+@pytest.mark.parametrize("name", sorted(__import__("cases").PREP2_CASES))
+def test_prep2_golden(name, golden_dir):
+    """The preparateurs beside INC / STD / NRM: the numpy restatement
+    (oracle/preps.py) against the outputs frozen from the reference, fit state
+    reused on a second batch, same consumption of the global RNG."""
+    from cases import PREP2_CASES, PREP2_EXACT, make_prep2_inputs
+    from oracle import preps as more
+    g = np.load(os.path.join(golden_dir, "preps2.npz"))
+    desc = PREP2_CASES[name]
+    X, X2 = make_prep2_inputs(name)
+    np.random.seed(7)
+    st = more.fit_prep(desc, X)
+    assert np.random.random() == float(g[name + "_rng"])
+    with np.errstate(invalid="ignore"):
+        res = more.transform_prep(desc, st, X, orc.RawCache(X))
+        res2 = more.transform_prep(desc, st, X2, orc.RawCache(X2))
+    for got, key in ((res, name), (res2, name + "_2")):
+        if desc[0] in PREP2_EXACT:
+            assert_exact(got, g[key], key)
+        else:
+            assert_close(got, g[key], 1e-12, key)
+
+
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps"])
 def test_pipeline_golden(name, golden_dir):
     from cases import COS_PIPE_CASES, EXTRA_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
