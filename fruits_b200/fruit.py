@@ -781,32 +781,41 @@ class FruitSlice:
         input (everything but ``INC`` / ``STD`` / ``NEW``) write a prepared copy
         with their own streaming kernel; the rest of the slice then takes the
         fused route on that copy, so the iterated sums still never reach HBM.
+        An ISS over Python letters is replaced by its SimpleWord twin over the
+        prepared input plus one dimension per extended letter (``ISS._lettered``).
         False if the slice cannot be fused behind any prefix."""
-        preps = self._preparateurs
-        if callbacks or not preps:
+        saved, saved_iss = self._preparateurs, self._iss
+        generic = len(saved_iss) == 1 and getattr(saved_iss[0], "_generic", False)
+        if callbacks or not (saved or generic):
             return False
-        saved = preps
         try:
-            for k in range(1, len(saved) + 1):
-                self._preparateurs = saved[k:]
-                if self._fused_dims(1) is not None:
-                    break
-            else:
-                return False
-            if not self._is_fusable(X.shape[1], callbacks, X.shape[2]):
-                return False          # ISS or sieves keep the slice off the fused route anyway
+            k = len(saved)
+            if not generic:
+                for k in range(1, len(saved) + 1):
+                    self._preparateurs = saved[k:]
+                    if self._fused_dims(1) is not None:
+                        break
+                else:
+                    return False
+                if not self._is_fusable(X.shape[1], callbacks, X.shape[2]):
+                    return False      # ISS or sieves keep the slice off the fused route anyway
+            self._preparateurs = saved[k:]
             prepared = X
             for prep in saved[:k]:
                 prep._cache = cache
                 prepared = prep._transform_device(prepared)
             if prepared.dim() != 3:
                 raise ValueError("preparateurs must return (n_series, n_dimensions, length)")
+            if generic:
+                saved_iss[0]._check_input(prepared)
+                prepared, twin = saved_iss[0]._lettered(prepared.contiguous())
+                self._iss = [twin]
             if not self._is_fusable(prepared.shape[1], callbacks, prepared.shape[2]):
                 return False
             self._transform_fused(prepared.contiguous(), cache, out, col0, sanitize)
             return True
         finally:
-            self._preparateurs = saved
+            self._preparateurs, self._iss = saved, saved_iss
 
     def _transform_fused(self, X, cache, out, col0, sanitize) -> None:
         iss = self._iss[0]

@@ -31,7 +31,8 @@ class ISS(Seed):
     """Iterated sums signature of a list of words.
 
     Args:
-        words: ``SimpleWord`` objects.
+        words: ``SimpleWord`` objects, or generic ``Word`` objects over Python
+            letters (evaluated on the host, see ``_lettered``).
         mode: ``ISSMode.SINGLE`` (one iterated sum per word) or
             ``ISSMode.EXTENDED`` (additionally every prefix of every word
             that was not already emitted by an earlier word).
@@ -43,15 +44,28 @@ class ISS(Seed):
                  semiring: Optional[Semiring] = None,
                  weighting: Optional[Weighting] = None) -> None:
         for w in words:
-            if not isinstance(w, SimpleWord):
-                raise NotImplementedError(
-                    "only SimpleWord objects can be evaluated on the GPU")
+            if not isinstance(w, Word):
+                raise TypeError(f"ISS takes words, got {type(w)}")
         self.words = words
         self.mode = mode
         self.semiring = semiring if semiring is not None else Reals()
         if not isinstance(self.semiring, (Reals, Arctic, Bayesian)):
             raise NotImplementedError(
                 f"semiring {type(self.semiring).__name__} is not supported")
+        # words over Python letters (reference: Semiring._iterated_sum,
+        # semiring.py:54-75, Arctic :428-446)
+        self._generic = any(not isinstance(w, SimpleWord) for w in words)
+        if self._generic:
+            if any(len(w) == 0 for w in words):
+                raise NotImplementedError("a word needs at least one extended letter")
+            if isinstance(self.semiring, Bayesian):
+                raise NotImplementedError(
+                    "generic words in the Bayesian semiring take the reference's shifted "
+                    "general recursion (semiring.py:54-75), which has no kernel")
+            if weighting is not None and any(isinstance(w, SimpleWord) for w in words):
+                raise NotImplementedError(
+                    "the reference weights SimpleWords and ignores the weighting for generic "
+                    "words; put them into separate ISS objects")
         self._cache_plan = CachePlan(self.words if mode == ISSMode.EXTENDED else [])
         self.weighting = weighting
         self._trie_memo = None
@@ -64,8 +78,59 @@ class ISS(Seed):
     @property
     def _fusable_iss(self) -> bool:
         # the Bayesian semiring has no generic trie kernel: unweighted it is compiled
-        # into the generated kernel (_jit.py), weighted it is sieved on materialised sums
+        # into the generated kernel (_jit.py), weighted it is sieved on materialised sums;
+        # generic words are fused through their SimpleWord twin (FruitSlice)
+        if self._generic:
+            return False
         return not isinstance(self.semiring, Bayesian) or self.weighting is None
+
+    # -- words over Python letters -----------------------------------------------
+    def _lettered(self, X: torch.Tensor):
+        """``(Xs, twin)`` for an ISS with generic words: every distinct extended
+        letter is evaluated once for the batch -- on the host, series by series,
+        because a letter is the caller's Python function of one series
+        ``[n_dims, length]`` (reference: semiring.py:61-66) -- and appended to X as
+        one more input dimension; ``twin`` is the ISS of SimpleWords over those
+        dimensions.  The semiring's operation is applied once per extended letter
+        (``tmp * C``, ``tmp + C``), exactly what a single-occurrence letter of a
+        SimpleWord does in the kernels, so every route (trie kernel, block scan,
+        generated kernels) serves generic words bit for bit like the reference.
+        Weightings are ignored for generic words, like in the reference
+        (semiring.py:40)."""
+        n, d, t = X.shape
+        arctic = isinstance(self.semiring, Arctic)
+        Z = X.cpu().numpy()
+        index, rows = {}, []
+        for w in self.words:
+            if isinstance(w, SimpleWord):
+                continue
+            for el in w._extended_letters:
+                key = str(el)
+                if key in index:
+                    continue
+                index[key] = d + len(rows)
+                C = np.empty((n, t), dtype=np.float64)
+                fns = [el[k] for k in range(len(el))]
+                for i in range(n):
+                    c = np.zeros(t) if arctic else np.ones(t)
+                    for fn in fns:
+                        c = c + fn(Z[i]) if arctic else c * fn(Z[i])
+                    C[i] = c
+                rows.append(C)
+        extra = be.to_device(np.ascontiguousarray(np.stack(rows, axis=1)))
+        Xs = torch.cat((X, extra), dim=1).contiguous()
+        memo = self.__dict__.get("_twin_memo")
+        sig = (d, tuple(str(w) for w in self.words), self.mode)
+        if memo is None or memo[0] != sig:
+            twins = [w if isinstance(w, SimpleWord) else SimpleWord(
+                "".join(f"[({index[str(el)] + 1})]" for el in w._extended_letters))
+                for w in self.words]
+            memo = (sig, ISS(twins, mode=self.mode, semiring=self.semiring, weighting=None))
+            self._twin_memo = memo
+        twin = memo[1]
+        if hasattr(self, "_cache"):
+            twin._cache = self._cache
+        return Xs, twin
 
     # -- plan ------------------------------------------------------------------
     def _weight_mode(self) -> int:
@@ -146,6 +211,10 @@ class ISS(Seed):
         return pieces
 
     def max_dim(self) -> int:
+        if self._generic:
+            return max([len(el) for w in self.words if isinstance(w, SimpleWord) for el in w]
+                       + [dim + 1 for w in self.words if not isinstance(w, SimpleWord)
+                          for el in w._extended_letters for dim in el._dimensions] + [0])
         memo = self.__dict__.get("_max_dim_memo")
         if memo is None or memo[0] is not self.words or memo[1] != len(self.words):
             memo = (self.words, len(self.words),
@@ -162,7 +231,7 @@ class ISS(Seed):
     # -- execution ---------------------------------------------------------------
     def _lookup(self, X: torch.Tensor):
         """-> (g tensor or None, row stride)"""
-        if self.weighting is None:
+        if self.weighting is None or self._generic:
             return None, 0
         if hasattr(self, "_cache"):
             self.weighting._cache = self._cache
@@ -200,6 +269,9 @@ class ISS(Seed):
         if not trusted:
             self._check_input(X)
         X = X.contiguous()
+        if self._generic:
+            Xs, twin = self._lettered(X)
+            return twin.materialize(Xs, emit_range)
         if isinstance(self.semiring, Bayesian):
             return self._materialize_scan(X, emit_range, lookup)
         if isinstance(self.semiring, Arctic) and self._arctic_scan(X.shape[0], emit_range):
@@ -285,6 +357,11 @@ class ISS(Seed):
         ``emit_range``), at most ``max_bytes`` per chunk (sized as if ``X`` had
         ``rows_for_size`` rows: ranks with different shards then cut the same
         chunks) and at most 65,535 emissions (one select launch)."""
+        if self._generic:
+            self._check_input(X)
+            Xs, twin = self._lettered(X.contiguous())       # the letters once, not per chunk
+            yield from twin.iter_chunks(Xs, max_bytes, emit_range, rows_for_size)
+            return
         n_emit = self.n_iterated_sums()
         first, last = (0, n_emit) if emit_range is None else emit_range
         per = (X.shape[0] if rows_for_size is None else rows_for_size) * X.shape[2] * 8
@@ -304,6 +381,12 @@ class ISS(Seed):
         if batch_size > len(self.words):
             raise ValueError("batch_size too large, has to be < len(words)")
         Xd = be.to_device(X)
+        if self._generic:
+            self._check_input(Xd)
+            Xs, twin = self._lettered(Xd.contiguous())
+            for res in twin.batch_transform(Xs, batch_size):
+                yield res if isinstance(X, torch.Tensor) else res.cpu().numpy()
+            return
         had_cache = hasattr(self, "_cache")
         if not had_cache:
             self._cache = SharedSeedCache(Xd)

@@ -108,9 +108,6 @@ class _IncrementSum(Weighting):
                  transform: Optional[Callable[[float], float]] = None,
                  scale: float = 50, total: bool = False) -> None:
         super().__init__(total=total)
-        if transform is not None:
-            raise NotImplementedError(
-                "a Python `transform` of the lookup cannot run on the GPU")
         self._on_prepared = on_prepared
         self._relative = relative
         self._transform = transform
@@ -122,10 +119,20 @@ class _IncrementSum(Weighting):
             r = self._cache.get_device(CacheType.ISS, self._key, X)
         else:
             r = SharedSeedCache._lsum(X.contiguous(), self._key == "L2")
+        relative = int(self._relative)
+        if self._transform is not None:
+            # the caller's scalar Python function (np.vectorize, weighting.py:155-156):
+            # the sums make one round trip through the host, the normalisation stays
+            # on the GPU
+            host = r.cpu().numpy()
+            if self._relative:
+                host = host / (host[:, -1:] + 1e-5)
+            r = be.to_device(np.ascontiguousarray(np.vectorize(self._transform)(host),
+                                                  dtype=np.float64))
+            relative = 0
         out = torch.empty_like(r)
         be.check(be.lib().fb_nrm_scale(r.data_ptr(), out.data_ptr(), r.shape[0], r.shape[1],
-                                       int(self._relative), float(self._scale),
-                                       be.stream_ptr()))
+                                       relative, float(self._scale), be.stream_ptr()))
         return out, False
 
 

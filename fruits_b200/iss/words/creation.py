@@ -9,7 +9,8 @@ CPython's hash order for tuples of small ints.
 import itertools
 from collections.abc import Sequence
 
-from .word import SimpleWord
+from .letters import ExtendedLetter
+from .word import SimpleWord, Word
 
 
 def _partitions(n: int, smallest: int = 1):
@@ -54,9 +55,15 @@ def alternate_sign(words: Sequence[SimpleWord]) -> list:
     return out
 
 
-def replace_letters(word, letter_gen):
-    """Reference: creation.py:53-83.  Produces a generic ``Word`` with Python
-    letter functions, which cannot run on the device."""
-    raise NotImplementedError(
-        "replace_letters builds generic Words (Python callables); only "
-        "SimpleWord is supported by the GPU path")
+def replace_letters(word: SimpleWord, letter_gen) -> Word:
+    """A generic word with the shape of ``word`` whose letters are the names
+    ``letter_gen`` yields, one per letter occurrence in ascending dimension
+    order; ``DIM`` once the iterator is exhausted (reference: creation.py:53-83)."""
+    out = Word()
+    for expo in word:
+        el = ExtendedLetter()
+        for dim, count in enumerate(expo):
+            for _ in range(count):
+                el.append(next(letter_gen, "DIM"), dim)
+        out.multiply(el)
+    return out

@@ -4,8 +4,10 @@ Mirrors the public behaviour of the reference's ``fruits/iss/words/word.py``
 (``SimpleWord`` :128-268, ``Word`` :9-125).  A ``SimpleWord`` is a sequence of
 extended letters; each extended letter is stored as its exponent vector over
 the input dimensions (``"[112][2]"`` -> ``[[2, 1], [0, 1]]``), negative
-exponents meaning division.  Only ``SimpleWord`` can run on the GPU; generic
-``Word`` objects carry Python callables and are rejected by ``ISS``.
+exponents meaning division.  A generic ``Word`` is a sequence of
+:class:`~fruits_b200.iss.words.letters.ExtendedLetter` objects (Python
+functions of one series); ``ISS`` evaluates those on the host and feeds their
+rows to the same kernels as extra input dimensions.
 """
 import re
 from typing import Optional, Sequence
@@ -17,8 +19,8 @@ _TOKEN = re.compile(r"\((-?\d+)\)|(-\d?)|(\d)")
 
 
 class Word:
-    """Base class of all words (reference: word.py:9-125).  Generic words
-    (arbitrary letter functions) are not supported on the device."""
+    """A sequence of extended letters, e.g. ``Word("[ABS(1)DIM(2)][DIM(1)]")``
+    (reference: word.py:9-125)."""
 
     def __init__(self, word_string: Optional[str] = None) -> None:
         self._extended_letters: list = []
@@ -42,9 +44,23 @@ class Word:
         self._alpha = np.array(alpha, dtype=np.float32)
 
     def multiply(self, other) -> None:
-        raise NotImplementedError(
-            "generic Word objects hold Python letter functions and cannot run "
-            "on the GPU; use SimpleWord")
+        """Appends an extended letter, the letters of another word or of a
+        string like ``"[DIM(1)][ABS(2)DIM(1)]"`` (reference: word.py:84-98)."""
+        from .letters import ExtendedLetter
+        if isinstance(other, ExtendedLetter):
+            self._extended_letters.append(other)
+        elif isinstance(other, Word):
+            self._extended_letters.extend(other._extended_letters)
+        elif isinstance(other, str):
+            for part in other.split("]")[:-1]:
+                self._extended_letters.append(ExtendedLetter(part[1:]))
+        else:
+            raise TypeError(f"Cannot multiply Word with {type(other)}")
+
+    def copy(self) -> "Word":
+        twin = Word()
+        twin._extended_letters = [el.copy() for el in self._extended_letters]
+        return twin
 
     def __len__(self) -> int:
         return len(self._extended_letters)

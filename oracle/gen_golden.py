@@ -196,6 +196,15 @@ def gen_preps2():
             else:
                 check_close(a, b, f"prep {what}", rtol=1e-12)
         out[name], out[name + "_2"], out[name + "_rng"] = r, r2, np.array(state_r)
+    # L1 / L2 weightings with a Python transform of the lookup (fruits/iss/weighting.py:155-156)
+    X = make_prep_input()
+    for key, w in (("L1_sqrt_relative", ref.iss.weighting.L1(relative=True, transform=np.sqrt)),
+                   ("L2_log1p", ref.iss.weighting.L2(transform=np.log1p, scale=5, total=True))):
+        iss = ref.ISS([ref.words.SimpleWord("[1][2]"), ref.words.SimpleWord("[3][1][1]")],
+                      mode=ref.ISSMode.EXTENDED, weighting=w)
+        out["iss_" + key] = iss.transform(X)
+        w._cache = ref.cache.SharedSeedCache(X)
+        out["lookup_" + key] = w.get_lookup(X)
     np.savez_compressed(os.path.join(GOLD, "preps2.npz"), **out)
 
 

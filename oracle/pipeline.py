@@ -324,6 +324,52 @@ def iss_word(X, word: str, extended: int, semiring: str, weighting,
     return np.ascontiguousarray(np.swapaxes(res, 0, 1))
 
 
+# letters of generic words (fruits/iss/words/letters.py:95-110 DIM / ABS; the others are
+# what the tests register through ``fruits.words.letter`` -- tests/specs.py)
+LETTERS = {
+    "DIM": lambda X, i: X[i, :],
+    "ABS": lambda X, i: np.abs(X[i, :]),
+    "RELU": lambda X, i: X[i, :] * (X[i, :] > 0),
+    "LAGDIFF": lambda X, i: X[i, :] - np.roll(X[i, :], 2),
+}
+
+
+def is_generic_word(word: str) -> bool:
+    return any(c.isalpha() for c in word)
+
+
+def iss_generic_word(X, word: str, extended: int, semiring: str):
+    """Iterated sums of a word over Python letters, ``[extended, n, t]``:
+    Semiring._iterated_sum (fruits/iss/semiring.py:54-75: Reals -- identity ones,
+    product, cumsum over ``tmp[k:]`` behind a shift) and Arctic._iterated_sum
+    (:428-446: identity zeros, sum, running maximum, no shift).  Weightings do
+    not reach this function in the reference (:40)."""
+    if semiring not in ("reals", "arctic"):
+        raise NotImplementedError(semiring)
+    els = [[(part.split("(")[0], int(part.split("(")[1]) - 1)
+            for part in el[1:].split(")")[:-1]] for el in word.split("]")[:-1]]
+    n, _, t = X.shape
+    out = np.zeros((n, extended, t))
+    for i in range(n):
+        Z = X[i]
+        tmp = np.ones(t) if semiring == "reals" else np.zeros(t)
+        for k, el in enumerate(els):
+            C = np.ones(t) if semiring == "reals" else np.zeros(t)
+            for name, dim in el:
+                C = C * LETTERS[name](Z, dim) if semiring == "reals" else C + LETTERS[name](Z, dim)
+            if semiring == "reals":
+                if k > 0:
+                    tmp = np.roll(tmp, 1)
+                    tmp[0] = 0
+                tmp[k:] = tmp[k:] * C[k:]
+                tmp[k:] = np.cumsum(tmp[k:])
+            else:
+                tmp = np.maximum.accumulate(tmp + C)
+            if len(els) - k <= extended:
+                out[i, extended - (len(els) - k), :] = tmp.copy()
+    return np.ascontiguousarray(np.swapaxes(out, 0, 1))
+
+
 def coswiss_weightings(n_letters: int, exponent: int, total: bool) -> np.ndarray:
     """Expansion of ``cos(a-b)**exponent`` into products of powers of sines
     and cosines (fruits/iss/cos.py:265-287): row = (binomial coefficient
@@ -398,9 +444,14 @@ def iss_iter(X, iss, cache: RawCache):
     plan = cache_plan(words) if extended else [1] * len(words)
     alphas = iss.get("alphas")
     for i, w in enumerate(words):
-        out = iss_word(X, w, plan[i], iss.get("semiring", "reals"),
-                       iss.get("weighting"),
-                       None if alphas is None else alphas[i], cache)
+        if plan[i] == 0:
+            continue
+        if is_generic_word(w):
+            out = iss_generic_word(X, w, plan[i], iss.get("semiring", "reals"))
+        else:
+            out = iss_word(X, w, plan[i], iss.get("semiring", "reals"),
+                           iss.get("weighting"),
+                           None if alphas is None else alphas[i], cache)
         for e in range(out.shape[0]):
             yield out[e]
 

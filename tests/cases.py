@@ -253,7 +253,7 @@ COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
 # pipelines of the rank 2-3 components, frozen from the reference
 EXTRA_PIPE_CASES = {"R_mixed": ("R_mixed", 40), "R_rng": ("R_rng", 30),
-                    "R_preps": ("R_preps", 36)}
+                    "R_preps": ("R_preps", 36), "R_letters": ("R_letters", 33)}
 
 
 

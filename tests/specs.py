@@ -143,6 +143,27 @@ SPECS["R_preps"] = {"slices": [
      "sieves": [["NPI", {"q": [0.5, 1.0]}], ["END", {"cut": [7, -1]}]],
      "fit_sample_size": 1}]}
 
+# words over Python letters (fruits/iss/words/letters.py; Semiring._iterated_sum): a slice
+# of generic words behind a preparateur, a mixed ISS, an arctic one, chained behind an ISS
+SPECS["R_letters"] = {"slices": [
+    {"preps": [["INC", {}]],
+     "iss": [{"words": ["[ABS(1)DIM(2)][DIM(1)]", "[ABS(1)DIM(2)][RELU(2)][DIM(1)DIM(1)]",
+                        "[LAGDIFF(1)]", "[RELU(2)][DIM(1)DIM(1)]"], "mode": "extended"}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MAX", {}], ["END", {}]], "fit_sample_size": 1.0},
+    {"preps": [],
+     "iss": [{"words": ["[1][2]", "[DIM(1)][DIM(2)]", "[12]", "[ABS(1)ABS(2)]"],
+              "mode": "single"}],
+     "sieves": [["PPV", {}], ["MPI", {"q": [0.3, 1.0]}]], "fit_sample_size": 1.0},
+    {"preps": [],
+     "iss": [{"words": ["[ABS(1)][DIM(2)RELU(1)][DIM(1)]", "[ABS(1)][LAGDIFF(2)]"],
+              "mode": "extended", "semiring": "arctic"}],
+     "sieves": [["MIN", {}], ["NPI", {"inc": 0, "q": [0.5, 1.0]}], ["END", {"cut": [5, -1]}]],
+     "fit_sample_size": 0.5},
+    {"preps": [],
+     "iss": [{"words": ["[1]", "[2]"], "mode": "single"},
+             {"words": ["[ABS(1)][RELU(1)]"], "mode": "extended"}],
+     "sieves": [["NPI", {}], ["END", {}]], "fit_sample_size": 1}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -151,7 +172,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
-              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48), "R_letters": (33, 2, 45),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -162,6 +183,8 @@ def make_input(name: str, n: int = None) -> np.ndarray:
         return np.random.default_rng(1234).standard_normal((n, D, T))
     if name == "R_mixed":
         return np.random.default_rng(42).random((n, D, T)) + 0.1
+    if name == "R_letters":
+        return np.random.default_rng(45).standard_normal((n, D, T)).cumsum(axis=2) / 4
     if name == "R_preps":
         return np.random.default_rng(44).standard_normal((n, D, T)).cumsum(axis=2)
     if name == "R_rng":
@@ -180,7 +203,25 @@ def _words(mod, desc):
         if "concat" in desc:
             return [w for d in desc["concat"] for w in _words(mod, d)]
         raise ValueError(desc)
-    return [mod.words.SimpleWord(w) for w in desc]
+    _register_letters(mod)
+    return [mod.words.Word(w) if any(c.isalpha() for c in w) else mod.words.SimpleWord(w)
+            for w in desc]
+
+
+def _register_letters(mod):
+    """The letters the generic words of the specs use beside DIM / ABS, registered
+    once per package through its own decorator (fruits/iss/words/letters.py:137-206);
+    the same functions as ``oracle.pipeline.LETTERS``."""
+    if "RELU" in mod.words.letters.get_available():
+        return
+
+    @mod.words.letter(name="RELU")
+    def relu(X, i):
+        return X[i, :] * (X[i, :] > 0)
+
+    @mod.words.letter
+    def LAGDIFF(X, i):
+        return X[i, :] - np.roll(X[i, :], 2)
 
 
 def _prep(mod, desc):

@@ -1095,6 +1095,26 @@ def test_prep2_golden(name, golden_dir):
     assert not hasattr(again, "_kernel") and not hasattr(again, "_weights")    # copies are unfitted
 
 
+@pytest.mark.parametrize("key", ["L1_sqrt_relative", "L2_log1p"])
+def test_increment_sum_weighting_with_python_transform(key, golden_dir):
+    """L1 / L2 lookups whose sums go through the caller's scalar function
+    (np.vectorize in the reference, fruits/iss/weighting.py:155-156), frozen from
+    the reference: the lookup and the weighted iterated sums."""
+    g = np.load(os.path.join(golden_dir, "preps2.npz"))
+    W = fruits.iss.weighting
+    w = (W.L1(relative=True, transform=np.sqrt) if key.startswith("L1")
+         else W.L2(transform=np.log1p, scale=5, total=True))
+    X = make_prep_input()
+    iss = fruits.ISS([fruits.words.SimpleWord("[1][2]"), fruits.words.SimpleWord("[3][1][1]")],
+                     mode=fruits.ISSMode.EXTENDED, weighting=w)
+    assert_close(iss.transform(X), g["iss_" + key], 1e-9, "weighted iterated sums")
+    w._cache = fruits.cache.SharedSeedCache(X)
+    try:
+        assert_close(w.get_lookup(X), g["lookup_" + key], 1e-14, "lookup")
+    finally:
+        del w._cache
+
+
 def test_preparateur_edge_shapes():
     """Shapes at the edges: one time step, windows longer than the series, empty
     batches, the cache-row quirk of WIN / SPE on a one-series fit sample."""
@@ -1173,7 +1193,55 @@ def test_prepared_copy_then_fused_kernels(golden_dir, monkeypatch):
     _assert_features_close(a, b, "generated kernels on the prepared copy vs composed route")
 
 
-@pytest.mark.parametrize("name", ["R_mixed", "R_rng", "R_preps"])
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
+@pytest.mark.parametrize("mode", ["single", "extended"])
+def test_generic_words_equal_the_oracle(semiring, mode):
+    """Words over Python letters: the letters are evaluated on the host, their
+    rows go through the kernels as extra dimensions -- bit for bit the
+    reference's Semiring._iterated_sum (oracle restatement, pinned by the
+    R_letters golden), through transform, batch_transform and device tensors."""
+    from oracle import pipeline as orc
+    words = ["[ABS(1)DIM(2)][DIM(1)]", "[ABS(1)DIM(2)][RELU(2)][DIM(1)DIM(1)]", "[LAGDIFF(1)]",
+             "[RELU(2)][DIM(1)DIM(1)]", "[ABS(1)DIM(2)]"]
+    desc = {"words": words, "mode": mode, "semiring": semiring}
+    X = np.random.default_rng(11).standard_normal((9, 2, 37)).cumsum(axis=2) / 3
+    iss = specs.build_iss(fruits, desc)
+    want = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    got = iss.transform(X)
+    assert got.shape == want.shape == (iss.n_iterated_sums(), 9, 37)
+    assert_exact(got, want, "generic words")
+    assert_exact(iss.transform(torch.from_numpy(X).cuda()).cpu().numpy(), want, "device input")
+    batches = list(iss.batch_transform(X, batch_size=2))
+    assert len(batches) == 3
+    assert_exact(np.concatenate(batches), want, "batch_transform")
+    with pytest.raises(IndexError):
+        iss.transform(X[:, :1])
+
+
+def test_generic_words_take_the_fused_kernels(monkeypatch):
+    """A slice whose ISS holds generic words runs its SimpleWord twin through
+    the fused kernels (iterated sums never materialised) with the features of
+    the composed route, for small batches and for the generated kernels."""
+    spec = {"slices": [specs.SPECS["R_letters"]["slices"][0], specs.SPECS["R_letters"]["slices"][1]]}
+    fruit = specs.build_fruit(fruits, spec)
+    X = specs.make_input("R_letters")
+    np.random.seed(0)
+    fruit.fit(X)
+    FS = fruits.fruit.FruitSlice
+    routes = []
+    fused = FS._transform_fused
+    monkeypatch.setattr(FS, "_transform_fused",
+                        lambda self, *a, **k: (routes.append("fused"), fused(self, *a, **k))[1])
+    big = np.random.default_rng(12).standard_normal((4200, 2, 45)).cumsum(axis=2) / 4
+    res, res_big = fruit.transform(X), fruit.transform(big)
+    assert routes == ["fused"] * 4
+    monkeypatch.setattr(FS, "_transform_prepared_fused", lambda self, *a, **k: False)
+    _assert_features_close(res, fruit.transform(X), "generic words: fused vs composed")
+    _assert_features_close(res_big, fruit.transform(big), "generic words: generated vs composed")
+    assert routes == ["fused"] * 4
+
+
+@pytest.mark.parametrize("name", ["R_mixed", "R_rng", "R_preps", "R_letters"])
 def test_extra_pipeline_golden(name, golden_dir):
     """Frozen outputs of the real reference: ``R_mixed`` -- a Bayesian slice
     (rank-2 sieves, sieve wrappers) and a slice of two chained ISS; ``R_rng``
@@ -1192,7 +1260,9 @@ def test_extra_pipeline_golden(name, golden_dir):
         _assert_features_close(res, g["features"], name)
     else:
         assert_exact(fitted_thresholds(fruit), g["thresholds"], "thresholds")
-        if name == "R_rng":
+        if name == "R_letters":
+            assert_close(res, g["features"], 1e-12, "features")      # MPI: summation order
+        elif name == "R_rng":
             assert_exact(res, g["features"], "features")
         else:
             assert_close(res, g["features"], 1e-12, "features")      # CUR: summation order

@@ -158,7 +158,14 @@ def test_error_behaviour():
     with pytest.raises(NotImplementedError):
         fruits.semiring.Arctic(argmax=True)
     with pytest.raises(NotImplementedError):
-        fruits.ISS([fruits.words.Word()])
+        fruits.ISS([fruits.words.Word()])                      # no extended letter
+    with pytest.raises(TypeError):
+        fruits.ISS(["[1]"])
+    with pytest.raises(NotImplementedError):
+        fruits.ISS([fruits.words.Word("[DIM(1)]")], semiring=fruits.semiring.Bayesian())
+    with pytest.raises(NotImplementedError):
+        fruits.ISS([fruits.words.Word("[DIM(1)]"), fruits.words.SimpleWord("[1]")],
+                   weighting=fruits.iss.weighting.Indices())
     with pytest.raises(ValueError):
         fruits.preparation.MAV(width=1.5)
     with pytest.raises(ValueError):
@@ -456,3 +463,44 @@ def test_preparateur_fits_draw_like_the_oracle():
         for key, val in st.items():
             np.testing.assert_array_equal(np.asarray(getattr(prep, got[key])), np.asarray(val),
                                           err_msg=f"{name}.{key}")
+
+
+def test_letters_and_generic_words():
+    """Host side of words over Python letters (reference:
+    fruits/iss/words/letters.py, word.py:9-125, creation.py:53-83)."""
+    W = fruits.words
+    assert W.letters.get_available()[:2] == ["DIM", "ABS"]
+    el = W.ExtendedLetter("ABS(1)DIM(3)")
+    assert str(el) == "[ABS(1)DIM(3)]" and len(el) == 2 and str(el.copy()) == str(el)
+    X = np.array([[1.0, -2.0], [3.0, 4.0], [-5.0, 6.0]])
+    np.testing.assert_array_equal(el[0](X), [1.0, 2.0])
+    np.testing.assert_array_equal([f(X) for f in el][1], [-5.0, 6.0])
+    el.append("DIM", 1)
+    assert str(el) == "[ABS(1)DIM(3)DIM(2)]"
+    with pytest.raises(RuntimeError, match="does not exist"):
+        W.ExtendedLetter("NOPE(1)")
+    name = "T_HALF"
+    if name not in W.letters.get_available():
+        @W.letter(name=name)
+        def half(X, i):
+            return X[i, :] / 2
+    with pytest.raises(RuntimeError, match="already exists"):
+        W.letter(name=name)(lambda X, i: X[i, :])
+    with pytest.raises(ValueError):
+        W.letter()
+    with pytest.raises(RuntimeError):
+        W.letter(abs, abs)
+    word = W.Word("[ABS(1)][T_HALF(2)DIM(1)]")
+    assert len(word) == 2 and str(word) == "[ABS(1)][T_HALF(2)DIM(1)]"
+    word.multiply(W.ExtendedLetter("DIM(2)"))
+    word.multiply(W.Word("[ABS(2)]"))
+    assert str(word) == "[ABS(1)][T_HALF(2)DIM(1)][DIM(2)][ABS(2)]" and str(word.copy()) == str(word)
+    with pytest.raises(TypeError):
+        word.multiply(3)
+    np.testing.assert_array_equal(word.alpha, np.ones(4, dtype=np.float32))
+    swapped = W.replace_letters(W.SimpleWord("[112][2]"), iter(["ABS", "T_HALF"]))
+    assert str(swapped) == "[ABS(1)T_HALF(1)DIM(2)][DIM(2)]"
+    iss = fruits.ISS([word, swapped, W.SimpleWord("[13]")], mode=fruits.ISSMode.EXTENDED)
+    assert iss.n_iterated_sums() == 4 + 2 + 1 and iss.max_dim() == 3
+    assert iss.label(1) == "[ABS(1)][T_HALF(2)DIM(1)]" and iss.label(6) == "[13]"
+    assert str(iss.copy().words[0]) == str(word)

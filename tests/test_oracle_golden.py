@@ -148,7 +148,7 @@ def test_prep2_golden(name, golden_dir):
             assert_close(got, g[key], 1e-12, key)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps"])
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps", "R_letters"])
 def test_pipeline_golden(name, golden_dir):
     from cases import COS_PIPE_CASES, EXTRA_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
