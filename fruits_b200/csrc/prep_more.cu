@@ -15,17 +15,30 @@
 
 namespace fb {
 
-static inline unsigned stream_grid(long long total, int block)
+// Thread layout of every kernel here: a CTA of 256 threads is tx x ty with tx =
+// the power of two >= min(t, 256) (>= 32), threadIdx.x walks the time axis of one
+// row (one series x dimension, consecutive lanes on consecutive 8-byte values),
+// threadIdx.y picks the row; rows are grid-strided.  No index division on the
+// element path (a 64-bit division per value would cost more than its 16 bytes
+// of HBM traffic).
+#define FB_ROWS(row, rows)                                                               \
+    for (long long row = blockIdx.x * (long long)blockDim.y + threadIdx.y; row < (rows); \
+         row += (long long)gridDim.x * blockDim.y)
+#define FB_COLS(k, t) _Pragma("unroll 4") for (int k = threadIdx.x; k < (t); k += blockDim.x)
+
+struct RowLaunch {
+    dim3 grid, block;
+};
+static inline RowLaunch row_launch(long long rows, long long t)
 {
-    long long g = (total + block - 1) / block;
+    unsigned tx = 32;
+    while (tx < 256 && tx < t) tx <<= 1;
+    const unsigned ty = 256 / tx;
+    long long g = (rows + ty - 1) / ty;
     if (g < 1) g = 1;
     if (g > 148LL * 32) g = 148LL * 32;
-    return (unsigned)g;
+    return {dim3((unsigned)g), dim3(tx, ty)};
 }
-
-#define FB_GRID_STRIDE(idx, total)                                                        \
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (total); \
-         idx += (long long)gridDim.x * blockDim.x)
 
 // Python's slice normalisation for one bound (start or stop, step 1).
 __device__ __forceinline__ long long py_bound(long long v, long long t)
@@ -48,67 +61,74 @@ __device__ __forceinline__ long long py_bound(long long v, long long t)
 //   CTS(pseudo_shift) transform.py:940-941         keep = 0 for t < shift
 //   WIN  filter.py:97-113   X[i, j, coq_start[i]-1 : coq_end[i]], lo_off = -1
 __global__ void time_mask_kernel(const double *__restrict__ X, double *__restrict__ out,
-                                 long long n, long long d, long long t,
+                                 long long rows, long long d, int t,
                                  const unsigned char *__restrict__ keep,
                                  const long long *__restrict__ lo,
                                  const long long *__restrict__ hi, long long lo_off)
 {
-    const long long total = n * d * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        bool on = keep ? keep[k] != 0 : true;
+    FB_ROWS(row, rows) {
+        long long a = 0, b = t;
         if (lo) {
-            const long long i = idx / (d * t);
-            const long long a = py_bound(lo[i] + lo_off, t), b = py_bound(hi[i], t);
-            on = on && k >= a && k < b;
+            const long long i = row / d;
+            a = py_bound(lo[i] + lo_off, t);
+            b = py_bound(hi[i], t);
         }
-        out[idx] = on ? X[idx] : 0.0;
+        const double *x = X + row * t;
+        double *o = out + row * t;
+        FB_COLS(k, t) {
+            const bool on = (keep ? keep[k] != 0 : true) && k >= a && k < b;
+            o[k] = on ? x[k] : 0.0;
+        }
     }
 }
 
 // CTS transform.py:943-944: y[k] = x[k + s] for k < T - s, x[T-1] behind.
 __global__ void time_shift_kernel(const double *__restrict__ X, double *__restrict__ out,
-                                  long long rows, long long t, long long shift)
+                                  long long rows, int t, long long shift)
 {
-    const long long total = rows * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        const long long src = k + shift < t ? k + shift : t - 1;
-        out[idx] = X[idx - k + src];
+    FB_ROWS(row, rows) {
+        const double *x = X + row * t;
+        double *o = out + row * t;
+        FB_COLS(k, t) o[k] = x[k + shift < t ? k + shift : t - 1];
     }
 }
 
 // LAG transform.py:291-298: out[i][2j][2k] = out[i][2j+1][2k] = x[k],
 // out[i][2j][2k+1] = x[k+1] (lead), out[i][2j+1][2k+1] = x[k] (lag).
+// One pass over the 2t-1 output columns writes both rows of an input row.
 __global__ void lead_lag_kernel(const double *__restrict__ X, double *__restrict__ out,
-                                long long rows, long long t)
+                                long long rows, int t)
 {
-    const long long t2 = 2 * t - 1, total = rows * 2 * t2;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k2 = idx % t2;
-        const long long r2 = idx / t2;           // output row = 2 * input row + (0 lead | 1 lag)
-        const long long k = k2 >> 1;
-        const bool lead = (r2 & 1) == 0;
-        const long long src = (k2 & 1) && lead ? k + 1 : k;
-        out[idx] = X[(r2 >> 1) * t + src];
+    const int t2 = 2 * t - 1;
+    FB_ROWS(row, rows) {
+        const double *x = X + row * t;
+        double *lead = out + 2 * row * t2, *lag = lead + t2;
+        FB_COLS(k2, t2) {
+            const int k = k2 >> 1;
+            const double here = x[k];
+            lag[k2] = here;
+            lead[k2] = (k2 & 1) ? x[k + 1] : here;
+        }
     }
 }
 
 // MAV transform.py:233-239: result[k-1] = sum(x[k-w:k]) / w for k = w..T, 0 in front.
 __global__ void moving_average_kernel(const double *__restrict__ X, double *__restrict__ out,
-                                      long long rows, long long t, long long w)
+                                      long long rows, int t, long long w)
 {
-    const long long total = rows * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;              // output index k = (window end) - 1
-        double v = 0.0;
-        if (k + 1 >= w) {
-            const double *x = X + idx - (w - 1);
-            double s = 0.0;
-            for (long long l = 0; l < w; l++) s = __dadd_rn(s, x[l]);
-            v = s / (double)w;
+    FB_ROWS(row, rows) {
+        const double *x = X + row * t;
+        double *o = out + row * t;
+        FB_COLS(k, t) {                           // output index k = (window end) - 1
+            double v = 0.0;
+            if (k + 1 >= w) {
+                const double *win = x + k - (w - 1);
+                double s = 0.0;
+                for (long long l = 0; l < w; l++) s = __dadd_rn(s, win[l]);
+                v = s / (double)w;
+            }
+            o[k] = v;
         }
-        out[idx] = v;
     }
 }
 
@@ -116,38 +136,39 @@ __global__ void moving_average_kernel(const double *__restrict__ X, double *__re
 // (adaptive_width, :537-543; pad = 0 otherwise):
 //   out[i][o][k] = sum_{j in group o} ( sum_{l=k-w}^{k-1} -x[dims[j]][l] * kern[j][l-k+w] + x[j][k] )
 // for padded positions k >= w, 0 in front.  (The reference adds x[i, j, k], not
-// x[i, dims[j], k]; kept.)
+// x[i, dims[j], k]; kept.)  Rows are (series, output dimension).
 __global__ void random_increments_kernel(const double *__restrict__ X,
                                          const double *__restrict__ kern,
                                          const int *__restrict__ ndim,
                                          const int *__restrict__ dims, double *__restrict__ out,
-                                         long long n, long long d, long long t, int n_out,
-                                         int w, int pad)
+                                         long long n, long long d, int t, int n_out, int w,
+                                         int pad)
 {
-    const long long total = n * n_out * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        const int o = (int)((idx / t) % n_out);
-        const long long i = idx / (t * n_out);
-        const long long kp = k + pad;                 // position in the padded series
-        double s = 0.0;
-        if (kp >= w) {
-            int start = 0;
-            for (int q = 0; q < o; q++) start += ndim[q];
-            const int end = start + ndim[o];
-            const double *xi = X + i * d * t;
-            for (int j = start; j < end; j++) {
-                const double *xr = xi + (long long)dims[j] * t;
-                const double *kr = kern + (long long)j * w;
-                for (int l = 0; l < w; l++) {
-                    const long long src = kp - w + l - pad;
-                    const double xv = src >= 0 ? xr[src] : 0.0;
-                    s = __dadd_rn(s, __dmul_rn(-xv, kr[l]));
+    FB_ROWS(row, n * n_out) {
+        const long long i = row / n_out;
+        const int o = (int)(row - i * n_out);
+        int start = 0;
+        for (int q = 0; q < o; q++) start += ndim[q];
+        const int end = start + ndim[o];
+        const double *xi = X + i * d * t;
+        double *dst = out + row * t;
+        FB_COLS(k, t) {
+            const int kp = k + pad;                   // position in the padded series
+            double s = 0.0;
+            if (kp >= w) {
+                for (int j = start; j < end; j++) {
+                    const double *xr = xi + (long long)dims[j] * t;
+                    const double *kr = kern + (long long)j * w;
+                    for (int l = 0; l < w; l++) {
+                        const int src = kp - w + l - pad;
+                        const double xv = src >= 0 ? xr[src] : 0.0;
+                        s = __dadd_rn(s, __dmul_rn(-xv, kr[l]));
+                    }
+                    s = __dadd_rn(s, xi[(long long)j * t + k]);
                 }
-                s = __dadd_rn(s, xi[(long long)j * t + k]);
             }
+            dst[k] = s;
         }
-        out[idx] = s;
     }
 }
 
@@ -155,65 +176,69 @@ __global__ void random_increments_kernel(const double *__restrict__ X,
 __global__ void dim_project_kernel(const double *__restrict__ X, const double *__restrict__ kern,
                                    const double *__restrict__ bias,
                                    const int *__restrict__ ndim, const int *__restrict__ dims,
-                                   double *__restrict__ out, long long n, long long d,
-                                   long long t, int n_out)
+                                   double *__restrict__ out, long long n, long long d, int t,
+                                   int n_out)
 {
-    const long long total = n * n_out * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        const int o = (int)((idx / t) % n_out);
-        const long long i = idx / (t * n_out);
+    FB_ROWS(row, n * n_out) {
+        const long long i = row / n_out;
+        const int o = (int)(row - i * n_out);
         int start = 0;
         for (int q = 0; q < o; q++) start += ndim[q];
         const int end = start + ndim[o];
-        const double *xi = X + i * d * t + k;
+        const double *xi = X + i * d * t;
         const double b = bias[o];
-        double s = 0.0;
-        for (int j = start; j < end; j++)
-            s = __dadd_rn(s, __dadd_rn(__dmul_rn(xi[(long long)dims[j] * t], kern[j]), b));
-        out[idx] = s;
+        double *dst = out + row * t;
+        FB_COLS(k, t) {
+            double s = 0.0;
+            for (int j = start; j < end; j++)
+                s = __dadd_rn(s, __dadd_rn(__dmul_rn(xi[(long long)dims[j] * t + k], kern[j]), b));
+            dst[k] = s;
+        }
     }
 }
 
 // FFN transform.py:362-376: hidden = W1 (x - mean) + b, relu as h * (h > 0),
-// out = W2 hidden, optional relu on the output.  One thread per (series, t);
-// the hidden layer is recomputed per output dimension (d_out is 1 by default).
+// out = W2 hidden, optional relu on the output.  Rows are (series, output
+// dimension); the hidden layer is recomputed per output dimension (d_out is 1
+// by default).
 __global__ void ffn_kernel(const double *__restrict__ X, const double *__restrict__ mean,
                            const double *__restrict__ W1, const double *__restrict__ b1,
                            const double *__restrict__ W2, double *__restrict__ out, long long n,
-                           long long d, long long t, int h, int d_out, int relu_out)
+                           long long d, int t, int h, int d_out, int relu_out)
 {
-    const long long total = n * d_out * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        const int o = (int)((idx / t) % d_out);
-        const long long i = idx / (t * d_out);
-        const double *xi = X + i * d * t + k;
-        double acc = 0.0;
-        for (int u = 0; u < h; u++) {
-            double hv = 0.0;
-            for (long long j = 0; j < d; j++) {
-                double xv = xi[j * t];
-                if (mean) xv = __dadd_rn(xv, -mean[2 * (i * d + j)]);
-                hv = __dadd_rn(hv, __dmul_rn(W1[u * d + j], xv));
+    FB_ROWS(row, n * d_out) {
+        const long long i = row / d_out;
+        const int o = (int)(row - i * d_out);
+        const double *xi = X + i * d * t;
+        double *dst = out + row * t;
+        FB_COLS(k, t) {
+            double acc = 0.0;
+            for (int u = 0; u < h; u++) {
+                double hv = 0.0;
+                for (long long j = 0; j < d; j++) {
+                    double xv = xi[j * t + k];
+                    if (mean) xv = __dadd_rn(xv, -mean[2 * (i * d + j)]);
+                    hv = __dadd_rn(hv, __dmul_rn(W1[u * d + j], xv));
+                }
+                hv = __dadd_rn(hv, b1[u]);
+                hv = __dmul_rn(hv, hv > 0.0 ? 1.0 : 0.0);
+                acc = __dadd_rn(acc, __dmul_rn(W2[(long long)o * h + u], hv));
             }
-            hv = __dadd_rn(hv, b1[u]);
-            hv = __dmul_rn(hv, hv > 0.0 ? 1.0 : 0.0);
-            acc = __dadd_rn(acc, __dmul_rn(W2[(long long)o * h + u], hv));
+            if (relu_out) acc = __dmul_rn(acc, acc > 0.0 ? 1.0 : 0.0);
+            dst[k] = acc;
         }
-        if (relu_out) acc = __dmul_rn(acc, acc > 0.0 ? 1.0 : 0.0);
-        out[idx] = acc;
     }
 }
 
 // RDW transform.py:601-602: x ** w[dim].
 __global__ void dim_pow_kernel(const double *__restrict__ X, const double *__restrict__ w,
-                               double *__restrict__ out, long long n, long long d, long long t)
+                               double *__restrict__ out, long long rows, long long d, int t)
 {
-    const long long total = n * d * t;
-    FB_GRID_STRIDE(idx, total) {
-        const int j = (int)((idx / t) % d);
-        out[idx] = pow(X[idx], w[j]);
+    FB_ROWS(row, rows) {
+        const double e = w[row % d];
+        const double *x = X + row * t;
+        double *o = out + row * t;
+        FB_COLS(k, t) o[k] = pow(x[k], e);
     }
 }
 
@@ -248,19 +273,20 @@ __global__ void abs_mean_max_kernel(const double *__restrict__ X, double *__rest
 }
 
 // RPE transform.py:859-875: rotation of the two dimensions by k / den,
-// den = T ** freq from the host.
+// den = T ** freq from the host.  Rows are series.
 __global__ void rotate2_kernel(const double *__restrict__ X, double *__restrict__ out,
-                               long long n, long long t, double den)
+                               long long n, int t, double den)
 {
-    const long long total = n * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long i = idx / t, k = idx % t;
-        const double a = (double)k / den;
-        double sn, cs;
-        sincos(a, &sn, &cs);
-        const double x0 = X[(2 * i) * t + k], x1 = X[(2 * i + 1) * t + k];
-        out[(2 * i) * t + k] = __dadd_rn(__dmul_rn(cs, x0), -__dmul_rn(sn, x1));
-        out[(2 * i + 1) * t + k] = __dadd_rn(__dmul_rn(sn, x0), __dmul_rn(cs, x1));
+    FB_ROWS(i, n) {
+        const double *x0 = X + 2 * i * t, *x1 = x0 + t;
+        double *o0 = out + 2 * i * t, *o1 = o0 + t;
+        FB_COLS(k, t) {
+            double sn, cs;
+            sincos((double)k / den, &sn, &cs);
+            const double a = x0[k], b = x1[k];
+            o0[k] = __dadd_rn(__dmul_rn(cs, a), -__dmul_rn(sn, b));
+            o1[k] = __dadd_rn(__dmul_rn(sn, a), __dmul_rn(cs, b));
+        }
     }
 }
 
@@ -270,37 +296,35 @@ __global__ void rotate2_kernel(const double *__restrict__ X, double *__restrict_
 //                                                             (step_transform L1 / L2)
 // apply_sin: the default wave function np.sin.
 __global__ void spe_range_kernel(const double *__restrict__ src, double *__restrict__ out,
-                                 long long rows, long long t, double den, double freq,
+                                 long long rows, int t, double den, double freq,
                                  int per_row_last, int apply_sin)
 {
-    const long long total = rows * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        double v;
-        if (!src) {
-            v = (double)k / den;
-        } else {
-            v = src[idx] / (per_row_last ? pow(src[idx - k + t - 1], freq) : den);
+    FB_ROWS(row, rows) {
+        const double *x = src ? src + row * t : nullptr;
+        const double dd = (x && per_row_last) ? pow(x[t - 1], freq) : den;
+        double *o = out + row * t;
+        FB_COLS(k, t) {
+            const double v = (x ? x[k] : (double)k) / dd;
+            o[k] = apply_sin ? sin(v) : v;
         }
-        out[idx] = apply_sin ? sin(v) : v;
     }
 }
 
 // SPE transform.py:803-810: X * wave or X + wave with numpy's broadcasting of
 // X[x_rows][d][t] against wave[wave_rows][1][t]: out has max(x_rows, wave_rows)
-// rows, a side with one row is repeated (a fit sample of one series against the
+// series, a side with one row is repeated (a fit sample of one series against the
 // cached sums of the whole batch, fruits/cache.py:97-112).
 __global__ void wave_embed_kernel(const double *__restrict__ X, const double *__restrict__ wave,
                                   double *__restrict__ out, long long x_rows,
-                                  long long wave_rows, long long d, long long t, int additive)
+                                  long long wave_rows, long long d, int t, int additive)
 {
-    const long long n = x_rows > wave_rows ? x_rows : wave_rows, total = n * d * t;
-    FB_GRID_STRIDE(idx, total) {
-        const long long k = idx % t;
-        const long long i = idx / (d * t);
-        const double w = wave[(wave_rows == 1 ? 0 : i) * t + k];
-        const double x = X[x_rows == 1 ? idx - i * d * t : idx];
-        out[idx] = additive ? __dadd_rn(x, w) : __dmul_rn(x, w);
+    const long long n = x_rows > wave_rows ? x_rows : wave_rows;
+    FB_ROWS(row, n * d) {
+        const long long i = row / d;
+        const double *w = wave + (wave_rows == 1 ? 0 : i) * t;
+        const double *x = X + (x_rows == 1 ? row - i * d : row) * t;
+        double *o = out + row * t;
+        FB_COLS(k, t) o[k] = additive ? __dadd_rn(x[k], w[k]) : __dmul_rn(x[k], w[k]);
     }
 }
 
@@ -308,7 +332,8 @@ __global__ void wave_embed_kernel(const double *__restrict__ X, const double *__
 __global__ void clip_where_kernel(const double *__restrict__ X, double *__restrict__ out,
                                   long long total, double q, double bound, int lower)
 {
-    FB_GRID_STRIDE(idx, total) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
         const double v = X[idx];
         out[idx] = (lower ? v < q : v > q) ? bound : v;
     }
@@ -318,12 +343,15 @@ __global__ void clip_where_kernel(const double *__restrict__ X, double *__restri
 
 using namespace fb;
 
-#define FB_LAUNCH(kernel, total, ...)                                                       \
-    do {                                                                                    \
-        if ((total) > 0) {                                                                  \
-            kernel<<<stream_grid((total), 256), 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
-            FB_CUDA(cudaGetLastError());                                                    \
-        }                                                                                   \
+#define FB_LAUNCH_ROWS(kernel, rows, t, ...)                                               \
+    do {                                                                                   \
+        if ((long long)(t) > (1LL << 30))                                                  \
+            return fb::set_err(FB_ENOSUP, "series longer than 2^30 time steps");           \
+        if ((rows) > 0) {                                                                  \
+            const RowLaunch rl_ = row_launch((rows), (t));                                 \
+            kernel<<<rl_.grid, rl_.block, 0, (cudaStream_t)stream>>>(__VA_ARGS__);         \
+            FB_CUDA(cudaGetLastError());                                                   \
+        }                                                                                  \
     } while (0)
 
 extern "C" {
@@ -334,7 +362,7 @@ int fb_time_mask(const double *X, double *out, int64_t n, int64_t d, int64_t t,
 {
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && (n == 0 || (X && out)), "bad arguments");
     FB_REQUIRE((lo == nullptr) == (hi == nullptr), "lo and hi come together");
-    FB_LAUNCH(time_mask_kernel, n * d * t, X, out, n, d, t, keep, (const long long *)lo,
+    FB_LAUNCH_ROWS(time_mask_kernel, n * d, t, X, out, n * d, d, (int)t, keep, (const long long *)lo,
               (const long long *)hi, lo_off);
     return 0;
 }
@@ -343,14 +371,14 @@ int fb_time_shift(const double *X, double *out, int64_t rows, int64_t t, int64_t
                   void *stream)
 {
     FB_REQUIRE(rows >= 0 && t >= 1 && shift >= 0 && (rows == 0 || (X && out)), "bad arguments");
-    FB_LAUNCH(time_shift_kernel, rows * t, X, out, rows, t, shift);
+    FB_LAUNCH_ROWS(time_shift_kernel, rows, t, X, out, rows, (int)t, shift);
     return 0;
 }
 
 int fb_lead_lag(const double *X, double *out, int64_t rows, int64_t t, void *stream)
 {
     FB_REQUIRE(rows >= 0 && t >= 1 && (rows == 0 || (X && out)), "bad arguments");
-    FB_LAUNCH(lead_lag_kernel, rows * 2 * (2 * t - 1), X, out, rows, t);
+    FB_LAUNCH_ROWS(lead_lag_kernel, rows, 2 * t - 1, X, out, rows, (int)t);
     return 0;
 }
 
@@ -358,7 +386,7 @@ int fb_moving_average(const double *X, double *out, int64_t rows, int64_t t, int
                       void *stream)
 {
     FB_REQUIRE(rows >= 0 && t >= 1 && width >= 1 && (rows == 0 || (X && out)), "bad arguments");
-    FB_LAUNCH(moving_average_kernel, rows * t, X, out, rows, t, width);
+    FB_LAUNCH_ROWS(moving_average_kernel, rows, t, X, out, rows, (int)t, width);
     return 0;
 }
 
@@ -369,8 +397,8 @@ int fb_random_increments(const double *X, const double *kernel, const int32_t *n
     FB_REQUIRE(n == 0 || (X && kernel && ndim && dims && out), "null pointer");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && n_out >= 1 && width >= 0 && (pad == 0 || pad == width),
                "bad arguments");
-    FB_LAUNCH(random_increments_kernel, n * n_out * t, X, kernel, ndim, dims, out, n, d, t, n_out,
-              width, pad);
+    FB_LAUNCH_ROWS(random_increments_kernel, n * n_out, t, X, kernel, ndim, dims, out, n, d,
+                   (int)t, n_out, width, pad);
     return 0;
 }
 
@@ -380,7 +408,8 @@ int fb_dim_project(const double *X, const double *kernel, const double *bias,
 {
     FB_REQUIRE(n == 0 || (X && kernel && bias && ndim && dims && out), "null pointer");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && n_out >= 1, "bad arguments");
-    FB_LAUNCH(dim_project_kernel, n * n_out * t, X, kernel, bias, ndim, dims, out, n, d, t, n_out);
+    FB_LAUNCH_ROWS(dim_project_kernel, n * n_out, t, X, kernel, bias, ndim, dims, out, n, d, (int)t,
+                   n_out);
     return 0;
 }
 
@@ -390,8 +419,8 @@ int fb_ffn(const double *X, const double *mean, const double *W1, const double *
 {
     FB_REQUIRE(n == 0 || (X && W1 && b1 && W2 && out), "null pointer");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && d_hidden >= 1 && d_out >= 1, "bad arguments");
-    FB_LAUNCH(ffn_kernel, n * d_out * t, X, mean, W1, b1, W2, out, n, d, t, d_hidden, d_out,
-              relu_out);
+    FB_LAUNCH_ROWS(ffn_kernel, n * d_out, t, X, mean, W1, b1, W2, out, n, d, (int)t, d_hidden, d_out,
+                   relu_out);
     return 0;
 }
 
@@ -399,7 +428,7 @@ int fb_dim_pow(const double *X, const double *w, double *out, int64_t n, int64_t
                void *stream)
 {
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && (n == 0 || (X && w && out)), "bad arguments");
-    FB_LAUNCH(dim_pow_kernel, n * d * t, X, w, out, n, d, t);
+    FB_LAUNCH_ROWS(dim_pow_kernel, n * d, t, X, w, out, n * d, d, (int)t);
     return 0;
 }
 
@@ -414,7 +443,7 @@ int fb_abs_mean_max(const double *X, double *out, int64_t n, int64_t d, int64_t 
 int fb_rotate2(const double *X, double *out, int64_t n, int64_t t, double den, void *stream)
 {
     FB_REQUIRE(n >= 0 && t >= 1 && (n == 0 || (X && out)), "bad arguments");
-    FB_LAUNCH(rotate2_kernel, n * t, X, out, n, t, den);
+    FB_LAUNCH_ROWS(rotate2_kernel, n, t, X, out, n, (int)t, den);
     return 0;
 }
 
@@ -423,7 +452,8 @@ int fb_spe_range(const double *src, double *out, int64_t rows, int64_t t, double
 {
     FB_REQUIRE(rows >= 0 && t >= 1 && (rows == 0 || out), "bad arguments");
     FB_REQUIRE(src || rows <= 1, "the index range is one row");
-    FB_LAUNCH(spe_range_kernel, rows * t, src, out, rows, t, den, freq, per_row_last, apply_sin);
+    FB_LAUNCH_ROWS(spe_range_kernel, rows, t, src, out, rows, (int)t, den, freq, per_row_last,
+                   apply_sin);
     return 0;
 }
 
@@ -436,7 +466,7 @@ int fb_wave_embed(const double *X, const double *wave, double *out, int64_t x_ro
                "operands could not be broadcast together: %lld series, %lld wave rows",
                (long long)x_rows, (long long)wave_rows);
     const int64_t n = x_rows == 0 ? 0 : (x_rows > wave_rows ? x_rows : wave_rows);
-    FB_LAUNCH(wave_embed_kernel, n * d * t, X, wave, out, x_rows, wave_rows, d, t, additive);
+    FB_LAUNCH_ROWS(wave_embed_kernel, n * d, t, X, wave, out, x_rows, wave_rows, d, (int)t, additive);
     return 0;
 }
 
@@ -444,7 +474,13 @@ int fb_clip_where(const double *X, double *out, int64_t total, double q, double 
                   void *stream)
 {
     FB_REQUIRE(total >= 0 && (total == 0 || (X && out)), "bad arguments");
-    FB_LAUNCH(clip_where_kernel, total, X, out, total, q, bound, lower);
+    if (total > 0) {
+        long long g = (total + 255) / 256;
+        if (g > 148LL * 32) g = 148LL * 32;
+        clip_where_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(X, out, total, q, bound,
+                                                                          lower);
+        FB_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -280,7 +280,6 @@ class FFN(Preparateur):
         self._weights1 = np.random.normal(loc=0, scale=1.0, size=(d_hidden, d))
         self._biases = np.random.normal(loc=0, scale=1.0, size=(d_hidden,))
         self._weights2 = np.random.normal(loc=0, scale=1.0, size=(self._d_out, d_hidden))
-        self._dev_weights = None
 
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         if not hasattr(self, "_weights1"):
@@ -289,10 +288,8 @@ class FFN(Preparateur):
         n, d, t = X.shape
         if self._weights1.shape[1] != d:
             raise ValueError(f"FFN was fitted on {self._weights1.shape[1]} dimensions, got {d}")
-        if getattr(self, "_dev_weights", None) is None or self._dev_weights[0].device != X.device:
-            self._dev_weights = tuple(_dev(w, np.float64) for w in
-                                      (self._weights1, self._biases, self._weights2))
-        w1, b1, w2 = self._dev_weights
+        # (uploaded per call: the fitted arrays are public attributes a caller may replace)
+        w1, b1, w2 = (_dev(w, np.float64) for w in (self._weights1, self._biases, self._weights2))
         mean = STD._row_stats(X.reshape(n * d, t), False, 0.0) if self._center and n else None
         out = be.empty((n, self._d_out, t))
         be.check(be.lib().fb_ffn(X.data_ptr(), be.ptr(mean), w1.data_ptr(), b1.data_ptr(),
@@ -323,7 +320,6 @@ class RIN(Preparateur):
 
     def _fit_device(self, X: torch.Tensor) -> None:
         d, t = X.shape[1], X.shape[2]
-        self._dev_state = None
         if self._const_kernel is not None:
             self._kernel = self._const_kernel.copy()
             self._ndim_per_kernel = np.ones((d,), dtype=np.int32)
@@ -359,10 +355,8 @@ class RIN(Preparateur):
             raise ValueError("RIN kernel needs one row per input dimension")
         if int(self._dims_per_kernel.max(initial=0)) >= d or len(self._dims_per_kernel) > d:
             raise IndexError(f"RIN was fitted on {len(self._dims_per_kernel)} dimensions, got {d}")
-        if getattr(self, "_dev_state", None) is None or self._dev_state[0].device != X.device:
-            self._dev_state = (_dev(kern, np.float64), _dev(self._ndim_per_kernel, np.int32),
+        k_d, ndim_d, dims_d = (_dev(kern, np.float64), _dev(self._ndim_per_kernel, np.int32),
                                _dev(self._dims_per_kernel, np.int32))
-        k_d, ndim_d, dims_d = self._dev_state
         n_out, w = len(self._ndim_per_kernel), kern.shape[1]
         out = be.empty((n, n_out, t))
         be.check(be.lib().fb_random_increments(
@@ -474,7 +468,6 @@ class JLD(Preparateur):
             self._bias_weights = np.random.standard_normal(out_dim)
         else:
             self._bias_weights = np.zeros(out_dim, dtype=np.float64)
-        self._dev_state = None
 
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         if not hasattr(self, "_kernel"):
@@ -483,11 +476,10 @@ class JLD(Preparateur):
         n, d, t = X.shape
         if int(self._dims_per_kernel.max(initial=0)) >= d:
             raise IndexError(f"JLD was fitted on more dimensions than the {d} given")
-        if getattr(self, "_dev_state", None) is None or self._dev_state[0].device != X.device:
-            self._dev_state = (_dev(self._kernel, np.float64), _dev(self._bias_weights, np.float64),
-                               _dev(self._ndim_per_kernel, np.int32),
-                               _dev(self._dims_per_kernel, np.int32))
-        k_d, b_d, ndim_d, dims_d = self._dev_state
+        k_d, b_d, ndim_d, dims_d = (_dev(self._kernel, np.float64),
+                                    _dev(self._bias_weights, np.float64),
+                                    _dev(self._ndim_per_kernel, np.int32),
+                                    _dev(self._dims_per_kernel, np.int32))
         n_out = len(self._ndim_per_kernel)
         out = be.empty((n, n_out, t))
         be.check(be.lib().fb_dim_project(X.data_ptr(), k_d.data_ptr(), b_d.data_ptr(),

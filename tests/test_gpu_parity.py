@@ -1115,6 +1115,68 @@ def test_increment_sum_weighting_with_python_transform(key, golden_dir):
         del w._cache
 
 
+def test_reference_preparateur_known_answers():
+    """The hand-computed vectors of the reference's own preparateur tests
+    (tests/preparation/test_filter.py:13-66, test_transform.py:12-160) through
+    the GPU path: WIN, DOT, NRM(scale_dim), MAV, LAG, RIN with a planted kernel,
+    JLD shapes, FFN against its own weights."""
+    P = fruits.preparation
+    Xw = np.array([[[1, 2, 4, 5, 6], [11, 22, 33, 44, 55]],
+                   [[10, 20, 30, 40, 50], [111, 222, 333, 444, 555]]], dtype=float)
+    np.testing.assert_allclose(P.WIN(0.0, 0.7).fit_transform(Xw), [
+        [[1, 2, 0, 0, 0], [11, 22, 0, 0, 0]], [[10, 20, 30, 0, 0], [111, 222, 333, 0, 0]]])
+    np.testing.assert_allclose(P.WIN(0.7, 1.0).fit_transform(Xw), [
+        [[0, 2, 4, 5, 6], [0, 22, 33, 44, 55]], [[0, 0, 30, 40, 50], [0, 0, 333, 444, 555]]])
+    np.testing.assert_allclose(P.DOT(0.4).fit_transform(X_1), [
+        [[0., 0.8, 0., 5., 0.], [0., 1., 0., 0., 0.]], [[0., 8., 0., 6., 0.], [0., -1., 0., -0.5, 0.]]])
+    np.testing.assert_allclose(P.DOT(0.9).fit_transform(X_1), [
+        [[0, 0, 0, 5, 0], [0, 0, 0, 0, 0]], [[0, 0, 0, 6, 0], [0, 0, 0, -0.5, 0]]])
+    ramp = np.arange(100, dtype=float)[np.newaxis, np.newaxis, :]
+    want = np.zeros(ramp.shape)
+    want[:, :, 9::10] = ramp[:, :, 9::10]
+    np.testing.assert_allclose(P.DOT(0.1).fit_transform(ramp), want)
+    np.testing.assert_allclose(P.NRM(scale_dim=True).fit_transform(X_1), [
+        [[3/12, 7.8/12, 7/12, 1., 4/12], [9/12, 8/12, 7/12, 7/12, 0.]],
+        [[13/16, 1., 10/16, 14/16, 8/16], [3/16, 7/16, 4/16, 7.5/16, 0.]]])
+    np.testing.assert_allclose(P.MAV(2).fit_transform(X_1), [
+        [[0, -1.6, 0.4, 2.5, 1], [0, 1.5, 0.5, 0, -3.5]],
+        [[0, 6.5, 5, 4, 3], [0, -3, -2.5, -2.25, -4.25]]])
+    np.testing.assert_allclose(P.MAV(0.6).fit_transform(X_1), np.array([
+        [[0, 0, -3.2, 5.8, 2.], [0, 0, 3., 1., -7.]],
+        [[0, 0, 15., 16., 8.], [0, 0, -10., -5.5, -12.5]]]) / 3)
+    np.testing.assert_allclose(P.LAG().fit_transform(X_1), [
+        [[-4., 0.8, 0.8, 0., 0., 5., 5., -3., -3.], [-4., -4., 0.8, 0.8, 0., 0., 5., 5., -3.],
+         [2., 1., 1., 0., 0., 0., 0., -7., -7.], [2., 2., 1., 1., 0., 0., 0., 0., -7.]],
+        [[5., 8., 8., 2., 2., 6., 6., 0., 0.], [5., 5., 8., 8., 2., 2., 6., 6., 0.],
+         [-5., -1., -1., -4., -4., -0.5, -0.5, -8., -8.],
+         [-5., -5., -1., -1., -4., -4., -0.5, -0.5, -8.]]])
+    other = np.random.default_rng(0).random((46, 2, 189))
+    rin = P.RIN(2, adaptive_width=True)
+    rin.fit(other)
+    rin._kernel = np.array([[4., 1.], [4., 1.]])
+    rin._ndim_per_kernel = np.array([1, 1], dtype=np.int32)
+    rin._dims_per_kernel = np.array([0, 1], dtype=np.int32)
+    np.testing.assert_allclose(rin.transform(X_1), [
+        [[-4., 4.8, 15.2, 1.8, -8.], [2., -1., -9., -4., -7.]],
+        [[5., 3., -26., -28., -14.], [-5., 4., 17., 7.5, 8.5]]])
+    rin = P.RIN(width=2, adaptive_width=False, out_dim=1)
+    rin.fit(other)
+    assert rin._kernel.shape == (2, 2)
+    rin._kernel = np.array([[4., 1.], [2., 3.]])
+    rin._ndim_per_kernel = np.array([2], dtype=np.int32)
+    rin._dims_per_kernel = np.array([0, 1], dtype=np.int32)
+    np.testing.assert_allclose(rin.transform(X_1), [[[0., 0, 8.2, -.2, -15.]],
+                                                    [[0., 0., -17., -14.5, -12.5]]])
+    wide = np.random.default_rng(1).random((46, 100, 189))
+    assert P.JLD(25).fit_transform(wide).shape == (46, 25, 189)
+    ffn = P.FFN(d_hidden=3, center=False, relu_out=False)
+    ffn.fit(X_1)
+    hidden = np.stack([ffn._weights1 @ X_1[i] + ffn._biases[:, np.newaxis] for i in range(2)])
+    hidden = hidden * (hidden > 0)
+    np.testing.assert_allclose(ffn.transform(X_1),
+                               np.stack([ffn._weights2 @ hidden[i] for i in range(2)]))
+
+
 def test_preparateur_edge_shapes():
     """Shapes at the edges: one time step, windows longer than the series, empty
     batches, the cache-row quirk of WIN / SPE on a one-series fit sample."""
