@@ -24,7 +24,7 @@ namespace fb {
 #define FB_ROWS(row, rows)                                                               \
     for (long long row = blockIdx.x * (long long)blockDim.y + threadIdx.y; row < (rows); \
          row += (long long)gridDim.x * blockDim.y)
-#define FB_COLS(k, t) _Pragma("unroll 4") for (int k = threadIdx.x; k < (t); k += blockDim.x)
+#define FB_COLS(k, t) for (int k = threadIdx.x; k < (t); k += blockDim.x)
 
 struct RowLaunch {
     dim3 grid, block;

@@ -554,6 +554,8 @@ class FruitSlice:
         for iss in self._iss:
             iss._cache = cache
             iss._check_input(prepared)
+            if iss.requires_fitting:            # (randomised CosWISS; fruit.py:478-481)
+                iss._fit_device(prepared)
         if not any(sieve.requires_fitting for sieve in self._sieves):
             self._sieves_extended = []
             self._fitted = True

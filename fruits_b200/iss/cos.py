@@ -8,8 +8,13 @@ every expansion term is an ordinary iterated sum with extra per-level
 factors; ``csrc/cos.cu`` evaluates all terms of one word for all frequencies
 in one launch.  Emission order: word-major, frequency-minor.
 
-The randomised variants of the reference (``ffn_size``, ``dropout``) are out
-of scope and raise ``NotImplementedError``.
+The randomised variants of the reference (``ffn_size``: every word and
+frequency sees the input through its own random two-layer network; ``dropout``:
+random time steps are zeroed ahead of every cumulative sum) are served per
+(word, frequency) by the same kernels on a transformed input: the network output
+(``fb_ffn``), or the input plus one 0/1 mask dimension per level that joins the
+letters of the word (a factor 1.0 leaves a product unchanged bit for bit, a
+factor 0.0 zeroes the summand like the reference's assignment does).
 """
 import itertools
 import os
@@ -33,9 +38,13 @@ class CosWISS(ISS):
 
     # In a FruitSlice the expansion is compiled into the plan-specialised kernel
     # (``_jit_trie``); there is no generic fused kernel for it, so small batches
-    # and plans that do not fit run on materialised iterated sums.
-    _fusable_iss = True
+    # and plans that do not fit run on materialised iterated sums (and so do the
+    # randomised variants).
     _jit_only = True
+
+    @property
+    def _fusable_iss(self) -> bool:
+        return self._ffn_size is None and self._dropout is None
 
     def __init__(self, words: Sequence[Word], freqs: Sequence[float], exponent: int = 2,
                  total_weighting: bool = False, ffn_size: Optional[int] = None,
@@ -43,9 +52,6 @@ class CosWISS(ISS):
         for word in words:
             if not isinstance(word, SimpleWord):
                 raise ValueError("CosWISS only implemented for simple words")
-        if ffn_size is not None or dropout is not None:
-            raise NotImplementedError(
-                "the randomised CosWISS variants (ffn_size, dropout) are not built")
         super().__init__(words)
         self._total_weighting = total_weighting
         self._freqs = freqs
@@ -56,10 +62,80 @@ class CosWISS(ISS):
 
     @property
     def requires_fitting(self) -> bool:
-        return False
+        return self._ffn_size is not None or self._dropout is not None
+
+    def _fit_device(self, X: torch.Tensor) -> None:
+        """The reference's draws in its order (cos.py:243-260): uniform network
+        weights per (word, frequency), then dropped time steps per (word, frequency,
+        level)."""
+        d, t = X.shape[1], X.shape[2]
+        nw, nf = len(self.words), len(self._freqs)
+        if (h := self._ffn_size) is not None:
+            self._A = np.random.random((nw, nf, h, d))
+            self._b = np.random.random((nw, nf, h))
+            self._C = np.random.random((nw, nf, d, h))
+        if (p := self._dropout) is not None:
+            rate = int(p * t)
+            self._dropout_indices = np.array([
+                [[np.random.choice(t, size=(rate,), replace=False)
+                  for _ in range(max(map(len, self.words)))]
+                 for _ in range(nf)]
+                for _ in range(nw)], dtype=np.int32)
+        self._tables.pop("randomised", None)
 
     def n_iterated_sums(self) -> int:
         return len(self._freqs) * len(self.words)
+
+    def _materialize_randomised(self, X: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+        """``ffn_size`` / ``dropout``: one plain CosWISS of one word and one
+        frequency per emission, on the input that (word, frequency) sees
+        (reference: ``_ffn_coswiss`` cos.py:116-138, ``_leaky_coswiss`` :141-160;
+        the network wins if both are set, :306-324)."""
+        ffn = self._ffn_size is not None
+        if not hasattr(self, "_A" if ffn else "_dropout_indices"):
+            raise RuntimeError("Missing call of self.fit")
+        n, d, t = X.shape
+        nf = len(self._freqs)
+        out = be.empty((hi - lo, n, t))
+        subs = self._tables.setdefault("randomised", {})
+        for e in range(lo, hi):
+            w, f = divmod(e, nf)
+            word = self.words[w]
+            if ffn:
+                if self._A.shape[3] != d:
+                    raise ValueError(f"CosWISS was fitted on {self._A.shape[3]} dimensions, got {d}")
+                A, b, C = (torch.from_numpy(np.ascontiguousarray(a[w, f])).to(X.device)
+                           for a in (self._A, self._b, self._C))
+                Xe = be.empty((n, d, t))
+                be.check(be.lib().fb_ffn(X.data_ptr(), 0, A.data_ptr(), b.data_ptr(),
+                                         C.data_ptr(), Xe.data_ptr(), n, d, t,
+                                         self._ffn_size, d, 0, be.stream_ptr()))
+                masked = word
+            else:
+                if self._dropout_indices.shape[3] > t:
+                    raise IndexError("CosWISS was fitted on longer series")
+                p = len(word)
+                mask = np.ones((p, t))
+                for k in range(p):
+                    mask[k, self._dropout_indices[w, f, k]] = 0.0
+                extra = torch.from_numpy(mask).to(X.device)[None].expand(n, p, t)
+                Xe = torch.cat((X, extra), dim=1).contiguous()
+                # level k of the word additionally multiplies by mask dimension d + k
+                masked = subs.get(("word", w))
+                if masked is None or masked[0] != d:
+                    text = "".join(
+                        "[" + "".join((f"({i + 1})" if c > 0 else f"(-{i + 1})") * abs(int(c))
+                                      for i, c in enumerate(el)) + f"({d + k + 1})]"
+                        for k, el in enumerate(word))
+                    masked = subs[("word", w)] = (d, SimpleWord(text))
+                masked = masked[1]
+            sub = subs.get((w, f, ffn, d))
+            if sub is None:
+                sub = subs[(w, f, ffn, d)] = CosWISS(
+                    [masked], [self._freqs[f]], exponent=self._exponent,
+                    total_weighting=self._total_weighting)
+            out[e - lo] = sub.materialize(Xe)[0]
+        return out
 
     def trie(self):
         raise NotImplementedError("CosWISS has no prefix trie of its own (see _jit_trie)")
@@ -245,10 +321,13 @@ class CosWISS(ISS):
         if key not in self._tables:
             spec = torch.tensor(np.asarray(rows, dtype=np.int32).reshape(-1, 4), device=X.device)
             freqs = torch.tensor(np.asarray(self._freqs, dtype=np.float32), device=X.device)
-            out = be.empty((len(rows), X.shape[2]))
-            be.check(be.lib().fb_cos_rows(freqs.data_ptr(), len(self._freqs), X.shape[2],
-                                          spec.data_ptr(), len(rows), out.data_ptr(),
-                                          be.stream_ptr()))
+            # (one-letter words without total weighting have no junction: no row at all --
+            # the kernels still get a valid pointer)
+            out = be.zeros((max(len(rows), 1), X.shape[2]))
+            if rows:
+                be.check(be.lib().fb_cos_rows(freqs.data_ptr(), len(self._freqs), X.shape[2],
+                                              spec.data_ptr(), len(rows), out.data_ptr(),
+                                              be.stream_ptr()))
             self._tables = {k: v for k, v in self._tables.items() if k[0] != "rows"}
             self._tables[key] = out
         return self._tables[key]
@@ -316,6 +395,8 @@ class CosWISS(ISS):
         n, d, t = X.shape
         nf = len(self._freqs)
         lo, hi = (0, self.n_iterated_sums()) if emit_range is None else emit_range
+        if self.requires_fitting:
+            return self._materialize_randomised(X, lo, hi)
         out = be.empty((hi - lo, n, t))
         L = be.lib()
         ns = self._exponent + 1
@@ -359,7 +440,8 @@ class CosWISS(ISS):
 
     def _copy(self) -> "CosWISS":
         return CosWISS(freqs=self._freqs, words=self.words, exponent=self._exponent,
-                       total_weighting=self._total_weighting)
+                       total_weighting=self._total_weighting, ffn_size=self._ffn_size,
+                       dropout=self._dropout)
 
     def _label(self, index: int) -> str:
         d, r = divmod(index, len(self._freqs))

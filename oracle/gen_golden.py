@@ -254,6 +254,33 @@ def gen_cos():
     gen_pipelines(COS_PIPE_CASES)
 
 
+def gen_cos2():
+    """The randomised CosWISS variants (ffn_size, dropout): fit under a seed,
+    transform, where the generator stands after fit."""
+    import copy
+    from cases import COS_RANDOM_CASES
+    print("[coswiss, randomised]")
+    out = {}
+    for name, (desc, shape, kind) in COS_RANDOM_CASES.items():
+        X = make_iss_input(shape, kind)
+        iss = specs.build_iss(ref, desc)
+        assert iss.requires_fitting
+        np.random.seed(3)
+        iss.fit(X)
+        state_r = np.random.random()
+        r = iss.transform(X)
+        odesc = copy.deepcopy(desc)
+        np.random.seed(3)
+        odesc["_state"] = orc.coswiss_fit(odesc, X)
+        assert np.random.random() == state_r, f"{name}: fit consumed the RNG differently"
+        o = np.stack(list(orc.iss_iter(X, odesc, orc.RawCache(X))))
+        check_close(o, r, f"coswiss {name}", rtol=1e-11)
+        out[name], out[name + "_rng"] = r, np.array(state_r)
+        out[name + "_xsha"] = np.array(sha(X))
+    np.savez_compressed(os.path.join(GOLD, "cos2.npz"), **out)
+    gen_pipelines({"R_cosrand": EXTRA_PIPE_CASES["R_cosrand"]})
+
+
 def gen_extra():
     """Pipelines of the rank 2-3 components (Bayesian semiring, CUR / CPV / XPI /
     LPI, sieve wrappers, chained ISS)."""

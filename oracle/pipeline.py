@@ -393,11 +393,40 @@ def coswiss_weightings(n_letters: int, exponent: int, total: bool) -> np.ndarray
     return np.array(rows, dtype=np.int32).reshape(len(rows), 2 * p + 1)
 
 
-def coswiss_word(X, word: str, freqs, exponent: int, total: bool):
+def coswiss_fit(iss, X):
+    """State of a randomised CosWISS after ``fit`` (fruits/iss/cos.py:243-260):
+    the uniform weights of the per-(word, frequency) two-layer network
+    (``ffn_size``) and / or the dropped time steps per (word, frequency, level)
+    (``dropout``); the draws in the reference's order."""
+    c = iss["coswiss"]
+    words = expand_words(iss["words"])
+    nw, nf, d, t = len(words), len(c["freqs"]), X.shape[1], X.shape[2]
+    st = {}
+    if c.get("ffn_size") is not None:
+        h = c["ffn_size"]
+        st["A"] = np.random.random((nw, nf, h, d))
+        st["b"] = np.random.random((nw, nf, h))
+        st["C"] = np.random.random((nw, nf, d, h))
+    if c.get("dropout") is not None:
+        rate = int(c["dropout"] * t)
+        depth = max(len(parse_word(w)) for w in words)
+        st["drop"] = np.array([[[np.random.choice(t, size=(rate,), replace=False)
+                                 for _ in range(depth)] for _ in range(nf)]
+                               for _ in range(nw)], dtype=np.int32)
+    return st
+
+
+def coswiss_word(X, word: str, freqs, exponent: int, total: bool, ffn=None, drop=None):
     """``[n_freqs, n, t]`` cosine weighted iterated sums of one word
-    (fruits/iss/cos.py:16-49, :171-181), same operation order."""
+    (fruits/iss/cos.py:16-49, :171-181), same operation order.  ``ffn`` =
+    ``(A, b, C)`` of this word: every frequency sees the input through its own
+    two-layer network first (``_ffn`` :96-113, ``_ffn_coswiss`` :116-138);
+    ``drop[f][k]``: time steps set to zero ahead of the cumulative sum of level
+    ``k`` (``_leaky_coswiss_single`` :52-93).  The network wins if both are set
+    (:306-324)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     n, d, t = X.shape
+    X_raw = X
     mat = parse_word(word)
     p = mat.shape[0]
     wts = coswiss_weightings(p, exponent, total)
@@ -407,6 +436,12 @@ def coswiss_word(X, word: str, freqs, exponent: int, total: bool):
         with np.errstate(divide="ignore", invalid="ignore"):
             arg = np.pi * np.arange(t) / den
         sin_w, cos_w = np.sin(arg), np.cos(arg)
+        if ffn is not None:
+            A, b, C = ffn[0][f], ffn[1][f], ffn[2][f]
+            Y = (A[np.newaxis, :, :, np.newaxis] * X_raw[:, np.newaxis, :, :]).sum(axis=2) \
+                + b[np.newaxis, :, np.newaxis]
+            Y = Y * (Y > 0)
+            X = (C[np.newaxis, :, :, np.newaxis] * Y[:, np.newaxis, :, :]).sum(axis=2)
         for row in wts:
             tmp = np.ones((n, t))
             for k in range(p):
@@ -420,6 +455,8 @@ def coswiss_word(X, word: str, freqs, exponent: int, total: bool):
                     tmp = tmp * sin_w
                 for _ in range(row[2 * k + 2]):
                     tmp = tmp * cos_w
+                if drop is not None and ffn is None:
+                    tmp[:, drop[f][k]] = 0
                 tmp = np.cumsum(tmp, axis=1)
             if total:
                 for _ in range(row[2 * p + 1]):
@@ -435,8 +472,13 @@ def iss_iter(X, iss, cache: RawCache):
     words = expand_words(iss["words"])
     if iss.get("coswiss") is not None:
         c = iss["coswiss"]
-        for w in words:      # word-major, frequency-minor (fruits/iss/cos.py:289-333)
-            out = coswiss_word(X, w, c["freqs"], c.get("exponent", 2), c.get("total", False))
+        st = iss.get("_state") or {}
+        if (c.get("ffn_size") is not None or c.get("dropout") is not None) and not st:
+            raise RuntimeError("randomised CosWISS: coswiss_fit first")
+        for i, w in enumerate(words):      # word-major, frequency-minor (fruits/iss/cos.py:289-333)
+            out = coswiss_word(X, w, c["freqs"], c.get("exponent", 2), c.get("total", False),
+                               ffn=(st["A"][i], st["b"][i], st["C"][i]) if "A" in st else None,
+                               drop=st["drop"][i] if "drop" in st else None)
             for f in range(out.shape[0]):
                 yield out[f]
         return
@@ -717,6 +759,10 @@ class OracleSlice:
         for prep in self.spec.get("preps", []):
             self.prep_states.append(fit_prep_state(prep, prepared))
             prepared = apply_prep(prep, prepared, self.prep_states[-1], cache)
+        for iss in self.spec["iss"]:          # fruits/fruit.py:478-481
+            c = iss.get("coswiss")
+            if c is not None and (c.get("ffn_size") is not None or c.get("dropout") is not None):
+                iss["_state"] = coswiss_fit(iss, prepared)
         if not any(s.requires_fitting() for s in self.sieves):
             self.sieves_extended = []
             return

@@ -251,9 +251,30 @@ PIPE_CASES = {
 
 COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
+# the randomised CosWISS variants (fruits/iss/cos.py:243-260, :306-324): fit under
+# np.random.seed(3), then transform; frozen by ``oracle/gen_golden.py cos2``
+COS_RANDOM_CASES = {
+    "cos_ffn": ({"words": ["[1]", "[1][2]", "[12][1]"],
+                 "coswiss": {"freqs": [0.25, 0.05], "exponent": 2, "ffn_size": 4}},
+                (4, 2, 60), "std"),
+    "cos_ffn_total_e1": ({"words": ["[2][1]", "[1][2][11]"],
+                          "coswiss": {"freqs": [0.15], "exponent": 1, "total": True,
+                                      "ffn_size": 3}}, (3, 2, 50), "std"),
+    "cos_dropout": ({"words": ["[1]", "[1][2]", "[12][1]", "[1][-2][11]"],
+                     "coswiss": {"freqs": [0.25, 0.05], "exponent": 2, "dropout": 0.2}},
+                    (4, 2, 60), "uniform1"),
+    "cos_dropout_total_e3": ({"words": ["[2][1]", "[1][2][1]"],
+                              "coswiss": {"freqs": [0.3], "exponent": 3, "total": True,
+                                          "dropout": 0.5}}, (3, 2, 50), "std"),
+    "cos_ffn_and_dropout": ({"words": ["[1][2]"],
+                             "coswiss": {"freqs": [0.1, 0.4], "exponent": 2, "ffn_size": 2,
+                                         "dropout": 0.3}}, (3, 2, 40), "std"),
+}
+
 # pipelines of the rank 2-3 components, frozen from the reference
 EXTRA_PIPE_CASES = {"R_mixed": ("R_mixed", 40), "R_rng": ("R_rng", 30),
-                    "R_preps": ("R_preps", 36), "R_letters": ("R_letters", 33)}
+                    "R_preps": ("R_preps", 36), "R_letters": ("R_letters", 33),
+                    "R_cosrand": ("R_cosrand", 30)}
 
 
 

@@ -164,6 +164,19 @@ SPECS["R_letters"] = {"slices": [
              {"words": ["[ABS(1)][RELU(1)]"], "mode": "extended"}],
      "sieves": [["NPI", {}], ["END", {}]], "fit_sample_size": 1}]}
 
+# the randomised CosWISS variants inside a fruit: ISS.fit draws between the preparateurs
+# and the sieves (fruits/fruit.py:478-481)
+SPECS["R_cosrand"] = {"slices": [
+    {"preps": [["NEW", ["INC", {}]], ["STD", {}]],
+     "iss": [{"words": ["[1]", "[1][2]", "[3][1]"],
+              "coswiss": {"freqs": [0.1, 0.35], "exponent": 2, "total": True, "ffn_size": 3}}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MPI", {"q": [0.5, 1.0]}], ["END", {}]],
+     "fit_sample_size": 1.0},
+    {"preps": [["INC", {}]],
+     "iss": [{"words": ["[1][2]", "[2][1][1]"],
+              "coswiss": {"freqs": [0.2], "exponent": 1, "dropout": 0.25}}],
+     "sieves": [["PPV", {}], ["MAX", {}], ["END", {}]], "fit_sample_size": 0.5}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -172,7 +185,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
-              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48), "R_letters": (33, 2, 45),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48), "R_letters": (33, 2, 45), "R_cosrand": (30, 2, 44),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -183,6 +196,8 @@ def make_input(name: str, n: int = None) -> np.ndarray:
         return np.random.default_rng(1234).standard_normal((n, D, T))
     if name == "R_mixed":
         return np.random.default_rng(42).random((n, D, T)) + 0.1
+    if name == "R_cosrand":
+        return np.random.default_rng(46).standard_normal((n, D, T)).cumsum(axis=2) / 3
     if name == "R_letters":
         return np.random.default_rng(45).standard_normal((n, D, T)).cumsum(axis=2) / 4
     if name == "R_preps":
@@ -266,7 +281,8 @@ def build_iss(mod, desc):
     if desc.get("coswiss") is not None:
         c = desc["coswiss"]
         return mod.CosWISS(words=words, freqs=list(c["freqs"]), exponent=c.get("exponent", 2),
-                           total_weighting=c.get("total", False))
+                           total_weighting=c.get("total", False), ffn_size=c.get("ffn_size"),
+                           dropout=c.get("dropout"))
     if desc.get("alphas") is not None:
         for w, a in zip(words, desc["alphas"]):
             w.alpha = a

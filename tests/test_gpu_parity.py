@@ -625,12 +625,39 @@ def test_coswiss_pipeline_golden(golden_dir):
     _assert_features_close(res, composed, "generated kernel vs composed route")
 
 
-def test_coswiss_unsupported_variants():
-    words = [fruits.words.SimpleWord("[1][2]")]
-    with pytest.raises(NotImplementedError):
-        fruits.CosWISS(words, freqs=[0.1], ffn_size=4)
-    with pytest.raises(NotImplementedError):
-        fruits.CosWISS(words, freqs=[0.1], dropout=0.2)
+@pytest.mark.parametrize("name", sorted(__import__("cases").COS_RANDOM_CASES))
+def test_randomised_coswiss_golden(name, golden_dir):
+    """The randomised CosWISS variants (a random two-layer network per word and
+    frequency in front, random dropout ahead of every cumulative sum) against
+    outputs frozen from the reference: same draws in fit, same generator state,
+    iterated sums within the CosWISS bound."""
+    from cases import COS_RANDOM_CASES
+    g = np.load(os.path.join(golden_dir, "cos2.npz"))
+    desc, shape, kind = COS_RANDOM_CASES[name]
+    X = make_iss_input(shape, kind)
+    iss = specs.build_iss(fruits, desc)
+    assert iss.requires_fitting and iss.copy().requires_fitting
+    with pytest.raises(RuntimeError):
+        iss.transform(X)
+    np.random.seed(3)
+    iss.fit(X)
+    assert np.random.random() == float(g[name + "_rng"]), "fit consumed the RNG differently"
+    res = iss.transform(X)
+    assert_close(res, g[name], 1e-9, name)
+    batches = np.concatenate(list(iss.batch_transform(X, batch_size=2)))
+    assert_exact(batches, res, "batch_transform")
+
+
+def test_coswiss_of_one_letter_words_only():
+    """No junction anywhere (one-letter words, no total weighting): the cosine
+    weights drop out and the sums are plain cumulative sums."""
+    X = np.random.default_rng(2).standard_normal((5, 2, 33))
+    iss = fruits.CosWISS([fruits.words.SimpleWord("[1]"), fruits.words.SimpleWord("[12]")],
+                         freqs=[0.1, 0.3])
+    res = iss.transform(X)
+    assert_exact(res[0], np.cumsum(X[:, 0], axis=1), "[1]")
+    assert_exact(res[1], res[0], "[1], second frequency")
+    assert_exact(res[2], np.cumsum(X[:, 0] * X[:, 1], axis=1), "[12]")
 
 
 def test_coswiss_four_letter_words_generated_kernel():
@@ -1303,7 +1330,7 @@ def test_generic_words_take_the_fused_kernels(monkeypatch):
     assert routes == ["fused"] * 4
 
 
-@pytest.mark.parametrize("name", ["R_mixed", "R_rng", "R_preps", "R_letters"])
+@pytest.mark.parametrize("name", ["R_mixed", "R_rng", "R_preps", "R_letters", "R_cosrand"])
 def test_extra_pipeline_golden(name, golden_dir):
     """Frozen outputs of the real reference: ``R_mixed`` -- a Bayesian slice
     (rank-2 sieves, sieve wrappers) and a slice of two chained ISS; ``R_rng``
@@ -1316,7 +1343,7 @@ def test_extra_pipeline_golden(name, golden_dir):
     np.random.seed(0)
     fruit.fit(X)
     res = fruit.transform(X)
-    if name == "R_preps":
+    if name in ("R_preps", "R_cosrand"):
         # preparateurs in front (fastmath loops of the reference: 1e-12) and a weighted slice
         assert_close(fitted_thresholds(fruit), g["thresholds"], 1e-9, "thresholds")
         _assert_features_close(res, g["features"], name)

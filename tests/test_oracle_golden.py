@@ -125,6 +125,25 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
+@pytest.mark.parametrize("name", sorted(__import__("cases").COS_RANDOM_CASES))
+def test_randomised_coswiss_golden(name, golden_dir):
+    """CosWISS with a random network in front / random dropout (oracle
+    restatement of fruits/iss/cos.py:52-160, :243-260) against the reference's
+    frozen output; same draws, same generator state."""
+    import copy
+    from cases import COS_RANDOM_CASES, make_iss_input
+    g = np.load(os.path.join(golden_dir, "cos2.npz"))
+    desc, shape, kind = COS_RANDOM_CASES[name]
+    X = make_iss_input(shape, kind)
+    assert sha(X) == str(g[name + "_xsha"])
+    desc = copy.deepcopy(desc)
+    np.random.seed(3)
+    desc["_state"] = orc.coswiss_fit(desc, X)
+    assert np.random.random() == float(g[name + "_rng"])
+    res = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    assert_close(res, g[name], 1e-11, name)
+
+
 @pytest.mark.parametrize("name", sorted(__import__("cases").PREP2_CASES))
 def test_prep2_golden(name, golden_dir):
     """The preparateurs beside INC / STD / NRM: the numpy restatement
@@ -148,7 +167,7 @@ def test_prep2_golden(name, golden_dir):
             assert_close(got, g[key], 1e-12, key)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps", "R_letters"])
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps", "R_letters", "R_cosrand"])
 def test_pipeline_golden(name, golden_dir):
     from cases import COS_PIPE_CASES, EXTRA_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
