@@ -1,17 +1,19 @@
 """Drop-in alias: ``import fruits`` resolves to the B200-native
 implementation ``fruits_b200`` (same public names as irkri/fruits 1.0.0).
 
-Scope: the alias is a drop-in for the *hot path* -- ``Fruit`` / ``FruitSlice`` /
-``ISS`` / ``CosWISS`` with ``SimpleWord`` words, the ``Reals`` / ``Arctic`` /
-``Bayesian`` semirings, the ``Indices`` / ``L1`` / ``L2`` / ``Plateaus`` weightings,
-the preparateurs ``INC``, ``STD``, ``NRM``, ``NEW``, ``DIM`` and every sieve of
-the reference.  Everything else of the reference's surface exists by name but
-raises ``NotImplementedError`` when constructed, because there is no CPU
-fallback to run it on: the preparateurs ``MAV, LAG, FFN, RIN, RDW, JLD, SPE, RPE,
-CTS, QTC, FUN, DIL, WIN, DOT, PDD``, ``NRM(scale_dim=True)``, weightings with a
-Python ``transform``, words with callable letters, ``Arctic(argmax=True)``, the
-randomised ``CosWISS`` variants, more than four distinct ``alpha`` values per
-ISS and letters with more than 15 occurrences ("Limits")."""
+Scope: ``Fruit`` / ``FruitSlice`` / ``ISS`` / ``CosWISS`` (plain and randomised)
+with ``SimpleWord`` words and words over Python letters, the ``Reals`` /
+``Arctic`` / ``Bayesian`` semirings, the ``Indices`` / ``L1`` / ``L2`` /
+``Plateaus`` / ``Custom`` weightings (with or without a Python ``transform``),
+all preparateurs (``INC, STD, NRM, MAV, LAG, FFN, RIN, RDW, JLD, SPE, RPE, CTS, QTC,
+FUN, DIL, WIN, DOT, PDD`` and the wrappers ``NEW``, ``DIM``) and every sieve of the
+reference.  All arithmetic runs on the GPU; user-supplied Python (``FUN``, letter
+functions, lookup transforms) is called on the host with numpy arrays, as in the
+reference.  There is no CPU fallback for anything else, so what is not built
+raises ``NotImplementedError`` when constructed: ``Arctic(argmax=True)``, generic
+words in the ``Bayesian`` semiring, an ISS that mixes weighted SimpleWords with
+generic words, more than four distinct ``alpha`` values per ISS and letters with
+more than 15 occurrences ("Limits")."""
 import sys as _sys
 
 import fruits_b200 as _impl

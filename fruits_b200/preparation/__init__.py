@@ -1,9 +1,10 @@
 """Preparateurs: transformations of the input series ahead of the ISS.
 
-``INC``, ``STD``, ``NRM`` and the wrappers ``NEW`` / ``DIM`` run on the GPU
-(``csrc/prep.cu``; ``INC`` and ``STD`` are folded into the loads of the fused
-kernels); the other names of the reference exist and raise
-``NotImplementedError`` -- they are outside the accelerated path.
+All twenty preparateurs of the reference run on the GPU.  ``INC`` and ``STD``
+(and ``NEW(INC)``) are folded into the loads of the fused kernels; the others
+write a prepared copy with the streaming kernels of ``csrc/prep.cu`` /
+``csrc/prep_more.cu``, after which the slice still takes a fused kernel.
+``FUN`` calls the user's function on the host.
 """
 from .abstract import Preparateur
 from .filter import DIL, DOT, PDD, WIN
