@@ -390,6 +390,15 @@ def config_block(fruits, peak_tflops: float):
         block[name] = entry
         del X, out
         torch.cuda.empty_cache()
+    # the preparateur kernels either side of the path (csrc/prep_more.cu): HBM-bound
+    # streaming kernels, each alone on 65,536 x 3 x 1,024 (1.6 GB in >> L2), algorithmic
+    # bytes (input once + prepared copy once) over the measured copy bandwidth
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import prep_bandwidth
+    head, rows = prep_bandwidth.measure(65536)
+    block["preparateurs"] = {**head, "bound": "hbm", "kernels": [
+        {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rows]}
+    torch.cuda.empty_cache()
     return block
 
 

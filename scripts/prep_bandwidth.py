@@ -41,36 +41,37 @@ def timed(fn, reps=5, warm=3):
     return best, out
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
-    d, t = 3, 1024
+def measure(n: int = 131072, d: int = 3, t: int = 1024):
+    """-> (header dict, [ {name, kernel, ms, gb_moved, gbs, frac, fit_ms} ])"""
     gen = torch.Generator(device="cuda").manual_seed(1)
     X = torch.randn((n, d, t), dtype=torch.float64, device="cuda", generator=gen).cumsum(dim=2)
     X2 = X[:, :2].contiguous()
     cases = [
-        ("DOT(3)            fb_time_mask", P.DOT(3), X),
-        ("PDD()             fb_time_mask", P.PDD(), X),
-        ("WIN(0.1, 0.9)     fb_time_mask + coquantiles", P.WIN(0.1, 0.9), X),
-        ("CTS(5)            fb_time_shift", P.CTS(5), X),
-        ("LAG()             fb_lead_lag", P.LAG(), X),
-        ("MAV(5)            fb_moving_average", P.MAV(5), X),
-        ("MAV(64)           fb_moving_average", P.MAV(64), X),
-        ("RIN(width=3)      fb_random_increments", P.RIN(width=3), X),
-        ("JLD(3)            fb_dim_project", P.JLD(3), X),
-        ("FFN()             fb_ffn + fb_row_stats", P.FFN(), X),
-        ("RDW('uniform')    fb_dim_pow", P.RDW("uniform"), X.abs() + 0.5),
-        ("SPE(0.5)          fb_wave_embed", P.SPE(0.5), X),
-        ("RPE(0.5)          fb_rotate2", P.RPE(0.5), X2),
-        ("QTC(0.9)          fb_clip_where", P.QTC(0.9), X),
-        ("NRM(True)         fb_nrm_scale", P.NRM(True), X),
+        ("DOT(3)", "fb_time_mask", P.DOT(3), X),
+        ("PDD()", "fb_time_mask", P.PDD(), X),
+        ("WIN(0.1, 0.9)", "fb_time_mask (coquantiles cached)", P.WIN(0.1, 0.9), X),
+        ("CTS(5)", "fb_time_shift", P.CTS(5), X),
+        ("LAG()", "fb_lead_lag", P.LAG(), X),
+        ("MAV(5)", "fb_moving_average", P.MAV(5), X),
+        ("MAV(64)", "fb_moving_average", P.MAV(64), X),
+        ("RIN(width=3)", "fb_random_increments", P.RIN(width=3), X),
+        ("JLD(3)", "fb_dim_project", P.JLD(3), X),
+        ("FFN()", "fb_ffn + fb_row_stats", P.FFN(), X),
+        ("RDW('uniform')", "fb_dim_pow", P.RDW("uniform"), X.abs() + 0.5),
+        ("SPE(0.5)", "fb_wave_embed", P.SPE(0.5), X),
+        ("RPE(0.5)", "fb_rotate2", P.RPE(0.5), X2),
+        ("QTC(0.9)", "fb_clip_where", P.QTC(0.9), X),
+        ("NRM(True)", "fb_nrm_scale", P.NRM(True), X),
     ]
-    print(f"# {n} x {d} x {t} float64 ({X.numel() * 8 / 1e9:.2f} GB in), peak {PEAK:.0f} GB/s "
-          f"(MEASURED_PEAKS.json), {torch.cuda.get_device_name()}")
-    print(f"{'preparateur / kernel':48s} {'ms':>8s} {'GB moved':>9s} {'GB/s':>8s} {'of peak':>8s}")
+    head = {"series": n, "dims": d, "length": t, "gb_in": X.numel() * 8 / 1e9,
+            "peak_gbs": PEAK, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+            "bytes": "input read once + prepared copy written once",
+            "device": torch.cuda.get_device_name()}
+    rows = []
+    state = np.random.get_state()
     np.random.seed(0)
-    for name, prep, inp in cases:
-        cache = fruits.cache.SharedSeedCache(inp)
-        prep._cache = cache
+    for name, kernel, prep, inp in cases:
+        prep._cache = fruits.cache.SharedSeedCache(inp)
         fit_ms = 0.0
         if prep.requires_fitting:
             fit_ms, _ = timed(lambda: prep._fit_device(inp), reps=1, warm=0)
@@ -78,10 +79,25 @@ def main():
             prep._transform_device(inp)          # (the coquantiles are cached per batch)
         ms, out = timed(lambda: prep._transform_device(inp))
         moved = (inp.numel() + out.numel()) * 8 / 1e9
-        gbs = moved / (ms * 1e-3)
-        print(f"{name:48s} {ms:8.3f} {moved:9.2f} {gbs:8.0f} {gbs / PEAK:8.2f}"
-              + (f"   (fit {fit_ms:.1f} ms)" if fit_ms else ""))
+        rows.append({"preparateur": name, "kernel": kernel, "ms": ms, "gb_moved": moved,
+                     "gbs": moved / (ms * 1e-3), "frac": moved / (ms * 1e-3) / PEAK,
+                     "fit_ms": fit_ms})
         del out, prep._cache
+    np.random.set_state(state)
+    return head, rows
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
+    head, rows = measure(n)
+    print(f"# {head['series']} x {head['dims']} x {head['length']} float64 ({head['gb_in']:.2f} GB "
+          f"in), peak {PEAK:.0f} GB/s (MEASURED_PEAKS.json), {head['device']}")
+    print(f"{'preparateur':16s} {'kernel':36s} {'ms':>8s} {'GB moved':>9s} {'GB/s':>8s} "
+          f"{'of peak':>8s}")
+    for r in rows:
+        print(f"{r['preparateur']:16s} {r['kernel']:36s} {r['ms']:8.3f} {r['gb_moved']:9.2f} "
+              f"{r['gbs']:8.0f} {r['frac']:8.2f}"
+              + (f"   (fit {r['fit_ms']:.1f} ms)" if r['fit_ms'] else ""))
 
 
 if __name__ == "__main__":
