@@ -178,32 +178,43 @@ class ISS(Seed):
     def _dim_pieces(self, emit_range, trusted: bool = False) -> list:
         """Split ``emit_range`` (None = all) into consecutive emission ranges
         whose sub-tries reference at most ``FB_MAX_USED_DIMS`` distinct input
-        dimensions each (one range if the whole already does)."""
+        dimensions and, in a weighted ISS, at most ``FB_MAX_ALPHAS`` distinct
+        alpha values each (one range if the whole already does)."""
         trie = self.trie(trusted)
         lo, hi = (0, len(trie.emits)) if emit_range is None else emit_range
         memo = self.__dict__.setdefault("_piece_memo", {})
         key = (id(trie), lo, hi)
         if key in memo:
             return memo[key]
+        weighted = self.weighting is not None
 
-        def dims_of(v, acc):
+        def needs_of(v):
+            dims, alphas = set(), set()
             while v >= 0:
                 n = trie.nodes[v]
-                acc.update(d for d, e in enumerate(n.expo) if e != 0)
+                dims.update(d for d, e in enumerate(n.expo) if e != 0)
+                if weighted:
+                    alphas.add(n.alpha)
                 v = n.parent
-            return acc
+            return dims, alphas
 
-        pieces, start, used = [], lo, set()
+        pieces, start, used, used_a = [], lo, set(), set()
         for e in range(lo, hi):
-            need = dims_of(trie.emits[e], set())
+            need, need_a = needs_of(trie.emits[e])
             if len(need) > be.FB_MAX_USED_DIMS:
                 raise NotImplementedError(
                     f"one word references {len(need)} distinct dimensions; the kernel "
                     f"supports {be.FB_MAX_USED_DIMS}")
-            if len(used | need) > be.FB_MAX_USED_DIMS:
+            if len(need_a) > be.FB_MAX_ALPHAS:
+                raise NotImplementedError(
+                    f"one word carries {len(need_a)} distinct alpha values; the kernel "
+                    f"supports {be.FB_MAX_ALPHAS}")
+            if (len(used | need) > be.FB_MAX_USED_DIMS
+                    or len(used_a | need_a) > be.FB_MAX_ALPHAS):
                 pieces.append((start, e))
-                start, used = e, set()
+                start, used, used_a = e, set(), set()
             used |= need
+            used_a |= need_a
         pieces.append((start, hi))
         if len(pieces) == 1:
             pieces = [emit_range]

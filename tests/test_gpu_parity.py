@@ -1283,6 +1283,38 @@ def test_prepared_copy_then_fused_kernels(golden_dir, monkeypatch):
 
 
 @pytest.mark.parametrize("semiring", ["reals", "arctic"])
+def test_more_distinct_alphas_than_one_launch_holds(semiring):
+    """Seven words with seven different alpha vectors: one launch holds four
+    distinct alpha values, so the emissions are materialised in consecutive ranges
+    (ISS._dim_pieces) and a slice with such an ISS takes the composed route; same
+    numbers as the oracle."""
+    from oracle import pipeline as orc
+    words = ["[1][2]", "[2][1]", "[1][1]", "[2][2]", "[12][1]", "[1][12]", "[2][1][2]"]
+    alphas = [[0.1 * (i + 1), 0.05 * (i + 2), 0.3][:w.count("[")] for i, w in enumerate(words)]
+    desc = {"words": words, "mode": "extended", "semiring": semiring, "alphas": alphas,
+            "weighting": ["Indices", {"scale": 3}]}
+    X = np.random.default_rng(21).standard_normal((11, 2, 50)).cumsum(axis=2) / 4
+    iss = specs.build_iss(fruits, desc)
+    assert len(iss._dim_pieces(None)) > 1
+    want = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    got = iss.transform(X)
+    if semiring == "arctic":
+        assert_exact(got, want, "arctic, seven alpha vectors")
+    else:
+        assert_close(got, want, 1e-9, "reals, seven alpha vectors")
+    spec = {"slices": [{"preps": [], "iss": [desc],
+                        "sieves": [["NPI", {"q": [0.5, 1.0]}], ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(0)
+    fruit.fit(X)
+    np.random.seed(0)
+    of.fit(X)
+    _assert_features_close(fruit.transform(X), of.transform(X), "slice with seven alpha vectors")
+
+
+@pytest.mark.parametrize("semiring", ["reals", "arctic"])
 @pytest.mark.parametrize("mode", ["single", "extended"])
 def test_generic_words_equal_the_oracle(semiring, mode):
     """Words over Python letters: the letters are evaluated on the host, their
