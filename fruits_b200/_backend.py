@@ -139,6 +139,8 @@ def lib() -> ctypes.CDLL:
         "fb_bayes_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, i32, i32, vp, vp], i32),
         "fb_arctic_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, i32, i32, vp, vp], i32),
         "fb_exp_rows": ([vp, vp, i64, i64, ctypes.POINTER(ctypes.c_float), i32, vp], i32),
+        "fb_arctic_argmax_workspace": ([i64, i64, i32], i64),
+        "fb_arctic_argmax_word": ([vp, i64, i64, i64, vp, i32, i32, vp, vp, i64, vp, vp, vp], i32),
         # csrc/prep_more.cu: the preparateurs beside INC / STD / NRM
         "fb_time_mask": ([vp, vp, i64, i64, i64, vp, vp, vp, i64, vp], i32),
         "fb_time_shift": ([vp, vp, i64, i64, i64, vp], i32),
@@ -175,6 +177,7 @@ EXPORTED = [
     "fb_bayes_word", "fb_arctic_word", "fb_order_stats_multi_workspace", "fb_order_stats_multi",
     "fb_order_stats_dist_layout", "fb_order_stats_dist", "fb_order_stats_dist8_layout",
     "fb_order_stats_dist8",
+    "fb_arctic_argmax_workspace", "fb_arctic_argmax_word",
     "fb_time_mask", "fb_time_shift", "fb_lead_lag", "fb_moving_average",
     "fb_random_increments", "fb_dim_project", "fb_ffn", "fb_dim_pow", "fb_abs_mean_max",
     "fb_rotate2", "fb_spe_range", "fb_wave_embed", "fb_clip_where",

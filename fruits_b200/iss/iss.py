@@ -55,6 +55,8 @@ class ISS(Seed):
         # words over Python letters (reference: Semiring._iterated_sum,
         # semiring.py:54-75, Arctic :428-446)
         self._generic = any(not isinstance(w, SimpleWord) for w in words)
+        if self._argmax and self._generic:
+            raise NotImplementedError("Arctic(argmax=True) takes SimpleWords only")
         if self._generic:
             if any(len(w) == 0 for w in words):
                 raise NotImplementedError("a word needs at least one extended letter")
@@ -76,11 +78,15 @@ class ISS(Seed):
         return False
 
     @property
+    def _argmax(self) -> bool:
+        return isinstance(self.semiring, Arctic) and self.semiring._argmax
+
+    @property
     def _fusable_iss(self) -> bool:
         # the Bayesian semiring has no generic trie kernel: unweighted it is compiled
         # into the generated kernel (_jit.py), weighted it is sieved on materialised sums;
         # generic words are fused through their SimpleWord twin (FruitSlice)
-        if self._generic:
+        if self._generic or self._argmax:
             return False
         return not isinstance(self.semiring, Bayesian) or self.weighting is None
 
@@ -235,9 +241,52 @@ class ISS(Seed):
 
     def n_iterated_sums(self) -> int:
         """Number of iterated sums ``transform`` returns (reference :135-150)."""
+        if self._argmax:
+            if self.mode != ISSMode.EXTENDED:
+                raise NotImplementedError(
+                    "Arctic argmax is not implemented when using ISSMode.SINGLE")
+            return sum(self._argmax_rows(w) for w in self.words)
         if self.mode == ISSMode.EXTENDED:
             return self._cache_plan.n_iterated_sums()
         return len(self.words)
+
+    @staticmethod
+    def _argmax_rows(word) -> int:
+        return len(word) + len(word) * (len(word) + 1) // 2
+
+    def _materialize_argmax(self, X: torch.Tensor, emit_range, lookup) -> torch.Tensor:
+        """``Arctic(argmax=True)``: per word the running maxima of every level and
+        the positions that produced them (``fb_arctic_argmax_word``; reference:
+        iss.py:41-58 with ``_arctic_argmax_single``, semiring.py:234-279).  Every
+        word is computed from its first letter and contributes all its rows --
+        the cache plan does not apply (iss.py:53-54)."""
+        n, d, t = X.shape
+        g, g_ld = self._lookup(X) if lookup is None else lookup
+        lo, hi = (0, self.n_iterated_sums()) if emit_range is None else emit_range
+        out = be.empty((hi - lo, n, t))
+        first = 0
+        for word in self.words:
+            rows = self._argmax_rows(word)
+            last = first + rows
+            if last > lo and first < hi:
+                mat = np.ascontiguousarray(np.array(list(word), dtype=np.int32))
+                alpha = (np.asarray(word.alpha, dtype=np.float32) if self.weighting is not None
+                         else np.zeros(len(mat), dtype=np.float32))
+                mat_d = torch.from_numpy(mat).to(X.device)
+                alpha_d = torch.from_numpy(np.ascontiguousarray(alpha)).to(X.device)
+                work = be.empty((max(be.lib().fb_arctic_argmax_workspace(n, t, len(mat)), 8),),
+                                dtype=torch.uint8)
+                whole = first >= lo and last <= hi
+                dst = out[first - lo:last - lo] if whole else be.empty((rows, n, t))
+                be.check(be.lib().fb_arctic_argmax_word(
+                    X.data_ptr(), n, d, t, mat_d.data_ptr(), mat.shape[0], mat.shape[1],
+                    alpha_d.data_ptr(), be.ptr(g), g_ld, dst.data_ptr(), work.data_ptr(),
+                    be.stream_ptr()))
+                if not whole:
+                    a, b = max(first, lo), min(last, hi)
+                    out[a - lo:b - lo] = dst[a - first:b - first]
+            first = last
+        return out
 
     # -- execution ---------------------------------------------------------------
     def _lookup(self, X: torch.Tensor):
@@ -283,6 +332,8 @@ class ISS(Seed):
         if self._generic:
             Xs, twin = self._lettered(X)
             return twin.materialize(Xs, emit_range)
+        if self._argmax:
+            return self._materialize_argmax(X, emit_range, lookup)
         if isinstance(self.semiring, Bayesian):
             return self._materialize_scan(X, emit_range, lookup)
         if isinstance(self.semiring, Arctic) and self._arctic_scan(X.shape[0], emit_range):
@@ -406,7 +457,10 @@ class ISS(Seed):
             i, e = 0, 0
             while i < len(self.words):
                 nb = min(batch_size, len(self.words) - i)
-                if self.mode == ISSMode.EXTENDED:
+                if self._argmax:
+                    self.n_iterated_sums()                 # (raises in SINGLE mode)
+                    ne = sum(self._argmax_rows(w) for w in self.words[i:i + nb])
+                elif self.mode == ISSMode.EXTENDED:
                     ne = self._cache_plan.n_iterated_sums(range(i, i + nb))
                 else:
                     ne = nb

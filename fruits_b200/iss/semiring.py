@@ -3,8 +3,8 @@
 On the GPU a semiring is only a tag that selects the instantiation of the ISS
 kernel (``csrc/lns.cuh``): ``Reals`` (:161-231, sum / product, the standard
 iterated sums) and ``Arctic`` (:341-457, max / plus); ``Bayesian``
-(:461-601, max / times) has its own scan kernel (``csrc/bayes.cu``).
-``Arctic(argmax=True)`` is not part of the accelerated path.
+(:461-601, max / times) has its own scan kernel (``csrc/bayes.cu``), and so
+has ``Arctic(argmax=True)`` (``csrc/arctic_argmax.cu``).
 """
 from abc import ABC
 
@@ -26,15 +26,13 @@ class Reals(Semiring):
 class Arctic(Semiring):
     """Max-plus semiring: "sum" is the maximum, "product" the addition.
 
-    ``argmax=True`` (positions of the maxima, reference :234-279) is not
-    supported by the GPU path."""
+    ``argmax=True`` additionally returns the positions of all involved maxima
+    (reference :234-279): per word of ``p`` letters ``p + p(p+1)/2`` rows, in
+    ``ISSMode.EXTENDED`` only."""
     _code = be.SEMIRING_ARCTIC
 
     def __init__(self, argmax: bool = False) -> None:
-        if argmax:
-            raise NotImplementedError(
-                "Arctic(argmax=True) is outside the accelerated hot path")
-        self._argmax = False
+        self._argmax = bool(argmax)
 
 
 class Bayesian(Semiring):

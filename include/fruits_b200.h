@@ -324,6 +324,18 @@ FB_API int fb_arctic_word(const double *X, int64_t n, int64_t d, int64_t t, cons
                           int p, int md, const float *alpha, const double *g, int64_t g_ld,
                           int weight_mode, int extended, double *out, void *stream);
 
+/* Arctic(argmax=True) for one word (fruits/iss/semiring.py:234-279
+ * _arctic_argmax_single via Arctic._iterated_sum_fast :385-392): out holds
+ * p + p(p+1)/2 rows [row][n][t] -- for every level k its running maximum
+ * (row k + k(k+1)/2) followed by the k+1 position rows of the levels k..0 that
+ * produced it.  alpha f32[p] (zeros when unweighted), g = lookup rows or NULL;
+ * work = fb_arctic_argmax_workspace(n, t, p) bytes of device scratch. */
+FB_API int64_t fb_arctic_argmax_workspace(int64_t n, int64_t t, int p);
+FB_API int fb_arctic_argmax_word(const double *X, int64_t n, int64_t d, int64_t t,
+                                 const int32_t *word, int p, int md, const float *alpha,
+                                 const double *g, int64_t g_ld, double *out, void *work,
+                                 void *stream);
+
 /* -- preparateurs, lookups, raw-input cache -- */
 
 /* fruits/cache.py:8-13 _increments on rows x t; pad_src != NULL keeps the

@@ -324,6 +324,56 @@ def iss_word(X, word: str, extended: int, semiring: str, weighting,
     return np.ascontiguousarray(np.swapaxes(res, 0, 1))
 
 
+def arctic_argmax_word(X, word: str, weighting, alpha, cache):
+    """``[p + p(p+1)/2, n, t]``: Arctic(argmax=True) for one word --
+    _arctic_argmax_single (fruits/iss/semiring.py:234-279) series by series, as
+    Arctic._iterated_sum_fast calls it (:385-392; the total / non-total flag and
+    ``extended`` play no role there)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, d, t = X.shape
+    mat = parse_word(word)
+    p = mat.shape[0]
+    if weighting is not None:
+        lk = np.ascontiguousarray(lookup(weighting, X, cache))
+        a = (np.ones(p, dtype=np.float32) if alpha is None else np.asarray(alpha, dtype=np.float32))
+    else:
+        lk, a = np.zeros((n, t)), np.zeros(p, dtype=np.float32)
+    rows = p + p * (p + 1) // 2
+    out = np.zeros((rows, n, t))
+    for j in range(n):
+        Z, w = X[j], lk[j]
+        result = np.zeros((2 * p, t))
+        tmp = np.zeros(t)
+        for k in range(p):
+            if not np.any(mat[k]):
+                continue
+            C = np.zeros(t)
+            for dim, el in enumerate(mat[k]):
+                C = C + el * Z[dim, :]
+            tmp = tmp + C
+            if k > 0:
+                tmp = tmp - w * a[k - 1]
+            result[2 * k, 0] = tmp[0]
+            for i in range(1, t):
+                if result[2 * k, i - 1] >= tmp[i]:
+                    result[2 * k, i] = result[2 * k, i - 1]
+                    result[2 * k + 1, i] = result[2 * k + 1, i - 1]
+                else:
+                    result[2 * k, i] = tmp[i]
+                    result[2 * k + 1, i] = i
+            if k < p - 1:
+                tmp = np.maximum.accumulate(tmp + w * a[k])
+        for k in range(p - 1, -1, -1):
+            index = k + k * (k + 1) // 2
+            out[index, j] = result[2 * k]
+            out[index + k + 1, j] = result[2 * k + 1]
+            for s_ in range(k, 0, -1):
+                c = int(out[index + s_ + 1, j, -1]) + 1
+                out[index + s_, j, :c] = result[2 * (s_ - 1) + 1, :c]
+                out[index + s_, j, c:] = result[2 * (s_ - 1) + 1, c - 1]
+    return out
+
+
 # letters of generic words (fruits/iss/words/letters.py:95-110 DIM / ABS; the others are
 # what the tests register through ``fruits.words.letter`` -- tests/specs.py)
 LETTERS = {
@@ -483,8 +533,17 @@ def iss_iter(X, iss, cache: RawCache):
                 yield out[f]
         return
     extended = iss.get("mode", "single") == "extended"
-    plan = cache_plan(words) if extended else [1] * len(words)
     alphas = iss.get("alphas")
+    if iss.get("semiring") == "arctic_argmax":
+        if not extended:            # fruits/iss/iss.py:37-40
+            raise NotImplementedError("Arctic argmax is not implemented when using ISSMode.SINGLE")
+        for i, w in enumerate(words):
+            out = arctic_argmax_word(X, w, iss.get("weighting"),
+                                     None if alphas is None else alphas[i], cache)
+            for e in range(out.shape[0]):
+                yield out[e]
+        return
+    plan = cache_plan(words) if extended else [1] * len(words)
     for i, w in enumerate(words):
         if plan[i] == 0:
             continue
@@ -502,6 +561,9 @@ def n_iterated_sums(iss):
     words = expand_words(iss["words"])
     if iss.get("coswiss") is not None:
         return len(words) * len(iss["coswiss"]["freqs"])
+    if iss.get("semiring") == "arctic_argmax":      # fruits/iss/iss.py:139-144
+        return sum(len(parse_word(w)) + len(parse_word(w)) * (len(parse_word(w)) + 1) // 2
+                   for w in words)
     if iss.get("mode", "single") == "extended":
         return sum(cache_plan(words))
     return len(words)

@@ -249,6 +249,20 @@ PIPE_CASES = {
     "C5_sweep": ("C5_sweep", 32),
 }
 
+# Arctic(argmax=True): maxima and the positions that produced them
+# (fruits/iss/semiring.py:234-279), frozen by ``oracle/gen_golden.py argmax``
+ARGMAX_CASES = {
+    "argmax": ({"words": ["[1]", "[1][2]", "[2][1][12]"], "mode": "extended",
+                "semiring": "arctic_argmax"}, (5, 2, 40), "walk"),
+    "argmax_signs_long": ({"words": ["[-1][2][-2][1][11][-2-2]", "[2]"], "mode": "extended",
+                           "semiring": "arctic_argmax"}, (3, 2, 300), "normal"),
+    "argmax_indices": ({"words": ["[1][2]", "[2][1][1]"], "mode": "extended",
+                        "semiring": "arctic_argmax", "weighting": ["Indices", {"scale": 2}],
+                        "alphas": [[0.5, 0.2], [0.3, 0.1, 0.7]]}, (4, 2, 64), "walk"),
+    "argmax_L1_total": ({"words": ["[1][1][2]"], "mode": "extended", "semiring": "arctic_argmax",
+                         "weighting": ["L1", {"total": True, "scale": 3}]}, (4, 2, 50), "walk"),
+}
+
 COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
 # the randomised CosWISS variants (fruits/iss/cos.py:243-260, :306-324): fit under
@@ -274,7 +288,7 @@ COS_RANDOM_CASES = {
 # pipelines of the rank 2-3 components, frozen from the reference
 EXTRA_PIPE_CASES = {"R_mixed": ("R_mixed", 40), "R_rng": ("R_rng", 30),
                     "R_preps": ("R_preps", 36), "R_letters": ("R_letters", 33),
-                    "R_cosrand": ("R_cosrand", 30)}
+                    "R_cosrand": ("R_cosrand", 30), "R_argmax": ("R_argmax", 28)}
 
 
 

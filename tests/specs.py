@@ -177,6 +177,12 @@ SPECS["R_cosrand"] = {"slices": [
               "coswiss": {"freqs": [0.2], "exponent": 1, "dropout": 0.25}}],
      "sieves": [["PPV", {}], ["MAX", {}], ["END", {}]], "fit_sample_size": 0.5}]}
 
+# Arctic(argmax=True) inside a fruit: maxima and position rows alike are sieved
+SPECS["R_argmax"] = {"slices": [
+    {"preps": [["INC", {}]],
+     "iss": [{"words": ["[1][2]", "[2][1][1]"], "mode": "extended", "semiring": "arctic_argmax"}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MAX", {}], ["END", {}]], "fit_sample_size": 1.0}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 
@@ -185,7 +191,7 @@ def make_input(name: str, n: int = None) -> np.ndarray:
     """Seeded synthetic input of SURVEY.md section 8(d) for a config; ``n``
     overrides the number of series (same generator, first ``n`` rows)."""
     shapes = {"C1_readme": (200, 3, 100), "C2_reduced": (1000, 1, 512), "C2_cos": (1000, 1, 512), "C2_full": (1000, 1, 512),
-              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48), "R_letters": (33, 2, 45), "R_cosrand": (30, 2, 44),
+              "C3_cos": (10000, 6, 1024), "C3_full": (10000, 6, 1024), "R_mixed": (40, 2, 60), "R_rng": (30, 2, 50), "R_preps": (36, 2, 48), "R_letters": (33, 2, 45), "R_cosrand": (30, 2, 44), "R_argmax": (28, 2, 52),
               "C3_general": (10000, 6, 1024), "C4_twi": (100000, 3, 2048),
               "C5_sweep": (4096, 3, 1024)}
     N, D, T = shapes[name]
@@ -196,6 +202,8 @@ def make_input(name: str, n: int = None) -> np.ndarray:
         return np.random.default_rng(1234).standard_normal((n, D, T))
     if name == "R_mixed":
         return np.random.default_rng(42).random((n, D, T)) + 0.1
+    if name == "R_argmax":
+        return np.random.default_rng(47).standard_normal((n, D, T)).cumsum(axis=2) / 3
     if name == "R_cosrand":
         return np.random.default_rng(46).standard_normal((n, D, T)).cumsum(axis=2) / 3
     if name == "R_letters":
@@ -259,6 +267,8 @@ def _weighting(mod, desc):
 
 
 def _semiring(mod, name):
+    if name == "arctic_argmax":
+        return mod.iss.semiring.Arctic(argmax=True)
     return {"reals": mod.iss.semiring.Reals,
             "arctic": mod.iss.semiring.Arctic,
             "bayesian": mod.iss.semiring.Bayesian}[name]()

@@ -155,8 +155,13 @@ def test_error_behaviour():
     iss = fruits.ISS(fruits.words.of_weight(2, 1))
     with pytest.raises(ValueError):
         next(iss.batch_transform(np.zeros((1, 1, 4)), batch_size=10))
-    with pytest.raises(NotImplementedError):
-        fruits.semiring.Arctic(argmax=True)
+    argmax = fruits.ISS([fruits.words.SimpleWord("[1][2]")],
+                        semiring=fruits.semiring.Arctic(argmax=True))
+    with pytest.raises(NotImplementedError, match="ISSMode.SINGLE"):
+        argmax.n_iterated_sums()
+    assert fruits.ISS([fruits.words.SimpleWord("[1][2]"), fruits.words.SimpleWord("[1][2][1]")],
+                      mode=fruits.ISSMode.EXTENDED,
+                      semiring=fruits.semiring.Arctic(argmax=True)).n_iterated_sums() == 5 + 9
     with pytest.raises(NotImplementedError):
         fruits.ISS([fruits.words.Word()])                      # no extended letter
     with pytest.raises(TypeError):

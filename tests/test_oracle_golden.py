@@ -125,6 +125,22 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
+@pytest.mark.parametrize("name", sorted(__import__("cases").ARGMAX_CASES))
+def test_arctic_argmax_golden(name, golden_dir):
+    """Arctic(argmax=True): maxima and their positions (oracle restatement of
+    fruits/iss/semiring.py:234-279) against the reference's frozen output."""
+    from cases import ARGMAX_CASES, make_iss_input
+    g = np.load(os.path.join(golden_dir, "argmax.npz"))
+    desc, shape, kind = ARGMAX_CASES[name]
+    X = make_iss_input(shape, kind)
+    assert sha(X) == str(g[name + "_xsha"])
+    res = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+    if desc.get("weighting") is None:
+        assert_exact(res, g[name], name)
+    else:
+        assert_close(res, g[name], 1e-12, name)
+
+
 @pytest.mark.parametrize("name", sorted(__import__("cases").COS_RANDOM_CASES))
 def test_randomised_coswiss_golden(name, golden_dir):
     """CosWISS with a random network in front / random dropout (oracle
@@ -167,7 +183,7 @@ def test_prep2_golden(name, golden_dir):
             assert_close(got, g[key], 1e-12, key)
 
 
-@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps", "R_letters", "R_cosrand"])
+@pytest.mark.parametrize("name", sorted(PIPE_CASES) + ["C2_cos", "R_mixed", "R_rng", "R_preps", "R_letters", "R_cosrand", "R_argmax"])
 def test_pipeline_golden(name, golden_dir):
     from cases import COS_PIPE_CASES, EXTRA_PIPE_CASES
     g = np.load(os.path.join(golden_dir, f"pipeline_{name}.npz"))
