@@ -66,18 +66,28 @@ __global__ void time_mask_kernel(const double *__restrict__ X, double *__restric
                                  const long long *__restrict__ lo,
                                  const long long *__restrict__ hi, long long lo_off)
 {
+    // a thread visits the same columns in every row: its bits of the keep mask are read
+    // once (bit j = column threadIdx.x + j * blockDim.x), not once per value
+    const bool packed = t <= 32 * (int)blockDim.x;
+    unsigned mine = 0xffffffffu;
+    if (keep && packed) {
+        mine = 0;
+        int j = 0;
+        FB_COLS(k, t) mine |= (keep[k] != 0 ? 1u : 0u) << j++;
+    }
     FB_ROWS(row, rows) {
-        long long a = 0, b = t;
+        int a = 0, b = t;
         if (lo) {
             const long long i = row / d;
-            a = py_bound(lo[i] + lo_off, t);
-            b = py_bound(hi[i], t);
+            a = (int)py_bound(lo[i] + lo_off, t);
+            b = (int)py_bound(hi[i], t);
         }
         const double *x = X + row * t;
         double *o = out + row * t;
+        int j = 0;
         FB_COLS(k, t) {
-            const bool on = (keep ? keep[k] != 0 : true) && k >= a && k < b;
-            o[k] = on ? x[k] : 0.0;
+            const bool kept = packed ? ((mine >> j++) & 1u) != 0 : (keep ? keep[k] != 0 : true);
+            o[k] = (kept && k >= a && k < b) ? x[k] : 0.0;
         }
     }
 }
