@@ -26,6 +26,24 @@ namespace fb {
          row += (long long)gridDim.x * blockDim.y)
 #define FB_COLS(k, t) for (int k = threadIdx.x; k < (t); k += blockDim.x)
 
+// One row: four independent loads in flight per thread before the first store
+// (a streaming kernel with one 8-byte load outstanding per thread is bound by the
+// load latency, not by HBM: ncu `long_scoreboard` 45 stall cycles per issue).
+template <class LoadF, class StoreF>
+__device__ __forceinline__ void cols4(int t, LoadF ld, StoreF st)
+{
+    const int step = blockDim.x;
+    int k = threadIdx.x;
+    for (; k + 3 * step < t; k += 4 * step) {
+        const double v0 = ld(k), v1 = ld(k + step), v2 = ld(k + 2 * step), v3 = ld(k + 3 * step);
+        st(k, v0);
+        st(k + step, v1);
+        st(k + 2 * step, v2);
+        st(k + 3 * step, v3);
+    }
+    for (; k < t; k += step) st(k, ld(k));
+}
+
 struct RowLaunch {
     dim3 grid, block;
 };
@@ -84,11 +102,15 @@ __global__ void time_mask_kernel(const double *__restrict__ X, double *__restric
         }
         const double *x = X + row * t;
         double *o = out + row * t;
-        int j = 0;
-        FB_COLS(k, t) {
-            const bool kept = packed ? ((mine >> j++) & 1u) != 0 : (keep ? keep[k] != 0 : true);
-            o[k] = (kept && k >= a && k < b) ? x[k] : 0.0;
-        }
+        const int sh = __ffs(blockDim.x) - 1;        // column k is bit k >> sh of `mine`
+        // (the load is unconditional: a dropped value shares its 32-byte sector with kept
+        // ones in every mask but long strips, and independent loads can be batched)
+        cols4(t, [&](int k) { return x[k]; },
+              [&](int k, double v) {
+                  const bool kept = packed ? ((mine >> (k >> sh)) & 1u) != 0
+                                           : (keep ? keep[k] != 0 : true);
+                  o[k] = (kept && k >= a && k < b) ? v : 0.0;
+              });
     }
 }
 
@@ -99,7 +121,8 @@ __global__ void time_shift_kernel(const double *__restrict__ X, double *__restri
     FB_ROWS(row, rows) {
         const double *x = X + row * t;
         double *o = out + row * t;
-        FB_COLS(k, t) o[k] = x[k + shift < t ? k + shift : t - 1];
+        cols4(t, [&](int k) { return x[k + shift < t ? k + shift : t - 1]; },
+              [&](int k, double v) { o[k] = v; });
     }
 }
 
@@ -113,6 +136,8 @@ __global__ void lead_lag_kernel(const double *__restrict__ X, double *__restrict
     FB_ROWS(row, rows) {
         const double *x = X + row * t;
         double *lead = out + 2 * row * t2, *lag = lead + t2;
+        // (plain loop: batching the loads as in cols4 measured slower here, 0.57 vs 0.75 of
+        // the HBM peak -- four times as many bytes are written as read)
         FB_COLS(k2, t2) {
             const int k = k2 >> 1;
             const double here = x[k];

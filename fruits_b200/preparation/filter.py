@@ -17,13 +17,22 @@ from ..cache import CacheType
 from .abstract import Preparateur
 
 
-def _masked(X: torch.Tensor, keep=None, lo=None, hi=None, lo_off: int = 0) -> torch.Tensor:
+def _keep_mask(owner, X: torch.Tensor, state: tuple, build) -> torch.Tensor:
+    """The uint8 keep mask of a fitted preparateur on the device, rebuilt only when the
+    series length, the device or the fitted state changes (``build(t)`` is a host loop
+    over up to ``t`` strips)."""
+    key = (X.shape[2], X.device, state)
+    memo = owner.__dict__.get("_keep_memo")
+    if memo is None or memo[0] != key:
+        mask = torch.from_numpy(np.ascontiguousarray(build(X.shape[2]), dtype=np.uint8))
+        memo = owner._keep_memo = (key, mask.to(X.device))
+    return memo[1]
+
+
+def _masked(X: torch.Tensor, keep_d=None, lo=None, hi=None, lo_off: int = 0) -> torch.Tensor:
     X = X.contiguous()
     n, d, t = X.shape
     out = torch.empty_like(X)
-    keep_d = None
-    if keep is not None:
-        keep_d = torch.from_numpy(np.ascontiguousarray(keep, dtype=np.uint8)).to(X.device)
     be.check(be.lib().fb_time_mask(X.data_ptr(), out.data_ptr(), n, d, t, be.ptr(keep_d),
                                    be.ptr(lo), be.ptr(hi), lo_off, be.stream_ptr()))
     return out
@@ -58,10 +67,13 @@ class DIL(Preparateur):
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         if not hasattr(self, "_indices") or not hasattr(self, "_lengths"):
             raise RuntimeError("Missing call of self.fit()")
-        keep = np.ones(X.shape[2], dtype=np.uint8)
-        for i, index in enumerate(self._indices):
-            keep[index:index + self._lengths[i]] = 0
-        return _masked(X, keep)
+        def build(t):
+            keep = np.ones(t, dtype=np.uint8)
+            for i, index in enumerate(self._indices):
+                keep[index:index + self._lengths[i]] = 0
+            return keep
+        state = (np.asarray(self._indices).tobytes(), tuple(int(x) for x in self._lengths))
+        return _masked(X, _keep_mask(self, X, state, build))
 
     def _copy(self) -> "DIL":
         return DIL(self._clusters)
@@ -144,9 +156,11 @@ class DOT(Preparateur):
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         if not hasattr(self, "_n") or not hasattr(self, "_first"):
             raise RuntimeError("Missing call of self.fit()")
-        keep = np.zeros(X.shape[2], dtype=np.uint8)
-        keep[self._first::self._n] = 1
-        return _masked(X, keep)
+        def build(t):
+            keep = np.zeros(t, dtype=np.uint8)
+            keep[self._first::self._n] = 1
+            return keep
+        return _masked(X, _keep_mask(self, X, (self._first, self._n), build))
 
     def _copy(self) -> "DOT":
         return DOT(self._n_given, self._first_given)
@@ -186,10 +200,13 @@ class PDD(Preparateur):
     def _transform_device(self, X: torch.Tensor) -> torch.Tensor:
         if not hasattr(self, "_width") or not hasattr(self, "_indices"):
             raise RuntimeError("Missing call of self.fit()")
-        keep = np.ones(X.shape[2], dtype=np.uint8)
-        for index in self._indices:
-            keep[index:index + self._width] = 0
-        return _masked(X, keep)
+        def build(t):
+            keep = np.ones(t, dtype=np.uint8)
+            for index in self._indices:
+                keep[index:index + self._width] = 0
+            return keep
+        state = (np.asarray(self._indices).tobytes(), int(self._width))
+        return _masked(X, _keep_mask(self, X, state, build))
 
     def _copy(self) -> "PDD":
         return PDD(self._d_given, self._p_given)

@@ -624,11 +624,15 @@ class CTS(Preparateur):
         out = torch.empty_like(X)
         if self._pseudo_shift:
             # Y[:, :, :shift] = 0 with Python's slice rules for any integer
-            keep = np.ones(t, dtype=np.uint8)
-            keep[:shift] = 0
+            from .filter import _keep_mask
+
+            def build(length):
+                keep = np.ones(length, dtype=np.uint8)
+                keep[:shift] = 0
+                return keep
             be.check(be.lib().fb_time_mask(X.data_ptr(), out.data_ptr(), n, d, t,
-                                           _dev(keep, np.uint8).data_ptr(), 0, 0, 0,
-                                           be.stream_ptr()))
+                                           _keep_mask(self, X, (shift,), build).data_ptr(),
+                                           0, 0, 0, be.stream_ptr()))
             return out
         if shift < 1:
             # the reference's slice assignment Y[:, :, :-s] = Y[:, :, s:] only has matching
