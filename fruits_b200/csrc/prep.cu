@@ -232,7 +232,18 @@ __global__ void nrm_scale_kernel(const double *__restrict__ in, double *__restri
     double *o = out + r * t;
     const double den = relative ? x[t - 1] + 1e-5 : 1.0;
     double mn = d_inf(), mx = d_ninf();
-    for (int j = lane; j < t; j += 32) {
+    // four independent loads per lane and trip (one outstanding 8-byte load per lane is
+    // bound by the load latency, not by HBM)
+    int j = lane;
+    for (; j + 96 < t; j += 128) {
+        double v0 = x[j], v1 = x[j + 32], v2 = x[j + 64], v3 = x[j + 96];
+        if (relative) {
+            v0 = v0 / den; v1 = v1 / den; v2 = v2 / den; v3 = v3 / den;
+        }
+        mn = fmin(fmin(fmin(mn, v0), fmin(v1, v2)), v3);
+        mx = fmax(fmax(fmax(mx, v0), fmax(v1, v2)), v3);
+    }
+    for (; j < t; j += 32) {
         const double v = relative ? x[j] / den : x[j];
         mn = fmin(mn, v);
         mx = fmax(mx, v);
@@ -243,10 +254,20 @@ __global__ void nrm_scale_kernel(const double *__restrict__ in, double *__restri
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
     }
     const double range = mx - mn;
-    for (int j = lane; j < t; j += 32) {
-        const double v = relative ? x[j] / den : x[j];
-        o[j] = (mn != mx) ? __dmul_rn((v - mn) / range, scale) : __dmul_rn(0.0, scale);
+    const bool flat = !(mn != mx);
+    auto scaled = [&](double raw) {
+        const double v = relative ? raw / den : raw;
+        return flat ? __dmul_rn(0.0, scale) : __dmul_rn((v - mn) / range, scale);
+    };
+    j = lane;
+    for (; j + 96 < t; j += 128) {
+        const double v0 = x[j], v1 = x[j + 32], v2 = x[j + 64], v3 = x[j + 96];
+        o[j] = scaled(v0);
+        o[j + 32] = scaled(v1);
+        o[j + 64] = scaled(v2);
+        o[j + 96] = scaled(v3);
     }
+    for (; j < t; j += 32) o[j] = scaled(x[j]);
 }
 
 // fruits/cache.py:16-22 _coquantile: count(S[i,:] <= q*S[i,-1]); warp per row.
