@@ -201,21 +201,41 @@ __global__ void standardize_kernel(const double *__restrict__ X, const double *_
 
 // ---------------------------------------------------------------------------
 // fruits/cache.py:25-40 _L1_sum/_L2_sum: cumsum of |dx| (or dx^2) of dim 0,
-// summed sequentially in time; one thread per series.
-__global__ void lsum_kernel(const double *__restrict__ X, double *__restrict__ out, long long n,
-                            long long d, int t, int l2)
+// summed sequentially in time (the order is part of the result: the sums feed
+// the integer coquantile cuts).  A warp owns 32 series and walks them in tiles of
+// 32 time steps through shared memory: the tile is loaded and stored as 256-byte
+// row segments (lane = time step), the running sums are formed with lane = series.
+constexpr int LSUM_WARPS = 4;
+__global__ void __launch_bounds__(LSUM_WARPS * 32)
+lsum_kernel(const double *__restrict__ X, double *__restrict__ out, long long n, long long d,
+            int t, int l2)
 {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double *x = X + i * d * t;
-    double *o = out + i * t;
+    __shared__ double tile[LSUM_WARPS][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long s0 = (blockIdx.x * (long long)LSUM_WARPS + w) * 32;
+    if (s0 >= n) return;
+    const int live = (int)(n - s0 < 32 ? n - s0 : 32);
     double acc = 0.0, prev = 0.0;
-    for (int j = 0; j < t; j++) {
-        const double cur = x[j];
-        const double inc = j ? __dadd_rn(cur, -prev) : 0.0;
-        prev = cur;
-        acc = __dadd_rn(acc, l2 ? __dmul_rn(inc, inc) : fabs(inc));
-        o[j] = acc;
+    for (int t0 = 0; t0 < t; t0 += 32) {
+        const int cols = t - t0 < 32 ? t - t0 : 32;
+        if (lane < cols)
+            for (int r = 0; r < live; r++)
+                tile[w][r][lane] = X[(s0 + r) * d * t + t0 + lane];
+        __syncwarp();
+        if (lane < live) {
+            for (int j = 0; j < cols; j++) {
+                const double cur = tile[w][lane][j];
+                const double inc = (t0 + j) ? __dadd_rn(cur, -prev) : 0.0;
+                prev = cur;
+                acc = __dadd_rn(acc, l2 ? __dmul_rn(inc, inc) : fabs(inc));
+                tile[w][lane][j] = acc;
+            }
+        }
+        __syncwarp();
+        if (lane < cols)
+            for (int r = 0; r < live; r++)
+                out[(s0 + r) * t + t0 + lane] = tile[w][r][lane];
+        __syncwarp();
     }
 }
 
@@ -362,8 +382,9 @@ int fb_lsum(const double *X, double *out, int64_t n, int64_t d, int64_t t, int l
 {
     FB_REQUIRE(X && out && n >= 0 && d >= 1 && t >= 1, "bad arguments");
     if (n == 0) return 0;
-    lsum_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(X, out, n, d, (int)t,
-                                                                            l2);
+    const long long per_cta = 32LL * fb::LSUM_WARPS;
+    lsum_kernel<<<(unsigned)((n + per_cta - 1) / per_cta), fb::LSUM_WARPS * 32, 0,
+                  (cudaStream_t)stream>>>(X, out, n, d, (int)t, l2);
     FB_CUDA(cudaGetLastError());
     return 0;
 }
