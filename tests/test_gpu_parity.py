@@ -1210,6 +1210,50 @@ def test_reference_preparateur_known_answers():
                                np.stack([ffn._weights2 @ hidden[i] for i in range(2)]))
 
 
+def test_preparateur_properties_at_scale():
+    """Size-independent properties on 20,000 x 3 x 1,024 series (device tensors
+    in and out): masks are idempotent and only ever zero values, LAG interleaves
+    the series with itself, CTS shifts, QTC clips at a value of the batch, SPE is
+    linear in the series, a prepared slice gives the same features for the same
+    series whatever batch they arrive in."""
+    P = fruits.preparation
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn((20000, 3, 1024), dtype=torch.float64, device="cuda", generator=gen).cumsum(2)
+    np.random.seed(1)
+    for prep in (P.DOT(7, 2), P.DIL(0.05), P.PDD(0.9, 0.5), P.WIN(0.2, 0.8), P.CTS(9, True)):
+        prep.fit(X)
+        once = prep.transform(X)
+        assert torch.equal(prep.transform(once) if not isinstance(prep, P.WIN) else once, once)
+        kept = once != 0
+        assert torch.equal(once[kept], X[kept]) and 0 < int(kept.sum()) < X.numel()
+    lag = P.LAG().transform(X)
+    assert lag.shape == (20000, 6, 2047)
+    assert torch.equal(lag[:, 0::2, 0::2], X) and torch.equal(lag[:, 1::2, 0::2], X)
+    assert torch.equal(lag[:, 0::2, 1::2], X[:, :, 1:]) and torch.equal(lag[:, 1::2, 1::2], X[:, :, :-1])
+    cts = P.CTS(0.25).fit_transform(X)
+    assert torch.equal(cts[:, :, :768], X[:, :, 256:])
+    assert torch.equal(cts[:, :, 768:], X[:, :, -1:].expand(-1, -1, 256))
+    qtc = P.QTC(0.9)
+    qtc.fit(X)
+    cut = qtc.transform(X)
+    assert float(cut.max()) == float(qtc._quantile) and torch.equal(cut[X <= cut.max()], X[X <= cut.max()])
+    assert 0.099 < float((X > qtc._quantile).double().mean()) < 0.101
+    spe = P.SPE(0.5)
+    assert torch.allclose(spe.transform(2.0 * X), 2.0 * spe.transform(X), rtol=1e-15, atol=0.0)
+    mav = P.MAV(8)
+    mav.fit(X)
+    assert torch.equal(mav.transform(torch.ones_like(X))[:, :, 7:], torch.ones_like(X)[:, :, 7:])
+    # a slice behind a prepared copy: features of a series do not depend on its batch
+    fruit = fruits.Fruit()
+    fruit.add(P.LAG(), P.INC(), fruits.ISS(fruits.words.of_weight(2, 2), mode=fruits.ISSMode.EXTENDED),
+              fruits.sieving.NPI(q=(0.5, 1.0)), fruits.sieving.MAX(), fruits.sieving.END())
+    np.random.seed(0)
+    fruit.fit(X[:64, :1])
+    whole = fruit.transform(X[:, :1].contiguous())
+    part = fruit.transform(X[4096:4096 + 512, :1].contiguous())
+    assert torch.equal(whole[4096:4096 + 512], part)
+
+
 def test_preparateur_edge_shapes():
     """Shapes at the edges: one time step, windows longer than the series, empty
     batches, the cache-row quirk of WIN / SPE on a one-series fit sample."""
