@@ -1292,6 +1292,16 @@ def test_preparateur_edge_shapes():
         a, b = np.sum(l2[i] <= 0.2 * l2[i, -1]) - 1, np.sum(l2[i] <= 0.7 * l2[i, -1])
         want[i, :, a:b] = X[3 + i, :, a:b]
     np.testing.assert_array_equal(got, want)
+    # the cached keep mask follows the series length and the fitted state
+    dot = P.DOT(3)
+    dot.fit(X)
+    a = dot.transform(X)
+    longer = np.concatenate((X, X), axis=2)
+    b = dot.transform(longer)
+    assert b.shape == longer.shape and np.array_equal(b[:, :, :17], a)
+    assert np.array_equal(b[:, :, 2::3], longer[:, :, 2::3]) and np.count_nonzero(b) == b[:, :, 2::3].size
+    dot._n, dot._first = 2, 0                  # (what a second fit would change)
+    assert np.array_equal(dot.transform(X)[:, :, 0::2], X[:, :, 0::2])
     with pytest.raises(ValueError):
         P.RPE(0.5).transform(np.zeros((1, 3, 4)))
     with pytest.raises(RuntimeError):
