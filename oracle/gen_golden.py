@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  Run in the build container, where the reference
 checkout is mounted at /root/reference (it does not exist on the GPU box):
 
-    python oracle/gen_golden.py
+    python oracle/gen_golden.py            # words iss sieves preps pipelines
+    python oracle/gen_golden.py cos extra preps2 cos2 argmax corbeille   # the other groups
 
 The script
   1. imports the unmodified reference package (with the one-line
