@@ -8,11 +8,12 @@ against the GPU path::
     data = corbeille.data.load("path/to/UCR/Chinatown")
     seconds, accuracy = corbeille.fruitify(data, fruit)
 
-Only ``fruitify`` / ``fruitify_all`` and ``data.load`` / ``data.load_all`` /
-``data.replace_nan`` are mirrored; the analysis classes (``Fruitalyser``,
-plots) are outside the accelerated path.
+Mirrored: ``fruitify`` / ``fruitify_all`` / ``decide_which_fruit``, the whole
+``data`` module (``.txt`` and ``.arff`` readers, ``multisine``, the resampling
+helpers) and ``tools.split_index``; the analysis class ``Fruitalyser`` (matplotlib
+plots) is outside the path.
 """
-from . import data
-from .fruitifier import fruitify, fruitify_all
+from . import data, tools
+from .fruitifier import decide_which_fruit, fruitify, fruitify_all
 
-__all__ = ["data", "fruitify", "fruitify_all"]
+__all__ = ["data", "tools", "fruitify", "fruitify_all", "decide_which_fruit"]

@@ -1,5 +1,5 @@
 """Timing / accuracy harness (reference:
-``experiments/corbeille/corbeille/fruitifier.py:20-103``): fit a fruit on the
+``experiments/corbeille/corbeille/fruitifier.py:20-175``): fit a fruit on the
 training series, extract features of both splits, classify with a ridge
 classifier on standardised features, report (seconds, accuracy).  The timed
 region is exactly the reference's -- ``fit`` + two ``transform`` calls with
@@ -79,3 +79,36 @@ def fruitify_all(path: str, fruit, datasets: Optional[Sequence[str]] = None,
         pd.DataFrame(rows, columns=["Dataset", "Accuracy", "Time"]).to_csv(stem + ".csv",
                                                                            index=False)
     return pd.DataFrame(rows, columns=["Dataset", "Accuracy", "Time"])
+
+
+def decide_which_fruit(choices, n_splits: int = 1, validation_size: float = 0.2,
+                       classifier=None, mean_over_n_runs: int = 1) -> Callable:
+    """-> ``choose(X_train, y_train) -> Fruit`` for :func:`fruitify`: every
+    candidate in ``choices`` (a Fruit, or a pair ``(cheap fruit to judge by,
+    fruit to return)``) is scored on ``n_splits`` stratified validation splits of
+    the training data and a deep copy of the best one is returned; the first
+    candidate if some class has a single sample (no stratified split exists).
+    ``validation_size`` grows to one sample per class if it has to (reference
+    :106-175; the splits draw from the global numpy RNG through sklearn)."""
+    def second(choice):
+        return (choice[1] if isinstance(choice, tuple) else choice).deepcopy()
+
+    def choose(X: np.ndarray, y: np.ndarray):
+        from sklearn.model_selection import train_test_split
+        counts = np.unique(y, return_counts=True)[1]
+        if np.sum(counts == 1) >= 1:
+            return second(choices[0])
+        share = max(validation_size, len(counts) / X.shape[0])
+        means = []
+        for choice in choices:
+            judged = choice[0] if isinstance(choice, tuple) else choice
+            accuracies = []
+            for _ in range(n_splits):
+                split = train_test_split(X, y, test_size=share, stratify=y)
+                accuracies.append(fruitify((split[0], split[2], split[1], split[3]), judged,
+                                           classifier=classifier,
+                                           mean_over_n_runs=mean_over_n_runs)[1])
+            means.append(np.mean(accuracies))
+        return second(choices[int(np.argmax(means))])
+
+    return choose

@@ -411,6 +411,97 @@ def gen_corbeille():
     np.savez_compressed(os.path.join(GOLD, "corbeille.npz"), **out)
 
 
+def _reference_corbeille():
+    """The reference's whole ``corbeille`` package.  Its ``__init__`` pulls in the
+    plotting class, i.e. matplotlib, which this image lacks: empty stand-ins for
+    the matplotlib names it imports are enough (nothing here plots)."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.axes", "matplotlib.figure"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].cm = object()
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib.axes"].Axes = object
+    sys.modules["matplotlib.figure"].Figure = object
+    sys.path.insert(0, os.path.join(REF, "experiments", "corbeille"))
+    import corbeille as rc
+    assert os.path.realpath(rc.__file__).startswith(os.path.realpath(REF)), rc.__file__
+    return rc
+
+
+def gen_corbeille2():
+    """The rest of the harness: the multivariate .arff reader (fixture committed
+    under tests/golden/ucr_mv/), multisine and the resampling helpers under seeds,
+    tools.split_index, decide_which_fruit."""
+    print("[corbeille 2]")
+    rc = _reference_corbeille()
+    out = {}
+    root = os.path.join(GOLD, "ucr_mv", "Zeta")
+    os.makedirs(root, exist_ok=True)
+    rng = np.random.default_rng(3)
+
+    def write(path, n, labels):
+        d, t = 2, 6
+        with open(path, "w") as f:
+            f.write("@relation Zeta\n@attribute relationalAtt relational\n")
+            for k in range(t):
+                f.write(f"  @attribute att{k} numeric\n")
+            f.write("@end relationalAtt\n@attribute classAttribute {up,down,flat}\n@data\n")
+            for i in range(n):
+                X = np.round(rng.standard_normal((d, t)), 3)
+                if i == 1:
+                    X[0, 2] = np.nan
+                rows = "\\n".join(",".join("?" if np.isnan(v) else repr(float(v)) for v in row)
+                                   for row in X)
+                f.write(f"'{rows}',{labels[i % len(labels)]}\n")
+
+    write(os.path.join(root, "Zeta_TRAIN.arff"), 5, ["down", "up", "down", "flat"])
+    write(os.path.join(root, "Zeta_TEST.arff"), 4, ["flat", "up"])
+    for keep in (False, True):
+        got = rc.data.load(root, univariate=False, cache=False, keep_nan=keep)
+        for key, a in zip(("X_train", "y_train", "X_test", "y_test"), got):
+            out[f"arff_{key}" + ("_keep_nan" if keep else "")] = a
+    X = np.random.default_rng(0).standard_normal((4, 2, 30)).cumsum(axis=2)
+    out["util_X"] = X
+    out["lengthen"] = rc.data.lengthen(X, 0.2)
+    out["downsample"] = rc.data.downsample(X, 0.34)
+    out["upsample"] = rc.data.upsample(X)
+    out["upsample_1d"] = rc.data.upsample(X[:, :1])
+    for tag, sl in (("a", 0.1), ("b", 0.5)):
+        np.random.seed(5)
+        out["stutter_" + tag] = rc.data.implant_stuttering(X, sl)
+        out["stutter_" + tag + "_rng"] = np.array(np.random.random())
+    np.random.seed(9)
+    ms = rc.data.multisine(train_size=11, test_size=7, length=20, n_classes=3)
+    out["multisine_rng"] = np.array(np.random.random())
+    for key, a in zip(("X_train", "y_train", "X_test", "y_test"), ms):
+        out["multisine_" + key] = a
+    # tools.split_index over every index of a fruit with chained ISS and wide sieves
+    fruit = specs.build_fruit(ref, specs.SPECS["R_mixed"])
+    for level, count in (("prepared", len(fruit)),
+                         ("iterated sums", sum(int(np.prod([i.n_iterated_sums() for i in s.get_iss()]))
+                                               for s in fruit)),
+                         ("features", fruit.nfeatures())):
+        rows = [rc.tools.split_index(fruit, i, level) for i in range(count)]
+        out["split_" + level.replace(" ", "_")] = np.array(rows, dtype=np.int64)
+    # decide_which_fruit: which of three candidates the reference picks on a dataset
+    Xtr, ytr, Xte, yte = (np.load(os.path.join(GOLD, "corbeille.npz"))[f"Delta_{k}"]
+                          for k in ("X_train", "y_train", "X_test", "y_test"))
+    choices = [specs.build_fruit(ref, specs.SPECS[n]) for n in ("R_decide_a", "R_decide_b")]
+    choices.append((choices[0], specs.build_fruit(ref, specs.SPECS["C2_reduced"])))
+    picked = []
+    for seed in (0, 1, 2):
+        np.random.seed(seed)
+        chosen = rc.fruitifier.decide_which_fruit(choices, n_splits=2)(np.nan_to_num(Xtr), ytr)
+        picked.append(chosen.nfeatures())
+    out["decide_nfeatures"] = np.array(picked)
+    lonely = ytr.copy()
+    lonely[0] = 7                                   # a class with a single sample
+    out["decide_lonely"] = np.array(rc.fruitifier.decide_which_fruit(choices)(Xtr, lonely).nfeatures())
+    print("  decide_which_fruit picked fruits with", picked, "features")
+    np.savez_compressed(os.path.join(GOLD, "corbeille2.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["words", "iss", "sieves", "preps", "pipelines"]
     for w in which:

@@ -183,6 +183,14 @@ SPECS["R_argmax"] = {"slices": [
      "iss": [{"words": ["[1][2]", "[2][1][1]"], "mode": "extended", "semiring": "arctic_argmax"}],
      "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MAX", {}], ["END", {}]], "fit_sample_size": 1.0}]}
 
+# two small candidates for corbeille.decide_which_fruit
+SPECS["R_decide_a"] = {"slices": [
+    {"preps": [["INC", {}]], "iss": [{"words": {"of_weight": [2, 1]}, "mode": "extended"}],
+     "sieves": [["NPI", {"q": [0.5, 1.0]}], ["END", {}]], "fit_sample_size": 1.0}]}
+SPECS["R_decide_b"] = {"slices": [
+    {"preps": [], "iss": [{"words": ["[1]"], "mode": "single", "semiring": "arctic"}],
+     "sieves": [["MAX", {}]], "fit_sample_size": 1.0}]}
+
 # the complete experiments/fruit_reduced.py pipeline: all four slices (4,431 features)
 SPECS["C2_full"] = {"slices": SPECS["C2_reduced"]["slices"] + SPECS["C2_cos"]["slices"]}
 

@@ -777,6 +777,28 @@ def test_corbeille_fruitify_on_ucr_layout(tmp_path):
     assert (tmp_path / "res.csv").exists()
 
 
+def test_corbeille_decide_which_fruit_equals_the_reference(golden_dir):
+    """decide_which_fruit on the committed dataset under three seeds picks the
+    candidates the reference's harness picks with the reference's Fruit (the
+    validation splits come from the global numpy RNG through sklearn)."""
+    import corbeille
+    g = np.load(os.path.join(golden_dir, "corbeille2.npz"))
+    d = np.load(os.path.join(golden_dir, "corbeille.npz"))
+    Xtr, ytr = np.nan_to_num(d["Delta_X_train"]), d["Delta_y_train"]
+    choices = [specs.build_fruit(fruits, specs.SPECS[n]) for n in ("R_decide_a", "R_decide_b")]
+    choices.append((choices[0], specs.build_fruit(fruits, specs.SPECS["C2_reduced"])))
+    picked = []
+    for seed in (0, 1, 2):
+        np.random.seed(seed)
+        chosen = corbeille.decide_which_fruit(choices, n_splits=2)(Xtr, ytr)
+        assert chosen is not choices[0] and chosen is not choices[1]        # a deep copy
+        picked.append(chosen.nfeatures())
+    assert picked == list(g["decide_nfeatures"])
+    lonely = ytr.copy()
+    lonely[0] = 7
+    assert corbeille.decide_which_fruit(choices)(Xtr, lonely).nfeatures() == int(g["decide_lonely"])
+
+
 def test_corbeille_fruitify_equals_the_reference(golden_dir):
     """``corbeille.fruitify`` on the committed UCR-layout datasets: the features it
     classifies are ``Fruit.transform`` of the loaded arrays, they agree with the

@@ -274,8 +274,101 @@ def test_corbeille_loader(tmp_path):
     names = [d[0] for d in corbeille.data.load_all(str(tmp_path))]
     assert names == ["Alpha", "Beta"]
     assert [d[0] for d in corbeille.data.load_all(str(tmp_path), datasets=["Beta"])] == ["Beta"]
-    with pytest.raises(NotImplementedError):
-        corbeille.data.load(str(tmp_path / "Alpha"), univariate=False)
+    with pytest.raises(FileNotFoundError):
+        corbeille.data.load(str(tmp_path / "Alpha"), univariate=False)      # no .arff there
+
+
+def test_corbeille_data_module_equals_the_reference(golden_dir, tmp_path):
+    """The multivariate .arff reader (+ its .npy cache), multisine and the
+    resampling helpers against what the reference's module returns for the same
+    files / seeds (frozen by ``oracle/gen_golden.py corbeille2``)."""
+    import shutil
+    import corbeille
+    g = np.load(os.path.join(golden_dir, "corbeille2.npz"))
+    root = str(tmp_path / "Zeta")
+    shutil.copytree(os.path.join(golden_dir, "ucr_mv", "Zeta"), root)
+    for keep, tag in ((False, ""), (True, "_keep_nan")):
+        got = corbeille.data.load(root, univariate=False, cache=False, keep_nan=keep)
+        for key, a in zip(("X_train", "y_train", "X_test", "y_test"), got):
+            want = g[f"arff_{key}{tag}"]
+            assert a.dtype == want.dtype and np.array_equal(a, want, equal_nan=True), key
+    assert not [f for f in os.listdir(root) if f.endswith(".npy")]
+    first = corbeille.data.load(root, univariate=False)                # writes the cache
+    assert sorted(f for f in os.listdir(root) if f.endswith(".npy")) == [
+        "Zeta_XTEST.npy", "Zeta_XTRAIN.npy", "Zeta_yTEST.npy", "Zeta_yTRAIN.npy"]
+    os.remove(os.path.join(root, "Zeta_TRAIN.arff"))                  # ... and reads it back
+    for a, b in zip(first, corbeille.data.load(root, univariate=False)):
+        assert np.array_equal(a, b)
+    assert [d[0] for d in corbeille.data.load_all(str(tmp_path), univariate=False)] == ["Zeta"]
+    X = g["util_X"]
+    assert np.array_equal(corbeille.data.lengthen(X, 0.2), g["lengthen"])
+    assert np.array_equal(corbeille.data.downsample(X, 0.34), g["downsample"])
+    assert np.array_equal(corbeille.data.upsample(X), g["upsample"])
+    assert np.array_equal(corbeille.data.upsample(X[:, :1]), g["upsample_1d"])
+    mid = corbeille.data.upsample(X[:, :1])
+    assert np.array_equal(mid[:, :, 0::2], X[:, :1]) and mid.shape[2] == 59
+    for tag, sl in (("a", 0.1), ("b", 0.5)):
+        np.random.seed(5)
+        assert np.array_equal(corbeille.data.implant_stuttering(X, sl), g["stutter_" + tag])
+        assert np.random.random() == float(g[f"stutter_{tag}_rng"])
+    np.random.seed(9)
+    ms = corbeille.data.multisine(train_size=11, test_size=7, length=20, n_classes=3)
+    assert np.random.random() == float(g["multisine_rng"])
+    for key, a in zip(("X_train", "y_train", "X_test", "y_test"), ms):
+        assert np.array_equal(a, g["multisine_" + key]), key
+    sized = corbeille.data.multisine(train_size=4, test_size=5, length=9, noise=lambda: 0.25)
+    assert sized[0].shape == (4, 1, 9) and sorted(sized[3]) == [0, 0, 1, 1, 1]
+
+
+def test_corbeille_split_index_equals_the_reference(golden_dir):
+    """tools.split_index over every prepared / iterated-sum / feature index of
+    a fruit with chained ISS and sieves of several features."""
+    import corbeille
+    g = np.load(os.path.join(golden_dir, "corbeille2.npz"))
+    fruit = specs.build_fruit(fruits, specs.SPECS["R_mixed"])
+    for level in ("prepared", "iterated sums", "features"):
+        want = g["split_" + level.replace(" ", "_")]
+        got = [corbeille.tools.split_index(fruit, i, level) for i in range(len(want))]
+        assert np.array_equal(np.array(got), want), level
+        for bad in (-1, len(want)):
+            with pytest.raises(ValueError):
+                corbeille.tools.split_index(fruit, bad, level)
+    with pytest.raises(ValueError):
+        corbeille.tools.split_index(fruit, 0, "words")
+
+
+def test_corbeille_decide_which_fruit_logic():
+    """decide_which_fruit with stand-in fruits (no GPU): the candidate whose
+    features classify best on the validation splits wins, a pair returns its
+    second member, a class with one sample short-cuts to the first candidate."""
+    import corbeille
+
+    class Stub:
+        def __init__(self, name, informative):
+            self.name, self.informative = name, informative
+
+        def fit(self, X):
+            pass
+
+        def transform(self, X):
+            signal = X[:, 0, :1] if self.informative else np.zeros((len(X), 1))
+            return np.concatenate((signal, np.ones((len(X), 1))), axis=1)
+
+        def deepcopy(self):
+            return Stub(self.name + "'", self.informative)
+
+    rng = np.random.default_rng(0)
+    y = np.repeat([0, 1], 30)
+    X = rng.standard_normal((60, 1, 8)) * 0.1
+    X[:, 0, 0] += 3.0 * y
+    blind, sharp, big = Stub("blind", False), Stub("sharp", True), Stub("big", True)
+    np.random.seed(0)
+    assert corbeille.decide_which_fruit([blind, sharp], n_splits=3)(X, y).name == "sharp'"
+    np.random.seed(0)
+    assert corbeille.decide_which_fruit([blind, (sharp, big)])(X, y).name == "big'"
+    lonely = y.copy()
+    lonely[0] = 5
+    assert corbeille.decide_which_fruit([(blind, big), sharp])(X, lonely).name == "big'"
 
 
 def test_copy_threads_copy_rows():
