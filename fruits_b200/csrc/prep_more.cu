@@ -208,26 +208,28 @@ __global__ void random_increments_kernel(const double *__restrict__ X,
 }
 
 // JLD transform.py:651-670: out[i][o][k] = sum_{j in group o} (x[dims[j]][k] * kern[j] + bias[o]).
+// Rows are series: a thread forms ALL output dimensions of its (series, time step), so
+// the d input values it needs are fetched from HBM once and re-read from L1.
 __global__ void dim_project_kernel(const double *__restrict__ X, const double *__restrict__ kern,
                                    const double *__restrict__ bias,
                                    const int *__restrict__ ndim, const int *__restrict__ dims,
                                    double *__restrict__ out, long long n, long long d, int t,
                                    int n_out)
 {
-    FB_ROWS(row, n * n_out) {
-        const long long i = row / n_out;
-        const int o = (int)(row - i * n_out);
-        int start = 0;
-        for (int q = 0; q < o; q++) start += ndim[q];
-        const int end = start + ndim[o];
+    FB_ROWS(i, n) {
         const double *xi = X + i * d * t;
-        const double b = bias[o];
-        double *dst = out + row * t;
+        double *oi = out + i * n_out * t;
         FB_COLS(k, t) {
-            double s = 0.0;
-            for (int j = start; j < end; j++)
-                s = __dadd_rn(s, __dadd_rn(__dmul_rn(xi[(long long)dims[j] * t + k], kern[j]), b));
-            dst[k] = s;
+            int start = 0;
+            for (int o = 0; o < n_out; o++) {
+                const int end = start + ndim[o];
+                const double b = bias[o];
+                double s = 0.0;
+                for (int j = start; j < end; j++)
+                    s = __dadd_rn(s, __dadd_rn(__dmul_rn(xi[(long long)dims[j] * t + k], kern[j]), b));
+                oi[(long long)o * t + k] = s;
+                start = end;
+            }
         }
     }
 }
@@ -247,13 +249,32 @@ __global__ void ffn_kernel(const double *__restrict__ X, const double *__restric
         const double *xi = X + i * d * t;
         double *dst = out + row * t;
         FB_COLS(k, t) {
+            // the (centred) inputs of this time step: registers for up to 8 dimensions,
+            // instead of one load per hidden unit and dimension
+            double xc[8];
+            const bool small = d <= 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double xv = 0.0;
+                if (small && j < d) {
+                    xv = xi[(long long)j * t + k];
+                    if (mean) xv = __dadd_rn(xv, -mean[2 * (i * d + j)]);
+                }
+                xc[j] = xv;
+            }
             double acc = 0.0;
             for (int u = 0; u < h; u++) {
                 double hv = 0.0;
-                for (long long j = 0; j < d; j++) {
-                    double xv = xi[j * t + k];
-                    if (mean) xv = __dadd_rn(xv, -mean[2 * (i * d + j)]);
-                    hv = __dadd_rn(hv, __dmul_rn(W1[u * d + j], xv));
+                if (small) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (j < d) hv = __dadd_rn(hv, __dmul_rn(W1[u * d + j], xc[j]));
+                } else {
+                    for (long long j = 0; j < d; j++) {
+                        double xv = xi[j * t + k];
+                        if (mean) xv = __dadd_rn(xv, -mean[2 * (i * d + j)]);
+                        hv = __dadd_rn(hv, __dmul_rn(W1[u * d + j], xv));
+                    }
                 }
                 hv = __dadd_rn(hv, b1[u]);
                 hv = __dmul_rn(hv, hv > 0.0 ? 1.0 : 0.0);
@@ -443,8 +464,7 @@ int fb_dim_project(const double *X, const double *kernel, const double *bias,
 {
     FB_REQUIRE(n == 0 || (X && kernel && bias && ndim && dims && out), "null pointer");
     FB_REQUIRE(n >= 0 && d >= 1 && t >= 1 && n_out >= 1, "bad arguments");
-    FB_LAUNCH_ROWS(dim_project_kernel, n * n_out, t, X, kernel, bias, ndim, dims, out, n, d, (int)t,
-                   n_out);
+    FB_LAUNCH_ROWS(dim_project_kernel, n, t, X, kernel, bias, ndim, dims, out, n, d, (int)t, n_out);
     return 0;
 }
 
