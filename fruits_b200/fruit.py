@@ -787,7 +787,10 @@ class FruitSlice:
         prepared input plus one dimension per extended letter (``ISS._lettered``).
         False if the slice cannot be fused behind any prefix."""
         saved, saved_iss = self._preparateurs, self._iss
-        generic = len(saved_iss) == 1 and getattr(saved_iss[0], "_generic", False)
+        # (Bayesian generic words: their twin's rows are moved in time afterwards, so the
+        # sieves have to see materialised rows)
+        generic = (len(saved_iss) == 1 and getattr(saved_iss[0], "_generic", False)
+                   and saved_iss[0].semiring._code != be.SEMIRING_BAYESIAN)
         if callbacks or not (saved or generic):
             return False
         try:

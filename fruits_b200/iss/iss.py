@@ -60,10 +60,6 @@ class ISS(Seed):
         if self._generic:
             if any(len(w) == 0 for w in words):
                 raise NotImplementedError("a word needs at least one extended letter")
-            if isinstance(self.semiring, Bayesian):
-                raise NotImplementedError(
-                    "generic words in the Bayesian semiring take the reference's shifted "
-                    "general recursion (semiring.py:54-75), which has no kernel")
             if weighting is not None and any(isinstance(w, SimpleWord) for w in words):
                 raise NotImplementedError(
                     "the reference weights SimpleWords and ignores the weighting for generic "
@@ -105,23 +101,36 @@ class ISS(Seed):
         (semiring.py:40)."""
         n, d, t = X.shape
         arctic = isinstance(self.semiring, Arctic)
+        # Bayesian: the reference's general recursion keeps the shift between levels
+        # (semiring.py:66-71), unlike its fast path for SimpleWords (:530-566).  With the
+        # row of level k moved k steps to the left the shifted recursion IS the unshifted
+        # one, D_k[u] = max_{v<=u} D_{k-1}[v] * C_k[v + k]; the emitted rows are moved back
+        # k steps to the right (zeros in front) afterwards (_ShiftedRows).
+        shifted = isinstance(self.semiring, Bayesian)
         Z = X.cpu().numpy()
-        index, rows = {}, []
+        index, rows, base = {}, [], {}
         for w in self.words:
             if isinstance(w, SimpleWord):
                 continue
-            for el in w._extended_letters:
-                key = str(el)
+            for k, el in enumerate(w._extended_letters):
+                key = (str(el), k if shifted else 0)
                 if key in index:
                     continue
                 index[key] = d + len(rows)
-                C = np.empty((n, t), dtype=np.float64)
-                fns = [el[k] for k in range(len(el))]
-                for i in range(n):
-                    c = np.zeros(t) if arctic else np.ones(t)
-                    for fn in fns:
-                        c = c + fn(Z[i]) if arctic else c * fn(Z[i])
-                    C[i] = c
+                C = base.get(key[0])
+                if C is None:
+                    C = np.empty((n, t), dtype=np.float64)
+                    fns = [el[q] for q in range(len(el))]
+                    for i in range(n):
+                        c = np.zeros(t) if arctic else np.ones(t)
+                        for fn in fns:
+                            c = c + fn(Z[i]) if arctic else c * fn(Z[i])
+                        C[i] = c
+                    base[key[0]] = C
+                if key[1]:
+                    moved = np.ones((n, t), dtype=np.float64)
+                    moved[:, :max(t - k, 0)] = C[:, k:]
+                    C = moved
                 rows.append(C)
         extra = be.to_device(np.ascontiguousarray(np.stack(rows, axis=1)))
         Xs = torch.cat((X, extra), dim=1).contiguous()
@@ -129,9 +138,19 @@ class ISS(Seed):
         sig = (d, tuple(str(w) for w in self.words), self.mode)
         if memo is None or memo[0] != sig:
             twins = [w if isinstance(w, SimpleWord) else SimpleWord(
-                "".join(f"[({index[str(el)] + 1})]" for el in w._extended_letters))
+                "".join(f"[({index[(str(el), k if shifted else 0)] + 1})]"
+                        for k, el in enumerate(w._extended_letters)))
                 for w in self.words]
-            memo = (sig, ISS(twins, mode=self.mode, semiring=self.semiring, weighting=None))
+            twin = ISS(twins, mode=self.mode, semiring=self.semiring, weighting=None)
+            if shifted:
+                shifts = []
+                for i, w in enumerate(self.words):
+                    ext = (self._cache_plan.unique_el_depth(i) if self.mode == ISSMode.EXTENDED
+                           else 1)
+                    generic = not isinstance(w, SimpleWord)
+                    shifts += [k if generic else 0 for k in range(len(w) - ext, len(w))]
+                twin = _ShiftedRows(twin, shifts)
+            memo = (sig, twin)
             self._twin_memo = memo
         twin = memo[1]
         if hasattr(self, "_cache"):
@@ -489,3 +508,42 @@ class ISS(Seed):
         if self.weighting is not None:
             string += " : " + self.weighting.__class__.__name__
         return string
+
+
+class _ShiftedRows:
+    """The SimpleWord twin of an ISS with generic words in the Bayesian semiring:
+    emission ``e`` comes out of the kernels ``shifts[e]`` time steps early (see
+    ``ISS._lettered``) and is moved back here, zeros in front."""
+
+    def __init__(self, inner: ISS, shifts: list) -> None:
+        self._inner, self._shifts = inner, shifts
+
+    def __setattr__(self, name, value) -> None:
+        if name == "_cache":
+            self._inner._cache = value
+        else:
+            object.__setattr__(self, name, value)
+
+    def _back(self, rows: torch.Tensor, first: int) -> torch.Tensor:
+        t = rows.shape[2]
+        for j in range(rows.shape[0]):
+            k = self._shifts[first + j]
+            if k:
+                kept = rows[j, :, :max(t - k, 0)].clone()
+                rows[j, :, :k] = 0.0
+                rows[j, :, k:] = kept
+        return rows
+
+    def materialize(self, X, emit_range=None, lookup=None, trusted: bool = False):
+        return self._back(self._inner.materialize(X, emit_range),
+                          0 if emit_range is None else emit_range[0])
+
+    def iter_chunks(self, X, max_bytes: int = 1 << 30, emit_range=None, rows_for_size=None):
+        for lo, chunk in self._inner.iter_chunks(X, max_bytes, emit_range, rows_for_size):
+            yield lo, self._back(chunk, lo)
+
+    def batch_transform(self, X, batch_size: int = 1):
+        first = 0
+        for rows in self._inner.batch_transform(X, batch_size):
+            yield self._back(rows, first)
+            first += rows.shape[0]

@@ -276,6 +276,23 @@ def gen_argmax():
     gen_pipelines({"R_argmax": EXTRA_PIPE_CASES["R_argmax"]})
 
 
+def gen_letters():
+    """Generic words (Python letters) through ISS.transform in all three semirings."""
+    from cases import LETTER_CASES
+    print("[letters]")
+    out = {}
+    for name, (desc, shape, kind) in LETTER_CASES.items():
+        X = make_iss_input(shape, kind)
+        iss = specs.build_iss(ref, desc)
+        r = iss.transform(X)
+        o = np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X))))
+        assert iss.n_iterated_sums() == orc.n_iterated_sums(desc) == r.shape[0]
+        check_equal(o, r, f"letters {name}")
+        out[name] = r
+        out[name + "_xsha"] = np.array(sha(X))
+    np.savez_compressed(os.path.join(GOLD, "letters.npz"), **out)
+
+
 def gen_cos2():
     """The randomised CosWISS variants (ffn_size, dropout): fit under a seed,
     transform, where the generator stands after fit."""

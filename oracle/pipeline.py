@@ -394,7 +394,7 @@ def iss_generic_word(X, word: str, extended: int, semiring: str):
     product, cumsum over ``tmp[k:]`` behind a shift) and Arctic._iterated_sum
     (:428-446: identity zeros, sum, running maximum, no shift).  Weightings do
     not reach this function in the reference (:40)."""
-    if semiring not in ("reals", "arctic"):
+    if semiring not in ("reals", "arctic", "bayesian"):
         raise NotImplementedError(semiring)
     els = [[(part.split("(")[0], int(part.split("(")[1]) - 1)
             for part in el[1:].split(")")[:-1]] for el in word.split("]")[:-1]]
@@ -402,17 +402,19 @@ def iss_generic_word(X, word: str, extended: int, semiring: str):
     out = np.zeros((n, extended, t))
     for i in range(n):
         Z = X[i]
-        tmp = np.ones(t) if semiring == "reals" else np.zeros(t)
+        tmp = np.zeros(t) if semiring == "arctic" else np.ones(t)
         for k, el in enumerate(els):
-            C = np.ones(t) if semiring == "reals" else np.zeros(t)
+            C = np.zeros(t) if semiring == "arctic" else np.ones(t)
             for name, dim in el:
-                C = C * LETTERS[name](Z, dim) if semiring == "reals" else C + LETTERS[name](Z, dim)
-            if semiring == "reals":
+                C = C + LETTERS[name](Z, dim) if semiring == "arctic" else C * LETTERS[name](Z, dim)
+            if semiring in ("reals", "bayesian"):
+                # (Bayesian inherits the general recursion WITH the shift, :54-75 -- unlike
+                # its fast path for SimpleWords, :530-566 -- and a running maximum, :598-601)
                 if k > 0:
                     tmp = np.roll(tmp, 1)
                     tmp[0] = 0
                 tmp[k:] = tmp[k:] * C[k:]
-                tmp[k:] = np.cumsum(tmp[k:])
+                tmp[k:] = np.cumsum(tmp[k:]) if semiring == "reals" else np.maximum.accumulate(tmp[k:])
             else:
                 tmp = np.maximum.accumulate(tmp + C)
             if len(els) - k <= extended:

@@ -263,6 +263,22 @@ ARGMAX_CASES = {
                          "weighting": ["L1", {"total": True, "scale": 3}]}, (4, 2, 50), "walk"),
 }
 
+# words over Python letters through ISS.transform (Semiring._iterated_sum,
+# fruits/iss/semiring.py:54-75, :428-446), frozen by ``oracle/gen_golden.py letters``
+LETTER_CASES = {
+    "letters_reals": ({"words": ["[ABS(1)DIM(2)][DIM(1)]", "[ABS(1)DIM(2)][RELU(2)][DIM(1)DIM(1)]",
+                                 "[LAGDIFF(1)]", "[12][1]"], "mode": "extended"},
+                      (5, 2, 40), "std"),
+    "letters_arctic": ({"words": ["[ABS(1)][DIM(2)RELU(1)][DIM(1)]", "[ABS(1)][LAGDIFF(2)]",
+                                  "[1][-2]"], "mode": "extended", "semiring": "arctic"},
+                       (4, 2, 33), "walk"),
+    "letters_bayesian": ({"words": ["[ABS(1)][DIM(2)DIM(2)][ABS(1)DIM(2)]", "[ABS(1)][ABS(2)]",
+                                    "[1][2]", "[RELU(1)]"], "mode": "extended",
+                          "semiring": "bayesian"}, (4, 2, 30), "unit"),
+    "letters_bayesian_single": ({"words": ["[ABS(2)][ABS(1)][DIM(2)]", "[2][1]"], "mode": "single",
+                                 "semiring": "bayesian"}, (3, 2, 260), "unit"),
+}
+
 COS_PIPE_CASES = {"C2_cos": ("C2_cos", 16)}
 
 # the randomised CosWISS variants (fruits/iss/cos.py:243-260, :306-324): fit under

@@ -1464,6 +1464,46 @@ def test_generic_words_equal_the_oracle(semiring, mode):
         iss.transform(X[:, :1])
 
 
+@pytest.mark.parametrize("name", sorted(__import__("cases").LETTER_CASES))
+def test_generic_words_golden(name, golden_dir):
+    """Words over Python letters in the three semirings against ISS outputs frozen
+    from the reference, bit for bit -- the Bayesian semiring with the shift of the
+    reference's general recursion (letter rows moved in time around the unshifted
+    kernels), mixed with SimpleWords on its fast path."""
+    from cases import LETTER_CASES
+    g = np.load(os.path.join(golden_dir, "letters.npz"))
+    desc, shape, kind = LETTER_CASES[name]
+    X = make_iss_input(shape, kind)
+    iss = specs.build_iss(fruits, desc)
+    res = iss.transform(X)
+    assert_exact(res, g[name], name)
+    assert_exact(np.concatenate(list(iss.batch_transform(X, batch_size=2))), res, "batch_transform")
+    chunks = [c for _, c in iss.iter_chunks(torch.from_numpy(X).cuda(),
+                                           max_bytes=X.shape[0] * X.shape[2] * 8)]
+    assert len(chunks) > 1
+    assert_exact(torch.cat(chunks).cpu().numpy(), res, "iter_chunks")
+
+
+def test_generic_words_in_a_bayesian_slice_equal_the_oracle():
+    """A slice over generic words in the Bayesian semiring (sieved on materialised
+    rows) against the oracle pipeline."""
+    from oracle import pipeline as orc
+    spec = {"slices": [{"preps": [["NRM", {}]],
+                        "iss": [{"words": ["[ABS(1)][DIM(2)DIM(2)][ABS(1)DIM(2)]", "[ABS(1)][ABS(2)]",
+                                           "[1][2]"], "mode": "extended", "semiring": "bayesian"}],
+                        "sieves": [["NPI", {"q": [0.5, 1.0]}], ["MAX", {}], ["END", {}]],
+                        "fit_sample_size": 1.0}]}
+    X = np.random.default_rng(31).random((25, 2, 41)) + 0.05
+    fruit = specs.build_fruit(fruits, spec)
+    of = orc.OracleFruit(spec)
+    np.random.seed(0)
+    fruit.fit(X)
+    np.random.seed(0)
+    of.fit(X)
+    assert_exact(fitted_thresholds(fruit), oracle_thresholds(of), "thresholds")
+    assert_exact(fruit.transform(X), of.transform(X), "features")
+
+
 def test_generic_words_take_the_fused_kernels(monkeypatch):
     """A slice whose ISS holds generic words runs its SimpleWord twin through
     the fused kernels (iterated sums never materialised) with the features of

@@ -167,7 +167,8 @@ def test_error_behaviour():
     with pytest.raises(TypeError):
         fruits.ISS(["[1]"])
     with pytest.raises(NotImplementedError):
-        fruits.ISS([fruits.words.Word("[DIM(1)]")], semiring=fruits.semiring.Bayesian())
+        fruits.ISS([fruits.words.Word("[DIM(1)]")], mode=fruits.ISSMode.EXTENDED,
+                   semiring=fruits.semiring.Arctic(argmax=True))
     with pytest.raises(NotImplementedError):
         fruits.ISS([fruits.words.Word("[DIM(1)]"), fruits.words.SimpleWord("[1]")],
                    weighting=fruits.iss.weighting.Indices())

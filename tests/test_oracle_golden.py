@@ -125,6 +125,19 @@ def test_prep_golden(name, golden_dir):
     assert_exact(orc.apply_prep(PREP_CASES[name], X), g[name], name)
 
 
+@pytest.mark.parametrize("name", sorted(__import__("cases").LETTER_CASES))
+def test_generic_words_golden(name, golden_dir):
+    """Words over Python letters in the three semirings (oracle restatement of
+    Semiring._iterated_sum, fruits/iss/semiring.py:54-75, :428-446) against the
+    reference's frozen ISS output, bit for bit."""
+    from cases import LETTER_CASES, make_iss_input
+    g = np.load(os.path.join(golden_dir, "letters.npz"))
+    desc, shape, kind = LETTER_CASES[name]
+    X = make_iss_input(shape, kind)
+    assert sha(X) == str(g[name + "_xsha"])
+    assert_exact(np.stack(list(orc.iss_iter(X, desc, orc.RawCache(X)))), g[name], name)
+
+
 @pytest.mark.parametrize("name", sorted(__import__("cases").ARGMAX_CASES))
 def test_arctic_argmax_golden(name, golden_dir):
     """Arctic(argmax=True): maxima and their positions (oracle restatement of
