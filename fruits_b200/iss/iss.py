@@ -60,10 +60,6 @@ class ISS(Seed):
         if self._generic:
             if any(len(w) == 0 for w in words):
                 raise NotImplementedError("a word needs at least one extended letter")
-            if weighting is not None and any(isinstance(w, SimpleWord) for w in words):
-                raise NotImplementedError(
-                    "the reference weights SimpleWords and ignores the weighting for generic "
-                    "words; put them into separate ISS objects")
         self._cache_plan = CachePlan(self.words if mode == ISSMode.EXTENDED else [])
         self.weighting = weighting
         self._trie_memo = None
@@ -98,7 +94,9 @@ class ISS(Seed):
         SimpleWord does in the kernels, so every route (trie kernel, block scan,
         generated kernels) serves generic words bit for bit like the reference.
         Weightings are ignored for generic words, like in the reference
-        (semiring.py:40)."""
+        (semiring.py:40): in an ISS that also holds SimpleWords the twin keeps the
+        weighting and the generic words get ``alpha = 0`` -- a factor ``exp(0) = 1.0``
+        (Arctic: ``+ 0.0``) that changes no bit."""
         n, d, t = X.shape
         arctic = isinstance(self.semiring, Arctic)
         # Bayesian: the reference's general recursion keeps the shift between levels
@@ -141,7 +139,14 @@ class ISS(Seed):
                 "".join(f"[({index[(str(el), k if shifted else 0)] + 1})]"
                         for k, el in enumerate(w._extended_letters)))
                 for w in self.words]
-            twin = ISS(twins, mode=self.mode, semiring=self.semiring, weighting=None)
+            weighted = self.weighting is not None and any(
+                isinstance(w, SimpleWord) for w in self.words)
+            if weighted:
+                for w, tw in zip(self.words, twins):
+                    if tw is not w:
+                        tw.alpha = np.zeros(len(tw), dtype=np.float32)
+            twin = ISS(twins, mode=self.mode, semiring=self.semiring,
+                       weighting=self.weighting if weighted else None)
             if shifted:
                 shifts = []
                 for i, w in enumerate(self.words):

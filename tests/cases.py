@@ -275,6 +275,14 @@ LETTER_CASES = {
     "letters_bayesian": ({"words": ["[ABS(1)][DIM(2)DIM(2)][ABS(1)DIM(2)]", "[ABS(1)][ABS(2)]",
                                     "[1][2]", "[RELU(1)]"], "mode": "extended",
                           "semiring": "bayesian"}, (4, 2, 30), "unit"),
+    "letters_mixed_weighted": ({"words": ["[1][2]", "[ABS(1)][DIM(2)]", "[2][1][1]", "[RELU(2)]"],
+                                "mode": "extended", "weighting": ["Indices", {"scale": 3}],
+                                "alphas": [[0.6, 0.2], None, [0.3, 0.1, 0.5], None]},
+                               (4, 2, 36), "std"),
+    "letters_mixed_weighted_arctic": ({"words": ["[ABS(1)][LAGDIFF(2)]", "[1][-2]", "[2]"],
+                                       "mode": "single", "semiring": "arctic",
+                                       "weighting": ["L1", {"total": True, "scale": 2}]},
+                                      (4, 2, 33), "walk"),
     "letters_bayesian_single": ({"words": ["[ABS(2)][ABS(1)][DIM(2)]", "[2][1]"], "mode": "single",
                                  "semiring": "bayesian"}, (3, 2, 260), "unit"),
 }

@@ -303,7 +303,8 @@ def build_iss(mod, desc):
                            dropout=c.get("dropout"))
     if desc.get("alphas") is not None:
         for w, a in zip(words, desc["alphas"]):
-            w.alpha = a
+            if a is not None:
+                w.alpha = a
     mode = (mod.ISSMode.EXTENDED if desc.get("mode", "single") == "extended"
             else mod.ISSMode.SINGLE)
     return mod.ISS(words, mode=mode,

@@ -169,9 +169,6 @@ def test_error_behaviour():
     with pytest.raises(NotImplementedError):
         fruits.ISS([fruits.words.Word("[DIM(1)]")], mode=fruits.ISSMode.EXTENDED,
                    semiring=fruits.semiring.Arctic(argmax=True))
-    with pytest.raises(NotImplementedError):
-        fruits.ISS([fruits.words.Word("[DIM(1)]"), fruits.words.SimpleWord("[1]")],
-                   weighting=fruits.iss.weighting.Indices())
     with pytest.raises(ValueError):
         fruits.preparation.MAV(width=1.5)
     with pytest.raises(ValueError):
