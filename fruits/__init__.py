@@ -10,9 +10,9 @@ FUN, DIL, WIN, DOT, PDD`` and the wrappers ``NEW``, ``DIM``) and every sieve of 
 reference.  All arithmetic runs on the GPU; user-supplied Python (``FUN``, letter
 functions, lookup transforms) is called on the host with numpy arrays, as in the
 reference.  There is no CPU fallback for anything else, so what is not built
-raises ``NotImplementedError``: generic words with ``Arctic(argmax=True)``, an
-ISS that mixes weighted SimpleWords with generic words, more than four distinct ``alpha`` values in one word and letters with more
-than 15 occurrences ("Limits")."""
+raises ``NotImplementedError``: generic words with ``Arctic(argmax=True)``, more
+than four distinct ``alpha`` values in one word and letters with more than 15
+occurrences (DESIGN.md, "Limits")."""
 import sys as _sys
 
 import fruits_b200 as _impl
