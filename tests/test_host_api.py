@@ -600,3 +600,38 @@ def test_letters_and_generic_words():
     assert iss.n_iterated_sums() == 4 + 2 + 1 and iss.max_dim() == 3
     assert iss.label(1) == "[ABS(1)][T_HALF(2)DIM(1)]" and iss.label(6) == "[13]"
     assert str(iss.copy().words[0]) == str(word)
+
+
+def test_shifted_rows_move_emissions_back_in_time():
+    """Generic words in the Bayesian semiring run through the unshifted kernels on
+    letter rows moved left; ``_ShiftedRows`` moves emission ``e`` back ``shifts[e]``
+    steps (zeros in front) in every access path: whole, ranges, chunks, batches."""
+    import torch
+    from fruits_b200.iss.iss import _ShiftedRows
+
+    rows = torch.arange(1, 4 * 2 * 6 + 1, dtype=torch.float64).reshape(4, 2, 6)
+
+    class Inner:
+        def materialize(self, X, emit_range=None, lookup=None, trusted=False):
+            lo, hi = (0, 4) if emit_range is None else emit_range
+            return rows[lo:hi].clone()
+
+        def iter_chunks(self, X, max_bytes=0, emit_range=None, rows_for_size=None):
+            for lo in range(0, 4, 3):
+                yield lo, rows[lo:lo + 3].clone()
+
+        def batch_transform(self, X, batch_size=1):
+            yield rows[:1].clone()
+            yield rows[1:].clone()
+
+    twin = _ShiftedRows(Inner(), [0, 2, 6, 9])
+    twin._cache = "shared"
+    assert twin._inner._cache == "shared"
+    want = torch.zeros_like(rows)
+    want[0] = rows[0]
+    want[1, :, 2:] = rows[1, :, :4]                     # (6 and 9 steps: nothing is left)
+    assert torch.equal(twin.materialize(None), want)
+    assert torch.equal(twin.materialize(None, (1, 3)), want[1:3])
+    assert torch.equal(torch.cat([c for _, c in twin.iter_chunks(None)]), want)
+    assert [lo for lo, _ in twin.iter_chunks(None)] == [0, 3]
+    assert torch.equal(torch.cat(list(twin.batch_transform(None, 2))), want)
