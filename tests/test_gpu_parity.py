@@ -1232,6 +1232,56 @@ def test_reference_preparateur_known_answers():
                                np.stack([ffn._weights2 @ hidden[i] for i in range(2)]))
 
 
+@pytest.mark.parametrize("shape", [(3, 1, 5), (2, 3, 9), (4, 2, 17), (3, 3, 100), (2, 2, 257),
+                                   (5, 4, 12), (7, 3, 1030)])
+def test_preparateurs_equal_the_oracle_over_shapes(shape):
+    """Every preparateur case on other shapes -- short series, one dimension,
+    lengths across the 256-column tile of the kernels, corner cases of the fitted
+    parameters (no room for DIL strips, DOT with n >= T, PDD of width zero, windows
+    longer than the series) -- against the numpy restatement, which
+    ``oracle/check_preps_sweep.py`` holds against the real reference on the same
+    shapes: same draws in fit, same outputs."""
+    from cases import PREP2_CASES, PREP2_EXACT
+    from oracle import pipeline as orc
+    from oracle import preps as more
+    n, d, t = shape
+    X = np.random.default_rng(n * 1000 + t).standard_normal(shape).cumsum(axis=2)
+    checked = 0
+    for name, desc in PREP2_CASES.items():
+        kind, args = desc
+        Xc = X
+        if kind == "RPE":
+            if d < 2:
+                continue
+            Xc = np.ascontiguousarray(X[:, :2])
+        if kind == "RDW":
+            Xc = np.abs(X) + 0.5
+        if kind == "RIN" and ((args.get("kernel") is not None and d != 3)
+                              or args.get("out_dim", -1) > d):
+            continue
+        if kind == "JLD" and args.get("distribute") and args.get("dim", 1) > d:
+            continue
+        np.random.seed(11)
+        try:
+            st = more.fit_prep(desc, Xc)
+            after = np.random.random()
+            with np.errstate(invalid="ignore"):
+                want = more.transform_prep(desc, st, Xc, orc.RawCache(Xc))
+        except Exception:
+            continue                   # (the reference rejects this shape, too)
+        prep = specs._prep(fruits, desc)
+        np.random.seed(11)
+        prep.fit(Xc)
+        assert np.random.random() == after, f"{name}: fit consumed the RNG differently"
+        got = prep.transform(Xc)
+        if kind in PREP2_EXACT:
+            assert_exact(got, want, f"{name} {shape}")
+        else:
+            assert_close(got, want, 1e-12, f"{name} {shape}")
+        checked += 1
+    assert checked >= 30
+
+
 def test_preparateur_properties_at_scale():
     """Size-independent properties on 20,000 x 3 x 1,024 series (device tensors
     in and out): masks are idempotent and only ever zero values, LAG interleaves
